@@ -1,0 +1,99 @@
+/*
+ * oracle.h — CPU restatement of the reference BiCGSTAB path (TEST INFRASTRUCTURE ONLY).
+ *
+ * This is the checker, never the product: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product library
+ * (libcudamat_b200.so) never links or calls anything in oracle/.
+ *
+ * PARITY STATUS: "parity unpinned" against the reference's GPU arithmetic — every
+ * floating-point operation of the reference's hot path lives in closed-source
+ * cuSPARSE/cuBLAS (CUDA <= 10.2, no version pinned: /root/reference/CMakeLists.txt:9,28)
+ * whose summation orders are unknowable, the reference cannot be compiled here
+ * (legacy cuSPARSE API removed in CUDA 11, <conio.h>), and the reference has no tests
+ * or golden outputs.  What IS pinned: the loader semantics (against
+ * the reference's own mmio.c + mmio_wrapper.h compiled into oracle/_ref), the 3x3
+ * known answer, and the iteration-count anchors of BASELINE.md §5.
+ *
+ * The oracle therefore fixes an ARITHMETIC SPEC that both sides share
+ * bit for bit: same recurrences as the reference loops, explicit fma()/mul/add forms,
+ * fixed per-row summation order, fixed partition-independent reduction tree.
+ */
+#ifndef CUDAMAT_ORACLE_H
+#define CUDAMAT_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_LONG_ROW 32      /* rows longer than this use the 32-lane interleaved row sum */
+#define ORC_LEAF 1024        /* reduction leaf: 32 lanes x 32 strided elements            */
+#define ORC_GROUP 1024       /* leaves per level-2 group (1 Mi elements)                   */
+
+typedef struct {
+    int    iterations;   /* value of the reference's loop counter i at exit               */
+    int    converged;    /* 1 iff ||r|| < tol*||r0|| was observed                          */
+    int    breakdown;    /* 0 none, 1 |omega|<1e-5 (unprec. only), 2 NaN omega, 3 maxit    */
+    int    half_steps;   /* number of residual norms written to hist                      */
+    double nrm_r0;
+    double nrm_r;
+} orc_stats;
+
+/* ---- spec primitives ------------------------------------------------------------ */
+/* y = A*x (+ d.*x), CSR, index base from ia[0]; follows cusparseDcsrmv call sites
+ * pbicgstab.cu:67,104,132,646,676,704 and mult_spec pbicgstab.cu:36-42. d may be NULL. */
+void   orc_spmv(int n, const int *ia, const int *ja, const double *a,
+                const double *x, const double *d, double *y);
+/* spec reduction tree (replaces cublasDdot pbicgstab.cu:81,106,135,136) */
+double orc_dot(int64_t n, const double *a, const double *b);
+/* tree-reduce already formed leaf partials / generic values with the lane-strided R() */
+double orc_reduce_values(int64_t m, const double *v);
+/* leaf partials only (for sharded-reduction tests): out has ceil(n/1024) entries */
+void   orc_dot_leaves(int64_t n, const double *a, const double *b, double *out);
+/* combine leaf partials -> groups -> final, exactly as orc_dot does internally */
+double orc_combine_leaves(int64_t nleaf, const double *leaf);
+
+/* ---- ILU(0) and triangular sweeps (cusparseDcsrilu0 pbicgstab.cu:359; csrsv :94,98) */
+/* M_out gets the factor in A's pattern. returns 0 ok, >0 = 1+row with structurally
+ * missing diagonal, <0 = -(1+row) of first exact-zero pivot (factor still written). */
+int    orc_ilu0(int n, const int *ia, const int *ja, const double *a, double *M_out);
+void   orc_sptrsv_lower_unit(int n, const int *ia, const int *ja, const double *M,
+                             const double *rhs, double *out);
+void   orc_sptrsv_upper(int n, const int *ia, const int *ja, const double *M,
+                        const double *rhs, double *out);
+/* level sets of the lower (upper=0) / upper (upper=1) triangular dependency graph;
+ * level[] gets 0-based level per row, returns number of levels (csrsv_analysis :338,345) */
+int    orc_levels(int n, const int *ia, const int *ja, int upper, int *level);
+
+/* ---- the three solver loops ------------------------------------------------------ */
+/* gpu_pbicgstab2 shifted overload pbicgstab.cu:581-754; d==NULL -> no diag term,
+ * x0==NULL -> ones (the *intended* plain bicgstab, pbicgstab.cu:756-922). hist (may be
+ * NULL) receives ||r0|| then one norm per iteration; hist_cap entries max. */
+int    orc_bicgstab_unprec(int n, const int *ia, const int *ja, const double *a,
+                           const double *d, const double *x0, const double *b,
+                           int maxit, double tol, double *x, orc_stats *st,
+                           double *hist, int hist_cap);
+/* gpu_pbicgstab pbicgstab.cu:45-154 with driver defaults :306-308 (x0 = ones);
+ * hist receives ||r0|| then two norms per full iteration (check 1, check 2). */
+int    orc_bicgstab_ilu0(int n, const int *ia, const int *ja, const double *a,
+                         const double *b, int maxit, double tol, double *x,
+                         orc_stats *st, double *hist, int hist_cap);
+
+/* ---- generators -------------------------------------- */
+/* rows [row0,row1) of the N^3 7-point Dirichlet Poisson matrix, base-0, global column
+ * ids, natural ordering idx=(k*N+j)*N+i, diag 6, off-diag -1.  ia has row1-row0+1
+ * entries starting at 0. returns nnz written (call with ja==NULL to count only). */
+int64_t orc_poisson3d(int N, int64_t row0, int64_t row1, int *ia, int *ja, double *a);
+/* x_true[i] = 2*u-1, u = splitmix64-hash(seed, i) 53-bit uniform; i in [i0, i0+cnt) */
+void   orc_xtrue(uint64_t seed, int64_t i0, int64_t cnt, double *out);
+/* generator.cpp-style random nonsymmetric, made diagonally dominant (config 4):
+ * two-pass; pass 1 (ja==NULL) fills ia (n+1, base-0) and returns nnz. */
+int64_t orc_random_dd(int n, uint64_t seed, int *ia, int *ja, double *a);
+/* gen_rand_vector(n,b,p,min,max) pbicgstab.cu:1093-1097 under glibc rand() default seed */
+void   orc_glibc_rand_vector(int n, double p_zero, double vmin, double vmax, double *out);
+/* toDenseVector pbicgstab.cu:1101-1115 */
+void   orc_to_dense_vector(int n, const double *A, const int *IA, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
