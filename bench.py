@@ -1,0 +1,389 @@
+#!/usr/bin/env python3
+"""bench.py — BiCGSTAB iterations/s + SpMV HBM GB/s on the 3-D 7-point Poisson 256^3 system (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid 256]
+
+A "step" is ONE BiCGSTAB iteration (2 SpMV + the fused vector updates / reductions) of the unpreconditioned
+loop on the Poisson N^3 system, inputs resident in HBM.  The K timed steps run as ceil(K/chunk) restarts of
+`chunk` iterations from x0 = ones (tol = 0 so nothing stops early; the one-time residual set-up of each
+restart, 1 SpMV per chunk, is inside the timed region).  Matrix + vectors (>= 2.4 GB at 256^3) are far
+larger than the 126 MB L2, so no explicit L2 flush is needed.
+
+N > 1 (torchrun, one rank per GPU): the SAME global system row-sharded over the ranks (strong scaling).
+
+JSON line keys: see the task contract; extras: "converge" (full solve to 1e-10), "roofline", "cpu_baseline",
+"clocks", "e2e" (host-pointer C-ABI solve incl. H2D/D2H), "ilu0" and "mat10000" (other BASELINE configs).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "BiCGSTAB iters/s + SpMV HBM GB/s (% peak), 3D Poisson 256^3 at 1/2/4/8 B200"
+UNIT = "iterations/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def bytes_spmv(n, nnz):
+    return 12 * nnz + 4 * (n + 1) + 16 * n
+
+
+def bytes_iter(n, nnz):
+    return 2 * bytes_spmv(n, nnz) + 120 * n
+
+
+class ClockSampler:
+    """samples SM clock / throttle reasons of one GPU with NVML while the timed region runs"""
+
+    def __init__(self, index=0, period=0.05):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:      # noqa: BLE001
+            self.nv, self.err = None, str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:       # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own CPU implementation (bicstab_omp BiCG) on host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(N, budget_s=25.0, iters=None):
+    """Times the reference's bicstab_omp BiCG() (oracle/_ref, compiled from the reference sources) on the
+    Poisson N^3 system, x0 = ones. BiCG() transposes the matrix inside the call, so the rate is taken from
+    the difference of two calls with different iteration caps.  Falls back to the oracle port (1 core)."""
+    O = ge.load_oracle()
+    ia, ja, a = O.poisson3d(N)
+    n = N ** 3
+    xt = O.xtrue(1234, 0, n)
+    b = O.spmv(ia, ja, a, xt)
+    if O.ref_available("bicg"):
+        cores = O.ref_omp_threads()
+        t0 = time.time(); O.ref_bicg(ia, ja, a, b, maxit=1); t1 = time.time() - t0
+        t0 = time.time(); O.ref_bicg(ia, ja, a, b, maxit=3); t3 = time.time() - t0
+        per_it = max((t3 - t1) / 2.0, 1e-9)
+        k2 = iters if iters else int(max(4, min(200, (budget_s - t1) / per_it)))
+        t0 = time.time(); _, it_done = O.ref_bicg(ia, ja, a, b, maxit=k2); tk = time.time() - t0
+        rate = (it_done - 1) / max(tk - t1, 1e-9)
+        return {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": "reference bicstab_omp BiCG() (BiCG, 2 SpMV/iteration incl. A^T) on Poisson %d^3, x0=ones: "
+                          "(%d-1) iterations / (T(maxit=%d)-T(maxit=1)) = %.2f s; OMP threads=%d"
+                          % (N, it_done, k2, tk - t1, cores)}, (it_done - 1), (tk - t1)
+    # oracle port of the BiCGSTAB loop, scalar, 1 core
+    k = iters if iters else 3
+    t0 = time.time(); O.bicgstab_unprec(ia, ja, a, b, maxit=k, tol=0.0); tk = time.time() - t0
+    return {"value": k / tk, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle port of the unpreconditioned BiCGSTAB loop on Poisson %d^3, %d iterations, 1 core" % (N, k)}, k, tk
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, its, secs = cpu_reference_run(args.grid, budget_s=60.0, iters=None if args.steps <= 0 else min(args.steps, 200))
+    n = args.grid ** 3
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "poisson3d_%d" % args.grid, "n": n, "mode": "reference CPU path (bicstab_omp BiCG)",
+                       "timed_iterations": its},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    cm = ge.load_package()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or cm.device_count() <= 0:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    N = args.grid
+    n = N ** 3
+    # row shard of this rank: multiples of the reduction group (2 Mi rows) when possible, else of the tile
+    gran = 2048 * 1024 if n % (2048 * 1024 * world) == 0 else 2048
+    per = ((n // world + gran - 1) // gran) * gran if world > 1 else n
+    row0, row1 = min(rank * per, n), min((rank + 1) * per, n)
+    if world > 1 and rank == world - 1:
+        row1 = n
+    nloc = row1 - row0
+    nnz_loc = cm.poisson3d_nnz(N, row0, row1)
+    nnz = cm.poisson3d_nnz(N)
+    stream = torch.cuda.current_stream().cuda_stream
+    f64 = dict(dtype=torch.float64, device="cuda")
+    ia = torch.empty(nloc + 1, dtype=torch.int32, device="cuda")
+    ja = torch.empty(nnz_loc, dtype=torch.int32, device="cuda")
+    a = torch.empty(nnz_loc, **f64)
+    cm.gen_poisson3d_device(N, row0, row1, ia.data_ptr(), ja.data_ptr(), a.data_ptr(), stream)
+    s = cm.Solver(n, row0, row1, stream=stream)
+    s.set_csr_device(nnz_loc, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes
+            raw = (ctypes.c_ubyte * 128)()
+            cm._check(cm.lib.cudamat_comm_unique_id(raw))
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = (ctypes.c_ubyte * 128)(*idbuf.cpu().tolist()) if rank != 0 else raw
+        cm._check(cm.lib.cudamat_comm_init(s.h, raw, rank, world))
+    if args.variant:
+        s.set_option("spmv_variant", args.variant)
+    sa = s.analyze(cm.MODE_PLAIN)
+    xt = torch.empty(nloc, **f64)
+    cm.gen_xtrue_device(1234, row0, nloc, xt.data_ptr(), stream)
+    b = torch.empty(nloc, **f64)
+    s.spmv(xt.data_ptr(), b.data_ptr())          # b = A x_true (distributed SpMV when sharded)
+    x = torch.zeros(nloc, **f64)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- full solve to 1e-10: the convergence claim of the metric (also part of the warm-up) ----
+    barrier()
+    t0 = time.time()
+    stc = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=5000, tol=1e-10)
+    torch.cuda.synchronize()
+    t_conv = time.time() - t0
+    err = torch.stack([torch.sum((x - xt) ** 2), torch.sum(xt ** 2)])
+    if world > 1:
+        dist.all_reduce(err)
+    relerr = float(torch.sqrt(err[0] / err[1]))
+    converge = {"tol": 1e-10, "iterations": stc["iterations"], "converged": bool(stc["converged"]),
+                "relres": stc["nrm_r"] / stc["nrm_r0"], "rel_err_vs_xtrue": relerr, "seconds": t_conv,
+                "iters_per_s": stc["iterations"] / stc["t_loop"]}
+
+    # ---- warm-up: W iterations ----
+    chunk = max(1, min(args.chunk, converge["iterations"] // 2 if converge["converged"] else args.chunk))
+    s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=max(args.warmup, 3), tol=0.0)
+
+    # ---- timed region: exactly K iterations, CUDA events on the launching stream, max over ranks ----
+    s.set_option("time_spmv", 1)
+    K = args.steps
+    plan = [chunk] * (K // chunk) + ([K % chunk] if K % chunk else [])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = 0
+    t_spmv, n_spmv, done = 0.0, 0, 0
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for m in plan:
+            st = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=m, tol=0.0)
+            done += st["iterations"]
+            t_spmv += st["t_spmv"]; n_spmv += st["n_spmv"]
+            launches0 = st["kernel_launches"] if not launches0 else launches0
+            last_launches = st["kernel_launches"]
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    if done != K:
+        raise SystemExit("timed region ran %d iterations instead of %d (break-down?)" % (done, K))
+    s.set_option("time_spmv", 0)
+    its_per_s = K / (ms * 1e-3)
+    peak, peak_src = peaks()
+    b_spmv = bytes_spmv(n, nnz)           # whole-problem algorithmic bytes of one SpMV
+    b_it = bytes_iter(n, nnz)
+    spmv_ms = (t_spmv * 1e3 / n_spmv) if n_spmv else None
+    # per-GPU share of one SpMV launch on this rank
+    b_spmv_loc = 12 * nnz_loc + 4 * (nloc + 1) + 16 * nloc
+    roof = None
+    if spmv_ms:
+        ach = b_spmv_loc / (spmv_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch_256")
+            except Exception:       # noqa: BLE001
+                traffic = None
+        roof = {"bound": "hbm", "kernel": "k_spmv_%s (fused dot epilogue)" % ("staged" if sa["spmv_variant"] == 2 else "rowlane"),
+                "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
+                "frac_of_8TBps_datasheet": ach / 8000.0, "traffic": traffic,
+                "algorithmic_bytes_per_launch": b_spmv_loc, "avg_launch_ms": spmv_ms, "launches_timed": n_spmv,
+                "iteration": {"algorithmic_bytes": b_it, "achieved_GBps": b_it / world * its_per_s / 1e9,
+                              "frac": b_it / world * its_per_s / 1e9 / peak, "spmv_share_of_step": 2 * spmv_ms / (ms / K)}}
+
+    line = {"metric": METRIC, "value": its_per_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "poisson3d_%d" % N, "n": n, "nnz": nnz, "mode": "unpreconditioned BiCGSTAB (pbicgstab.h:113)",
+                       "x0": "ones", "b": "A*x_true, x_true=hash(1234,i) in (-1,1)", "chunk": chunk,
+                       "l2": "inputs (%.1f GB CSR + vectors) larger than the 126 MB L2, no flush" % ((12 * nnz + 4 * n) / 1e9),
+                       "spmv_variant": sa["spmv_variant"], "sharding": "row slabs, %d rank(s)" % world},
+            "gpu_launches": int(last_launches - 0) if world >= 1 else 0,
+            "converge": converge, "roofline": roof, "clocks": clk.summary()}
+    line["gpu_launches"] = int(last_launches)
+
+    if rank == 0 and world == 1:
+        line.update(single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, converge))
+    elif world > 1:
+        line["e2e"] = None
+    s.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, converge):
+    out = {}
+    # ---- e2e: the reference-facing host-pointer C-ABI call (cudamat_bicgstab_host), pinned HOST buffers,
+    #      H2D of CSR + b and D2H of x inside the timed region; full solve to 1e-10 ----
+    try:
+        h_ia = torch.empty(n + 1, dtype=torch.int32, pin_memory=True); h_ia.copy_(ia)
+        h_ja = torch.empty(nnz, dtype=torch.int32, pin_memory=True); h_ja.copy_(ja)
+        h_a = torch.empty(nnz, dtype=torch.float64, pin_memory=True); h_a.copy_(a)
+        h_b = torch.empty(n, dtype=torch.float64, pin_memory=True); h_b.copy_(b)
+        h_x = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        torch.cuda.synchronize()
+        import ctypes as C
+        st = cm.Stats(); dt = C.c_double(0.0)
+        t0 = time.time()
+        rc = cm.lib.cudamat_bicgstab_host(cm.MODE_PLAIN, n, nnz, C.cast(h_a.data_ptr(), cm.c_dp), C.cast(h_ia.data_ptr(), cm.c_ip),
+                                          C.cast(h_ja.data_ptr(), cm.c_ip), None, None, C.cast(h_b.data_ptr(), cm.c_dp),
+                                          5000, 1e-10, 0, C.cast(h_x.data_ptr(), cm.c_dp), C.byref(dt), C.byref(st))
+        wall = time.time() - t0
+        cm._check(rc)
+        h2d = 12 * nnz + 4 * (n + 1) + 8 * n
+        out["e2e"] = {"value": st.iterations / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(st.iterations, 1),
+                      "d2h_bytes_per_step": 8 * n / max(st.iterations, 1), "iterations": st.iterations, "wall_s": wall,
+                      "t_h2d_s": st.t_h2d, "t_analysis_s": st.t_analysis, "t_loop_s": st.t_loop, "t_d2h_s": st.t_d2h,
+                      "converged": bool(st.converged),
+                      "call": "cudamat_bicgstab_host(MODE_PLAIN, tol=1e-10) on pinned host CSR/b/x"}
+        del h_ia, h_ja, h_a, h_b, h_x
+    except Exception as e:      # noqa: BLE001
+        out["e2e"] = {"value": None, "error": str(e)}
+
+    # ---- ILU0 mode on the same system (BASELINE config 3, second mode) ----
+    if not args.no_ilu0:
+        try:
+            s2 = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
+            s2.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr())
+            sa = s2.analyze(cm.MODE_ILU0)
+            st = s2.solve(cm.MODE_ILU0, b.data_ptr(), x.data_ptr(), maxit=5000, tol=1e-10)
+            relerr = float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt))
+            out["ilu0"] = {"iterations": st["iterations"], "converged": bool(st["converged"]), "t_loop_s": st["t_loop"],
+                           "iters_per_s": st["iterations"] / st["t_loop"], "t_analysis_s": sa["t_analysis"], "t_ilu0_s": sa["t_ilu0"],
+                           "levels": [sa["levels_l"], sa["levels_u"]], "rel_err_vs_xtrue": relerr}
+            s2.close()
+        except Exception as e:      # noqa: BLE001
+            out["ilu0"] = {"error": str(e)}
+
+    # ---- BASELINE config 2: mat10000.mtx with ILU0 (example.cpp defaults: tol 1e-6, glibc-rand b) ----
+    try:
+        m, _, mia, mja, ma = cm.load_mm(os.path.join(ROOT, "tests", "golden", "mat10000.mtx"))
+        rs = np.random.RandomState(0)
+        bb = 1.0 + 4.0 * rs.rand(m)
+        best = None
+        for _ in range(3):
+            xx, dt, st = cm.bicgstab_lu_precond(ma, mia, mja, bb, maxit=2000, tol=1e-6)
+            if best is None or dt < best[0]:
+                best = (dt, st)
+        out["mat10000_ilu0"] = {"iterations": best[1]["iterations"], "t_loop_ms": best[0] * 1e3,
+                                "us_per_iteration": best[0] * 1e6 / max(best[1]["iterations"], 1),
+                                "iters_per_s": best[1]["iterations"] / best[0], "roofline": "n/a (latency-bound)"}
+    except Exception as e:      # noqa: BLE001
+        out["mat10000_ilu0"] = {"error": str(e)}
+
+    # ---- CPU baseline (reported, not the target): reference bicstab_omp on the host cores ----
+    if not args.no_cpu:
+        try:
+            cb, _, _ = cpu_reference_run(N, budget_s=20.0)
+            out["cpu_baseline"] = cb
+        except Exception as e:      # noqa: BLE001
+            out["cpu_baseline"] = {"value": None, "error": str(e)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=256, help="Poisson grid edge N (n = N^3 rows)")
+    ap.add_argument("--chunk", type=int, default=250, help="iterations per restart inside the timed region")
+    ap.add_argument("--variant", type=int, default=0, help="force an SpMV variant (1 rowlane, 2 staged)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-ilu0", action="store_true", help="skip the ILU0 extra")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,263 @@
+// ilu0.cu — ILU(0) preconditioner: level analysis, level-scheduled factorisation and the
+// forward/backward triangular sweeps.  Replaces cusparseDcsrsv_analysis (pbicgstab.cu:338,345),
+// cusparseDcsrilu0 (:359) and cusparseDcsrsv_solve (:94,98,123,127).
+//
+// Arithmetic (bit-identical to oracle/oracle.c orc_ilu0 / orc_sptrsv_*): row-wise IKJ elimination
+// with ascending k, updates restricted to the row's own pattern, l = a_ik / a_kk (IEEE division),
+// a_ij = fma(-l, a_kj, a_ij); L sweep acc = fma(-L_ik, y_k, acc) over ascending k from acc = rhs_i;
+// U sweep the same over ascending upper columns, then one IEEE division by the diagonal.
+// The parallel schedule (levels / sync-free flags) never changes the per-row operation order.
+#include "solver.h"
+#include <algorithm>
+
+namespace cudamat {
+
+// ------------------------------------------------------------------------------------------
+// factorisation: one launch per level, one thread per row of the level
+// ------------------------------------------------------------------------------------------
+__global__ void k_ilu0_level(const int *order, int cnt, const int *ia, const int *ja, const int *diag,
+                             double *M, int *zero_pivot) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const int i = order[t];
+    if (i < 0) return;
+    const int rs = ia[i], re = ia[i + 1];
+    for (int p = rs; p < re; ++p) {
+        const int k = ja[p];
+        if (k >= i) break;
+        const double piv = M[diag[k]];
+        const double l = __ddiv_rn(M[p], piv);
+        M[p] = l;
+        int q = p + 1;
+        const int ke = ia[k + 1];
+        for (int pk = diag[k] + 1; pk < ke; ++pk) {
+            const int j = ja[pk];
+            while (q < re && ja[q] < j) ++q;
+            if (q >= re) break;
+            if (ja[q] == j) M[q] = __fma_rn(-l, M[pk], M[q]);
+        }
+    }
+    if (M[diag[i]] == 0.0) atomicMin(zero_pivot, i);
+}
+
+// ------------------------------------------------------------------------------------------
+// triangular sweeps, variant A: one launch per level (simple, used for small level counts and as
+// the cross-check of variant B)
+// ------------------------------------------------------------------------------------------
+template <bool UPPER>
+__global__ void k_sptrsv_level(const int *order, int cnt, const int *ia, const int *ja, const int *diag,
+                               const double *M, const double *rhs, double *out, const int *status) {
+    if (status && *status != ST_RUNNING) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const int i = order[t];
+    if (i < 0) return;
+    double acc = rhs[i];
+    if (!UPPER) {
+        const int pe = diag[i];
+        for (int p = ia[i]; p < pe; ++p) acc = __fma_rn(-M[p], out[ja[p]], acc);
+        out[i] = acc;
+    } else {
+        const int pd = diag[i], pe = ia[i + 1];
+        for (int p = pd + 1; p < pe; ++p) acc = __fma_rn(-M[p], out[ja[p]], acc);
+        out[i] = __ddiv_rn(acc, M[pd]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// triangular sweeps, variant B: ONE launch per sweep, sync-free. Rows are laid out level by
+// level (each level padded to a warp multiple so a warp never mixes levels); CTAs take a
+// ticket so that logical CTA order == start order, which makes "wait for an earlier row"
+// deadlock-free; a row publishes its value and then its epoch flag.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_relaxed_i32(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_i32(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool UPPER>
+__global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int order_len, const int *ia, const int *ja,
+                                                        const int *diag, const double *M, const double *rhs,
+                                                        double *out, int *flag, int epoch, unsigned *ticket,
+                                                        unsigned ticket_base, const int *status) {
+    // every CTA takes its ticket (even when the solve already stopped) so the host-side
+    // ticket_base stays in step with the device counter
+    __shared__ unsigned s_blk;
+    if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u) - ticket_base;
+    __syncthreads();
+    if (status && *status != ST_RUNNING) return;
+    const int t = (int)s_blk * 256 + threadIdx.x;
+    if (t >= order_len) return;
+    const int i = order[t];
+    if (i < 0) return;
+    double acc = rhs[i];
+    int p, pe, pd = diag[i];
+    if (!UPPER) { p = ia[i]; pe = pd; } else { p = pd + 1; pe = ia[i + 1]; }
+    for (; p < pe; ++p) {
+        const int c = ja[p];
+        const double m = M[p];
+        unsigned spins = 0;
+        while (ld_relaxed_i32(flag + c) != epoch) {
+            if (++spins > (1u << 22)) __trap();       // never hang the GPU on a broken schedule
+        }
+        acc = __fma_rn(-m, ld_relaxed_f64(out + c), acc);
+    }
+    if (UPPER) acc = __ddiv_rn(acc, M[pd]);
+    st_relaxed_f64(out + i, acc);
+    st_release_i32(flag + i, epoch);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side analysis (v1): level sets from the CSR pattern on the host
+// ------------------------------------------------------------------------------------------
+static int build_schedule(cudamat_solver *s, const std::vector<int> &level, int nlevels, LevelSchedule &out) {
+    const int n = s->n;
+    std::vector<int> cnt(nlevels + 1, 0);
+    for (int i = 0; i < n; ++i) cnt[level[i] + 1]++;
+    out.level_ptr.assign(nlevels + 1, 0);
+    for (int l = 0; l < nlevels; ++l) out.level_ptr[l + 1] = out.level_ptr[l] + ((cnt[l + 1] + 31) / 32) * 32;
+    out.order_len = out.level_ptr[nlevels];
+    std::vector<int> order(out.order_len, -1), fill(nlevels, 0);
+    for (int i = 0; i < n; ++i) { const int l = level[i]; order[out.level_ptr[l] + fill[l]++] = i; }
+    out.nlevels = nlevels;
+    CM_CUDA(cudaMalloc(&out.d_order, sizeof(int) * (size_t)std::max(out.order_len, 1)));
+    CM_CUDA(cudaMemcpyAsync(out.d_order, order.data(), sizeof(int) * (size_t)out.order_len, cudaMemcpyHostToDevice, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    return CUDAMAT_OK;
+}
+
+void ilu0_release(cudamat_solver *s) {
+    if (s->d_M) cudaFree(s->d_M);
+    if (s->d_diag) cudaFree(s->d_diag);
+    if (s->lvl_l.d_order) cudaFree(s->lvl_l.d_order);
+    if (s->lvl_u.d_order) cudaFree(s->lvl_u.d_order);
+    if (s->d_flag) cudaFree(s->d_flag);
+    if (s->d_ticket) cudaFree(s->d_ticket);
+    s->d_M = nullptr; s->d_diag = nullptr; s->lvl_l = LevelSchedule(); s->lvl_u = LevelSchedule();
+    s->d_flag = nullptr; s->d_ticket = nullptr;
+    s->ticket_base_l = s->ticket_base_u = 0; s->epoch = 0;
+}
+
+static double now_s() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
+    if (s->row0 != 0 || s->row1 != s->n_global) {
+        set_error("ILU0 is only available on a single shard (multi-GPU ILU0 is out of scope, SURVEY.md §8e)");
+        return CUDAMAT_E_INVALID;
+    }
+    ilu0_release(s);
+    const int n = s->n;
+    const int64_t nnz = s->nnz;
+    double t0 = now_s();
+    std::vector<int> ia(n + 1), ja((size_t)nnz);
+    CM_CUDA(cudaMemcpyAsync(ia.data(), s->d_ia, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaMemcpyAsync(ja.data(), s->d_ja, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<int> diag(n), lvl(n);
+    for (int i = 0; i < n; ++i) {
+        int dp = -1;
+        for (int p = ia[i]; p < ia[i + 1]; ++p) if (ja[p] == i) { dp = p; break; }
+        if (dp < 0) {
+            set_error("ILU0: row %d has no structural diagonal entry (precondition pbicgstab.h:118)", i);
+            return CUDAMAT_E_NO_DIAGONAL;
+        }
+        diag[i] = dp;
+    }
+    int nl = 0, nu = 0;
+    for (int i = 0; i < n; ++i) {
+        int lv = 0;
+        for (int p = ia[i]; p < diag[i]; ++p) lv = std::max(lv, lvl[ja[p]] + 1);
+        lvl[i] = lv; nl = std::max(nl, lv + 1);
+    }
+    int rc = build_schedule(s, lvl, nl, s->lvl_l);
+    if (rc) return rc;
+    for (int i = n - 1; i >= 0; --i) {
+        int lv = 0;
+        for (int p = diag[i] + 1; p < ia[i + 1]; ++p) lv = std::max(lv, lvl[ja[p]] + 1);
+        lvl[i] = lv; nu = std::max(nu, lv + 1);
+    }
+    rc = build_schedule(s, lvl, nu, s->lvl_u);
+    if (rc) return rc;
+    CM_CUDA(cudaMalloc(&s->d_diag, sizeof(int) * (size_t)std::max(n, 1)));
+    CM_CUDA(cudaMemcpyAsync(s->d_diag, diag.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    CM_CUDA(cudaMalloc(&s->d_flag, sizeof(int) * (size_t)std::max(n, 1)));
+    CM_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int) * (size_t)std::max(n, 1), s->stream));
+    CM_CUDA(cudaMalloc(&s->d_ticket, 2 * sizeof(unsigned)));
+    CM_CUDA(cudaMemsetAsync(s->d_ticket, 0, 2 * sizeof(unsigned), s->stream));
+    s->epoch = 0;
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    if (st) { st->t_analysis += now_s() - t0; st->levels_l = nl; st->levels_u = nu; }
+
+    // factorisation on a copy of A (pbicgstab.cu:316,359)
+    t0 = now_s();
+    CM_CUDA(cudaMalloc(&s->d_M, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
+    CM_CUDA(cudaMemcpyAsync(s->d_M, s->d_a, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, s->stream));
+    int *d_zp = nullptr;
+    CM_CUDA(cudaMalloc(&d_zp, sizeof(int)));
+    const int big = 0x7fffffff;
+    CM_CUDA(cudaMemcpyAsync(d_zp, &big, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    for (int l = 0; l < nl; ++l) {
+        const int off = s->lvl_l.level_ptr[l], cnt = s->lvl_l.level_ptr[l + 1] - off;
+        if (cnt == 0) continue;
+        k_ilu0_level<<<(cnt + 127) / 128, 128, 0, s->stream>>>(s->lvl_l.d_order + off, cnt, s->d_ia, s->d_ja, s->d_diag, s->d_M, d_zp);
+        s->launches++;
+    }
+    CM_CUDA(cudaGetLastError());
+    int zp = big;
+    CM_CUDA(cudaMemcpyAsync(&zp, d_zp, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    CM_CUDA(cudaFree(d_zp));
+    s->zero_pivot = (zp == big) ? 0 : -(1 + zp);
+    if (st) { st->t_ilu0 += now_s() - t0; st->zero_pivot = s->zero_pivot; }
+    return CUDAMAT_OK;
+}
+
+int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out) {
+    if (!s->d_M) { set_error("sptrsv: ILU0 factor not available (call cudamat_analyze with CUDAMAT_MODE_ILU0)"); return CUDAMAT_E_STATE; }
+    const LevelSchedule &L = upper ? s->lvl_u : s->lvl_l;
+    const int *status = s->d_sc ? &s->d_sc->status : nullptr;
+    if (s->opt_sptrsv_syncfree && L.order_len > 0) {
+        const int grid = (L.order_len + 255) / 256;
+        s->epoch += 1;
+        // ticket_base: the counter is monotone across launches; every launch consumes `grid` tickets
+        unsigned *ticket = s->d_ticket + (upper ? 1 : 0);
+        unsigned &base = upper ? s->ticket_base_u : s->ticket_base_l;
+        if (upper)
+            k_sptrsv_syncfree<true><<<grid, 256, 0, s->stream>>>(L.d_order, L.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M,
+                                                                rhs, out, s->d_flag, s->epoch, ticket, base, status);
+        else
+            k_sptrsv_syncfree<false><<<grid, 256, 0, s->stream>>>(L.d_order, L.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M,
+                                                                 rhs, out, s->d_flag, s->epoch, ticket, base, status);
+        base += (unsigned)grid;
+        s->launches++;
+    } else {
+        for (int l = 0; l < L.nlevels; ++l) {
+            const int off = L.level_ptr[l], cnt = L.level_ptr[l + 1] - off;
+            if (cnt == 0) continue;
+            if (upper)
+                k_sptrsv_level<true><<<(cnt + 127) / 128, 128, 0, s->stream>>>(L.d_order + off, cnt, s->d_ia, s->d_ja, s->d_diag, s->d_M, rhs, out, status);
+            else
+                k_sptrsv_level<false><<<(cnt + 127) / 128, 128, 0, s->stream>>>(L.d_order + off, cnt, s->d_ia, s->d_ja, s->d_diag, s->d_M, rhs, out, status);
+            s->launches++;
+        }
+    }
+    CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
+}  // namespace cudamat

@@ -1,0 +1,231 @@
+// internal.cuh — shared device helpers and host-side state of libcudamat_b200.
+//
+// Arithmetic spec (mirrored bit for bit by oracle/oracle.c):
+//   * every spec'd floating-point operation is an explicit __dmul_rn/__dadd_rn/__fma_rn/__ddiv_rn
+//     (the file is also compiled with --fmad=false) so no contraction can change a rounding;
+//   * reductions use the slab(32) -> tile(64 slabs) -> group(1024 tiles) -> final tree, all
+//     boundaries aligned in the GLOBAL row index.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/cudamat_b200.h"
+
+namespace cudamat {
+
+constexpr int kSlab        = 32;      // rows per slab (one per lane)
+constexpr int kTileSlabs   = 64;      // slabs per tile
+constexpr int kTile        = 2048;    // rows per tile == rows per CTA in reducing kernels
+constexpr int kGroupTiles  = 1024;    // tiles per group
+constexpr int kLongRow     = 32;      // rows longer than this use the interleaved row sum
+constexpr int kCtaThreads  = 256;
+constexpr int kCtaWarps    = 8;
+constexpr int kSlabsPerWarp = kTileSlabs / kCtaWarps;   // 8
+constexpr int kMaxQ        = 2;       // reduced quantities per kernel
+
+// solver status (device side)
+enum : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BRK_OMEGA = 2, ST_BRK_NAN = 3, ST_MAXIT = 4 };
+
+// phases of the scalar recurrences executed by the last CTA of a reducing kernel
+enum : int {
+    PH_NONE = 0,
+    PH_U_INIT,   // unprec: red0 = r.r            -> nrm0, rho' = red0, beta
+    PH_U_A,      // unprec: red0 = r0.v           -> alpha
+    PH_U_B,      // unprec: red0 = t.s, red1 = t.t -> omega
+    PH_U_C,      // unprec: red0 = r0.r', red1 = r'.r' -> nrm, checks, rho rotate, beta
+    PH_I_INIT,   // ilu0:   red0 = r.r            -> nrm0, rho = red0
+    PH_I_A,      // ilu0:   red0 = rw.v           -> alpha
+    PH_I_A2,     // ilu0:   red0 = r.r            -> nrm, check 1
+    PH_I_B,      // ilu0:   red0 = t.r, red1 = t.t -> omega
+    PH_I_C,      // ilu0:   red0 = rw.r, red1 = r.r -> nrm, i++, check 2, rho rotate, beta
+    PH_STORE     // red -> sc->red only (kernel-level dot entry point)
+};
+
+struct DevScalars {
+    double rho;        // unprec: rho (previous); ilu0: rho
+    double rho_new;    // unprec: rho' of the coming iteration
+    double alpha, omega, beta;
+    double nrm0, nrm, tol;
+    double red[kMaxQ];
+    int iter;          // reference loop counter i
+    int status;        // ST_*
+    int half;          // entries written to hist
+    int maxit;
+    int hist_cap;
+    int pad;
+};
+
+// reduction context of one shard
+struct RedCtx {
+    double   *tile_part;   // [kMaxQ][tile_stride]  tile partials, indexed by LOCAL tile
+    double   *slots;       // [kMaxQ][slot_stride]  group partials, indexed by GLOBAL group
+    unsigned *group_cnt;   // [local groups]
+    unsigned *done_cnt;    // [1]
+    int ntile;             // local tiles
+    int tile_stride;
+    int slot_stride;
+    int ngroup_loc;        // local groups
+    int group0;            // global index of the first local group
+    int nslots;            // global number of groups
+    int do_final;          // 1: last CTA reduces slots and runs the phase (single shard)
+};
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_butterfly(double v) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, s));
+    return v;
+}
+
+// R(): lane-strided chains over m values (read through L2), then butterfly
+__device__ __forceinline__ double warp_reduce_values_cg(const double *v, int m, int lane) {
+    double acc = 0.0;
+    for (int j = lane; j < m; j += 32) acc = __dadd_rn(acc, __ldcg(v + j));
+    return warp_butterfly(acc);
+}
+__device__ __forceinline__ double warp_reduce_values_smem(const double *v, int m, int lane) {
+    double acc = 0.0;
+    for (int j = lane; j < m; j += 32) acc = __dadd_rn(acc, v[j]);
+    return warp_butterfly(acc);
+}
+
+__device__ __forceinline__ void hist_push(DevScalars *sc, double *hist, double v) {
+    if (hist && sc->half < sc->hist_cap) hist[sc->half] = v;
+    sc->half += 1;
+}
+
+// scalar recurrences; executed by one thread. Forms follow pbicgstab.cu (cited per phase).
+__device__ __forceinline__ void apply_phase(DevScalars *sc, double *hist, int phase, const double *red) {
+    switch (phase) {
+    case PH_STORE:
+        sc->red[0] = red[0]; sc->red[1] = red[1];
+        break;
+    case PH_U_INIT: {                                   // pbicgstab.cu:655,665-666 (first pass)
+        double n0 = sqrt(red[0]);
+        sc->nrm0 = n0; sc->nrm = n0;
+        hist_push(sc, hist, n0);
+        sc->rho_new = red[0];                           // dot(r0,r) with r0 == r
+        sc->beta = __dmul_rn(__ddiv_rn(sc->rho_new, sc->rho), __ddiv_rn(sc->alpha, sc->omega));
+        if (sc->maxit <= 0) sc->status = ST_MAXIT;
+    } break;
+    case PH_U_A:                                        // :688-689
+        sc->alpha = __ddiv_rn(sc->rho_new, red[0]);
+        break;
+    case PH_U_B:                                        // :708-710
+        sc->omega = __ddiv_rn(red[0], red[1]);
+        break;
+    case PH_U_C: {                                      // :723-747
+        double nr = sqrt(red[1]);
+        sc->nrm = nr;
+        hist_push(sc, hist, nr);
+        sc->iter += 1;
+        double om = sc->omega;
+        if (nr < __dmul_rn(sc->tol, sc->nrm0)) sc->status = ST_CONVERGED;
+        else if (isnan(om)) sc->status = ST_BRK_NAN;
+        else if (fabs(om) < 1e-5) sc->status = ST_BRK_OMEGA;
+        else if (sc->iter >= sc->maxit) sc->status = ST_MAXIT;
+        sc->rho = sc->rho_new;                          // :748
+        sc->rho_new = red[0];                           // :665 of the next pass
+        sc->beta = __dmul_rn(__ddiv_rn(sc->rho_new, sc->rho), __ddiv_rn(sc->alpha, sc->omega));
+    } break;
+    case PH_I_INIT: {                                   // :74, :81 (first pass)
+        double n0 = sqrt(red[0]);
+        sc->nrm0 = n0; sc->nrm = n0;
+        hist_push(sc, hist, n0);
+        sc->rho = red[0];                               // dot(rw,r) with rw == r
+        if (sc->maxit <= 0) sc->status = ST_MAXIT;
+    } break;
+    case PH_I_A:                                        // :106-107
+        sc->alpha = __ddiv_rn(sc->rho, red[0]);
+        break;
+    case PH_I_A2: {                                     // :111-118  (break without i++)
+        double nr = sqrt(red[0]);
+        sc->nrm = nr;
+        hist_push(sc, hist, nr);
+        if (nr < __dmul_rn(sc->tol, sc->nrm0)) sc->status = ST_CONVERGED;
+    } break;
+    case PH_I_B:                                        // :135-137
+        sc->omega = __ddiv_rn(red[0], red[1]);
+        break;
+    case PH_I_C: {                                      // :142-151, then :80-84 of the next pass
+        double nr = sqrt(red[1]);
+        sc->nrm = nr;
+        hist_push(sc, hist, nr);
+        sc->iter += 1;
+        if (nr < __dmul_rn(sc->tol, sc->nrm0)) sc->status = ST_CONVERGED;
+        else if (sc->iter >= sc->maxit) sc->status = ST_MAXIT;
+        double rhop = sc->rho;
+        sc->rho = red[0];
+        sc->beta = __dmul_rn(__ddiv_rn(sc->rho, rhop), __ddiv_rn(sc->alpha, sc->omega));
+    } break;
+    default: break;
+    }
+}
+
+// Grid-level tail of a reducing kernel. Contract: gridDim.x == rc.ntile, CTA b owns local tile b,
+// s_slab[q][0..63] hold the tile's slab sums (all warps done, __syncthreads() issued by caller).
+template <int NQ>
+__device__ __forceinline__ void reduce_tail(const RedCtx &rc, DevScalars *sc, double *hist, int phase,
+                                            double (*s_slab)[kTileSlabs], int nslab_tile) {
+    __shared__ int s_flag;
+    __shared__ double s_red[kMaxQ];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    // tile partial: R() over the slab sums
+    if (warp < NQ) {
+        double tp = warp_reduce_values_smem(s_slab[warp], nslab_tile, lane);
+        if (lane == 0) {
+            __stcg(rc.tile_part + (size_t)warp * rc.tile_stride + tile, tp);
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    const int g = tile / kGroupTiles;
+    if (tid == 0) {
+        int in_group = min(kGroupTiles, rc.ntile - g * kGroupTiles);
+        unsigned old = atomicAdd(rc.group_cnt + g, 1u);
+        s_flag = (old == (unsigned)(in_group - 1));
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    if (warp < NQ) {
+        int in_group = min(kGroupTiles, rc.ntile - g * kGroupTiles);
+        double gp = warp_reduce_values_cg(rc.tile_part + (size_t)warp * rc.tile_stride + (size_t)g * kGroupTiles,
+                                          in_group, lane);
+        if (lane == 0) {
+            __stcg(rc.slots + (size_t)warp * rc.slot_stride + rc.group0 + g, gp);
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        rc.group_cnt[g] = 0u;
+        unsigned old = atomicAdd(rc.done_cnt, 1u);
+        s_flag = (old == (unsigned)(rc.ngroup_loc - 1));
+        if (s_flag) *rc.done_cnt = 0u;
+    }
+    __syncthreads();
+    if (!s_flag || !rc.do_final) return;
+    __threadfence();
+    if (warp < NQ) {
+        double f = warp_reduce_values_cg(rc.slots + (size_t)warp * rc.slot_stride, rc.nslots, lane);
+        if (lane == 0) s_red[warp] = f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double red[kMaxQ] = {0.0, 0.0};
+        for (int q = 0; q < NQ; ++q) red[q] = s_red[q];
+        apply_phase(sc, hist, phase, red);
+    }
+}
+
+// slab sum of one product per lane (inactive lanes pass +0.0) deposited for the tile tail
+__device__ __forceinline__ void slab_deposit(double (*s_slab)[kTileSlabs], int q, int slab_in_tile, double prod, int lane) {
+    double s = warp_butterfly(prod);
+    if (lane == 0) s_slab[q][slab_in_tile] = s;
+}
+
+}  // namespace cudamat

@@ -1,0 +1,763 @@
+// kernels.cu — hand-written sm_100a kernels of the BiCGSTAB iteration:
+//   CSR SpMV with fused dot epilogues (replaces cusparseDcsrmv + cublasDdot, pbicgstab.cu:67,104-106,
+//   132-136,646,676-688,704-709 and mult_spec :36-42), the fused vector updates with fused
+//   dot/nrm2 reductions (replaces the cublasDaxpy/Dscal/Dcopy/Dnrm2 + cudaMemcpy D2D chains
+//   :69-74,86-88,109-111,139-142,668-672,694-700,714-723,744-747), and the synthetic generators.
+// Every kernel that reduces runs one CTA per 2048-row tile so the reduction tree of the spec
+// (internal.cuh) is independent of scheduling; scalars never leave the device.
+#include "solver.h"
+#include <cub/device/device_scan.cuh>
+
+namespace cudamat {
+
+// ------------------------------------------------------------------------------------------
+// SpMV variant ROWLANE: one row per lane, direct global loads, 8-deep predicated batches.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rowsum_long(const SpmvArgs &a, int s, int e, int lane) {
+    double acc = 0.0;
+    for (int k = s + lane; k < e; k += 32) acc = __fma_rn(__ldg(a.val + k), __ldg(a.x + __ldg(a.ja + k)), acc);
+    return warp_butterfly(acc);
+}
+
+template <bool HAS_D, int NDOT>
+__global__ void __launch_bounds__(kCtaThreads) k_spmv_rowlane(const SpmvArgs a) {
+    if (a.check_status && a.sc->status != ST_RUNNING) return;
+    __shared__ double s_slab[kMaxQ][kTileSlabs];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row_base = blockIdx.x * kTile;
+#pragma unroll 1
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int slab = j * kCtaWarps + warp;
+        const int row0 = row_base + slab * kSlab;
+        if (row0 >= a.n) break;                                   // warp-uniform
+        const int row = row0 + lane;
+        const bool active = row < a.n;
+        int s = 0, e = 0;
+        if (active) { s = __ldg(a.ia + row); e = __ldg(a.ia + row + 1); }
+        const int len = e - s;
+        const int shortlen = (len <= kLongRow) ? len : 0;
+        const int maxlen = __reduce_max_sync(0xffffffffu, shortlen);
+        double sum = 0.0;
+        for (int k0 = 0; k0 < maxlen; k0 += 8) {
+            int cj[8]; double av[8], xv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const bool p = (k0 + q) < shortlen;
+                cj[q] = p ? __ldg(a.ja + s + k0 + q) : -1;
+                av[q] = p ? __ldg(a.val + s + k0 + q) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) xv[q] = (cj[q] >= 0) ? __ldg(a.x + cj[q]) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if ((k0 + q) < shortlen) sum = __fma_rn(av[q], xv[q], sum);
+        }
+        unsigned lm = __ballot_sync(0xffffffffu, len > kLongRow);
+        while (lm) {
+            const int src = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const int ss = __shfl_sync(0xffffffffu, s, src), ee = __shfl_sync(0xffffffffu, e, src);
+            const double acc = rowsum_long(a, ss, ee, lane);
+            if (lane == src) sum = acc;
+        }
+        if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
+        if (active) a.y[row] = sum;
+        if (NDOT >= 1) {
+            const double p0 = active ? __dmul_rn(sum, __ldg(a.u + row)) : 0.0;
+            slab_deposit(s_slab, 0, slab, p0, lane);
+        }
+        if (NDOT >= 2) {
+            const double p1 = active ? __dmul_rn(sum, sum) : 0.0;
+            slab_deposit(s_slab, 1, slab, p1, lane);
+        }
+    }
+    if (NDOT >= 1) {
+        __syncthreads();
+        const int rows_here = min(kTile, a.n - row_base);
+        reduce_tail<(NDOT >= 1 ? NDOT : 1)>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SpMV variant STAGED: each warp streams the contiguous (val, col) span of its 32-row slab into
+// shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), a ring of
+// `stages` slabs deep, then every lane walks its own row out of shared memory.  Global loads
+// issued by threads are only the row pointers and the coalesced x gathers.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct StagedArgs {
+    SpmvArgs a;
+    int cap_nnz;      // smem capacity per slab stage, multiple of 4
+    int stages;
+    int64_t nnz;      // to bound aligned over-reads
+};
+
+// shared layout per warp: [stages] x { double val[cap+2]; int col[cap+8]; } + mbarriers
+template <bool HAS_D, int NDOT>
+__global__ void __launch_bounds__(kCtaThreads) k_spmv_staged(const StagedArgs g) {
+    const SpmvArgs &a = g.a;
+    if (a.check_status && a.sc->status != ST_RUNNING) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_slab[kMaxQ][kTileSlabs];
+    __shared__ uint64_t s_bar[kCtaWarps][4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row_base = blockIdx.x * kTile;
+    const int S = g.stages;
+    const size_t val_bytes = (size_t)(g.cap_nnz + 2) * 8, col_bytes = (size_t)(g.cap_nnz + 8) * 4;
+    const size_t stage_bytes = val_bytes + col_bytes;
+    unsigned char *wbase = smem_raw + (size_t)warp * S * stage_bytes;
+    if (lane == 0)
+        for (int q = 0; q < S; ++q) mbar_init(&s_bar[warp][q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    // slab spans of this warp: rows row_base + (j*8+warp)*32 .. +32
+    int sp_s[kSlabsPerWarp], sp_e[kSlabsPerWarp];
+    int nj = 0;
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int r0 = row_base + (j * kCtaWarps + warp) * kSlab;
+        if (r0 < a.n) {
+            sp_s[j] = __ldg(a.ia + r0);
+            sp_e[j] = __ldg(a.ia + min(r0 + kSlab, a.n));
+            nj = j + 1;
+        } else { sp_s[j] = 0; sp_e[j] = 0; }
+    }
+    // issue: stage q <- slab j. Aligned span: vals from even index, cols from a multiple of 4.
+    // per-stage phase parity (bit q) and the parity each staged slab must wait for (bit j)
+    unsigned phase_bits = 0, parity_mask = 0, staged_mask = 0;
+    auto issue = [&](int j) {
+        const int q = j % S;
+        const int s0 = sp_s[j], e0 = sp_e[j];
+        const int vs = s0 & ~1, ve = (e0 + 1) & ~1;
+        const int cs = s0 & ~3, ce = (e0 + 3) & ~3;
+        const bool fits = e0 > s0 && (e0 - s0) <= g.cap_nnz && (int64_t)ve <= (g.nnz & ~1LL) && (int64_t)ce <= (g.nnz & ~3LL);
+        if (fits) {
+            if (lane == 0) {
+                unsigned char *st = wbase + (size_t)q * stage_bytes;
+                const uint32_t vb = (uint32_t)(ve - vs) * 8u, cb = (uint32_t)(ce - cs) * 4u;
+                mbar_expect_tx(&s_bar[warp][q], vb + cb);
+                tma_bulk_g2s(st, a.val + vs, vb, &s_bar[warp][q]);
+                tma_bulk_g2s(st + val_bytes, a.ja + cs, cb, &s_bar[warp][q]);
+            }
+            staged_mask |= 1u << j;
+            parity_mask |= ((phase_bits >> q) & 1u) << j;
+            phase_bits ^= 1u << q;
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j)
+        if (j < S - 1 && j < nj) issue(j);
+
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        if (j >= nj) break;
+        // keep S-1 slabs in flight
+        if (j + S - 1 < nj) {
+            __syncwarp();
+            issue(j + S - 1);
+        }
+        const int slab = j * kCtaWarps + warp;
+        const int row = row_base + slab * kSlab + lane;
+        const bool active = row < a.n;
+        int s = 0, e = 0;
+        if (active) { s = __ldg(a.ia + row); e = __ldg(a.ia + row + 1); }
+        const int len = e - s;
+        double sum = 0.0;
+        const bool is_staged = (staged_mask >> j) & 1u;
+        if (is_staged) {
+            const int q = j % S;
+            const uint32_t parity = (parity_mask >> j) & 1u;
+            unsigned spins = 0;
+            while (!mbar_try_wait(&s_bar[warp][q], parity)) { if (++spins > (1u << 24)) __trap(); }
+            const unsigned char *st = wbase + (size_t)q * stage_bytes;
+            // stage holds val[vs..ve) and col[cs..ce); rebase so that global nnz index k maps to sv[k]/sc[k]
+            const double *sv = reinterpret_cast<const double *>(st) - (sp_s[j] & ~1);
+            const int *sc = reinterpret_cast<const int *>(st + val_bytes) - (sp_s[j] & ~3);
+            const int shortlen = (len <= kLongRow) ? len : 0;
+            const int maxlen = __reduce_max_sync(0xffffffffu, shortlen);
+            for (int k0 = 0; k0 < maxlen; k0 += 8) {
+                int cj[8]; double xv[8];
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8) cj[q8] = ((k0 + q8) < shortlen) ? sc[s + k0 + q8] : -1;
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8) xv[q8] = (cj[q8] >= 0) ? __ldg(a.x + cj[q8]) : 0.0;
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8)
+                    if ((k0 + q8) < shortlen) sum = __fma_rn(sv[s + k0 + q8], xv[q8], sum);
+            }
+            unsigned lm = __ballot_sync(0xffffffffu, len > kLongRow);
+            while (lm) {
+                const int src = __ffs(lm) - 1;
+                lm &= lm - 1;
+                const int ss = __shfl_sync(0xffffffffu, s, src), ee = __shfl_sync(0xffffffffu, e, src);
+                double acc = 0.0;
+                for (int k = ss + lane; k < ee; k += 32) acc = __fma_rn(sv[k], __ldg(a.x + sc[k]), acc);
+                acc = warp_butterfly(acc);
+                if (lane == src) sum = acc;
+            }
+        } else {
+            // slab does not fit the stage (or is empty): direct global path, same arithmetic
+            const int shortlen = (len <= kLongRow) ? len : 0;
+            const int maxlen = __reduce_max_sync(0xffffffffu, shortlen);
+            for (int k0 = 0; k0 < maxlen; k0 += 8) {
+                int cj[8]; double av[8], xv[8];
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8) {
+                    const bool p = (k0 + q8) < shortlen;
+                    cj[q8] = p ? __ldg(a.ja + s + k0 + q8) : -1;
+                    av[q8] = p ? __ldg(a.val + s + k0 + q8) : 0.0;
+                }
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8) xv[q8] = (cj[q8] >= 0) ? __ldg(a.x + cj[q8]) : 0.0;
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8)
+                    if ((k0 + q8) < shortlen) sum = __fma_rn(av[q8], xv[q8], sum);
+            }
+            unsigned lm = __ballot_sync(0xffffffffu, len > kLongRow);
+            while (lm) {
+                const int src = __ffs(lm) - 1;
+                lm &= lm - 1;
+                const int ss = __shfl_sync(0xffffffffu, s, src), ee = __shfl_sync(0xffffffffu, e, src);
+                const double acc = rowsum_long(a, ss, ee, lane);
+                if (lane == src) sum = acc;
+            }
+        }
+        if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
+        if (active) a.y[row] = sum;
+        if (NDOT >= 1) {
+            const double p0 = active ? __dmul_rn(sum, __ldg(a.u + row)) : 0.0;
+            slab_deposit(s_slab, 0, slab, p0, lane);
+        }
+        if (NDOT >= 2) {
+            const double p1 = active ? __dmul_rn(sum, sum) : 0.0;
+            slab_deposit(s_slab, 1, slab, p1, lane);
+        }
+    }
+    if (NDOT >= 1) {
+        __syncthreads();
+        const int rows_here = min(kTile, a.n - row_base);
+        reduce_tail<(NDOT >= 1 ? NDOT : 1)>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
+    }
+}
+
+int plan_staged(cudamat_solver *s) {
+    // capacity = max slab span rounded up (+ alignment slack), stages to fill ~96 KB per CTA
+    s->staged = StagedPlan();
+    if (s->max_slab_nnz <= 0) return CUDAMAT_OK;
+    int cap = ((s->max_slab_nnz + 4 + 15) / 16) * 16;
+    if (cap > 1024) cap = 1024;                        // heavier slabs take the direct path
+    const size_t stage_bytes = (size_t)(cap + 2) * 8 + (size_t)(cap + 8) * 4;
+    int stages = (int)((100 * 1024) / (stage_bytes * kCtaWarps));
+    if (stages > 4) stages = 4;
+    if (stages < 2) return CUDAMAT_OK;
+    s->staged.cap_nnz = cap;
+    s->staged.stages = stages;
+    s->staged.smem_bytes = stage_bytes * kCtaWarps * stages;
+    return CUDAMAT_OK;
+}
+
+template <bool HAS_D, int NDOT>
+static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
+    const int grid = (a.n + kTile - 1) / kTile;
+    if (grid == 0) return CUDAMAT_OK;
+    if (variant == CUDAMAT_SPMV_STAGED && s->staged.cap_nnz > 0) {
+        StagedArgs g{a, s->staged.cap_nnz, s->staged.stages, s->nnz};
+        auto kern = k_spmv_staged<HAS_D, NDOT>;
+        CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->staged.smem_bytes));
+        kern<<<grid, kCtaThreads, s->staged.smem_bytes, s->stream>>>(g);
+    } else {
+        k_spmv_rowlane<HAS_D, NDOT><<<grid, kCtaThreads, 0, s->stream>>>(a);
+    }
+    s->launches++;
+    CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
+int launch_spmv(cudamat_solver *s, const SpmvArgs &a, int variant) {
+    if (variant == CUDAMAT_SPMV_AUTO) variant = s->spmv_variant;
+    const bool hd = a.d != nullptr;
+    switch (a.ndot) {
+    case 0: return hd ? launch_spmv_t<true, 0>(s, a, variant) : launch_spmv_t<false, 0>(s, a, variant);
+    case 1: return hd ? launch_spmv_t<true, 1>(s, a, variant) : launch_spmv_t<false, 1>(s, a, variant);
+    default: return hd ? launch_spmv_t<true, 2>(s, a, variant) : launch_spmv_t<false, 2>(s, a, variant);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused vector updates. Thread t of CTA b owns rows b*2048 + j*256 + t, j = 0..7, i.e. warp w
+// owns slabs j*8 + w — the same tile/slab geometry as the SpMV, so reductions share the tail.
+// ------------------------------------------------------------------------------------------
+struct VecArgs {
+    int n;
+    const double *in0, *in1, *in2, *in3, *in4;
+    double *out0, *out1, *out2;
+    RedCtx rc; DevScalars *sc; double *hist; int phase;
+};
+
+#define VEC_PROLOGUE                                                                  \
+    if (a.sc->status != ST_RUNNING) return;                                           \
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                    \
+    const int row_base = blockIdx.x * kTile;                                          \
+    (void)warp; (void)lane;
+
+// r = b - y ; c1 = r ; c2 = r (optional) ; red0 = r.r          (pbicgstab.cu:67-74, 645-655)
+__global__ void __launch_bounds__(kCtaThreads) k_init_resid(const VecArgs a) {
+    VEC_PROLOGUE
+    __shared__ double s_slab[kMaxQ][kTileSlabs];
+    double rv[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        rv[j] = (row < a.n) ? __dsub_rn(__ldg(a.in0 + row), __ldg(a.in1 + row)) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        const bool active = row < a.n;
+        if (active) {
+            a.out0[row] = rv[j];
+            a.out1[row] = rv[j];
+            if (a.out2) a.out2[row] = rv[j];
+        }
+        if (row_base + j * kCtaThreads + warp * kSlab < a.n)
+            slab_deposit(s_slab, 0, j * kCtaWarps + warp, active ? __dmul_rn(rv[j], rv[j]) : 0.0, lane);
+    }
+    __syncthreads();
+    const int rows_here = min(kTile, a.n - row_base);
+    reduce_tail<1>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
+}
+
+// p' = r + beta*(p - omega*v)
+//   unprec form (pbicgstab.cu:668-672): q=fl(-omega*v); q=fl(p+q); q=fl(beta*q); p'=fl(r+q)
+//   ilu0 form   (pbicgstab.cu:86-88):   q=fma(-omega,v,p); q=fl(beta*q); p'=fma(1,r,q)
+//   (ilu0: skipped on the first pass, i == 0, where p = r from the init)
+template <bool FMA_FORM>
+__global__ void __launch_bounds__(kCtaThreads) k_update_p(const VecArgs a) {
+    VEC_PROLOGUE
+    if (FMA_FORM && a.sc->iter == 0) return;
+    const double beta = a.sc->beta, momega = -a.sc->omega;
+    double rr[kSlabsPerWarp], vv[kSlabsPerWarp], pp[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        const bool act = row < a.n;
+        rr[j] = act ? __ldg(a.in0 + row) : 0.0;
+        vv[j] = act ? __ldg(a.in1 + row) : 0.0;
+        pp[j] = act ? a.out0[row] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        if (row < a.n) {
+            double q;
+            if (FMA_FORM) {
+                q = __fma_rn(momega, vv[j], pp[j]);
+                q = __dmul_rn(beta, q);
+                q = __fma_rn(1.0, rr[j], q);
+            } else {
+                q = __dmul_rn(momega, vv[j]);
+                q = __dadd_rn(pp[j], q);
+                q = __dmul_rn(beta, q);
+                q = __dadd_rn(rr[j], q);
+            }
+            a.out0[row] = q;
+        }
+    }
+}
+
+// s = r + fl(-alpha*v)                                            (pbicgstab.cu:698-700)
+__global__ void __launch_bounds__(kCtaThreads) k_update_s(const VecArgs a) {
+    VEC_PROLOGUE
+    const double malpha = -a.sc->alpha;
+    double rr[kSlabsPerWarp], vv[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        const bool act = row < a.n;
+        rr[j] = act ? __ldg(a.in0 + row) : 0.0;
+        vv[j] = act ? __ldg(a.in1 + row) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        if (row < a.n) a.out0[row] = __dadd_rn(rr[j], __dmul_rn(malpha, vv[j]));
+    }
+}
+
+// ilu0: r = fma(-alpha,v,r) ; x = fma(alpha,pw,x) ; red0 = r.r   (pbicgstab.cu:109-111)
+__global__ void __launch_bounds__(kCtaThreads) k_update_rx_ilu(const VecArgs a) {
+    VEC_PROLOGUE
+    __shared__ double s_slab[kMaxQ][kTileSlabs];
+    const double alpha = a.sc->alpha, malpha = -alpha;
+    double vv[kSlabsPerWarp], pw[kSlabsPerWarp], rr[kSlabsPerWarp], xx[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        const bool act = row < a.n;
+        vv[j] = act ? __ldg(a.in0 + row) : 0.0;
+        pw[j] = act ? __ldg(a.in1 + row) : 0.0;
+        rr[j] = act ? a.out0[row] : 0.0;
+        xx[j] = act ? a.out1[row] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        const bool act = row < a.n;
+        const double rn = __fma_rn(malpha, vv[j], rr[j]);
+        const double xn = __fma_rn(alpha, pw[j], xx[j]);
+        if (act) { a.out0[row] = rn; a.out1[row] = xn; }
+        if (row_base + j * kCtaThreads + warp * kSlab < a.n)
+            slab_deposit(s_slab, 0, j * kCtaWarps + warp, act ? __dmul_rn(rn, rn) : 0.0, lane);
+    }
+    __syncthreads();
+    const int rows_here = min(kTile, a.n - row_base);
+    reduce_tail<1>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
+}
+
+// end-of-iteration update with the two fused dots.
+//   unprec (pbicgstab.cu:694-696,714-723,665): h=fl(x+fl(alpha*p)); x=fl(h+fl(omega*s));
+//           r=fl(s+fl(-omega*t)); red0 = rhat.r ; red1 = r.r
+//   ilu0   (pbicgstab.cu:139-142,81):         x=fma(omega,s,x); r=fma(-omega,t,r); same dots
+// in0 = p, in1 = s, in2 = t, in3 = rhat ; out0 = x, out1 = r
+template <bool FMA_FORM>
+__global__ void __launch_bounds__(kCtaThreads) k_update_xr(const VecArgs a) {
+    VEC_PROLOGUE
+    __shared__ double s_slab[kMaxQ][kTileSlabs];
+    const double alpha = a.sc->alpha, omega = a.sc->omega, momega = -omega;
+#pragma unroll 2
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        const bool act = row < a.n;
+        double xn = 0.0, rn = 0.0, rh = 0.0;
+        if (act) {
+            const double sv = __ldg(a.in1 + row), tv = __ldg(a.in2 + row);
+            rh = __ldg(a.in3 + row);
+            const double xo = a.out0[row];
+            if (FMA_FORM) {
+                const double ro = a.out1[row];
+                xn = __fma_rn(omega, sv, xo);
+                rn = __fma_rn(momega, tv, ro);
+            } else {
+                const double pv = __ldg(a.in0 + row);
+                const double h = __dadd_rn(xo, __dmul_rn(alpha, pv));
+                xn = __dadd_rn(h, __dmul_rn(omega, sv));
+                rn = __dadd_rn(sv, __dmul_rn(momega, tv));
+            }
+            a.out0[row] = xn;
+            a.out1[row] = rn;
+        }
+        if (row_base + j * kCtaThreads + warp * kSlab < a.n) {
+            slab_deposit(s_slab, 0, j * kCtaWarps + warp, act ? __dmul_rn(rh, rn) : 0.0, lane);
+            slab_deposit(s_slab, 1, j * kCtaWarps + warp, act ? __dmul_rn(rn, rn) : 0.0, lane);
+        }
+    }
+    __syncthreads();
+    const int rows_here = min(kTile, a.n - row_base);
+    reduce_tail<2>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
+}
+
+// spec dot product of two arbitrary vectors -> sc->red[0]
+__global__ void __launch_bounds__(kCtaThreads) k_dot(const VecArgs a) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row_base = blockIdx.x * kTile;
+    __shared__ double s_slab[kMaxQ][kTileSlabs];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        const bool act = row < a.n;
+        const double p = act ? __dmul_rn(__ldg(a.in0 + row), __ldg(a.in1 + row)) : 0.0;
+        if (row_base + j * kCtaThreads + warp * kSlab < a.n) slab_deposit(s_slab, 0, j * kCtaWarps + warp, p, lane);
+    }
+    __syncthreads();
+    const int rows_here = min(kTile, a.n - row_base);
+    reduce_tail<1>(a.rc, a.sc, a.hist, PH_STORE, s_slab, (rows_here + kSlab - 1) / kSlab);
+}
+
+__global__ void k_fill(double *p, double v, int64_t cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < cnt; i += stride) p[i] = v;
+}
+
+static VecArgs vec_args(cudamat_solver *s, int phase) {
+    VecArgs a{};
+    a.n = s->n; a.rc = s->rc; a.sc = s->d_sc; a.hist = s->d_hist; a.phase = phase;
+    return a;
+}
+static inline int tiles_of(int n) { return (n + kTile - 1) / kTile; }
+
+#define LAUNCH_VEC(kern, a)                                                    \
+    do {                                                                       \
+        const int grid_ = tiles_of((a).n);                                     \
+        if (grid_ > 0) {                                                       \
+            kern<<<grid_, kCtaThreads, 0, s->stream>>>(a);                     \
+            s->launches++;                                                     \
+            CM_CUDA(cudaGetLastError());                                       \
+        }                                                                      \
+    } while (0)
+
+int launch_init_resid(cudamat_solver *s, const double *b, const double *y, double *r, double *c1, double *c2, int phase) {
+    VecArgs a = vec_args(s, phase);
+    a.in0 = b; a.in1 = y; a.out0 = r; a.out1 = c1; a.out2 = c2;
+    LAUNCH_VEC(k_init_resid, a);
+    return CUDAMAT_OK;
+}
+int launch_update_p(cudamat_solver *s, bool fma_form, const double *r, const double *v, double *p) {
+    VecArgs a = vec_args(s, PH_NONE);
+    a.in0 = r; a.in1 = v; a.out0 = p;
+    if (fma_form) LAUNCH_VEC(k_update_p<true>, a); else LAUNCH_VEC(k_update_p<false>, a);
+    return CUDAMAT_OK;
+}
+int launch_update_s(cudamat_solver *s, const double *r, const double *v, double *sv) {
+    VecArgs a = vec_args(s, PH_NONE);
+    a.in0 = r; a.in1 = v; a.out0 = sv;
+    LAUNCH_VEC(k_update_s, a);
+    return CUDAMAT_OK;
+}
+int launch_update_rx_ilu(cudamat_solver *s, const double *v, const double *pw, double *r, double *x) {
+    VecArgs a = vec_args(s, PH_I_A2);
+    a.in0 = v; a.in1 = pw; a.out0 = r; a.out1 = x;
+    LAUNCH_VEC(k_update_rx_ilu, a);
+    return CUDAMAT_OK;
+}
+int launch_update_xr(cudamat_solver *s, bool fma_form, const double *p, const double *sv, const double *t,
+                     const double *rhat, double *x, double *r) {
+    VecArgs a = vec_args(s, fma_form ? PH_I_C : PH_U_C);
+    a.in0 = p; a.in1 = sv; a.in2 = t; a.in3 = rhat; a.out0 = x; a.out1 = r;
+    if (fma_form) LAUNCH_VEC(k_update_xr<true>, a); else LAUNCH_VEC(k_update_xr<false>, a);
+    return CUDAMAT_OK;
+}
+int launch_dot(cudamat_solver *s, const double *x, const double *y) {
+    VecArgs a = vec_args(s, PH_STORE);
+    a.in0 = x; a.in1 = y;
+    LAUNCH_VEC(k_dot, a);
+    return CUDAMAT_OK;
+}
+int launch_fill(cudamat_solver *s, double *p, double v, int64_t cnt) {
+    if (cnt <= 0) return CUDAMAT_OK;
+    int grid = (int)((cnt + 1023) / 1024);
+    if (grid > 148 * 16) grid = 148 * 16;
+    k_fill<<<grid, 256, 0, s->stream>>>(p, v, cnt);
+    s->launches++;
+    CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// analysis helpers
+// ------------------------------------------------------------------------------------------
+__global__ void k_row_stats(int n, const int *ia, int *out /*max_len, n_long, max_slab_nnz*/) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int mx = 0, nl = 0, ms = 0;
+    if (i < n) {
+        const int len = ia[i + 1] - ia[i];
+        mx = len; nl = len > kLongRow ? 1 : 0;
+        if ((i & 31) == 0) ms = ia[min(i + 32, n)] - ia[i];
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    ms = __reduce_max_sync(0xffffffffu, ms);
+    nl = __reduce_add_sync(0xffffffffu, nl);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out + 0, mx);
+        if (nl) atomicAdd(out + 1, nl);
+        atomicMax(out + 2, ms);
+    }
+}
+
+int launch_row_stats(cudamat_solver *s, int *h_out, double *mean) {
+    int *d_out = nullptr;
+    CM_CUDA(cudaMalloc(&d_out, 3 * sizeof(int)));
+    CM_CUDA(cudaMemsetAsync(d_out, 0, 3 * sizeof(int), s->stream));
+    if (s->n > 0) {
+        k_row_stats<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->n, s->d_ia, d_out);
+        s->launches++;
+    }
+    CM_CUDA(cudaMemcpyAsync(h_out, d_out, 3 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    CM_CUDA(cudaFree(d_out));
+    *mean = s->n > 0 ? (double)s->nnz / s->n : 0.0;
+    return CUDAMAT_OK;
+}
+
+__global__ void k_sub_base(int *p, int64_t cnt, int base) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < cnt; i += stride) p[i] -= base;
+}
+int launch_normalize_base(cudaStream_t st, int *ia, int64_t n1, int *ja, int64_t nnz, int base) {
+    if (base == 0) return CUDAMAT_OK;
+    k_sub_base<<<1184, 256, 0, st>>>(ia, n1, base);
+    k_sub_base<<<1184, 256, 0, st>>>(ja, nnz, base);
+    CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// generators: bit-identical to oracle/oracle.c orc_poisson3d / orc_xtrue / orc_random_dd
+// ------------------------------------------------------------------------------------------
+__global__ void k_poisson_count(int N, int64_t row0, int64_t row1, int *cnt) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > row1 - row0) return;
+    if (q == row1 - row0) { cnt[q] = 0; return; }
+    const int64_t r = row0 + q, nn = (int64_t)N * N;
+    const int i = (int)(r % N), j = (int)((r / N) % N), k = (int)(r / nn);
+    cnt[q] = 1 + (k > 0) + (j > 0) + (i > 0) + (i < N - 1) + (j < N - 1) + (k < N - 1);
+}
+__global__ void k_poisson_fill(int N, int64_t row0, int64_t row1, const int *ia, int *ja, double *a) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= row1 - row0) return;
+    const int64_t r = row0 + q, nn = (int64_t)N * N;
+    const int i = (int)(r % N), j = (int)((r / N) % N), k = (int)(r / nn);
+    int p = ia[q];
+    if (k > 0)     { ja[p] = (int)(r - nn); a[p++] = -1.0; }
+    if (j > 0)     { ja[p] = (int)(r - N);  a[p++] = -1.0; }
+    if (i > 0)     { ja[p] = (int)(r - 1);  a[p++] = -1.0; }
+    ja[p] = (int)r; a[p++] = 6.0;
+    if (i < N - 1) { ja[p] = (int)(r + 1);  a[p++] = -1.0; }
+    if (j < N - 1) { ja[p] = (int)(r + N);  a[p++] = -1.0; }
+    if (k < N - 1) { ja[p] = (int)(r + nn); a[p++] = -1.0; }
+}
+
+static int exclusive_scan_inplace(int *d, int64_t cnt, cudaStream_t st) {
+    void *tmp = nullptr; size_t bytes = 0;
+    CM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, d, d, cnt, st));
+    CM_CUDA(cudaMalloc(&tmp, bytes ? bytes : 16));
+    CM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, d, d, cnt, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    CM_CUDA(cudaFree(tmp));
+    return CUDAMAT_OK;
+}
+
+int gen_poisson3d(int N, int64_t row0, int64_t row1, int *d_ia, int *d_ja, double *d_a, cudaStream_t st) {
+    const int64_t m = row1 - row0;
+    const int grid = (int)((m + 1 + 255) / 256);
+    k_poisson_count<<<grid, 256, 0, st>>>(N, row0, row1, d_ia);
+    CM_CUDA(cudaGetLastError());
+    int rc = exclusive_scan_inplace(d_ia, m + 1, st);
+    if (rc) return rc;
+    if (d_ja && d_a && m > 0) {
+        k_poisson_fill<<<(int)((m + 255) / 256), 256, 0, st>>>(N, row0, row1, d_ia, d_ja, d_a);
+        CM_CUDA(cudaGetLastError());
+    }
+    return CUDAMAT_OK;
+}
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t hash2(uint64_t seed, uint64_t a) {
+    return mix64(seed + 0x9E3779B97F4A7C15ULL * (a + 1));
+}
+__host__ __device__ __forceinline__ uint64_t hash3(uint64_t seed, uint64_t a, uint64_t b) {
+    return mix64(hash2(seed, a) + 0x9E3779B97F4A7C15ULL * (b + 1));
+}
+__device__ __forceinline__ double u01(uint64_t z) { return __dmul_rn((double)(z >> 11), 0x1.0p-53); }
+
+__global__ void k_xtrue(uint64_t seed, int64_t i0, int64_t cnt, double *out) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; q < cnt; q += stride)
+        out[q] = __dsub_rn(__dmul_rn(2.0, u01(hash2(seed, (uint64_t)(i0 + q)))), 1.0);
+}
+int gen_xtrue(uint64_t seed, int64_t i0, int64_t cnt, double *d_out, cudaStream_t st) {
+    if (cnt <= 0) return CUDAMAT_OK;
+    int grid = (int)((cnt + 255) / 256);
+    if (grid > 148 * 32) grid = 148 * 32;
+    k_xtrue<<<grid, 256, 0, st>>>(seed, i0, cnt, d_out);
+    CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
+// one row of the random diagonally-dominant generator; mirrors rdd_row() in oracle/oracle.c
+__device__ int rdd_row(int n, uint64_t seed, int i, int *cols, double *vals) {
+    const double uc = u01(hash3(seed, (uint64_t)i, 0));
+    int k;
+    if (uc < 0.90) k = __popcll(hash3(seed, (uint64_t)i, 1) & 0xFFFULL);
+    else if (uc < 0.99) k = __popcll(hash3(seed, (uint64_t)i, 1) & 0xFFFFFFFFFFFFULL);
+    else k = __popcll(hash3(seed, (uint64_t)i, 1)) + __popcll(hash3(seed, (uint64_t)i, 2)) + __popcll(hash3(seed, (uint64_t)i, 3));
+    if (k > n - 1) k = n - 1;
+    int m = 0;
+    for (int s = 0; s < k; ++s) {
+        const uint64_t hz = hash3(seed, (uint64_t)i, 16 + (uint64_t)s);
+        int c = (int)__umul64hi(hz, (uint64_t)(n - 1));
+        if (c >= i) c += 1;
+        int pos = m;
+        while (pos > 0 && cols[pos - 1] > c) --pos;
+        if (pos > 0 && cols[pos - 1] == c) continue;
+        for (int q = m; q > pos; --q) cols[q] = cols[q - 1];
+        cols[pos] = c;
+        ++m;
+    }
+    int pos = m;
+    while (pos > 0 && cols[pos - 1] > i) --pos;
+    for (int q = m; q > pos; --q) cols[q] = cols[q - 1];
+    cols[pos] = i;
+    ++m;
+    if (vals) {
+        double sum = 0.0;
+        for (int q = 0; q < m; ++q) {
+            if (cols[q] == i) continue;
+            const double u = u01(hash3(seed, (uint64_t)i, 0x100000000ULL + (uint64_t)cols[q]));
+            const double v = __dsub_rn(__dmul_rn(u, 20.0), 10.0);
+            vals[q] = v;
+            sum = __dadd_rn(sum, fabs(v));
+        }
+        const double ud = u01(hash3(seed, (uint64_t)i, 4));
+        vals[pos] = __dadd_rn(sum, __dadd_rn(__dmul_rn(ud, 9.0), 1.0));
+    }
+    return m;
+}
+__global__ void k_rdd_count(int n, uint64_t seed, int *cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { cnt[n] = 0; return; }
+    int cols[200];
+    cnt[i] = rdd_row(n, seed, i, cols, nullptr);
+}
+__global__ void k_rdd_fill(int n, uint64_t seed, const int *ia, int *ja, double *a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cols[200]; double vals[200];
+    const int m = rdd_row(n, seed, i, cols, vals);
+    const int p = ia[i];
+    for (int q = 0; q < m; ++q) { ja[p + q] = cols[q]; a[p + q] = vals[q]; }
+}
+int gen_random_dd(int n, uint64_t seed, int *d_ia, int *d_ja, double *d_a, int64_t *nnz_out, cudaStream_t st) {
+    if (!d_ja) {
+        k_rdd_count<<<(n + 1 + 127) / 128, 128, 0, st>>>(n, seed, d_ia);
+        CM_CUDA(cudaGetLastError());
+        int rc = exclusive_scan_inplace(d_ia, (int64_t)n + 1, st);
+        if (rc) return rc;
+        int last = 0;
+        CM_CUDA(cudaMemcpyAsync(&last, d_ia + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CM_CUDA(cudaStreamSynchronize(st));
+        if (nnz_out) *nnz_out = last;
+    } else {
+        k_rdd_fill<<<(n + 127) / 128, 128, 0, st>>>(n, seed, d_ia, d_ja, d_a);
+        CM_CUDA(cudaGetLastError());
+        CM_CUDA(cudaStreamSynchronize(st));
+    }
+    return CUDAMAT_OK;
+}
+
+}  // namespace cudamat

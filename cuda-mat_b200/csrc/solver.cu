@@ -1,0 +1,558 @@
+// solver.cu — host orchestration of the BiCGSTAB loops and the C ABI (include/cudamat_b200.h).
+//
+// The iteration is stream-ordered: scalars (rho, alpha, omega, beta, norms, status, iteration
+// counter) live in a device struct updated by the last CTA of each reducing kernel; the host only
+// enqueues kernels and polls the status word every `poll_every` iterations through a pinned
+// mirror.  Kernels of iterations enqueued past the stopping point return immediately.
+#include "solver.h"
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <time.h>
+
+namespace cudamat {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line) {
+    if (e == cudaSuccess) return true;
+    set_error("CUDA error at %s:%d code=%d(%s) \"%s\"", file, line, (int)e, cudaGetErrorName(e), what);
+    return false;
+}
+static double now_s() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static int alloc_reduction(cudamat_solver *s) {
+    RedCtx &rc = s->rc;
+    rc.ntile = (s->n + kTile - 1) / kTile;
+    rc.tile_stride = std::max(rc.ntile, 1);
+    rc.ngroup_loc = (rc.ntile + kGroupTiles - 1) / kGroupTiles;
+    const int64_t tiles_global = (s->n_global + kTile - 1) / kTile;
+    rc.nslots = (int)((tiles_global + kGroupTiles - 1) / kGroupTiles);
+    rc.slot_stride = std::max(rc.nslots, 1);
+    rc.group0 = (int)(s->row0 / ((int64_t)kTile * kGroupTiles));
+    rc.do_final = 1;
+    CM_CUDA(cudaMalloc(&rc.tile_part, sizeof(double) * kMaxQ * (size_t)rc.tile_stride));
+    CM_CUDA(cudaMalloc(&rc.slots, sizeof(double) * kMaxQ * (size_t)rc.slot_stride));
+    CM_CUDA(cudaMemsetAsync(rc.slots, 0, sizeof(double) * kMaxQ * (size_t)rc.slot_stride, s->stream));
+    CM_CUDA(cudaMalloc(&rc.group_cnt, sizeof(unsigned) * (size_t)std::max(rc.ngroup_loc, 1)));
+    CM_CUDA(cudaMemsetAsync(rc.group_cnt, 0, sizeof(unsigned) * (size_t)std::max(rc.ngroup_loc, 1), s->stream));
+    CM_CUDA(cudaMalloc(&rc.done_cnt, sizeof(unsigned)));
+    CM_CUDA(cudaMemsetAsync(rc.done_cnt, 0, sizeof(unsigned), s->stream));
+    CM_CUDA(cudaMalloc(&s->d_sc, sizeof(DevScalars)));
+    CM_CUDA(cudaMemsetAsync(s->d_sc, 0, sizeof(DevScalars), s->stream));
+    CM_CUDA(cudaMallocHost(&s->h_sc, sizeof(DevScalars)));
+    memset(s->h_sc, 0, sizeof(DevScalars));
+    return CUDAMAT_OK;
+}
+
+static int ensure_work(cudamat_solver *s, int nvec) {
+    const size_t elems = (size_t)s->n + (size_t)s->nhalo;
+    // keep each vector 256-byte aligned
+    const size_t stride = ((elems + 31) / 32) * 32;
+    if (s->work && s->work_nvec >= nvec && s->work_elems == stride) return CUDAMAT_OK;
+    if (s->work) { cudaFree(s->work); s->work = nullptr; }
+    CM_CUDA(cudaMalloc(&s->work, sizeof(double) * std::max<size_t>(stride * nvec, 32)));
+    s->work_elems = stride; s->work_nvec = nvec;
+    return CUDAMAT_OK;
+}
+static inline double *wv(cudamat_solver *s, int k) { return s->work + (size_t)k * s->work_elems; }
+
+static int ensure_hist(cudamat_solver *s, int cap) {
+    if (s->d_hist && s->hist_cap >= cap) return CUDAMAT_OK;
+    if (s->d_hist) cudaFree(s->d_hist);
+    s->d_hist = nullptr;
+    CM_CUDA(cudaMalloc(&s->d_hist, sizeof(double) * (size_t)std::max(cap, 1)));
+    s->hist_cap = cap;
+    return CUDAMAT_OK;
+}
+
+static SpmvArgs spmv_args(cudamat_solver *s, const double *x, const double *d, double *y, const double *u, int ndot, int phase, int check) {
+    SpmvArgs a{};
+    a.n = s->n; a.ia = s->d_ia; a.ja = s->d_ja; a.val = s->d_a; a.x = x; a.d = d; a.y = y; a.u = u;
+    a.ndot = ndot; a.phase = phase; a.rc = s->rc; a.sc = s->d_sc; a.hist = s->d_hist; a.check_status = check;
+    return a;
+}
+
+// SpMV launch bracketed by CUDA events on the launching stream when "time_spmv" is set
+static int timed_spmv(cudamat_solver *s, const SpmvArgs &a, int var) {
+    const bool timed = s->opt_time_spmv && s->ev_used + 2 <= 8192;
+    if (timed) {
+        while ((int)s->ev_pool.size() < s->ev_used + 2) {
+            cudaEvent_t e; CM_CUDA(cudaEventCreate(&e)); s->ev_pool.push_back(e);
+        }
+        CM_CUDA(cudaEventRecord(s->ev_pool[s->ev_used], s->stream));
+    }
+    int rc = launch_spmv(s, a, var);
+    if (rc) return rc;
+    if (timed) { CM_CUDA(cudaEventRecord(s->ev_pool[s->ev_used + 1], s->stream)); s->ev_used += 2; }
+    return CUDAMAT_OK;
+}
+
+static int poll_status(cudamat_solver *s) {
+    CM_CUDA(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    return CUDAMAT_OK;
+}
+
+static void fill_stats(cudamat_solver *s, cudamat_stats *st) {
+    const DevScalars &h = *s->h_sc;
+    st->iterations = h.iter;
+    st->converged = h.status == ST_CONVERGED;
+    st->breakdown = h.status == ST_CONVERGED ? CUDAMAT_BRK_NONE
+                  : h.status == ST_BRK_OMEGA ? CUDAMAT_BRK_OMEGA
+                  : h.status == ST_BRK_NAN   ? CUDAMAT_BRK_NAN : CUDAMAT_BRK_MAXIT;
+    st->half_steps = std::min(h.half, h.hist_cap);
+    st->nrm_r0 = h.nrm0;
+    st->nrm_r = h.nrm;
+    st->spmv_variant = s->spmv_variant;
+    st->levels_l = s->lvl_l.nlevels;
+    st->levels_u = s->lvl_u.nlevels;
+    st->zero_pivot = s->zero_pivot;
+    st->kernel_launches = s->launches;
+}
+
+static int start_scalars(cudamat_solver *s, int maxit, double tol, int hist_cap) {
+    DevScalars h{};
+    h.rho = 1.0; h.rho_new = 1.0; h.alpha = 1.0; h.omega = 1.0; h.beta = 0.0;   // pbicgstab.cu:614-618
+    h.tol = tol; h.maxit = maxit; h.hist_cap = hist_cap; h.status = ST_RUNNING;
+    *s->h_sc = h;
+    CM_CUDA(cudaMemcpyAsync(s->d_sc, s->h_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    return CUDAMAT_OK;
+}
+
+// ---- unpreconditioned loop (gpu_pbicgstab2 shifted overload, pbicgstab.cu:581-754) --------------
+static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0, const double *d_d,
+                        double *d_x, int maxit, double tol) {
+    int rc;
+    if ((rc = ensure_work(s, 7))) return rc;
+    if ((rc = ensure_hist(s, maxit + 2))) return rc;
+    double *r0 = wv(s, 0), *r = wv(s, 1), *v = wv(s, 2), *p = wv(s, 3), *sv = wv(s, 4), *t = wv(s, 5), *xk = wv(s, 6);
+    const int var = s->spmv_variant;
+    if ((rc = start_scalars(s, maxit, tol, maxit + 2))) return rc;
+    const size_t nb = sizeof(double) * (size_t)s->n;
+    if (d_x0) CM_CUDA(cudaMemcpyAsync(xk, d_x0, nb, cudaMemcpyDeviceToDevice, s->stream));
+    else if ((rc = launch_fill(s, xk, 1.0, s->n))) return rc;
+    CM_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * s->work_elems, s->stream));     // v = p = 0 (:611)
+    CM_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * s->work_elems, s->stream));
+    // r = b - (A0 + diag d) x0 ; r0 = r ; ||r0|| (:645-655)
+    if ((rc = launch_spmv(s, spmv_args(s, xk, d_d, t, nullptr, 0, PH_NONE, 0), var))) return rc;
+    if ((rc = launch_init_resid(s, d_b, t, r, r0, nullptr, PH_U_INIT))) return rc;
+    if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
+    const int poll = std::max(1, s->opt_poll_every);
+    for (int it = 0; it < maxit;) {
+        if ((rc = launch_update_p(s, false, r, v, p))) return rc;                                   // :668-672
+        if ((rc = timed_spmv(s, spmv_args(s, p, d_d, v, r0, 1, PH_U_A, 1), var))) return rc;       // :675-689
+        if ((rc = launch_update_s(s, r, v, sv))) return rc;                                         // :698-700
+        if ((rc = timed_spmv(s, spmv_args(s, sv, d_d, t, sv, 2, PH_U_B, 1), var))) return rc;      // :703-710
+        if ((rc = launch_update_xr(s, false, p, sv, t, r0, xk, r))) return rc;                      // :694-696,714-747
+        ++it;
+        if (it % poll == 0 || it == maxit) {
+            if ((rc = poll_status(s))) return rc;
+            if (s->h_sc->status != ST_RUNNING) break;
+        }
+    }
+    if ((rc = poll_status(s))) return rc;
+    CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
+    return CUDAMAT_OK;
+}
+
+// ---- ILU0 right-preconditioned loop (gpu_pbicgstab, pbicgstab.cu:45-154) -------------------------
+static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int maxit, double tol) {
+    int rc;
+    if ((rc = ensure_work(s, 8))) return rc;
+    if ((rc = ensure_hist(s, 2 * maxit + 2))) return rc;
+    double *r = wv(s, 0), *rw = wv(s, 1), *p = wv(s, 2), *pw = wv(s, 3), *sv = wv(s, 4), *t = wv(s, 5), *v = wv(s, 6), *xk = wv(s, 7);
+    const int var = s->spmv_variant;
+    if ((rc = start_scalars(s, maxit, tol, 2 * maxit + 2))) return rc;
+    const size_t nb = sizeof(double) * (size_t)s->n;
+    if ((rc = launch_fill(s, xk, 1.0, s->n))) return rc;                                            // :306-308
+    CM_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * s->work_elems, s->stream));
+    if ((rc = launch_spmv(s, spmv_args(s, xk, nullptr, t, nullptr, 0, PH_NONE, 0), var))) return rc; // :67
+    if ((rc = launch_init_resid(s, d_b, t, r, rw, p, PH_I_INIT))) return rc;                        // :69-74
+    const int poll = std::max(1, s->opt_poll_every);
+    for (int it = 0; it < maxit;) {
+        if ((rc = launch_update_p(s, true, r, v, p))) return rc;                                    // :83-89 (skips i == 0)
+        if ((rc = launch_sptrsv(s, false, p, t))) return rc;                                        // :92-94
+        if ((rc = launch_sptrsv(s, true, t, pw))) return rc;                                        // :96-98
+        if ((rc = timed_spmv(s, spmv_args(s, pw, nullptr, v, rw, 1, PH_I_A, 1), var))) return rc;  // :104-107
+        if ((rc = launch_update_rx_ilu(s, v, pw, r, xk))) return rc;                                // :109-118
+        if ((rc = launch_sptrsv(s, false, r, t))) return rc;                                        // :121-123
+        if ((rc = launch_sptrsv(s, true, t, sv))) return rc;                                        // :125-127
+        if ((rc = timed_spmv(s, spmv_args(s, sv, nullptr, t, r, 2, PH_I_B, 1), var))) return rc;   // :132-137
+        if ((rc = launch_update_xr(s, true, nullptr, sv, t, rw, xk, r))) return rc;                 // :139-151, :81
+        ++it;
+        if (it % poll == 0 || it == maxit) {
+            if ((rc = poll_status(s))) return rc;
+            if (s->h_sc->status != ST_RUNNING) break;
+        }
+    }
+    if ((rc = poll_status(s))) return rc;
+    CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
+    return CUDAMAT_OK;
+}
+
+static void print_debug_trace(cudamat_solver *s, int mode) {
+    // line formats of pbicgstab.cu:76,113,144 (ILU0) and :484,550 / :657,727 (unpreconditioned)
+    const std::vector<double> &h = s->last_hist;
+    if (h.empty()) return;
+    if (mode == CUDAMAT_MODE_ILU0) {
+        printf("gpu, init residual:norm %20.16f\n", h[0]);
+        for (size_t k = 1; k < h.size(); ++k) {
+            const size_t i = (k - 1) / 2;
+            if ((k - 1) % 2 == 0) printf("i = %zu, residual norm (before precond) = %g\n", i, h[k]);
+            else printf("i = %zu, residual norm = %g\n", i, h[k]);
+        }
+    } else {
+        printf("initial norm = %g\n", h[0]);
+        for (size_t k = 1; k < h.size(); ++k) printf("k = %zu, norm = %g\n", k - 1, h[k]);
+        if (s->h_sc->status == ST_BRK_OMEGA || s->h_sc->status == ST_BRK_NAN)
+            printf("omega is close to zero, cannot continue\nomega = %g\n", s->h_sc->omega);
+    }
+}
+
+}  // namespace cudamat
+
+using namespace cudamat;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int cudamat_abi_version(void) { return CUDAMAT_ABI_VERSION; }
+const char *cudamat_last_error(void) { return cudamat::g_err; }
+
+int cudamat_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+static int require_device() {
+    if (cudamat_device_count() <= 0) {
+        set_error("no CUDA device available: libcudamat_b200 has no CPU fallback");
+        return CUDAMAT_E_NO_DEVICE;
+    }
+    return CUDAMAT_OK;
+}
+
+int cudamat_create(cudamat_solver **out, int64_t n_global, int64_t row0, int64_t row1, void *stream) {
+    if (!out || n_global < 0 || row0 < 0 || row1 < row0 || row1 > n_global || row1 - row0 > 0x7fffffffLL) {
+        set_error("cudamat_create: invalid shard [%lld,%lld) of %lld", (long long)row0, (long long)row1, (long long)n_global);
+        return CUDAMAT_E_INVALID;
+    }
+    int rc = require_device();
+    if (rc) return rc;
+    if ((row0 % kTile) != 0 && row0 != 0) {
+        set_error("cudamat_create: row0 must be a multiple of %d (reduction tile)", kTile);
+        return CUDAMAT_E_INVALID;
+    }
+    cudamat_solver *s = new cudamat_solver();
+    s->n_global = n_global; s->row0 = row0; s->row1 = row1; s->n = (int)(row1 - row0);
+    s->stream = (cudaStream_t)stream;
+    cudaGetDevice(&s->device);
+    rc = alloc_reduction(s);
+    if (rc) { cudamat_destroy(s); return rc; }
+    *out = s;
+    return CUDAMAT_OK;
+}
+
+int cudamat_destroy(cudamat_solver *s) {
+    if (!s) return CUDAMAT_OK;
+    cudaStreamSynchronize(s->stream);
+    ilu0_release(s);
+    if (s->own_ia) cudaFree(s->own_ia);
+    if (s->own_ja) cudaFree(s->own_ja);
+    if (s->own_a) cudaFree(s->own_a);
+    if (s->rc.tile_part) cudaFree(s->rc.tile_part);
+    if (s->rc.slots) cudaFree(s->rc.slots);
+    if (s->rc.group_cnt) cudaFree(s->rc.group_cnt);
+    if (s->rc.done_cnt) cudaFree(s->rc.done_cnt);
+    if (s->d_sc) cudaFree(s->d_sc);
+    if (s->h_sc) cudaFreeHost(s->h_sc);
+    if (s->d_hist) cudaFree(s->d_hist);
+    if (s->work) cudaFree(s->work);
+    for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+    delete s;
+    return CUDAMAT_OK;
+}
+
+int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
+    if (!s || !key) return CUDAMAT_E_INVALID;
+    if (!strcmp(key, "spmv_variant")) { s->opt_spmv_variant = (int)value; s->analyzed = false; }
+    else if (!strcmp(key, "poll_every")) s->opt_poll_every = (int)value;
+    else if (!strcmp(key, "sptrsv_syncfree")) s->opt_sptrsv_syncfree = (int)value;
+    else if (!strcmp(key, "debug")) s->opt_debug = (int)value;
+    else if (!strcmp(key, "time_spmv")) s->opt_time_spmv = (int)value;
+    else { set_error("unknown option '%s'", key); return CUDAMAT_E_INVALID; }
+    return CUDAMAT_OK;
+}
+
+int cudamat_set_csr_host(cudamat_solver *s, int nnz, const double *A, const int *iA, const int *jA) {
+    if (!s || !iA || (nnz > 0 && (!A || !jA)) || nnz < 0) { set_error("set_csr_host: null argument"); return CUDAMAT_E_INVALID; }
+    const int n = s->n;
+    const int base = iA[0];
+    if (base != 0 && base != 1) { set_error("set_csr_host: index base %d is neither 0 nor 1 (pbicgstab.cu:201)", base); return CUDAMAT_E_INVALID; }
+    if (iA[n] - base != nnz) { set_error("set_csr_host: iA[n]-iA[0]=%d != nnz=%d", iA[n] - base, nnz); return CUDAMAT_E_INVALID; }
+    for (int i = 0; i < n; ++i)
+        if (iA[i + 1] < iA[i]) { set_error("set_csr_host: row pointers not monotone at row %d", i); return CUDAMAT_E_INVALID; }
+    for (int k = 0; k < nnz; ++k)
+        if (jA[k] - base < 0 || jA[k] - base >= s->n_global) { set_error("set_csr_host: column index out of range at entry %d", k); return CUDAMAT_E_INVALID; }
+    if (s->own_ia) { cudaFree(s->own_ia); cudaFree(s->own_ja); cudaFree(s->own_a); s->own_ia = nullptr; s->own_ja = nullptr; s->own_a = nullptr; }
+    // +16 bytes of slack so aligned bulk copies of the last slab stay inside the allocation
+    CM_CUDA(cudaMalloc(&s->own_ia, sizeof(int) * (size_t)(n + 1)));
+    CM_CUDA(cudaMalloc(&s->own_ja, sizeof(int) * (size_t)std::max(nnz, 1) + 16));
+    CM_CUDA(cudaMalloc(&s->own_a, sizeof(double) * (size_t)std::max(nnz, 1) + 16));
+    CM_CUDA(cudaMemcpyAsync(s->own_ia, iA, sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, s->stream));
+    if (nnz > 0) {
+        CM_CUDA(cudaMemcpyAsync(s->own_ja, jA, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
+        CM_CUDA(cudaMemcpyAsync(s->own_a, A, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
+    }
+    int rc = launch_normalize_base(s->stream, s->own_ia, n + 1, s->own_ja, nnz, base);
+    if (rc) return rc;
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    s->d_ia = s->own_ia; s->d_ja = s->own_ja; s->d_a = s->own_a; s->d_ja_global = s->own_ja;
+    s->nnz = nnz; s->analyzed = false;
+    return CUDAMAT_OK;
+}
+
+int cudamat_set_csr_device(cudamat_solver *s, int64_t nnz, const double *dA, const int *dIA, const int *dJA) {
+    if (!s || !dIA || (nnz > 0 && (!dA || !dJA)) || nnz < 0 || nnz > 0x7fffffffLL) { set_error("set_csr_device: invalid argument"); return CUDAMAT_E_INVALID; }
+    int ends[2] = {0, 0};
+    CM_CUDA(cudaMemcpyAsync(&ends[0], dIA, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaMemcpyAsync(&ends[1], dIA + s->n, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    if (ends[0] != 0 || ends[1] != nnz) { set_error("set_csr_device: expects base-0 row pointers with ia[n]==nnz (got ia[0]=%d ia[n]=%d nnz=%lld)", ends[0], ends[1], (long long)nnz); return CUDAMAT_E_INVALID; }
+    s->d_ia = dIA; s->d_ja = dJA; s->d_a = dA; s->d_ja_global = dJA; s->nnz = nnz; s->analyzed = false;
+    return CUDAMAT_OK;
+}
+
+int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
+    if (!s || !s->d_ia) { set_error("analyze: no matrix set"); return CUDAMAT_E_STATE; }
+    if (mode < 0 || mode > 2) { set_error("analyze: bad mode %d", mode); return CUDAMAT_E_INVALID; }
+    const double t0 = now_s();
+    int hs[3] = {0, 0, 0};
+    int rc = launch_row_stats(s, hs, &s->mean_row_len);
+    if (rc) return rc;
+    s->max_row_len = hs[0]; s->n_long_rows = hs[1]; s->max_slab_nnz = hs[2];
+    if ((rc = plan_staged(s))) return rc;
+    const bool aligned = (((uintptr_t)s->d_a) % 16 == 0) && (((uintptr_t)s->d_ja) % 16 == 0);
+    if (!aligned) s->staged = StagedPlan();
+    // variant choice from row-length statistics: short, near-uniform rows stream well through the
+    // TMA-staged row-block kernel; otherwise use the direct kernel (long rows go warp-per-row inside both)
+    int variant = s->opt_spmv_variant;
+    if (variant == CUDAMAT_SPMV_AUTO)
+        variant = (s->staged.cap_nnz > 0 && s->max_slab_nnz <= s->staged.cap_nnz - 4 && s->max_slab_nnz <= 4.0 * 32.0 * std::max(1.0, s->mean_row_len))
+                      ? CUDAMAT_SPMV_STAGED : CUDAMAT_SPMV_ROWLANE;
+    if (variant == CUDAMAT_SPMV_STAGED && s->staged.cap_nnz == 0) variant = CUDAMAT_SPMV_ROWLANE;
+    s->spmv_variant = variant;
+    if (st) st->t_analysis += now_s() - t0;
+    if (mode == CUDAMAT_MODE_ILU0) {
+        if ((rc = ilu0_analyze_and_factor(s, st))) return rc;
+    }
+    s->analyzed = true; s->analyzed_mode = mode;
+    if (st) { st->spmv_variant = s->spmv_variant; st->kernel_launches = s->launches; }
+    return CUDAMAT_OK;
+}
+
+int cudamat_solve_device(cudamat_solver *s, int mode, const double *d_b, const double *d_x0, const double *d_d,
+                         double *d_x, int maxit, double tol, cudamat_stats *st) {
+    if (!s || !d_b || !d_x) { set_error("solve_device: null argument"); return CUDAMAT_E_INVALID; }
+    if (!s->analyzed || (mode == CUDAMAT_MODE_ILU0 && !s->d_M)) { set_error("solve_device: call cudamat_analyze(mode) first"); return CUDAMAT_E_STATE; }
+    if (mode == CUDAMAT_MODE_SHIFTED && (!d_d || !d_x0)) { set_error("solve_device: shifted mode needs d and x0 (pbicgstab.h:116)"); return CUDAMAT_E_INVALID; }
+    if (maxit < 0) maxit = 0;
+    const double t0 = now_s();
+    s->ev_used = 0;
+    int rc;
+    if (mode == CUDAMAT_MODE_ILU0) rc = solve_ilu0(s, d_b, d_x, maxit, tol);
+    else rc = solve_unprec(s, d_b, d_x0, mode == CUDAMAT_MODE_SHIFTED ? d_d : d_d, d_x, maxit, tol);
+    if (rc) return rc;
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    const double t1 = now_s();
+    // residual history for the debug trace / cudamat_get_history
+    const int nh = std::min(s->h_sc->half, s->h_sc->hist_cap);
+    s->last_hist.assign((size_t)nh, 0.0);
+    if (nh > 0) {
+        CM_CUDA(cudaMemcpyAsync(s->last_hist.data(), s->d_hist, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    if (s->opt_debug) print_debug_trace(s, mode);
+    if (st) { fill_stats(s, st); st->t_loop = t1 - t0; }
+    if (st && s->ev_used > 0) {
+        double ms_total = 0.0;
+        for (int k = 0; k + 1 < s->ev_used; k += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s->ev_pool[k], s->ev_pool[k + 1]) == cudaSuccess) ms_total += ms;
+        }
+        st->t_spmv = ms_total * 1e-3; st->n_spmv = s->ev_used / 2;
+    }
+    return CUDAMAT_OK;
+}
+
+int cudamat_get_history(cudamat_solver *s, double *hist, int cap) {
+    if (!s || (!hist && cap > 0)) return 0;
+    const int m = std::min<int>(cap, (int)s->last_hist.size());
+    for (int i = 0; i < m; ++i) hist[i] = s->last_hist[i];
+    return m;
+}
+
+int cudamat_spmv_device(cudamat_solver *s, const double *d_x, const double *d_d, double *d_y, int variant) {
+    if (!s || !d_x || !d_y) { set_error("spmv_device: null argument"); return CUDAMAT_E_INVALID; }
+    if (!s->analyzed) { set_error("spmv_device: call cudamat_analyze first"); return CUDAMAT_E_STATE; }
+    if (s->nhalo != 0) { set_error("spmv_device: single-shard handles only"); return CUDAMAT_E_INVALID; }
+    return launch_spmv(s, spmv_args(s, d_x, d_d, d_y, nullptr, 0, PH_NONE, 0), variant);
+}
+
+int cudamat_dot_device(cudamat_solver *s, const double *d_a, const double *d_b, double *result) {
+    if (!s || !d_a || !d_b || !result) { set_error("dot_device: null argument"); return CUDAMAT_E_INVALID; }
+    if (s->n == 0) { *result = 0.0; return CUDAMAT_OK; }
+    int rc = launch_dot(s, d_a, d_b);
+    if (rc) return rc;
+    if ((rc = poll_status(s))) return rc;
+    *result = s->h_sc->red[0];
+    return CUDAMAT_OK;
+}
+
+int cudamat_get_ilu0_host(cudamat_solver *s, double *M_out) {
+    if (!s || !M_out) return CUDAMAT_E_INVALID;
+    if (!s->d_M) { set_error("get_ilu0_host: no factor (analyze with CUDAMAT_MODE_ILU0)"); return CUDAMAT_E_STATE; }
+    CM_CUDA(cudaMemcpyAsync(M_out, s->d_M, sizeof(double) * (size_t)s->nnz, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    return CUDAMAT_OK;
+}
+
+int cudamat_sptrsv_device(cudamat_solver *s, int upper, const double *d_rhs, double *d_out) {
+    if (!s || !d_rhs || !d_out) return CUDAMAT_E_INVALID;
+    // kernel-level calls must not be gated by a finished solve
+    int st = ST_RUNNING;
+    CM_CUDA(cudaMemcpyAsync(&s->d_sc->status, &st, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    int rc = launch_sptrsv(s, upper != 0, d_rhs, d_out);
+    if (rc) return rc;
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    return CUDAMAT_OK;
+}
+
+// ---- one-shot host entry points ---------------------------------------------------------------
+int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *iA, const int *jA,
+                          const double *d, const double *x0, const double *b,
+                          int maxit, double tol, int debug, double *x, double *dtAlg, cudamat_stats *st_out) {
+    if (n < 0 || !iA || !b || !x) { set_error("bicgstab_host: null argument"); return CUDAMAT_E_INVALID; }
+    if (mode == CUDAMAT_MODE_SHIFTED && (!d || !x0)) { set_error("bicgstab_host: shifted mode needs d and x0"); return CUDAMAT_E_INVALID; }
+    cudamat_stats st{};
+    cudamat_solver *s = nullptr;
+    int rc = cudamat_create(&s, n, 0, n, nullptr);
+    if (rc) return rc;
+    s->opt_debug = debug;
+    if (debug) printf("N=%d, nnz=%d\n", n, nnz);                                  // pbicgstab.cu:203
+    double *d_b = nullptr, *d_x = nullptr, *d_x0 = nullptr, *d_d = nullptr;
+    auto cleanup = [&]() {
+        if (d_b) cudaFree(d_b);
+        if (d_x) cudaFree(d_x);
+        if (d_x0) cudaFree(d_x0);
+        if (d_d) cudaFree(d_d);
+        cudamat_destroy(s);
+    };
+#define HOST_TRY(expr) do { rc = (expr); if (rc) { cleanup(); return rc; } } while (0)
+#define HOST_CUDA(call) do { if (!cuda_ok((call), #call, __FILE__, __LINE__)) { cleanup(); return CUDAMAT_E_CUDA; } } while (0)
+    double t0 = now_s();
+    HOST_TRY(cudamat_set_csr_host(s, nnz, A, iA, jA));
+    const size_t nb = sizeof(double) * (size_t)std::max(n, 1);
+    HOST_CUDA(cudaMalloc(&d_b, nb));
+    HOST_CUDA(cudaMalloc(&d_x, nb));
+    HOST_CUDA(cudaMemcpy(d_b, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    if (mode == CUDAMAT_MODE_SHIFTED || (mode == CUDAMAT_MODE_PLAIN && x0)) {
+        HOST_CUDA(cudaMalloc(&d_x0, nb));
+        HOST_CUDA(cudaMemcpy(d_x0, x0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    if (mode != CUDAMAT_MODE_ILU0 && d) {
+        HOST_CUDA(cudaMalloc(&d_d, nb));
+        HOST_CUDA(cudaMemcpy(d_d, d, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    st.t_h2d = now_s() - t0;
+    HOST_TRY(cudamat_analyze(s, mode, &st));
+    if (debug && mode == CUDAMAT_MODE_ILU0) {
+        printf("analysis lower+upper %f (s), levels %d / %d\n", st.t_analysis, st.levels_l, st.levels_u);   // cf. pbicgstab.cu:349
+        printf("ILU0 factorisation time(s) = %10.8f \n", st.t_ilu0);                                         // cf. :354-363
+    }
+    HOST_TRY(cudamat_solve_device(s, mode, d_b, d_x0, d_d, d_x, maxit, tol, &st));
+    t0 = now_s();
+    HOST_CUDA(cudaMemcpy(x, d_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    st.t_d2h = now_s() - t0;
+    st.kernel_launches = s->launches;
+    if (dtAlg) *dtAlg = st.t_loop;
+    if (st_out) *st_out = st;
+    cleanup();
+#undef HOST_TRY
+#undef HOST_CUDA
+    return CUDAMAT_OK;
+}
+
+int cudamat_ilu0_host(int n, int nnz, const double *A, const int *iA, const int *jA,
+                      double *M_out, int *levels, int *zero_pivot) {
+    if (n < 0 || !iA || !M_out) { set_error("ilu0_host: null argument"); return CUDAMAT_E_INVALID; }
+    cudamat_solver *s = nullptr;
+    int rc = cudamat_create(&s, n, 0, n, nullptr);
+    if (rc) return rc;
+    cudamat_stats st{};
+    rc = cudamat_set_csr_host(s, nnz, A, iA, jA);
+    if (!rc) rc = cudamat_analyze(s, CUDAMAT_MODE_ILU0, &st);
+    if (!rc) rc = cudamat_get_ilu0_host(s, M_out);
+    if (!rc) {
+        if (levels) { levels[0] = st.levels_l; levels[1] = st.levels_u; }
+        if (zero_pivot) *zero_pivot = st.zero_pivot;
+    }
+    cudamat_destroy(s);
+    return rc;
+}
+
+// ---- generators -------------------------------------------------------------------------------
+int64_t cudamat_poisson3d_nnz(int N, int64_t row0, int64_t row1) {
+    // closed form per row would do; a loop over planes is cheap enough on the host
+    const int64_t nn = (int64_t)N * N;
+    int64_t cnt = 0;
+    for (int64_t r = row0; r < row1;) {
+        // whole rows of the grid (N consecutive matrix rows) at once
+        const int64_t i = r % N, j = (r / N) % N, k = r / nn;
+        if (i == 0 && r + N <= row1) {
+            const int nb = (k > 0) + (j > 0) + (j < N - 1) + (k < N - 1);
+            cnt += (int64_t)N * (1 + nb) + 2 * (int64_t)(N - 1);
+            r += N;
+        } else {
+            cnt += 1 + (k > 0) + (j > 0) + (i > 0) + (i < N - 1) + (j < N - 1) + (k < N - 1);
+            r += 1;
+        }
+    }
+    return cnt;
+}
+int cudamat_gen_poisson3d_device(int N, int64_t row0, int64_t row1, int *d_ia, int *d_ja, double *d_a, void *stream) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (N <= 0 || row0 < 0 || row1 < row0 || row1 > (int64_t)N * N * N || !d_ia) { set_error("gen_poisson3d: invalid argument"); return CUDAMAT_E_INVALID; }
+    return gen_poisson3d(N, row0, row1, d_ia, d_ja, d_a, (cudaStream_t)stream);
+}
+int cudamat_gen_xtrue_device(uint64_t seed, int64_t i0, int64_t cnt, double *d_out, void *stream) {
+    int rc = require_device();
+    if (rc) return rc;
+    return gen_xtrue(seed, i0, cnt, d_out, (cudaStream_t)stream);
+}
+int cudamat_gen_random_dd_device(int n, uint64_t seed, int *d_ia, int *d_ja, double *d_a, int64_t *nnz_out, void *stream) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (n <= 0 || !d_ia) { set_error("gen_random_dd: invalid argument"); return CUDAMAT_E_INVALID; }
+    return gen_random_dd(n, seed, d_ia, d_ja, d_a, nnz_out, (cudaStream_t)stream);
+}
+
+// ---- multi-GPU: implemented in comm.cu --------------------------------------------------------
+
+void cudamat_free(void *p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// solver.h — host-side state of one cudamat_solver handle and the launch wrappers that
+// solver.cu (orchestration + C ABI) calls into kernels.cu / ilu0.cu / comm.cu.
+#pragma once
+#include "internal.cuh"
+#include <string>
+#include <vector>
+
+namespace cudamat {
+
+void set_error(const char *fmt, ...);
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
+#define CM_CUDA(call)                                                       \
+    do {                                                                    \
+        if (!::cudamat::cuda_ok((call), #call, __FILE__, __LINE__)) return CUDAMAT_E_CUDA; \
+    } while (0)
+
+struct SpmvArgs {
+    int n;                 // local rows
+    const int *ia;         // local row pointers (base 0)
+    const int *ja;         // local/halo column ids (base 0)
+    const double *val;
+    const double *x;       // n + nhalo entries
+    const double *d;       // optional diagonal shift (local rows) or nullptr
+    double *y;
+    const double *u;       // dot operand: red0 = y.u   (ndot >= 1)
+    int ndot;              // 0, 1 (y.u) or 2 (y.u and y.y)
+    int phase;
+    RedCtx rc;
+    DevScalars *sc;        // may be nullptr when ndot == 0 and status is not checked
+    double *hist;
+    int check_status;      // 1: return immediately unless sc->status == ST_RUNNING
+};
+
+// staged (TMA bulk copy) SpMV plan
+struct StagedPlan {
+    int cap_nnz = 0;       // per-slab smem capacity in nnz (0 = variant unusable)
+    int stages = 0;
+    size_t smem_bytes = 0;
+};
+
+struct Comm;   // comm.cu
+
+struct LevelSchedule {
+    int nlevels = 0;
+    int *d_order = nullptr;        // rows sorted by level, each level padded to a multiple of 32 with -1
+    int order_len = 0;
+    std::vector<int> level_ptr;    // host: offsets into d_order per level (padded)
+};
+
+}  // namespace cudamat
+
+struct cudamat_solver {
+    int64_t n_global = 0, row0 = 0, row1 = 0;
+    int n = 0;                       // local rows
+    int64_t nnz = 0;
+    cudaStream_t stream = nullptr;
+    int device = 0;
+    // CSR (base 0). owned_* are freed at destroy; the active pointers may alias borrowed memory.
+    const int *d_ia = nullptr; const int *d_ja = nullptr; const double *d_a = nullptr;
+    int *own_ia = nullptr; int *own_ja = nullptr; double *own_a = nullptr;
+    const int *d_ja_global = nullptr;      // global column ids (before halo remap)
+    int nhalo = 0;
+    // plan
+    bool analyzed = false; int analyzed_mode = -1;
+    int max_row_len = 0; double mean_row_len = 0; int n_long_rows = 0; int max_slab_nnz = 0;
+    int spmv_variant = CUDAMAT_SPMV_ROWLANE;
+    int opt_spmv_variant = CUDAMAT_SPMV_AUTO;
+    int opt_poll_every = 8;
+    int opt_sptrsv_syncfree = 1;
+    int opt_debug = 0;
+    int opt_time_spmv = 0;
+    std::vector<cudaEvent_t> ev_pool; int ev_used = 0;
+    cudamat::StagedPlan staged;
+    // reduction context + scalars
+    cudamat::RedCtx rc{};
+    cudamat::DevScalars *d_sc = nullptr;
+    cudamat::DevScalars *h_sc = nullptr;   // pinned mirror
+    double *d_hist = nullptr; int hist_cap = 0;
+    // work vectors (n + nhalo each)
+    double *work = nullptr; size_t work_elems = 0; int work_nvec = 0;
+    // ILU0
+    double *d_M = nullptr; int *d_diag = nullptr;
+    cudamat::LevelSchedule lvl_l, lvl_u;
+    int *d_flag = nullptr;                 // sync-free epoch flags (n)
+    unsigned *d_ticket = nullptr;          // sync-free CTA ticket
+    int epoch = 0;
+    unsigned ticket_base_l = 0, ticket_base_u = 0;
+    int zero_pivot = 0;
+    // comm
+    cudamat::Comm *comm = nullptr;
+    // stats
+    int64_t launches = 0;
+    std::vector<double> last_hist;
+};
+
+namespace cudamat {
+
+// kernels.cu
+int launch_spmv(cudamat_solver *s, const SpmvArgs &a, int variant);
+int launch_init_resid(cudamat_solver *s, const double *b, const double *y, double *r, double *c1, double *c2, int phase);
+int launch_update_p(cudamat_solver *s, bool fma_form, const double *r, const double *v, double *p);
+int launch_update_s(cudamat_solver *s, const double *r, const double *v, double *sv);
+int launch_update_rx_ilu(cudamat_solver *s, const double *v, const double *pw, double *r, double *x);
+int launch_update_xr(cudamat_solver *s, bool fma_form, const double *p, const double *sv, const double *t,
+                     const double *rhat, double *x, double *r);
+int launch_dot(cudamat_solver *s, const double *a, const double *b);
+int launch_fill(cudamat_solver *s, double *p, double v, int64_t cnt);
+int launch_row_stats(cudamat_solver *s, int *h_out /*[max_len, n_long, max_slab_nnz]*/, double *mean);
+int launch_normalize_base(cudaStream_t st, int *ia, int64_t n1, int *ja, int64_t nnz, int base);
+int plan_staged(cudamat_solver *s);
+
+// ilu0.cu
+int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st);
+int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out);
+void ilu0_release(cudamat_solver *s);
+
+// generators (kernels.cu)
+int gen_poisson3d(int N, int64_t row0, int64_t row1, int *d_ia, int *d_ja, double *d_a, cudaStream_t st);
+int gen_xtrue(uint64_t seed, int64_t i0, int64_t cnt, double *d_out, cudaStream_t st);
+int gen_random_dd(int n, uint64_t seed, int *d_ia, int *d_ja, double *d_a, int64_t *nnz_out, cudaStream_t st);
+
+}  // namespace cudamat

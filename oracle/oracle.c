@@ -40,29 +40,44 @@ double orc_reduce_values(int64_t m, const double *v) {
     return butterfly(acc);
 }
 
+/* A slab is 32 consecutive elements (one per lane): products are rounded, then butterflied.
+ * A tile is 64 consecutive slabs (2048 elements): R() over its slab sums.
+ * A group is 1024 consecutive tiles (2 Mi elements): R() over its tile sums.
+ * The result is R() over the group sums.  Slab/tile/group boundaries are multiples of
+ * 32/2048/2Mi in the GLOBAL index, so the tree is independent of grid and of row sharding. */
 ORC_CLONES
-static double dot_leaf(int64_t m, const double *a, const double *b) {
+static double dot_slab(int64_t m, const double *a, const double *b) {
     double acc[32];
-    for (int l = 0; l < 32; ++l) acc[l] = 0.0;
-    for (int64_t j = 0; j < m; ++j) acc[j & 31] = FMA(a[j], b[j], acc[j & 31]);
+    for (int l = 0; l < 32; ++l) acc[l] = (l < m) ? a[l] * b[l] : 0.0;
     return butterfly(acc);
 }
 
-void orc_dot_leaves(int64_t n, const double *a, const double *b, double *out) {
-    int64_t nleaf = (n + ORC_LEAF - 1) / ORC_LEAF;
-    for (int64_t q = 0; q < nleaf; ++q) {
-        int64_t lo = q * ORC_LEAF, m = n - lo < ORC_LEAF ? n - lo : ORC_LEAF;
-        out[q] = dot_leaf(m, a + lo, b + lo);
+ORC_CLONES
+static double dot_tile(int64_t m, const double *a, const double *b) {
+    double ss[ORC_TILE_SLABS];
+    int ns = (int)((m + 31) / 32);
+    for (int q = 0; q < ns; ++q) {
+        int64_t lo = (int64_t)q * 32, c = m - lo < 32 ? m - lo : 32;
+        ss[q] = dot_slab(c, a + lo, b + lo);
+    }
+    return orc_reduce_values(ns, ss);
+}
+
+void orc_dot_tiles(int64_t n, const double *a, const double *b, double *out) {
+    int64_t nt = (n + ORC_TILE - 1) / ORC_TILE;
+    for (int64_t q = 0; q < nt; ++q) {
+        int64_t lo = q * ORC_TILE, m = n - lo < ORC_TILE ? n - lo : ORC_TILE;
+        out[q] = dot_tile(m, a + lo, b + lo);
     }
 }
 
-double orc_combine_leaves(int64_t nleaf, const double *leaf) {
-    if (nleaf <= 0) return 0.0;
-    int64_t ngroup = (nleaf + ORC_GROUP - 1) / ORC_GROUP;
+double orc_combine_tiles(int64_t ntile, const double *tile) {
+    if (ntile <= 0) return 0.0;
+    int64_t ngroup = (ntile + ORC_GROUP - 1) / ORC_GROUP;
     double *g = (double *)malloc(sizeof(double) * (size_t)ngroup);
     for (int64_t q = 0; q < ngroup; ++q) {
-        int64_t lo = q * ORC_GROUP, m = nleaf - lo < ORC_GROUP ? nleaf - lo : ORC_GROUP;
-        g[q] = orc_reduce_values(m, leaf + lo);
+        int64_t lo = q * ORC_GROUP, m = ntile - lo < ORC_GROUP ? ntile - lo : ORC_GROUP;
+        g[q] = orc_reduce_values(m, tile + lo);
     }
     double r = orc_reduce_values(ngroup, g);
     free(g);
@@ -71,11 +86,11 @@ double orc_combine_leaves(int64_t nleaf, const double *leaf) {
 
 double orc_dot(int64_t n, const double *a, const double *b) {
     if (n <= 0) return 0.0;
-    int64_t nleaf = (n + ORC_LEAF - 1) / ORC_LEAF;
-    double *leaf = (double *)malloc(sizeof(double) * (size_t)nleaf);
-    orc_dot_leaves(n, a, b, leaf);
-    double r = orc_combine_leaves(nleaf, leaf);
-    free(leaf);
+    int64_t nt = (n + ORC_TILE - 1) / ORC_TILE;
+    double *tile = (double *)malloc(sizeof(double) * (size_t)nt);
+    orc_dot_tiles(n, a, b, tile);
+    double r = orc_combine_tiles(nt, tile);
+    free(tile);
     return r;
 }
 

@@ -26,8 +26,9 @@ extern "C" {
 #endif
 
 #define ORC_LONG_ROW 32      /* rows longer than this use the 32-lane interleaved row sum */
-#define ORC_LEAF 1024        /* reduction leaf: 32 lanes x 32 strided elements            */
-#define ORC_GROUP 1024       /* leaves per level-2 group (1 Mi elements)                   */
+#define ORC_TILE_SLABS 64     /* slabs (of 32 elements) per reduction tile                  */
+#define ORC_TILE 2048        /* elements per tile                                          */
+#define ORC_GROUP 1024       /* tiles per group (2 Mi elements)                            */
 
 typedef struct {
     int    iterations;   /* value of the reference's loop counter i at exit               */
@@ -47,10 +48,10 @@ void   orc_spmv(int n, const int *ia, const int *ja, const double *a,
 double orc_dot(int64_t n, const double *a, const double *b);
 /* tree-reduce already formed leaf partials / generic values with the lane-strided R() */
 double orc_reduce_values(int64_t m, const double *v);
-/* leaf partials only (for sharded-reduction tests): out has ceil(n/1024) entries */
-void   orc_dot_leaves(int64_t n, const double *a, const double *b, double *out);
-/* combine leaf partials -> groups -> final, exactly as orc_dot does internally */
-double orc_combine_leaves(int64_t nleaf, const double *leaf);
+/* tile partials only (for sharded-reduction tests): out has ceil(n/2048) entries */
+void   orc_dot_tiles(int64_t n, const double *a, const double *b, double *out);
+/* combine tile partials -> groups -> final, exactly as orc_dot does internally */
+double orc_combine_tiles(int64_t ntile, const double *tile);
 
 /* ---- ILU(0) and triangular sweeps (cusparseDcsrilu0 pbicgstab.cu:359; csrsv :94,98) */
 /* M_out gets the factor in A's pattern. returns 0 ok, >0 = 1+row with structurally

@@ -48,9 +48,9 @@ def lib():
         L.orc_dot.argtypes = [C.c_int64, c_dp, c_dp]
         L.orc_reduce_values.restype = C.c_double
         L.orc_reduce_values.argtypes = [C.c_int64, c_dp]
-        L.orc_combine_leaves.restype = C.c_double
-        L.orc_combine_leaves.argtypes = [C.c_int64, c_dp]
-        L.orc_dot_leaves.argtypes = [C.c_int64, c_dp, c_dp, c_dp]
+        L.orc_combine_tiles.restype = C.c_double
+        L.orc_combine_tiles.argtypes = [C.c_int64, c_dp]
+        L.orc_dot_tiles.argtypes = [C.c_int64, c_dp, c_dp, c_dp]
         L.orc_spmv.argtypes = [C.c_int, c_ip, c_ip, c_dp, c_dp, c_dp, c_dp]
         L.orc_ilu0.restype = C.c_int
         L.orc_ilu0.argtypes = [C.c_int, c_ip, c_ip, c_dp, c_dp]
@@ -97,16 +97,16 @@ def dot(a, b):
     return lib().orc_dot(len(a), _dp(a), _dp(b))
 
 
-def dot_leaves(a, b):
+def dot_tiles(a, b):
     a, b = _f64(a), _f64(b)
-    out = np.empty((len(a) + 1023) // 1024)
-    lib().orc_dot_leaves(len(a), _dp(a), _dp(b), _dp(out))
+    out = np.empty((len(a) + 2047) // 2048)
+    lib().orc_dot_tiles(len(a), _dp(a), _dp(b), _dp(out))
     return out
 
 
-def combine_leaves(leaf):
-    leaf = _f64(leaf)
-    return lib().orc_combine_leaves(len(leaf), _dp(leaf))
+def combine_tiles(tile):
+    tile = _f64(tile)
+    return lib().orc_combine_tiles(len(tile), _dp(tile))
 
 
 def reduce_values(v):

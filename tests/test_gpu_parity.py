@@ -1,0 +1,346 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C ABI of
+libcudamat_b200.so; the CPU oracle is only the checker.
+
+Bars: iteration count within +-2, solution relative error <= 1e-8, final relative
+residual <= tol, ILU0 factor bit-exact structure / values to 1e-12.  Because oracle and kernels share
+one arithmetic spec the tests additionally assert the much stronger property that actually holds:
+bit-identical results.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [1, 2]   # ROWLANE, STAGED
+
+
+def dev(torch, a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def csr(pin, nm):
+    return pin[nm + "_ia"], pin[nm + "_ja"], pin[nm + "_a"]
+
+
+def make_solver(cm, torch, ia, ja, a, mode=0, variant=0):
+    n = len(ia) - 1
+    s = cm.Solver(n)
+    if variant:
+        s.set_option("spmv_variant", variant)
+    s.set_csr_host(a, ia, ja)
+    st = s.analyze(mode)
+    return s, st
+
+
+def matrices(O, pin):
+    out = {}
+    for nm in ("mat3", "mat900", "mat10000"):
+        out[nm] = csr(pin, nm)
+    out["poisson12"] = O.poisson3d(12)
+    out["poisson20"] = O.poisson3d(20)          # 8000 rows: several tiles, ragged last tile
+    out["random_dd"] = O.random_dd(5000, 20240)  # irregular rows incl. > 32 and > 64 entries
+    rng = np.random.default_rng(5)
+    # ragged: empty rows, a very long row, n not a multiple of 32
+    import scipy.sparse as sp
+    R = sp.random(777, 777, density=0.01, random_state=7, format="lil")
+    R[5, :] = rng.standard_normal(777)
+    R[6, :] = 0
+    R[776, :] = 0
+    R = R.tocsr(); R.sort_indices()
+    out["ragged"] = (R.indptr.astype(np.int32), R.indices.astype(np.int32), R.data.copy())
+    return out
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_spmv_bit_exact(cm, O, pin, torch_cuda, variant):
+    torch = torch_cuda
+    rng = np.random.default_rng(11)
+    for nm, (ia, ja, a) in matrices(O, pin).items():
+        n = len(ia) - 1
+        s, st = make_solver(cm, torch, ia, ja, a, variant=variant)
+        for use_d in (False, True):
+            x = rng.standard_normal(n)
+            d = rng.standard_normal(n) if use_d else None
+            dx, dy = dev(torch, x), torch.zeros(n, dtype=torch.float64, device="cuda")
+            dd = dev(torch, d) if use_d else None
+            s.spmv(dx.data_ptr(), dy.data_ptr(), dd.data_ptr() if use_d else None, variant=variant)
+            torch.cuda.synchronize()
+            want = O.spmv(ia, ja, a, x, d=d)
+            got = dy.cpu().numpy()
+            assert np.array_equal(got, want), "%s variant %d d=%s: max diff %g" % (nm, variant, use_d, np.abs(got - want).max())
+        s.close()
+
+
+def test_spmv_linearity_and_variants_agree_large(cm, torch_cuda):
+    """size-independent properties at a size the oracle cannot do in seconds (Poisson 128^3):
+    variants agree bit for bit, A*(1) has the closed-form row sums, A is symmetric: x.(Ay) == y.(Ax)"""
+    torch = torch_cuda
+    N = 128
+    n = N ** 3
+    nnz = cm.poisson3d_nnz(N)
+    ia = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    ja = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    a = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    cm.gen_poisson3d_device(N, 0, n, ia.data_ptr(), ja.data_ptr(), a.data_ptr())
+    s = cm.Solver(n)
+    s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
+    s.analyze(0)
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    cm.gen_xtrue_device(1234, 0, n, x.data_ptr())
+    cm.gen_xtrue_device(99, 0, n, y.data_ptr())
+    ax1, ax2, ay = (torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3))
+    s.spmv(x.data_ptr(), ax1.data_ptr(), variant=1)
+    s.spmv(x.data_ptr(), ax2.data_ptr(), variant=2)
+    s.spmv(y.data_ptr(), ay.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(ax1, ax2)
+    ones = torch.ones(n, dtype=torch.float64, device="cuda")
+    r = torch.empty_like(ones)
+    s.spmv(ones.data_ptr(), r.data_ptr())
+    torch.cuda.synchronize()
+    rowsum = 6.0 - torch.diff(ia).double() + 1.0        # 6 - (#neighbours)
+    assert torch.equal(r, rowsum)
+    lhs, rhs = s.dot(x.data_ptr(), ay.data_ptr()), s.dot(y.data_ptr(), ax1.data_ptr())
+    assert abs(lhs - rhs) <= 1e-9 * abs(lhs)
+    # dot agrees with torch's own reduction to rounding
+    assert abs(s.dot(x.data_ptr(), y.data_ptr()) - float(torch.dot(x, y))) <= 1e-9 * n ** 0.5
+    s.close()
+
+
+def test_dot_bit_exact(cm, O, torch_cuda):
+    torch = torch_cuda
+    rng = np.random.default_rng(13)
+    for n in (1, 31, 32, 33, 2047, 2048, 2049, 70001, 2048 * 1024 + 4097):
+        a, b = rng.standard_normal(n), rng.standard_normal(n)
+        s = cm.Solver(n)
+        got = s.dot(dev(torch, a).data_ptr(), dev(torch, b).data_ptr())
+        assert got == O.dot(a, b), "n=%d" % n
+        # repeated use of the same reduction context (self-cleaning counters)
+        assert s.dot(dev(torch, a).data_ptr(), dev(torch, a).data_ptr()) == O.dot(a, a)
+        s.close()
+
+
+def test_generators_bit_exact(cm, O, torch_cuda):
+    torch = torch_cuda
+    N = 12
+    n = N ** 3
+    for (r0, r1) in ((0, n), (2 * N * N, 7 * N * N)):
+        ia_o, ja_o, a_o = O.poisson3d(N, r0, r1)
+        ia = torch.empty(r1 - r0 + 1, dtype=torch.int32, device="cuda")
+        ja = torch.empty(len(ja_o), dtype=torch.int32, device="cuda")
+        a = torch.empty(len(ja_o), dtype=torch.float64, device="cuda")
+        cm.gen_poisson3d_device(N, r0, r1, ia.data_ptr(), ja.data_ptr(), a.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(ia.cpu().numpy(), ia_o) and np.array_equal(ja.cpu().numpy(), ja_o) and np.array_equal(a.cpu().numpy(), a_o)
+    x = torch.empty(5000, dtype=torch.float64, device="cuda")
+    cm.gen_xtrue_device(1234, 777, 5000, x.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(x.cpu().numpy(), O.xtrue(1234, 777, 5000))
+    nn = 3000
+    ia_o, ja_o, a_o = O.random_dd(nn, 20240)
+    ia = torch.empty(nn + 1, dtype=torch.int32, device="cuda")
+    nnz = cm.gen_random_dd_device(nn, 20240, ia.data_ptr())
+    assert nnz == len(a_o)
+    ja = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    a = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    cm.gen_random_dd_device(nn, 20240, ia.data_ptr(), ja.data_ptr(), a.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(ia.cpu().numpy(), ia_o) and np.array_equal(ja.cpu().numpy(), ja_o) and np.array_equal(a.cpu().numpy(), a_o)
+
+
+@pytest.mark.parametrize("nm", ["mat900", "mat10000", "poisson12", "random_dd"])
+def test_ilu0_factor_and_sweeps(cm, O, pin, torch_cuda, nm):
+    """ILU0 factor: bit-exact structure (A's pattern, by construction) and values (bar: 1e-12; actual: 0);
+    L / U sweeps bit-exact, in both the sync-free and the level-per-launch schedule."""
+    torch = torch_cuda
+    ia, ja, a = matrices(O, pin)[nm]
+    n = len(ia) - 1
+    M_o, st_o = O.ilu0(ia, ja, a)
+    M, levels, zp = cm.ilu0_host(a, ia, ja)
+    assert zp == 0 and st_o == 0
+    assert np.max(np.abs(M - M_o) / np.maximum(np.abs(M_o), 1e-300)) <= 1e-12
+    assert np.array_equal(M, M_o)
+    lv, nl = O.levels(ia, ja, upper=False)
+    lu, nu = O.levels(ia, ja, upper=True)
+    assert levels == (nl, nu)
+    rhs = np.random.default_rng(17).standard_normal(n)
+    yl = O.sptrsv_lower_unit(ia, ja, M_o, rhs)
+    yu = O.sptrsv_upper(ia, ja, M_o, rhs)
+    for syncfree in (0, 1):
+        s, _ = make_solver(cm, torch, ia, ja, a, mode=2)
+        s.set_option("sptrsv_syncfree", syncfree)
+        drhs = dev(torch, rhs)
+        out = torch.zeros(n, dtype=torch.float64, device="cuda")
+        for rep in range(3):      # repeated sweeps reuse flags / tickets
+            s.sptrsv(False, drhs.data_ptr(), out.data_ptr())
+            assert np.array_equal(out.cpu().numpy(), yl), "L sweep syncfree=%d rep=%d" % (syncfree, rep)
+            s.sptrsv(True, drhs.data_ptr(), out.data_ptr())
+            assert np.array_equal(out.cpu().numpy(), yu), "U sweep syncfree=%d rep=%d" % (syncfree, rep)
+        s.close()
+
+
+def test_ilu0_missing_diagonal_is_reported(cm, pin):
+    """mat3 violates pbicgstab.h:118 ((2,2) absent): explicit error instead of the reference's silent NaNs"""
+    ia, ja, a = csr(pin, "mat3")
+    with pytest.raises(cm.CudamatError) as e:
+        cm.bicgstab_lu_precond(a, ia, ja, np.array([1.0, 2.0, 3.0]))
+    assert e.value.code == -4
+
+
+def check_solve(cm, O, ia, ja, a, b, mode, tol, maxit=5000, d=None, x0=None):
+    if mode == "ilu0":
+        x, dt, st = cm.bicgstab_lu_precond(a, ia, ja, b, maxit=maxit, tol=tol)
+        xo, so = O.bicgstab_ilu0(ia, ja, a, b, maxit=maxit, tol=tol)
+    elif mode == "shifted":
+        x, dt, st = cm.bicgstab_shifted(a, ia, ja, d, x0, b, maxit=maxit, tol=tol)
+        xo, so = O.bicgstab_unprec(ia, ja, a, b, d=d, x0=x0, maxit=maxit, tol=tol)
+    else:
+        x, dt, st = cm.bicgstab(a, ia, ja, b, maxit=maxit, tol=tol)
+        xo, so = O.bicgstab_unprec(ia, ja, a, b, maxit=maxit, tol=tol)
+    assert bool(st["converged"]) == so["converged"]
+    assert abs(st["iterations"] - so["iterations"]) <= 2                   # the bar
+    assert st["iterations"] == so["iterations"]                            # what the shared spec gives
+    assert st["nrm_r0"] == so["nrm_r0"]
+    if so["converged"]:
+        assert np.linalg.norm(x - xo) <= 1e-8 * np.linalg.norm(xo)         # the bar
+        assert np.array_equal(x, xo)                                       # bit-identical trajectory
+        r = b - O.spmv(ia, ja, a, x, d=d)
+        assert np.linalg.norm(r) <= 1.5 * tol * so["nrm_r0"]
+    assert dt > 0 and st["kernel_launches"] > 0
+    return st, so
+
+
+def test_mat3_shifted_known_answer(cm, O, pin):
+    ia, ja, a = csr(pin, "mat3_A0")
+    d = cm.to_dense_vector(3, pin["vec3_d_a"], pin["vec3_d_ia"])
+    b = cm.to_dense_vector(3, pin["vec3_a"], pin["vec3_ia"])
+    x, dt, st = cm.bicgstab_shifted(a, ia, ja, d, np.ones(3), b, maxit=2000, tol=1e-5)
+    assert st["converged"] and st["iterations"] == 3
+    np.testing.assert_allclose(x, [7 / 6, 17 / 3, -23 / 6], rtol=1e-12)
+    check_solve(cm, O, ia, ja, a, b, "shifted", 1e-5, d=d, x0=np.ones(3))
+    # the same system through the plain entry point on the assembled matrix
+    ia3, ja3, a3 = csr(pin, "mat3")
+    x2, _, st2 = cm.bicgstab(a3, ia3, ja3, b, maxit=2000, tol=1e-5)
+    assert st2["converged"]
+    np.testing.assert_allclose(x2, [7 / 6, 17 / 3, -23 / 6], rtol=1e-9)
+
+
+@pytest.mark.parametrize("nm", ["mat900", "mat10000"])
+@pytest.mark.parametrize("mode", ["ilu0", "plain"])
+def test_fixture_solves(cm, O, pin, nm, mode):
+    ia, ja, a = csr(pin, nm)
+    n = len(ia) - 1
+    for b in (np.ones(n), O.glibc_rand_vector(n)):
+        for tol in (1e-6, 1e-10):
+            check_solve(cm, O, ia, ja, a, b, mode, tol)
+
+
+def test_base0_base1_same_result(cm, pin):
+    ia, ja, a = csr(pin, "mat900")
+    b = np.ones(900)
+    x1, _, s1 = cm.bicgstab_lu_precond(a, ia, ja, b, tol=1e-10)
+    x0, _, s0 = cm.bicgstab_lu_precond(a, ia - 1, ja - 1, b, tol=1e-10)
+    assert s0["iterations"] == s1["iterations"] and np.array_equal(x0, x1)
+
+
+@pytest.mark.parametrize("N", [16, 32])
+def test_poisson_solves(cm, O, N):
+    ia, ja, a = O.poisson3d(N)
+    n = N ** 3
+    xt = O.xtrue(1234, 0, n)
+    b = O.spmv(ia, ja, a, xt)
+    for mode in ("plain", "ilu0"):
+        st, so = check_solve(cm, O, ia, ja, a, b, mode, 1e-10)
+    rng = np.random.default_rng(3)
+    d = rng.random(n)
+    check_solve(cm, O, ia, ja, a, b, "shifted", 1e-10, d=d, x0=rng.standard_normal(n))
+
+
+def test_random_dd_solves(cm, O):
+    ia, ja, a = O.random_dd(20000, 20240)
+    xt = O.xtrue(1234, 0, 20000)
+    b = O.spmv(ia, ja, a, xt)
+    check_solve(cm, O, ia, ja, a, b, "plain", 1e-10)
+    check_solve(cm, O, ia, ja, a, b, "ilu0", 1e-10)
+
+
+def test_breakdown_maxit_and_edge_cases(cm, O, pin):
+    ia, ja, a = csr(pin, "mat900")
+    b = np.ones(900)
+    x, _, st = cm.bicgstab(a, ia, ja, b, maxit=5, tol=1e-12)
+    xo, so = O.bicgstab_unprec(ia, ja, a, b, maxit=5, tol=1e-12)
+    assert not st["converged"] and st["breakdown"] == 3 and st["iterations"] == 5 and np.array_equal(x, xo)
+    x, _, st = cm.bicgstab_lu_precond(a, ia, ja, b, maxit=3, tol=1e-12)
+    xo, so = O.bicgstab_ilu0(ia, ja, a, b, maxit=3, tol=1e-12)
+    assert not st["converged"] and st["iterations"] == 3 and st["half_steps"] == 7 and np.array_equal(x, xo)
+    # NaN break-down: b = A*ones makes r0 = 0 (reference: returns false, pbicgstab.cu:735)
+    b0 = O.spmv(ia, ja, a, np.ones(900))
+    x, _, st = cm.bicgstab(a, ia, ja, b0, maxit=10, tol=1e-6)
+    assert st["breakdown"] == 2 and st["iterations"] == 1
+    # maxit = 0
+    x, _, st = cm.bicgstab(a, ia, ja, b, maxit=0, tol=1e-6)
+    assert st["iterations"] == 0 and not st["converged"] and np.all(x == 0)
+    # invalid CSR is rejected, not executed
+    with pytest.raises(cm.CudamatError):
+        cm.bicgstab(a, ia + 3, ja, b)
+    # 1x1 system
+    x, _, st = cm.bicgstab_lu_precond(np.array([4.0]), np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([2.0]))
+    assert st["converged"] and x[0] == 0.5
+
+
+def test_full_size_properties_poisson128(cm, torch_cuda):
+    """At a size the oracle does not finish in seconds: solve Poisson 128^3 (2.1 M rows) on device and check the
+    domain's size-independent properties: true residual <= tol*||r0||, solution error vs x_true, residual
+    history is what the stopping rule saw, both SpMV variants give the same iteration count and bits."""
+    torch = torch_cuda
+    N = 128
+    n = N ** 3
+    nnz = cm.poisson3d_nnz(N)
+    ia = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    ja = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    a = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    cm.gen_poisson3d_device(N, 0, n, ia.data_ptr(), ja.data_ptr(), a.data_ptr())
+    xt = torch.empty(n, dtype=torch.float64, device="cuda")
+    cm.gen_xtrue_device(1234, 0, n, xt.data_ptr())
+    results = []
+    for variant in VARIANTS:
+        s = cm.Solver(n)
+        s.set_option("spmv_variant", variant)
+        s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
+        s.analyze(0)
+        b = torch.empty(n, dtype=torch.float64, device="cuda")
+        s.spmv(xt.data_ptr(), b.data_ptr())
+        x = torch.zeros(n, dtype=torch.float64, device="cuda")
+        st = s.solve(0, b.data_ptr(), x.data_ptr(), maxit=5000, tol=1e-10)
+        assert st["converged"], st
+        ax = torch.empty_like(b)
+        s.spmv(x.data_ptr(), ax.data_ptr())
+        torch.cuda.synchronize()
+        relres = float(torch.linalg.norm(b - ax)) / st["nrm_r0"]
+        relerr = float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt))
+        assert relres <= 2e-10 and relerr <= 1e-8, (relres, relerr)
+        h = s.history()
+        assert len(h) == st["iterations"] + 1 and h[0] == st["nrm_r0"] and h[-1] == st["nrm_r"] and h[-1] < 1e-10 * h[0]
+        results.append((st["iterations"], x.clone()))
+        s.close()
+    assert results[0][0] == results[1][0] and torch.equal(results[0][1], results[1][1])
+    # ILU0 on the same system: fewer iterations, same answer to 1e-8
+    s = cm.Solver(n)
+    s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
+    sa = s.analyze(2)
+    assert sa["levels_l"] == 3 * (N - 1) + 1 and sa["levels_u"] == 3 * (N - 1) + 1     # wavefronts i+j+k
+    b = torch.empty(n, dtype=torch.float64, device="cuda")
+    s.spmv(xt.data_ptr(), b.data_ptr())
+    x = torch.zeros(n, dtype=torch.float64, device="cuda")
+    st = s.solve(2, b.data_ptr(), x.data_ptr(), maxit=5000, tol=1e-10)
+    assert st["converged"] and st["iterations"] < results[0][0]
+    assert float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt)) <= 1e-8
+    s.close()

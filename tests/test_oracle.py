@@ -1,0 +1,249 @@
+"""CPU tests: the oracle against the committed golden anchors, independent cross-checks (scipy /
+numpy dense), and the arithmetic-spec properties the GPU kernels rely on."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import GOLDEN
+
+
+def digest(x):
+    return hashlib.sha256(np.ascontiguousarray(x, dtype=np.float64).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def anchors():
+    return json.load(open(os.path.join(GOLDEN, "oracle_anchors.json")))
+
+
+def csr(pin, nm):
+    return pin[nm + "_ia"], pin[nm + "_ja"], pin[nm + "_a"]
+
+
+def scipy_csr(ia, ja, a):
+    n = len(ia) - 1
+    return sp.csr_matrix((a, ja - ia[0], ia - ia[0]), shape=(n, n))
+
+
+def test_mat3_known_answer(O, pin, anchors):
+    """3x3 system of example.cpp:33-106 (test_A0_d): x = (7/6, 17/3, -23/6) in 3 iterations."""
+    ia, ja, a = csr(pin, "mat3_A0")
+    d = O.to_dense_vector(3, pin["vec3_d_a"], pin["vec3_d_ia"])
+    b = O.to_dense_vector(3, pin["vec3_a"], pin["vec3_ia"])
+    assert d.tolist() == [1.0, 0.0, 1.0] and b.tolist() == [1.0, 2.0, 3.0]
+    x, st = O.bicgstab_unprec(ia, ja, a, b, d=d, x0=np.ones(3), maxit=2000, tol=1e-5)
+    assert st["converged"] and st["iterations"] == 3
+    np.testing.assert_allclose(x, [7 / 6, 17 / 3, -23 / 6], rtol=1e-12)
+    assert x.tolist() == anchors["mat3_shifted"]["x"]
+    # residual norms quoted in SURVEY.md §4: 2.905, 2.959, 4e-14-ish
+    np.testing.assert_allclose(st["hist"][1:3], [2.905, 2.959], rtol=1e-3)
+
+
+@pytest.mark.parametrize("nm", ["mat900", "mat10000"])
+@pytest.mark.parametrize("bname", ["ones", "glibc_rand"])
+def test_anchor_table(O, pin, anchors, nm, bname):
+    """BASELINE.md §5 anchor table: iteration counts and bit-exact digests do not drift."""
+    ia, ja, a = csr(pin, nm)
+    n = len(ia) - 1
+    b = np.ones(n) if bname == "ones" else O.glibc_rand_vector(n)
+    A = scipy_csr(ia, ja, a)
+    for tol in (1e-6, 1e-10):
+        for mode, fn in (("ilu0", O.bicgstab_ilu0), ("unprec", O.bicgstab_unprec)):
+            x, st = fn(ia, ja, a, b, maxit=2000, tol=tol)
+            ref = anchors["%s/%s/%s/%g" % (nm, bname, mode, tol)]
+            assert st["converged"]
+            assert st["iterations"] == ref["iterations"]
+            assert digest(x) == ref["x_sha256"]
+            # true residual agrees with the recurrence residual to the requested tolerance
+            assert np.linalg.norm(b - A @ x) <= 2.0 * tol * st["nrm_r0"]
+
+
+def test_surveyor_counts_are_close(anchors):
+    """the surveyor's indicative numpy counts differ only by reduction order"""
+    exp = {"mat900/ones/ilu0/1e-06": 10, "mat900/ones/ilu0/1e-10": 15, "mat10000/ones/ilu0/1e-06": 45,
+           "mat10000/ones/ilu0/1e-10": 70, "mat10000/glibc_rand/ilu0/1e-06": 54, "mat10000/glibc_rand/ilu0/1e-10": 76}
+    for k, v in exp.items():
+        assert abs(anchors[k]["iterations"] - v) <= 3, k
+
+
+def test_glibc_rand_vector(O, anchors):
+    """gen_rand_vector under glibc rand() default seed: first values quoted in SURVEY.md §8d"""
+    b = O.glibc_rand_vector(8)
+    np.testing.assert_allclose(b[:3], [2.5775317072763722, 4.1937601339042931, 1.7902054771735358], rtol=0, atol=0)
+    assert b.tolist() == anchors["glibc_rand_b_first"]
+
+
+def test_spmv_matches_scipy(O, pin):
+    rng = np.random.default_rng(0)
+    for nm in ("mat900", "mat10000"):
+        ia, ja, a = csr(pin, nm)
+        x = rng.standard_normal(len(ia) - 1)
+        d = rng.standard_normal(len(ia) - 1)
+        A = scipy_csr(ia, ja, a)
+        np.testing.assert_allclose(O.spmv(ia, ja, a, x), A @ x, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(O.spmv(ia, ja, a, x, d=d), A @ x + d * x, rtol=1e-13, atol=1e-13)
+
+
+def test_base0_base1_identical(O, pin):
+    ia, ja, a = csr(pin, "mat900")
+    assert ia[0] == 1
+    b = np.ones(len(ia) - 1)
+    x1, s1 = O.bicgstab_ilu0(ia, ja, a, b, tol=1e-10)
+    x0, s0 = O.bicgstab_ilu0(ia - 1, ja - 1, a, b, tol=1e-10)
+    assert s0["iterations"] == s1["iterations"] and np.array_equal(x0, x1)
+
+
+def test_long_row_rule(O):
+    """rows longer than 32 use the 32-lane interleaved sum; both rules agree with numpy to rounding"""
+    rng = np.random.default_rng(1)
+    n = 300
+    dense = rng.standard_normal((n, n)) * (rng.random((n, n)) < 0.2)
+    A = sp.csr_matrix(dense)
+    assert np.diff(A.indptr).max() > 32 and np.diff(A.indptr).min() <= 64
+    x = rng.standard_normal(n)
+    np.testing.assert_allclose(O.spmv(A.indptr, A.indices, A.data, x), dense @ x, rtol=1e-12, atol=1e-12)
+
+
+def test_dot_tree(O):
+    """the reduction tree: correct value, and the sharded (tile-level) evaluation is bit-identical"""
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 31, 32, 33, 2047, 2048, 2049, 5000, 2048 * 1024 + 77):
+        a, b = rng.standard_normal(n), rng.standard_normal(n)
+        v = O.dot(a, b)
+        assert abs(v - float(np.dot(a, b))) <= 1e-9 * max(1.0, np.sqrt(n))
+        tiles = O.dot_tiles(a, b)
+        assert O.combine_tiles(tiles) == v
+        # shard at a tile boundary: zero-padded partial arrays summed == same tile array
+        if n > 4096:
+            cut = 2048 * ((n // 2048) // 2)
+            t0 = np.zeros_like(tiles); t1 = np.zeros_like(tiles)
+            t0[:cut // 2048] = O.dot_tiles(a[:cut], b[:cut])
+            t1[cut // 2048:] = O.dot_tiles(a[cut:], b[cut:])
+            assert np.array_equal(t0 + t1, tiles)
+
+
+def dense_ilu0(Ad, pattern):
+    n = Ad.shape[0]
+    M = Ad.copy()
+    for i in range(n):
+        for k in range(i):
+            if not pattern[i, k]:
+                continue
+            M[i, k] = M[i, k] / M[k, k]
+            for j in range(k + 1, n):
+                if pattern[i, j] and pattern[k, j]:
+                    M[i, j] -= M[i, k] * M[k, j]
+    return M
+
+
+def test_ilu0_against_dense(O, pin, anchors):
+    ia, ja, a = csr(pin, "mat900")
+    M, st = O.ilu0(ia, ja, a)
+    assert st == 0
+    A = scipy_csr(ia, ja, a)
+    Md = dense_ilu0(A.toarray(), A.toarray() != 0)
+    Mo = scipy_csr(ia, ja, M).toarray()
+    np.testing.assert_allclose(Mo, Md * (A.toarray() != 0), rtol=1e-13, atol=1e-13)
+    assert digest(M) == anchors["mat900/ilu0_factor"]["sha256"]
+    # the factors really are a preconditioner: L U == A on A's pattern
+    L = np.tril(Mo, -1) + np.eye(900)
+    U = np.triu(Mo)
+    assert np.abs((L @ U - A.toarray())[A.toarray() != 0]).max() < 1e-12
+
+
+def test_ilu0_missing_diagonal(O, pin):
+    """mat3 has no (2,2) entry: violates pbicgstab.h:118; the oracle reports 1+row"""
+    ia, ja, a = csr(pin, "mat3")
+    M, st = O.ilu0(ia, ja, a)
+    assert st == 2
+
+
+def test_sptrsv_and_levels(O, pin, anchors):
+    for nm in ("mat900", "mat10000"):
+        ia, ja, a = csr(pin, nm)
+        M, _ = O.ilu0(ia, ja, a)
+        n = len(ia) - 1
+        rhs = np.random.default_rng(3).standard_normal(n)
+        Ms = scipy_csr(ia, ja, M)
+        L = sp.tril(Ms, -1) + sp.identity(n)
+        U = sp.triu(Ms)
+        np.testing.assert_allclose(O.sptrsv_lower_unit(ia, ja, M, rhs), spla.spsolve_triangular(L.tocsr(), rhs, lower=True), rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(O.sptrsv_upper(ia, ja, M, rhs), spla.spsolve_triangular(U.tocsr(), rhs, lower=False), rtol=1e-11, atol=1e-11)
+        lv, nl = O.levels(ia, ja, upper=False)
+        lu, nu = O.levels(ia, ja, upper=True)
+        assert (nl, nu) == (anchors[nm + "/levels"]["lower"], anchors[nm + "/levels"]["upper"])
+    assert anchors["mat900/levels"] == {"lower": 88, "upper": 88}
+    assert anchors["mat10000/levels"] == {"lower": 199, "upper": 199}
+
+
+def test_poisson_generator(O, anchors):
+    for N in (8, 16):
+        ia, ja, a = O.poisson3d(N)
+        n = N ** 3
+        # independent construction with scipy kron
+        I = sp.identity(N)
+        T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(N, N))
+        A = sp.kron(sp.kron(I, I), T) + sp.kron(sp.kron(I, T), I) + sp.kron(sp.kron(T, I), I)
+        A = A.tocsr(); A.sort_indices()
+        assert np.array_equal(A.indptr, ia) and np.array_equal(A.indices, ja) and np.array_equal(A.data, a)
+        # row-slab generation with global columns is consistent with the full matrix
+        r0, r1 = n // 4, n // 2
+        ia2, ja2, a2 = O.poisson3d(N, r0, r1)
+        assert np.array_equal(ia2, ia[r0:r1 + 1] - ia[r0]) and np.array_equal(ja2, ja[ia[r0]:ia[r1]])
+        xt = O.xtrue(1234, 0, n)
+        assert xt.min() > -1 and xt.max() < 1 and abs(xt.mean()) < 0.1
+        assert np.array_equal(O.xtrue(1234, 100, 50), xt[100:150])
+        b = O.spmv(ia, ja, a, xt)
+        ref = anchors["poisson%d" % N]
+        assert digest(b) == ref["b_sha256"]
+        x, st = O.bicgstab_unprec(ia, ja, a, b, maxit=5000, tol=1e-10)
+        assert st["iterations"] == ref["unprec_iterations"] and digest(x) == ref["unprec_x_sha256"]
+        assert np.linalg.norm(x - xt) / np.linalg.norm(xt) < 1e-8
+        x, st = O.bicgstab_ilu0(ia, ja, a, b, maxit=5000, tol=1e-10)
+        assert st["iterations"] == ref["ilu0_iterations"] and digest(x) == ref["ilu0_x_sha256"]
+        assert np.linalg.norm(x - xt) / np.linalg.norm(xt) < 1e-8
+
+
+def test_random_dd_generator(O, anchors):
+    ia, ja, a = O.random_dd(2000, 20240)
+    ref = anchors["random_dd_2000"]
+    assert len(a) == ref["nnz"] and digest(a) == ref["a_sha256"]
+    lens = np.diff(ia)
+    assert lens.max() == ref["maxlen"] and lens.max() > 64 and lens.min() >= 1      # irregular row lengths
+    A = sp.csr_matrix((a, ja, ia), shape=(2000, 2000))
+    dg = A.diagonal()
+    off = np.abs(A).sum(axis=1).A1 - np.abs(dg)
+    assert np.all(dg > off)                                                          # strictly diagonally dominant
+    for i in range(0, 2000, 97):
+        cols = ja[ia[i]:ia[i + 1]]
+        assert np.all(np.diff(cols) > 0) and i in cols
+    b = O.spmv(ia, ja, a, O.xtrue(1234, 0, 2000))
+    x, st = O.bicgstab_unprec(ia, ja, a, b, maxit=500, tol=1e-10)
+    xt = O.xtrue(1234, 0, 2000)
+    assert st["converged"] and np.linalg.norm(x - xt) / np.linalg.norm(xt) < 1e-8
+    x, st2 = O.bicgstab_ilu0(ia, ja, a, b, maxit=500, tol=1e-10)
+    assert st2["converged"] and st2["iterations"] <= st["iterations"]
+
+
+def test_breakdown_and_maxit(O, pin):
+    ia, ja, a = csr(pin, "mat900")
+    b = np.ones(900)
+    x, st = O.bicgstab_unprec(ia, ja, a, b, maxit=5, tol=1e-12)
+    assert not st["converged"] and st["breakdown"] == 3 and st["iterations"] == 5
+    x, st = O.bicgstab_ilu0(ia, ja, a, b, maxit=3, tol=1e-12)
+    assert not st["converged"] and st["iterations"] == 3 and len(st["hist"]) == 7
+    # b = A*ones => r0 = 0 => rho = 0 => NaN break-down on the first pass (reference behaviour, pbicgstab.cu:735)
+    b0 = O.spmv(ia, ja, a, np.ones(900))
+    x, st = O.bicgstab_unprec(ia, ja, a, b0, maxit=10, tol=1e-6)
+    assert st["breakdown"] == 2 and st["iterations"] == 1
+
+
+def test_reference_bicg_anchor():
+    """the reference's own CPU solver (bicstab_omp BiCG) on mat900, b = ones: 35 iterations"""
+    ref = json.load(open(os.path.join(GOLDEN, "ref_bicg_anchors.json")))
+    assert ref["mat900"]["iterations"] == 35 and ref["mat900"]["relres"] < 1e-6
