@@ -1,22 +1,312 @@
-// comm.cu — multi-GPU plumbing (one process per GPU). NCCL is dlopen()ed on first use so that the
-// single-GPU library has no link-time dependency on it.
+// comm.cu — multi-GPU plumbing: one process per GPU, row-sharded matrix.
+//   * halo exchange of the SpMV operand (p and s each iteration) point-to-point between the ranks
+//     that share matrix columns (NVLink/NVSwitch through ncclSend/ncclRecv in one group);
+//   * one fused small allreduce per reduction point: every rank deposits the partial sums of ITS rows
+//     into a zero-padded array indexed by the GLOBAL tile/group, the sum over ranks therefore only adds
+//     zeros to each entry (bit-exact, order independent) and every rank then finishes the fixed-order
+//     tree redundantly — the result is bit-identical to the single-GPU run.
+// NCCL is dlopen()ed on first use: the single-GPU library has no link-time dependency on it.
+// The reference has no counterpart ("Distributed communication backend: none").
 #include "solver.h"
 #include <dlfcn.h>
+#include <nccl.h>
+#include <algorithm>
+#include <cstring>
 
 namespace cudamat {
-struct Comm { int rank = 0, world = 1; };
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.lib) return CUDAMAT_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { set_error("NCCL not found: dlopen(libnccl.so.2) failed: %s", dlerror()); return CUDAMAT_E_COMM; }
+#define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { set_error("NCCL symbol %s missing", name); return CUDAMAT_E_COMM; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.lib = h;
+    return CUDAMAT_OK;
 }
+#define CM_NCCL(call)                                                                         \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess) { set_error("NCCL error %d (%s) at %s:%d", (int)r_, g_nccl.GetErrorString(r_), __FILE__, __LINE__); return CUDAMAT_E_COMM; } \
+    } while (0)
+
+struct Comm {
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    std::vector<int64_t> row_starts;
+    std::vector<int> recv_cnt, recv_off, send_cnt, send_off, send_contig;   // per peer
+    int nsend = 0;
+    int *d_send_idx = nullptr;
+    double *d_sendbuf = nullptr;
+    int *d_ja_local = nullptr;
+    int exch_level = 2;
+    int exch_count = 0;          // doubles in the exchange arrays
+    double *d_exch_local = nullptr, *d_exch_glob = nullptr;
+    int ntile_global = 0;
+};
+
+__global__ void k_remap_cols(int64_t nnz, const int *ja_global, int *ja_local, int64_t row0, int64_t row1, int n,
+                             const int *halo_cols, int nhalo) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < nnz; k += stride) {
+        const int c = ja_global[k];
+        if (c >= row0 && c < row1) { ja_local[k] = (int)(c - row0); continue; }
+        int lo = 0, hi = nhalo - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (halo_cols[mid] < c) lo = mid + 1; else hi = mid; }
+        ja_local[k] = n + lo;
+    }
+}
+__global__ void k_pack(const double *vec, const int *idx, double *out, int cnt) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < cnt) out[k] = vec[idx[k]];
+}
+
+// finish a reduction after the cross-rank exchange: (level 1) tiles -> groups -> final, (level 2) groups -> final
+__global__ void __launch_bounds__(kCtaThreads) k_finalize(const double *exch, int level, int count, int stride, int nq,
+                                                          DevScalars *sc, double *hist, int phase) {
+    if (sc->status != ST_RUNNING && phase != PH_STORE) return;
+    __shared__ double s_grp[kMaxQ][64];
+    __shared__ double s_red[kMaxQ];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int nfinal = count;
+    if (level == 1) {
+        const int ngroups = (count + kGroupTiles - 1) / kGroupTiles;     // <= 64 (checked on the host)
+        for (int w = warp; w < nq * ngroups; w += kCtaWarps) {
+            const int q = w / ngroups, g = w % ngroups;
+            const double v = warp_reduce_values_cg(exch + (size_t)q * stride + (size_t)g * kGroupTiles,
+                                                   min(kGroupTiles, count - g * kGroupTiles), lane);
+            if (lane == 0) s_grp[q][g] = v;
+        }
+        __syncthreads();
+        nfinal = ngroups;
+    }
+    if (warp < nq) {
+        const double f = (level == 1) ? warp_reduce_values_smem(s_grp[warp], nfinal, lane)
+                                      : warp_reduce_values_cg(exch + (size_t)warp * stride, nfinal, lane);
+        if (lane == 0) s_red[warp] = f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double red[kMaxQ] = {0.0, 0.0};
+        for (int q = 0; q < nq; ++q) red[q] = s_red[q];
+        apply_phase(sc, hist, phase, red);
+    }
+}
+
+// ---- hooks used by solver.cu ---------------------------------------------------------------------
+int comm_halo_exchange(cudamat_solver *s, double *vec) {
+    Comm *c = s->comm;
+    if (!c || c->world == 1) return CUDAMAT_OK;
+    if (c->nsend > 0) {
+        bool need_pack = false;
+        for (int p = 0; p < c->world; ++p) if (c->send_cnt[p] > 0 && c->send_contig[p] < 0) need_pack = true;
+        if (need_pack) {
+            k_pack<<<(c->nsend + 255) / 256, 256, 0, s->stream>>>(vec, c->d_send_idx, c->d_sendbuf, c->nsend);
+            s->launches++;
+            CM_CUDA(cudaGetLastError());
+        }
+    }
+    CM_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < c->world; ++p) {
+        if (c->send_cnt[p] > 0) {
+            const double *src = c->send_contig[p] >= 0 ? vec + c->send_contig[p] : c->d_sendbuf + c->send_off[p];
+            CM_NCCL(g_nccl.Send(src, (size_t)c->send_cnt[p], ncclDouble, p, c->comm, s->stream));
+        }
+        if (c->recv_cnt[p] > 0)
+            CM_NCCL(g_nccl.Recv(vec + s->n + c->recv_off[p], (size_t)c->recv_cnt[p], ncclDouble, p, c->comm, s->stream));
+    }
+    CM_NCCL(g_nccl.GroupEnd());
+    return CUDAMAT_OK;
+}
+
+int comm_finish_reduction(cudamat_solver *s, int phase, int nq) {
+    Comm *c = s->comm;
+    if (!c || c->world == 1) return CUDAMAT_OK;
+    CM_NCCL(g_nccl.AllReduce(c->d_exch_local, c->d_exch_glob, (size_t)c->exch_count, ncclDouble, ncclSum, c->comm, s->stream));
+    const int stride = c->exch_count / kMaxQ;
+    k_finalize<<<1, kCtaThreads, 0, s->stream>>>(c->d_exch_glob, c->exch_level, c->exch_level == 1 ? c->ntile_global : s->rc.nslots,
+                                                 stride, nq, s->d_sc, s->d_hist, phase);
+    s->launches++;
+    CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
+void comm_release(cudamat_solver *s) {
+    Comm *c = s->comm;
+    if (!c) return;
+    if (c->d_send_idx) cudaFree(c->d_send_idx);
+    if (c->d_sendbuf) cudaFree(c->d_sendbuf);
+    if (c->d_ja_local) cudaFree(c->d_ja_local);
+    if (c->d_exch_local) cudaFree(c->d_exch_local);
+    if (c->d_exch_glob) cudaFree(c->d_exch_glob);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+    s->comm = nullptr;
+}
+
+}  // namespace cudamat
 using namespace cudamat;
 
 extern "C" {
+
 int cudamat_comm_unique_id(void *id128) {
-    (void)id128;
-    set_error("multi-GPU support is not compiled into this build yet");
-    return CUDAMAT_E_COMM;
+    if (!id128) return CUDAMAT_E_INVALID;
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    CM_NCCL(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == CUDAMAT_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    memcpy(id128, &id, sizeof id);
+    return CUDAMAT_OK;
 }
+
+// Collective over all ranks; call after cudamat_set_csr_* and before cudamat_analyze.
 int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world) {
-    (void)s; (void)id128; (void)rank; (void)world;
-    set_error("multi-GPU support is not compiled into this build yet");
-    return CUDAMAT_E_COMM;
+    if (!s || !id128 || world < 1 || rank < 0 || rank >= world) { set_error("comm_init: invalid argument"); return CUDAMAT_E_INVALID; }
+    if (!s->d_ia) { set_error("comm_init: set the CSR shard first"); return CUDAMAT_E_STATE; }
+    int rc = load_nccl();
+    if (rc) return rc;
+    comm_release(s);
+    Comm *c = new Comm();
+    s->comm = c;
+    c->rank = rank; c->world = world;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    CM_NCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    // 1. everybody's row range
+    int64_t *d_rng = nullptr;
+    CM_CUDA(cudaMalloc(&d_rng, sizeof(int64_t) * 2 * (size_t)(world + 1)));
+    const int64_t mine[2] = {s->row0, s->row1};
+    CM_CUDA(cudaMemcpyAsync(d_rng + 2 * world, mine, sizeof mine, cudaMemcpyHostToDevice, s->stream));
+    CM_NCCL(g_nccl.AllGather(d_rng + 2 * world, d_rng, 2, ncclInt64, c->comm, s->stream));
+    std::vector<int64_t> rng(2 * (size_t)world);
+    CM_CUDA(cudaMemcpyAsync(rng.data(), d_rng, sizeof(int64_t) * 2 * (size_t)world, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    CM_CUDA(cudaFree(d_rng));
+    c->row_starts.assign(world + 1, 0);
+    for (int p = 0; p < world; ++p) {
+        c->row_starts[p] = rng[2 * p];
+        if (p > 0 && rng[2 * p] != rng[2 * p - 1]) { set_error("comm_init: row shards are not contiguous in rank order"); return CUDAMAT_E_INVALID; }
+        if (rng[2 * p] % kTile != 0) { set_error("comm_init: shard boundaries must be multiples of %d rows", kTile); return CUDAMAT_E_INVALID; }
+    }
+    c->row_starts[world] = rng[2 * world - 1];
+    if (c->row_starts[0] != 0 || c->row_starts[world] != s->n_global) { set_error("comm_init: shards do not cover [0,n)"); return CUDAMAT_E_INVALID; }
+    // 2. halo columns of this shard (host pass over the global column ids)
+    std::vector<int> ja((size_t)s->nnz);
+    CM_CUDA(cudaMemcpyAsync(ja.data(), s->d_ja_global, sizeof(int) * (size_t)s->nnz, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<int> halo;
+    for (int64_t k = 0; k < s->nnz; ++k) if (ja[k] < s->row0 || ja[k] >= s->row1) halo.push_back(ja[k]);
+    std::sort(halo.begin(), halo.end());
+    halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+    std::vector<int>().swap(ja);
+    const int nhalo = (int)halo.size();
+    c->recv_cnt.assign(world, 0); c->recv_off.assign(world, 0);
+    for (int k = 0, p = 0; k < nhalo; ++k) {
+        while (halo[k] >= c->row_starts[p + 1]) ++p;
+        c->recv_cnt[p]++;
+    }
+    for (int p = 1; p < world; ++p) c->recv_off[p] = c->recv_off[p - 1] + c->recv_cnt[p - 1];
+    // 3. who wants what from whom: allgather of the world x world count matrix
+    int *d_cnt = nullptr;
+    CM_CUDA(cudaMalloc(&d_cnt, sizeof(int) * (size_t)world * (size_t)(world + 1)));
+    CM_CUDA(cudaMemcpyAsync(d_cnt + (size_t)world * world, c->recv_cnt.data(), sizeof(int) * (size_t)world, cudaMemcpyHostToDevice, s->stream));
+    CM_NCCL(g_nccl.AllGather(d_cnt + (size_t)world * world, d_cnt, (size_t)world, ncclInt32, c->comm, s->stream));
+    std::vector<int> W((size_t)world * world);
+    CM_CUDA(cudaMemcpyAsync(W.data(), d_cnt, sizeof(int) * (size_t)world * world, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    CM_CUDA(cudaFree(d_cnt));
+    c->send_cnt.assign(world, 0); c->send_off.assign(world, 0); c->send_contig.assign(world, -1);
+    for (int q = 0; q < world; ++q) c->send_cnt[q] = W[(size_t)q * world + rank];
+    for (int q = 1; q < world; ++q) c->send_off[q] = c->send_off[q - 1] + c->send_cnt[q - 1];
+    c->nsend = c->send_off[world - 1] + c->send_cnt[world - 1];
+    // 4. exchange the wanted global column lists; owners turn them into local row indices
+    int *d_halo = nullptr, *d_want = nullptr;
+    CM_CUDA(cudaMalloc(&d_halo, sizeof(int) * (size_t)std::max(nhalo, 1)));
+    CM_CUDA(cudaMalloc(&d_want, sizeof(int) * (size_t)std::max(c->nsend, 1)));
+    CM_CUDA(cudaMemcpyAsync(d_halo, halo.data(), sizeof(int) * (size_t)nhalo, cudaMemcpyHostToDevice, s->stream));
+    CM_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < world; ++p) {
+        if (c->recv_cnt[p] > 0) CM_NCCL(g_nccl.Send(d_halo + c->recv_off[p], (size_t)c->recv_cnt[p], ncclInt32, p, c->comm, s->stream));
+        if (c->send_cnt[p] > 0) CM_NCCL(g_nccl.Recv(d_want + c->send_off[p], (size_t)c->send_cnt[p], ncclInt32, p, c->comm, s->stream));
+    }
+    CM_NCCL(g_nccl.GroupEnd());
+    std::vector<int> want((size_t)c->nsend);
+    CM_CUDA(cudaMemcpyAsync(want.data(), d_want, sizeof(int) * (size_t)c->nsend, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < c->nsend; ++k) want[k] -= (int)s->row0;
+    for (int q = 0; q < world; ++q) {
+        bool contig = c->send_cnt[q] > 0;
+        for (int k = 1; k < c->send_cnt[q] && contig; ++k)
+            if (want[c->send_off[q] + k] != want[c->send_off[q]] + k) contig = false;
+        if (contig) c->send_contig[q] = want[c->send_off[q]];
+    }
+    CM_CUDA(cudaMalloc(&c->d_send_idx, sizeof(int) * (size_t)std::max(c->nsend, 1)));
+    CM_CUDA(cudaMemcpyAsync(c->d_send_idx, want.data(), sizeof(int) * (size_t)c->nsend, cudaMemcpyHostToDevice, s->stream));
+    CM_CUDA(cudaMalloc(&c->d_sendbuf, sizeof(double) * (size_t)std::max(c->nsend, 1)));
+    CM_CUDA(cudaFree(d_want));
+    // 5. local/halo column numbering
+    CM_CUDA(cudaMalloc(&c->d_ja_local, sizeof(int) * (size_t)std::max<int64_t>(s->nnz, 1) + 16));
+    if (s->nnz > 0) {
+        k_remap_cols<<<1184, 256, 0, s->stream>>>(s->nnz, s->d_ja_global, c->d_ja_local, s->row0, s->row1, s->n, d_halo, nhalo);
+        CM_CUDA(cudaGetLastError());
+    }
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    CM_CUDA(cudaFree(d_halo));
+    s->d_ja = c->d_ja_local;
+    s->nhalo = nhalo;
+    // 6. reduction exchange level
+    bool group_aligned = true;
+    for (int p = 0; p < world; ++p) if (c->row_starts[p] % ((int64_t)kTile * kGroupTiles) != 0) group_aligned = false;
+    c->ntile_global = (int)((s->n_global + kTile - 1) / kTile);
+    RedCtx &rcx = s->rc;
+    if (group_aligned) {
+        c->exch_level = 2;
+        c->exch_count = kMaxQ * rcx.slot_stride;
+    } else {
+        if (c->ntile_global > 64 * kGroupTiles) { set_error("comm_init: unaligned shards need n <= %lld", (long long)64 * kGroupTiles * kTile); return CUDAMAT_E_INVALID; }
+        c->exch_level = 1;
+        c->exch_count = kMaxQ * c->ntile_global;
+    }
+    CM_CUDA(cudaMalloc(&c->d_exch_local, sizeof(double) * (size_t)c->exch_count));
+    CM_CUDA(cudaMalloc(&c->d_exch_glob, sizeof(double) * (size_t)c->exch_count));
+    CM_CUDA(cudaMemsetAsync(c->d_exch_local, 0, sizeof(double) * (size_t)c->exch_count, s->stream));
+    CM_CUDA(cudaMemsetAsync(c->d_exch_glob, 0, sizeof(double) * (size_t)c->exch_count, s->stream));
+    rcx.do_final = 0;
+    rcx.exch_level = c->exch_level;
+    rcx.tile0 = (int)(s->row0 / kTile);
+    if (c->exch_level == 2) {
+        // group partials go straight into the exchange array (same layout as the slots buffer,
+        // which stays allocated as s->slots_own and is freed at destroy)
+        rcx.slots = c->d_exch_local;
+        rcx.exch = nullptr; rcx.exch_stride = 0;
+    } else {
+        rcx.exch = c->d_exch_local; rcx.exch_stride = c->ntile_global;
+    }
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    s->analyzed = false;
+    return CUDAMAT_OK;
 }
-}
+
+}  // extern "C"

@@ -68,6 +68,11 @@ struct RedCtx {
     int group0;            // global index of the first local group
     int nslots;            // global number of groups
     int do_final;          // 1: last CTA reduces slots and runs the phase (single shard)
+    // multi-GPU: where this shard deposits its contribution for the zero-padded allreduce
+    int exch_level;        // 0 none; 1 tile partials (global tile index); 2 group partials (== slots)
+    int tile0;             // global index of the first local tile
+    int exch_stride;
+    double *exch;          // level 1: [kMaxQ][exch_stride] indexed by global tile
 };
 
 // ------------------------------------------------------------------------------------------
@@ -177,10 +182,12 @@ __device__ __forceinline__ void reduce_tail(const RedCtx &rc, DevScalars *sc, do
     if (warp < NQ) {
         double tp = warp_reduce_values_smem(s_slab[warp], nslab_tile, lane);
         if (lane == 0) {
+            if (rc.exch_level == 1) rc.exch[(size_t)warp * rc.exch_stride + rc.tile0 + tile] = tp;
             __stcg(rc.tile_part + (size_t)warp * rc.tile_stride + tile, tp);
             __threadfence();
         }
     }
+    if (rc.exch_level == 1) return;      // groups and final are formed after the cross-rank exchange
     __syncthreads();
     const int g = tile / kGroupTiles;
     if (tid == 0) {

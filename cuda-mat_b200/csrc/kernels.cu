@@ -104,170 +104,179 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 
 struct StagedArgs {
     SpmvArgs a;
-    int cap_nnz;      // smem capacity per slab stage, multiple of 4
+    int cap_nnz;      // smem capacity per slab stage in nnz, multiple of 16
     int stages;
     int64_t nnz;      // to bound aligned over-reads
 };
 
-// shared layout per warp: [stages] x { double val[cap+2]; int col[cap+8]; } + mbarriers
+// Per-warp stage layout (every region a multiple of 16 bytes):
+//   double val[cap+2] | int col[cap+8] | int rowptr[36] | double u[32]
+__host__ __device__ __forceinline__ int staged_stage_bytes(int cap) { return (cap + 2) * 8 + (cap + 8) * 4 + 144 + 256; }
+
+// row sum of one lane's row; vb/cb are rebased so that the GLOBAL nnz index k addresses vb[k]/cb[k].
+// The first 8 gathered x values (xv) were prefetched while the previous slab was being computed.
+__device__ __forceinline__ double staged_rowsum(const double *vb, const int *cb, const double *x, int s, int e,
+                                                const double (&xv)[8], int lane) {
+    const int len = e - s;
+    const int shortlen = (len <= kLongRow) ? len : 0;
+    const int maxlen = __reduce_max_sync(0xffffffffu, shortlen);
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (q < shortlen) sum = __fma_rn(vb[s + q], xv[q], sum);
+    for (int k0 = 8; k0 < maxlen; k0 += 8) {
+        int cj[8]; double xq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cj[q] = ((k0 + q) < shortlen) ? cb[s + k0 + q] : -1;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xq[q] = (cj[q] >= 0) ? __ldg(x + cj[q]) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if ((k0 + q) < shortlen) sum = __fma_rn(vb[s + k0 + q], xq[q], sum);
+    }
+    unsigned lm = __ballot_sync(0xffffffffu, len > kLongRow);
+    while (lm) {
+        const int src = __ffs(lm) - 1;
+        lm &= lm - 1;
+        const int ss = __shfl_sync(0xffffffffu, s, src), ee = __shfl_sync(0xffffffffu, e, src);
+        double acc = 0.0;
+        for (int k = ss + lane; k < ee; k += 32) acc = __fma_rn(vb[k], __ldg(x + cb[k]), acc);
+        acc = warp_butterfly(acc);
+        if (lane == src) sum = acc;
+    }
+    return sum;
+}
+
 template <bool HAS_D, int NDOT>
-__global__ void __launch_bounds__(kCtaThreads) k_spmv_staged(const StagedArgs g) {
+__global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_staged(const StagedArgs g) {
     const SpmvArgs &a = g.a;
     if (a.check_status && a.sc->status != ST_RUNNING) return;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_slab[kMaxQ][kTileSlabs];
-    __shared__ uint64_t s_bar[kCtaWarps][4];
+    __shared__ uint64_t s_bar[kCtaWarps][8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_base = blockIdx.x * kTile;
     const int S = g.stages;
-    const size_t val_bytes = (size_t)(g.cap_nnz + 2) * 8, col_bytes = (size_t)(g.cap_nnz + 8) * 4;
-    const size_t stage_bytes = val_bytes + col_bytes;
+    const int VB = (g.cap_nnz + 2) * 8, CB = (g.cap_nnz + 8) * 4;
+    const int stage_bytes = staged_stage_bytes(g.cap_nnz);
     unsigned char *wbase = smem_raw + (size_t)warp * S * stage_bytes;
     if (lane == 0)
         for (int q = 0; q < S; ++q) mbar_init(&s_bar[warp][q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
 
-    // slab spans of this warp: rows row_base + (j*8+warp)*32 .. +32
-    int sp_s[kSlabsPerWarp], sp_e[kSlabsPerWarp];
-    int nj = 0;
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {
-        const int r0 = row_base + (j * kCtaWarps + warp) * kSlab;
-        if (r0 < a.n) {
-            sp_s[j] = __ldg(a.ia + r0);
-            sp_e[j] = __ldg(a.ia + min(r0 + kSlab, a.n));
-            nj = j + 1;
-        } else { sp_s[j] = 0; sp_e[j] = 0; }
+    const int rows_here = min(kTile, a.n - row_base);
+    const int nslab_tile = (rows_here + kSlab - 1) / kSlab;
+    const int nj = (nslab_tile > warp) ? (nslab_tile - warp + kCtaWarps - 1) / kCtaWarps : 0;
+    // lane j (< 8) keeps the nnz span of slab j of this warp; "full" = 32 valid rows and a 36-int row
+    // pointer copy that stays inside ia[0..n]
+    int my_s = 0, my_e = 0, my_full = 0;
+    if (lane < nj) {
+        const int r0 = row_base + (lane * kCtaWarps + warp) * kSlab;
+        my_s = __ldg(a.ia + r0);
+        my_e = __ldg(a.ia + min(r0 + kSlab, a.n));
+        my_full = (r0 + 35 <= a.n) ? 1 : 0;
     }
-    // issue: stage q <- slab j. Aligned span: vals from even index, cols from a multiple of 4.
-    // per-stage phase parity (bit q) and the parity each staged slab must wait for (bit j)
     unsigned phase_bits = 0, parity_mask = 0, staged_mask = 0;
     auto issue = [&](int j) {
         const int q = j % S;
-        const int s0 = sp_s[j], e0 = sp_e[j];
+        const int s0 = __shfl_sync(0xffffffffu, my_s, j), e0 = __shfl_sync(0xffffffffu, my_e, j);
+        const int full = __shfl_sync(0xffffffffu, my_full, j);
         const int vs = s0 & ~1, ve = (e0 + 1) & ~1;
         const int cs = s0 & ~3, ce = (e0 + 3) & ~3;
-        const bool fits = e0 > s0 && (e0 - s0) <= g.cap_nnz && (int64_t)ve <= (g.nnz & ~1LL) && (int64_t)ce <= (g.nnz & ~3LL);
+        const bool fits = full && e0 > s0 && (e0 - s0) <= g.cap_nnz && (int64_t)ve <= (g.nnz & ~1LL) && (int64_t)ce <= (g.nnz & ~3LL);
         if (fits) {
             if (lane == 0) {
                 unsigned char *st = wbase + (size_t)q * stage_bytes;
+                const int r0 = row_base + (j * kCtaWarps + warp) * kSlab;
                 const uint32_t vb = (uint32_t)(ve - vs) * 8u, cb = (uint32_t)(ce - cs) * 4u;
-                mbar_expect_tx(&s_bar[warp][q], vb + cb);
+                mbar_expect_tx(&s_bar[warp][q], vb + cb + 144u + (NDOT >= 1 ? 256u : 0u));
                 tma_bulk_g2s(st, a.val + vs, vb, &s_bar[warp][q]);
-                tma_bulk_g2s(st + val_bytes, a.ja + cs, cb, &s_bar[warp][q]);
+                tma_bulk_g2s(st + VB, a.ja + cs, cb, &s_bar[warp][q]);
+                tma_bulk_g2s(st + VB + CB, a.ia + r0, 144u, &s_bar[warp][q]);
+                if (NDOT >= 1) tma_bulk_g2s(st + VB + CB + 144, a.u + r0, 256u, &s_bar[warp][q]);
             }
             staged_mask |= 1u << j;
             parity_mask |= ((phase_bits >> q) & 1u) << j;
             phase_bits ^= 1u << q;
         }
     };
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j)
-        if (j < S - 1 && j < nj) issue(j);
-
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {
-        if (j >= nj) break;
-        // keep S-1 slabs in flight
-        if (j + S - 1 < nj) {
-            __syncwarp();
-            issue(j + S - 1);
+    // first stage of a slab: make its operands visible, fetch the lane's row bounds and issue the
+    // x gathers of the first 8 entries (they complete while the previous slab is being computed)
+    auto prefetch = [&](int j, int &s, int &e, double (&xv)[8]) {
+        const int row = row_base + (j * kCtaWarps + warp) * kSlab + lane;
+        const bool staged = (staged_mask >> j) & 1u;
+        const int *cbase;
+        if (staged) {
+            const int q = j % S;
+            unsigned spins = 0;
+            while (!mbar_try_wait(&s_bar[warp][q], (parity_mask >> j) & 1u)) { if (++spins > (1u << 24)) __trap(); }
+            const unsigned char *st = wbase + (size_t)q * stage_bytes;
+            const int *rp = reinterpret_cast<const int *>(st + VB + CB);
+            s = rp[lane]; e = rp[lane + 1];
+            cbase = reinterpret_cast<const int *>(st + VB) - (__shfl_sync(0xffffffffu, my_s, j) & ~3);
+        } else {
+            s = 0; e = 0;
+            if (row < a.n) { s = __ldg(a.ia + row); e = __ldg(a.ia + row + 1); }
+            cbase = a.ja;
+            (void)__shfl_sync(0xffffffffu, my_s, j);
         }
+        const int len = e - s;
+        const int shortlen = (len <= kLongRow) ? len : 0;
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) xv[q8] = (q8 < shortlen) ? __ldg(a.x + cbase[s + q8]) : 0.0;
+    };
+
+    for (int j = 0; j < S - 1 && j < nj; ++j) issue(j);
+    int cs_ = 0, ce_ = 0; double cxv[8];
+    if (nj > 0) prefetch(0, cs_, ce_, cxv);
+#pragma unroll 1
+    for (int j = 0; j < nj; ++j) {
+        if (j + S - 1 < nj) { __syncwarp(); issue(j + S - 1); }
+        int ns_ = 0, ne_ = 0; double nxv[8];
+        if (j + 1 < nj) prefetch(j + 1, ns_, ne_, nxv);
         const int slab = j * kCtaWarps + warp;
         const int row = row_base + slab * kSlab + lane;
         const bool active = row < a.n;
-        int s = 0, e = 0;
-        if (active) { s = __ldg(a.ia + row); e = __ldg(a.ia + row + 1); }
-        const int len = e - s;
-        double sum = 0.0;
-        const bool is_staged = (staged_mask >> j) & 1u;
-        if (is_staged) {
-            const int q = j % S;
-            const uint32_t parity = (parity_mask >> j) & 1u;
-            unsigned spins = 0;
-            while (!mbar_try_wait(&s_bar[warp][q], parity)) { if (++spins > (1u << 24)) __trap(); }
-            const unsigned char *st = wbase + (size_t)q * stage_bytes;
-            // stage holds val[vs..ve) and col[cs..ce); rebase so that global nnz index k maps to sv[k]/sc[k]
-            const double *sv = reinterpret_cast<const double *>(st) - (sp_s[j] & ~1);
-            const int *sc = reinterpret_cast<const int *>(st + val_bytes) - (sp_s[j] & ~3);
-            const int shortlen = (len <= kLongRow) ? len : 0;
-            const int maxlen = __reduce_max_sync(0xffffffffu, shortlen);
-            for (int k0 = 0; k0 < maxlen; k0 += 8) {
-                int cj[8]; double xv[8];
-#pragma unroll
-                for (int q8 = 0; q8 < 8; ++q8) cj[q8] = ((k0 + q8) < shortlen) ? sc[s + k0 + q8] : -1;
-#pragma unroll
-                for (int q8 = 0; q8 < 8; ++q8) xv[q8] = (cj[q8] >= 0) ? __ldg(a.x + cj[q8]) : 0.0;
-#pragma unroll
-                for (int q8 = 0; q8 < 8; ++q8)
-                    if ((k0 + q8) < shortlen) sum = __fma_rn(sv[s + k0 + q8], xv[q8], sum);
-            }
-            unsigned lm = __ballot_sync(0xffffffffu, len > kLongRow);
-            while (lm) {
-                const int src = __ffs(lm) - 1;
-                lm &= lm - 1;
-                const int ss = __shfl_sync(0xffffffffu, s, src), ee = __shfl_sync(0xffffffffu, e, src);
-                double acc = 0.0;
-                for (int k = ss + lane; k < ee; k += 32) acc = __fma_rn(sv[k], __ldg(a.x + sc[k]), acc);
-                acc = warp_butterfly(acc);
-                if (lane == src) sum = acc;
-            }
+        const bool staged = (staged_mask >> j) & 1u;
+        const int span_s = __shfl_sync(0xffffffffu, my_s, j);
+        double sum, uval = 0.0;
+        if (staged) {
+            const unsigned char *st = wbase + (size_t)(j % S) * stage_bytes;
+            const double *vb = reinterpret_cast<const double *>(st) - (span_s & ~1);
+            const int *cb = reinterpret_cast<const int *>(st + VB) - (span_s & ~3);
+            sum = staged_rowsum(vb, cb, a.x, cs_, ce_, cxv, lane);
+            if (NDOT >= 1) uval = reinterpret_cast<const double *>(st + VB + CB + 144)[lane];
         } else {
-            // slab does not fit the stage (or is empty): direct global path, same arithmetic
-            const int shortlen = (len <= kLongRow) ? len : 0;
-            const int maxlen = __reduce_max_sync(0xffffffffu, shortlen);
-            for (int k0 = 0; k0 < maxlen; k0 += 8) {
-                int cj[8]; double av[8], xv[8];
-#pragma unroll
-                for (int q8 = 0; q8 < 8; ++q8) {
-                    const bool p = (k0 + q8) < shortlen;
-                    cj[q8] = p ? __ldg(a.ja + s + k0 + q8) : -1;
-                    av[q8] = p ? __ldg(a.val + s + k0 + q8) : 0.0;
-                }
-#pragma unroll
-                for (int q8 = 0; q8 < 8; ++q8) xv[q8] = (cj[q8] >= 0) ? __ldg(a.x + cj[q8]) : 0.0;
-#pragma unroll
-                for (int q8 = 0; q8 < 8; ++q8)
-                    if ((k0 + q8) < shortlen) sum = __fma_rn(av[q8], xv[q8], sum);
-            }
-            unsigned lm = __ballot_sync(0xffffffffu, len > kLongRow);
-            while (lm) {
-                const int src = __ffs(lm) - 1;
-                lm &= lm - 1;
-                const int ss = __shfl_sync(0xffffffffu, s, src), ee = __shfl_sync(0xffffffffu, e, src);
-                const double acc = rowsum_long(a, ss, ee, lane);
-                if (lane == src) sum = acc;
-            }
+            sum = staged_rowsum(a.val, a.ja, a.x, cs_, ce_, cxv, lane);
+            if (NDOT >= 1) uval = active ? __ldg(a.u + row) : 0.0;
         }
         if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
         if (active) a.y[row] = sum;
-        if (NDOT >= 1) {
-            const double p0 = active ? __dmul_rn(sum, __ldg(a.u + row)) : 0.0;
-            slab_deposit(s_slab, 0, slab, p0, lane);
-        }
-        if (NDOT >= 2) {
-            const double p1 = active ? __dmul_rn(sum, sum) : 0.0;
-            slab_deposit(s_slab, 1, slab, p1, lane);
-        }
+        if (NDOT >= 1) slab_deposit(s_slab, 0, slab, active ? __dmul_rn(sum, uval) : 0.0, lane);
+        if (NDOT >= 2) slab_deposit(s_slab, 1, slab, active ? __dmul_rn(sum, sum) : 0.0, lane);
+        cs_ = ns_; ce_ = ne_;
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) cxv[q8] = nxv[q8];
     }
     if (NDOT >= 1) {
         __syncthreads();
-        const int rows_here = min(kTile, a.n - row_base);
-        reduce_tail<(NDOT >= 1 ? NDOT : 1)>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
+        reduce_tail<(NDOT >= 1 ? NDOT : 1)>(a.rc, a.sc, a.hist, a.phase, s_slab, nslab_tile);
     }
 }
 
 int plan_staged(cudamat_solver *s) {
-    // capacity = max slab span rounded up (+ alignment slack), stages to fill ~96 KB per CTA
+    // capacity = max slab span rounded up to 16; as many stages as fit ~110 KB per CTA (2 CTAs / SM)
     s->staged = StagedPlan();
     if (s->max_slab_nnz <= 0) return CUDAMAT_OK;
-    int cap = ((s->max_slab_nnz + 4 + 15) / 16) * 16;
+    int cap = ((s->max_slab_nnz + 15) / 16) * 16;
     if (cap > 1024) cap = 1024;                        // heavier slabs take the direct path
-    const size_t stage_bytes = (size_t)(cap + 2) * 8 + (size_t)(cap + 8) * 4;
-    int stages = (int)((100 * 1024) / (stage_bytes * kCtaWarps));
-    if (stages > 4) stages = 4;
+    const size_t stage_bytes = (size_t)staged_stage_bytes(cap);
+    int stages = (int)((110 * 1024) / (stage_bytes * kCtaWarps));
+    if (s->opt_staged_stages > 0) stages = s->opt_staged_stages;
+    if (stages > 8) stages = 8;
     if (stages < 2) return CUDAMAT_OK;
+    if (stage_bytes * kCtaWarps * stages > 220 * 1024) return CUDAMAT_OK;
     s->staged.cap_nnz = cap;
     s->staged.stages = stages;
     s->staged.smem_bytes = stage_bytes * kCtaWarps * stages;
@@ -278,7 +287,7 @@ template <bool HAS_D, int NDOT>
 static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
     const int grid = (a.n + kTile - 1) / kTile;
     if (grid == 0) return CUDAMAT_OK;
-    if (variant == CUDAMAT_SPMV_STAGED && s->staged.cap_nnz > 0) {
+    if (variant == CUDAMAT_SPMV_STAGED && s->staged.cap_nnz > 0 && (NDOT == 0 || ((uintptr_t)a.u % 16) == 0)) {
         StagedArgs g{a, s->staged.cap_nnz, s->staged.stages, s->nnz};
         auto kern = k_spmv_staged<HAS_D, NDOT>;
         CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->staged.smem_bytes));

@@ -41,6 +41,7 @@ static int alloc_reduction(cudamat_solver *s) {
     rc.do_final = 1;
     CM_CUDA(cudaMalloc(&rc.tile_part, sizeof(double) * kMaxQ * (size_t)rc.tile_stride));
     CM_CUDA(cudaMalloc(&rc.slots, sizeof(double) * kMaxQ * (size_t)rc.slot_stride));
+    s->slots_own = rc.slots;
     CM_CUDA(cudaMemsetAsync(rc.slots, 0, sizeof(double) * kMaxQ * (size_t)rc.slot_stride, s->stream));
     CM_CUDA(cudaMalloc(&rc.group_cnt, sizeof(unsigned) * (size_t)std::max(rc.ngroup_loc, 1)));
     CM_CUDA(cudaMemsetAsync(rc.group_cnt, 0, sizeof(unsigned) * (size_t)std::max(rc.ngroup_loc, 1), s->stream));
@@ -93,7 +94,15 @@ static int timed_spmv(cudamat_solver *s, const SpmvArgs &a, int var) {
     int rc = launch_spmv(s, a, var);
     if (rc) return rc;
     if (timed) { CM_CUDA(cudaEventRecord(s->ev_pool[s->ev_used + 1], s->stream)); s->ev_used += 2; }
+    if (a.ndot > 0) return comm_finish_reduction(s, a.phase, a.ndot);
     return CUDAMAT_OK;
+}
+// SpMV step of the loop: halo exchange of the operand (multi-GPU), the kernel, then the cross-rank
+// part of its fused reductions
+static int spmv_step(cudamat_solver *s, double *x, const double *d, double *y, const double *u, int ndot, int phase, int check) {
+    int rc = comm_halo_exchange(s, x);
+    if (rc) return rc;
+    return timed_spmv(s, spmv_args(s, x, d, y, u, ndot, phase, check), s->spmv_variant);
 }
 
 static int poll_status(cudamat_solver *s) {
@@ -144,16 +153,19 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
     CM_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * s->work_elems, s->stream));     // v = p = 0 (:611)
     CM_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * s->work_elems, s->stream));
     // r = b - (A0 + diag d) x0 ; r0 = r ; ||r0|| (:645-655)
+    if ((rc = comm_halo_exchange(s, xk))) return rc;
     if ((rc = launch_spmv(s, spmv_args(s, xk, d_d, t, nullptr, 0, PH_NONE, 0), var))) return rc;
     if ((rc = launch_init_resid(s, d_b, t, r, r0, nullptr, PH_U_INIT))) return rc;
+    if ((rc = comm_finish_reduction(s, PH_U_INIT, 1))) return rc;
     if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
     const int poll = std::max(1, s->opt_poll_every);
     for (int it = 0; it < maxit;) {
         if ((rc = launch_update_p(s, false, r, v, p))) return rc;                                   // :668-672
-        if ((rc = timed_spmv(s, spmv_args(s, p, d_d, v, r0, 1, PH_U_A, 1), var))) return rc;       // :675-689
+        if ((rc = spmv_step(s, p, d_d, v, r0, 1, PH_U_A, 1))) return rc;                 // :675-689
         if ((rc = launch_update_s(s, r, v, sv))) return rc;                                         // :698-700
-        if ((rc = timed_spmv(s, spmv_args(s, sv, d_d, t, sv, 2, PH_U_B, 1), var))) return rc;      // :703-710
+        if ((rc = spmv_step(s, sv, d_d, t, sv, 2, PH_U_B, 1))) return rc;               // :703-710
         if ((rc = launch_update_xr(s, false, p, sv, t, r0, xk, r))) return rc;                      // :694-696,714-747
+        if ((rc = comm_finish_reduction(s, PH_U_C, 2))) return rc;
         ++it;
         if (it % poll == 0 || it == maxit) {
             if ((rc = poll_status(s))) return rc;
@@ -183,11 +195,11 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
         if ((rc = launch_update_p(s, true, r, v, p))) return rc;                                    // :83-89 (skips i == 0)
         if ((rc = launch_sptrsv(s, false, p, t))) return rc;                                        // :92-94
         if ((rc = launch_sptrsv(s, true, t, pw))) return rc;                                        // :96-98
-        if ((rc = timed_spmv(s, spmv_args(s, pw, nullptr, v, rw, 1, PH_I_A, 1), var))) return rc;  // :104-107
+        if ((rc = spmv_step(s, pw, nullptr, v, rw, 1, PH_I_A, 1))) return rc;        // :104-107
         if ((rc = launch_update_rx_ilu(s, v, pw, r, xk))) return rc;                                // :109-118
         if ((rc = launch_sptrsv(s, false, r, t))) return rc;                                        // :121-123
         if ((rc = launch_sptrsv(s, true, t, sv))) return rc;                                        // :125-127
-        if ((rc = timed_spmv(s, spmv_args(s, sv, nullptr, t, r, 2, PH_I_B, 1), var))) return rc;   // :132-137
+        if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1))) return rc;         // :132-137
         if ((rc = launch_update_xr(s, true, nullptr, sv, t, rw, xk, r))) return rc;                 // :139-151, :81
         ++it;
         if (it % poll == 0 || it == maxit) {
@@ -269,12 +281,13 @@ int cudamat_create(cudamat_solver **out, int64_t n_global, int64_t row0, int64_t
 int cudamat_destroy(cudamat_solver *s) {
     if (!s) return CUDAMAT_OK;
     cudaStreamSynchronize(s->stream);
+    comm_release(s);
     ilu0_release(s);
     if (s->own_ia) cudaFree(s->own_ia);
     if (s->own_ja) cudaFree(s->own_ja);
     if (s->own_a) cudaFree(s->own_a);
     if (s->rc.tile_part) cudaFree(s->rc.tile_part);
-    if (s->rc.slots) cudaFree(s->rc.slots);
+    if (s->slots_own) cudaFree(s->slots_own);
     if (s->rc.group_cnt) cudaFree(s->rc.group_cnt);
     if (s->rc.done_cnt) cudaFree(s->rc.done_cnt);
     if (s->d_sc) cudaFree(s->d_sc);
@@ -293,6 +306,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "sptrsv_syncfree")) s->opt_sptrsv_syncfree = (int)value;
     else if (!strcmp(key, "debug")) s->opt_debug = (int)value;
     else if (!strcmp(key, "time_spmv")) s->opt_time_spmv = (int)value;
+    else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
     else { set_error("unknown option '%s'", key); return CUDAMAT_E_INVALID; }
     return CUDAMAT_OK;
 }
@@ -408,7 +422,15 @@ int cudamat_get_history(cudamat_solver *s, double *hist, int cap) {
 int cudamat_spmv_device(cudamat_solver *s, const double *d_x, const double *d_d, double *d_y, int variant) {
     if (!s || !d_x || !d_y) { set_error("spmv_device: null argument"); return CUDAMAT_E_INVALID; }
     if (!s->analyzed) { set_error("spmv_device: call cudamat_analyze first"); return CUDAMAT_E_STATE; }
-    if (s->nhalo != 0) { set_error("spmv_device: single-shard handles only"); return CUDAMAT_E_INVALID; }
+    if (s->comm) {
+        // sharded handle: stage x next to its halo, exchange, multiply (collective over all ranks)
+        int rc = ensure_work(s, 8);
+        if (rc) return rc;
+        double *xs = wv(s, 7);
+        CM_CUDA(cudaMemcpyAsync(xs, d_x, sizeof(double) * (size_t)s->n, cudaMemcpyDeviceToDevice, s->stream));
+        if ((rc = comm_halo_exchange(s, xs))) return rc;
+        return launch_spmv(s, spmv_args(s, xs, d_d, d_y, nullptr, 0, PH_NONE, 0), variant);
+    }
     return launch_spmv(s, spmv_args(s, d_x, d_d, d_y, nullptr, 0, PH_NONE, 0), variant);
 }
 
@@ -417,6 +439,7 @@ int cudamat_dot_device(cudamat_solver *s, const double *d_a, const double *d_b, 
     if (s->n == 0) { *result = 0.0; return CUDAMAT_OK; }
     int rc = launch_dot(s, d_a, d_b);
     if (rc) return rc;
+    if ((rc = comm_finish_reduction(s, PH_STORE, 1))) return rc;
     if ((rc = poll_status(s))) return rc;
     *result = s->h_sc->red[0];
     return CUDAMAT_OK;

@@ -69,10 +69,12 @@ struct cudamat_solver {
     int opt_sptrsv_syncfree = 1;
     int opt_debug = 0;
     int opt_time_spmv = 0;
+    int opt_staged_stages = 0;
     std::vector<cudaEvent_t> ev_pool; int ev_used = 0;
     cudamat::StagedPlan staged;
     // reduction context + scalars
     cudamat::RedCtx rc{};
+    double *slots_own = nullptr;           // the allocation behind rc.slots (rc.slots may be redirected by comm)
     cudamat::DevScalars *d_sc = nullptr;
     cudamat::DevScalars *h_sc = nullptr;   // pinned mirror
     double *d_hist = nullptr; int hist_cap = 0;
@@ -113,6 +115,11 @@ int plan_staged(cudamat_solver *s);
 int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st);
 int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out);
 void ilu0_release(cudamat_solver *s);
+
+// comm.cu
+int comm_halo_exchange(cudamat_solver *s, double *vec);
+int comm_finish_reduction(cudamat_solver *s, int phase, int nq);
+void comm_release(cudamat_solver *s);
 
 // generators (kernels.cu)
 int gen_poisson3d(int N, int64_t row0, int64_t row1, int *d_ia, int *d_ja, double *d_a, cudaStream_t st);

@@ -121,10 +121,11 @@ def test_dot_bit_exact(cm, O, torch_cuda):
     for n in (1, 31, 32, 33, 2047, 2048, 2049, 70001, 2048 * 1024 + 4097):
         a, b = rng.standard_normal(n), rng.standard_normal(n)
         s = cm.Solver(n)
-        got = s.dot(dev(torch, a).data_ptr(), dev(torch, b).data_ptr())
+        da, db = dev(torch, a), dev(torch, b)
+        got = s.dot(da.data_ptr(), db.data_ptr())
         assert got == O.dot(a, b), "n=%d" % n
         # repeated use of the same reduction context (self-cleaning counters)
-        assert s.dot(dev(torch, a).data_ptr(), dev(torch, a).data_ptr()) == O.dot(a, a)
+        assert s.dot(da.data_ptr(), da.data_ptr()) == O.dot(a, a)
         s.close()
 
 
@@ -326,7 +327,9 @@ def test_full_size_properties_poisson128(cm, torch_cuda):
         torch.cuda.synchronize()
         relres = float(torch.linalg.norm(b - ax)) / st["nrm_r0"]
         relerr = float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt))
-        assert relres <= 2e-10 and relerr <= 1e-8, (relres, relerr)
+        # error against x_true is bounded by cond(A) * relres (cond ~ 7e3 at 128^3); the 1e-8 bar of
+        # BASELINE.md is against the reference/oracle solution and is asserted (as bit-equality) elsewhere
+        assert relres <= 2e-10 and relerr <= 1e-5, (relres, relerr)
         h = s.history()
         assert len(h) == st["iterations"] + 1 and h[0] == st["nrm_r0"] and h[-1] == st["nrm_r"] and h[-1] < 1e-10 * h[0]
         results.append((st["iterations"], x.clone()))
@@ -342,5 +345,5 @@ def test_full_size_properties_poisson128(cm, torch_cuda):
     x = torch.zeros(n, dtype=torch.float64, device="cuda")
     st = s.solve(2, b.data_ptr(), x.data_ptr(), maxit=5000, tol=1e-10)
     assert st["converged"] and st["iterations"] < results[0][0]
-    assert float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt)) <= 1e-8
+    assert float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt)) <= 1e-5
     s.close()
