@@ -210,7 +210,7 @@ def run_ours(args):
     # ---- full solve to 1e-10: the convergence claim of the metric (also part of the warm-up) ----
     barrier()
     t0 = time.time()
-    stc = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=5000, tol=1e-10)
+    stc = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=5 if args.no_converge else 5000, tol=1e-10)
     torch.cuda.synchronize()
     t_conv = time.time() - t0
     err = torch.stack([torch.sum((x - xt) ** 2), torch.sum(xt ** 2)])
@@ -285,7 +285,7 @@ def run_ours(args):
             "converge": converge, "roofline": roof, "clocks": clk.summary()}
     line["gpu_launches"] = int(last_launches)
 
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_extras:
         line.update(single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, converge))
     elif world > 1:
         line["e2e"] = None
@@ -378,6 +378,8 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="force an SpMV variant (1 rowlane, 2 staged)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-ilu0", action="store_true", help="skip the ILU0 extra")
+    ap.add_argument("--no-converge", action="store_true", help="skip the full solve to 1e-10 (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / ilu0 / mat10000 / cpu extras (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

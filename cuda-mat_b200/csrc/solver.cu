@@ -361,12 +361,12 @@ int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
     if ((rc = plan_staged(s))) return rc;
     const bool aligned = (((uintptr_t)s->d_a) % 16 == 0) && (((uintptr_t)s->d_ja) % 16 == 0);
     if (!aligned) s->staged = StagedPlan();
-    // variant choice from row-length statistics: short, near-uniform rows stream well through the
-    // TMA-staged row-block kernel; otherwise use the direct kernel (long rows go warp-per-row inside both)
+    // variant choice from row-length statistics. Measured on B200 (profiles/r1_spmv_variants.md): with
+    // <= 32 entries per row the direct row-per-lane kernel already streams at ~95% of the copy roofline
+    // (full occupancy hides the strided val/col loads behind L1), ahead of the TMA-staged kernel whose
+    // shared-memory ring caps occupancy; it is therefore the default and the staged kernel is opt-in.
     int variant = s->opt_spmv_variant;
-    if (variant == CUDAMAT_SPMV_AUTO)
-        variant = (s->staged.cap_nnz > 0 && s->max_slab_nnz <= s->staged.cap_nnz - 4 && s->max_slab_nnz <= 4.0 * 32.0 * std::max(1.0, s->mean_row_len))
-                      ? CUDAMAT_SPMV_STAGED : CUDAMAT_SPMV_ROWLANE;
+    if (variant == CUDAMAT_SPMV_AUTO) variant = CUDAMAT_SPMV_ROWLANE;
     if (variant == CUDAMAT_SPMV_STAGED && s->staged.cap_nnz == 0) variant = CUDAMAT_SPMV_ROWLANE;
     s->spmv_variant = variant;
     if (st) st->t_analysis += now_s() - t0;
