@@ -163,12 +163,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N = args.grid
     n = N ** 3
-    # row shard of this rank: multiples of the reduction group (2 Mi rows) when possible, else of the tile
-    gran = 2048 * 1024 if n % (2048 * 1024 * world) == 0 else 2048
-    per = ((n // world + gran - 1) // gran) * gran if world > 1 else n
-    row0, row1 = min(rank * per, n), min((rank + 1) * per, n)
-    if world > 1 and rank == world - 1:
-        row1 = n
+    row0, row1 = cm.partition_rows(n, world, rank)
     nloc = row1 - row0
     nnz_loc = cm.poisson3d_nnz(N, row0, row1)
     nnz = cm.poisson3d_nnz(N)
@@ -181,16 +176,11 @@ def run_ours(args):
     s = cm.Solver(n, row0, row1, stream=stream)
     s.set_csr_device(nnz_loc, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
     if world > 1:
-        idbuf = torch.zeros(128, dtype=torch.uint8)
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
-            import ctypes
-            raw = (ctypes.c_ubyte * 128)()
-            cm._check(cm.lib.cudamat_comm_unique_id(raw))
-            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
-        idbuf = idbuf.cuda()
+            idbuf = torch.tensor(list(cm.Comm.unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(idbuf, 0)
-        raw = (ctypes.c_ubyte * 128)(*idbuf.cpu().tolist()) if rank != 0 else raw
-        cm._check(cm.lib.cudamat_comm_init(s.h, raw, rank, world))
+        cm.Comm.init(s, bytes(idbuf.cpu().tolist()), rank, world)
     if args.variant:
         s.set_option("spmv_variant", args.variant)
     sa = s.analyze(cm.MODE_PLAIN)

@@ -55,7 +55,8 @@ EXPORTS = [
     "cudamat_ilu0_host", "cudamat_create", "cudamat_destroy", "cudamat_set_option",
     "cudamat_set_csr_host", "cudamat_set_csr_device", "cudamat_analyze", "cudamat_solve_device",
     "cudamat_get_history", "cudamat_spmv_device", "cudamat_dot_device", "cudamat_get_ilu0_host",
-    "cudamat_sptrsv_device", "cudamat_comm_unique_id", "cudamat_comm_init",
+    "cudamat_sptrsv_device", "cudamat_comm_unique_id", "cudamat_comm_init", "cudamat_partition_rows",
+    "cudamat_halo_plan_host",
     "cudamat_gen_poisson3d_device", "cudamat_poisson3d_nnz", "cudamat_gen_xtrue_device",
     "cudamat_gen_random_dd_device", "cudamat_load_mm", "cudamat_free",
 ]
@@ -82,6 +83,9 @@ lib.cudamat_spmv_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void
 lib.cudamat_dot_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, c_dp]
 lib.cudamat_get_ilu0_host.argtypes = [C.c_void_p, c_dp]
 lib.cudamat_sptrsv_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+lib.cudamat_partition_rows.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+lib.cudamat_halo_plan_host.argtypes = [C.c_int64, C.c_int64, C.c_int64, c_ip, C.c_int, C.POINTER(C.c_int64), c_ip,
+                                       C.POINTER(c_ip), c_ip]
 lib.cudamat_comm_unique_id.argtypes = [C.c_void_p]
 lib.cudamat_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
 lib.cudamat_gen_poisson3d_device.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -252,6 +256,42 @@ class Solver:
 
     def sptrsv(self, upper, d_rhs, d_out):
         _check(lib.cudamat_sptrsv_device(self.h, int(upper), d_rhs, d_out))
+
+
+def partition_rows(n_global, world, rank):
+    """contiguous row shard [row0,row1) of `rank`, aligned to the reduction group / tile"""
+    r0, r1 = C.c_int64(0), C.c_int64(0)
+    _check(lib.cudamat_partition_rows(n_global, world, rank, C.byref(r0), C.byref(r1)))
+    return r0.value, r1.value
+
+
+def halo_plan_host(row0, row1, ja_global, row_starts):
+    """(halo_cols, recv_cnt): sorted unique off-shard columns and how many each owner rank holds"""
+    ja_global = _i32(ja_global)
+    world = len(row_starts) - 1
+    rs = (C.c_int64 * (world + 1))(*[int(v) for v in row_starts])
+    nh = C.c_int(0)
+    hp = c_ip()
+    rc = (C.c_int * world)()
+    _check(lib.cudamat_halo_plan_host(row0, row1, len(ja_global), _ip(ja_global), world, rs, C.byref(nh), C.byref(hp), rc))
+    halo = np.ctypeslib.as_array(hp, (max(nh.value, 1),))[:nh.value].copy()
+    lib.cudamat_free(C.cast(hp, C.c_void_p))
+    return halo, np.array(list(rc), dtype=np.int64)
+
+
+class Comm:
+    """NCCL communicator of a sharded Solver; the unique id travels through torch.distributed."""
+
+    @staticmethod
+    def unique_id():
+        raw = (C.c_ubyte * 128)()
+        _check(lib.cudamat_comm_unique_id(raw))
+        return bytes(raw)
+
+    @staticmethod
+    def init(solver, uid, rank, world):
+        raw = (C.c_ubyte * 128)(*uid)
+        _check(lib.cudamat_comm_init(solver.h, raw, rank, world))
 
 
 def gen_poisson3d_device(N, row0, row1, d_ia, d_ja, d_a, stream=0):

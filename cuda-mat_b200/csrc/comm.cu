@@ -170,6 +170,44 @@ using namespace cudamat;
 
 extern "C" {
 
+// ---- pure host planners (no GPU / NCCL needed; exercised by the gloo CPU tests) ----------------------
+// Row shard of `rank`: contiguous, boundaries aligned to the reduction group (2 Mi rows) when every rank
+// can get at least one group, else to the reduction tile (2048 rows).
+int cudamat_partition_rows(int64_t n_global, int world, int rank, int64_t *row0, int64_t *row1) {
+    if (n_global < 0 || world < 1 || rank < 0 || rank >= world || !row0 || !row1) { set_error("partition_rows: invalid argument"); return CUDAMAT_E_INVALID; }
+    const int64_t group = (int64_t)kTile * kGroupTiles;
+    const int64_t gran = (n_global >= group * world) ? group : kTile;
+    const int64_t per = ((n_global + world - 1) / world + gran - 1) / gran * gran;
+    *row0 = std::min<int64_t>((int64_t)rank * per, n_global);
+    *row1 = std::min<int64_t>(*row0 + per, n_global);
+    return CUDAMAT_OK;
+}
+
+// Halo plan of one shard: the sorted unique global columns outside [row0,row1) (malloc()ed into
+// *halo_cols, release with cudamat_free) and how many of them each owner rank holds (recv_cnt[world]).
+// Local column numbering is then: c in [row0,row1) -> c-row0, else n_local + position in halo_cols.
+int cudamat_halo_plan_host(int64_t row0, int64_t row1, int64_t nnz, const int *ja_global, int world,
+                           const int64_t *row_starts, int *nhalo, int **halo_cols, int *recv_cnt) {
+    if (!ja_global && nnz > 0) { set_error("halo_plan: null argument"); return CUDAMAT_E_INVALID; }
+    if (!row_starts || !nhalo || !halo_cols || !recv_cnt || world < 1) { set_error("halo_plan: null argument"); return CUDAMAT_E_INVALID; }
+    std::vector<int> halo;
+    for (int64_t k = 0; k < nnz; ++k) if (ja_global[k] < row0 || ja_global[k] >= row1) halo.push_back(ja_global[k]);
+    std::sort(halo.begin(), halo.end());
+    halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+    for (int p = 0; p < world; ++p) recv_cnt[p] = 0;
+    int p = 0;
+    for (size_t k = 0; k < halo.size(); ++k) {
+        if (halo[k] < 0 || halo[k] >= row_starts[world]) { set_error("halo_plan: column %d out of range", halo[k]); return CUDAMAT_E_INVALID; }
+        while (halo[k] >= row_starts[p + 1]) ++p;
+        recv_cnt[p]++;
+    }
+    *nhalo = (int)halo.size();
+    *halo_cols = (int *)malloc(sizeof(int) * std::max<size_t>(halo.size(), 1));
+    if (!*halo_cols) { set_error("halo_plan: out of memory"); return CUDAMAT_E_INVALID; }
+    std::copy(halo.begin(), halo.end(), *halo_cols);
+    return CUDAMAT_OK;
+}
+
 int cudamat_comm_unique_id(void *id128) {
     if (!id128) return CUDAMAT_E_INVALID;
     int rc = load_nccl();
@@ -216,17 +254,13 @@ int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world)
     std::vector<int> ja((size_t)s->nnz);
     CM_CUDA(cudaMemcpyAsync(ja.data(), s->d_ja_global, sizeof(int) * (size_t)s->nnz, cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));
-    std::vector<int> halo;
-    for (int64_t k = 0; k < s->nnz; ++k) if (ja[k] < s->row0 || ja[k] >= s->row1) halo.push_back(ja[k]);
-    std::sort(halo.begin(), halo.end());
-    halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
-    std::vector<int>().swap(ja);
-    const int nhalo = (int)halo.size();
+    int nhalo = 0; int *halo_raw = nullptr;
     c->recv_cnt.assign(world, 0); c->recv_off.assign(world, 0);
-    for (int k = 0, p = 0; k < nhalo; ++k) {
-        while (halo[k] >= c->row_starts[p + 1]) ++p;
-        c->recv_cnt[p]++;
-    }
+    int prc = cudamat_halo_plan_host(s->row0, s->row1, s->nnz, ja.data(), world, c->row_starts.data(), &nhalo, &halo_raw, c->recv_cnt.data());
+    if (prc) return prc;
+    std::vector<int> halo(halo_raw, halo_raw + nhalo);
+    free(halo_raw);
+    std::vector<int>().swap(ja);
     for (int p = 1; p < world; ++p) c->recv_off[p] = c->recv_off[p - 1] + c->recv_cnt[p - 1];
     // 3. who wants what from whom: allgather of the world x world count matrix
     int *d_cnt = nullptr;

@@ -65,32 +65,43 @@ __global__ void k_sptrsv_level(const int *order, int cnt, const int *ia, const i
 }
 
 // ------------------------------------------------------------------------------------------
-// triangular sweeps, variant B: ONE launch per sweep, sync-free. Rows are laid out level by
-// level (each level padded to a warp multiple so a warp never mixes levels); CTAs take a
-// ticket so that logical CTA order == start order, which makes "wait for an earlier row"
-// deadlock-free; a row publishes its value and then its epoch flag.
+// triangular sweeps, variant B: ONE launch per sweep, sync-free.
+//   * rows are laid out level by level (each level padded to a warp multiple so a warp never mixes
+//     levels); CTAs take a ticket so that logical CTA order == start order, which makes "wait for an
+//     earlier row" deadlock-free;
+//   * the output vector itself carries the "ready" signal: it is pre-filled with a quiet-NaN sentinel
+//     of a payload no arithmetic result can have, a dependent row spins (one L2 round trip per poll)
+//     until the cell differs from the sentinel — a single 8-byte store publishes a row, no flag array,
+//     no fence;
+//   * the row's matrix entries are loaded before the first wait, so the dependent chain per level is
+//     just poll -> fma -> store.
+//   The sentinel is re-armed for free: the L sweep clears the output cell of the following U sweep, the
+//   U sweep clears the cell of its right-hand side (the L sweep's private output) after reading it.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_relaxed_i32(const int *p) {
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_relaxed_f64(const double *p) {
-    double v;
-    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+constexpr unsigned long long kSentinelBits = 0xFFF8B200C0DEFACEull;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
-__device__ __forceinline__ void st_release_i32(int *p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ double wait_value(const double *cell) {
+    unsigned long long v = ld_relaxed_u64(cell);
+    unsigned spins = 0;
+    while (v == kSentinelBits) {
+        if (++spins > (1u << 22)) __trap();            // never hang the GPU on a broken schedule
+        v = ld_relaxed_u64(cell);
+    }
+    return __longlong_as_double((long long)v);
 }
 
 template <bool UPPER>
 __global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int order_len, const int *ia, const int *ja,
-                                                        const int *diag, const double *M, const double *rhs,
-                                                        double *out, int *flag, int epoch, unsigned *ticket,
+                                                        const int *diag, const double *M, double *rhs,
+                                                        double *out, double *rearm, int rearm_rhs, unsigned *ticket,
                                                         unsigned ticket_base, const int *status) {
     // every CTA takes its ticket (even when the solve already stopped) so the host-side
     // ticket_base stays in step with the device counter
@@ -102,21 +113,42 @@ __global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int o
     if (t >= order_len) return;
     const int i = order[t];
     if (i < 0) return;
-    double acc = rhs[i];
-    int p, pe, pd = diag[i];
+    const int pd = diag[i];
+    int p, pe;
     if (!UPPER) { p = ia[i]; pe = pd; } else { p = pd + 1; pe = ia[i + 1]; }
-    for (; p < pe; ++p) {
-        const int c = ja[p];
-        const double m = M[p];
-        unsigned spins = 0;
-        while (ld_relaxed_i32(flag + c) != epoch) {
-            if (++spins > (1u << 22)) __trap();       // never hang the GPU on a broken schedule
-        }
-        acc = __fma_rn(-m, ld_relaxed_f64(out + c), acc);
+    const int cnt = pe - p;
+    int c[8]; double m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        c[q] = (q < cnt) ? ja[p + q] : 0;
+        m[q] = (q < cnt) ? M[p + q] : 0.0;
     }
-    if (UPPER) acc = __ddiv_rn(acc, M[pd]);
+    const double dg = UPPER ? M[pd] : 1.0;
+    double acc = rhs[i];
+    const double sentinel = __longlong_as_double((long long)kSentinelBits);
+    if (rearm_rhs) rhs[i] = sentinel;
+    if (rearm) rearm[i] = sentinel;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (q < cnt) acc = __fma_rn(-m[q], wait_value(out + c[q]), acc);
+    for (int pp = p + 8; pp < pe; ++pp) acc = __fma_rn(-M[pp], wait_value(out + ja[pp]), acc);
+    if (UPPER) acc = __ddiv_rn(acc, dg);
     st_relaxed_f64(out + i, acc);
-    st_release_i32(flag + i, epoch);
+}
+
+__global__ void k_fill_bits(unsigned long long *p, unsigned long long v, int64_t cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < cnt; i += stride) p[i] = v;
+}
+int sptrsv_arm(cudamat_solver *s, double *vec) {
+    if (s->n <= 0) return CUDAMAT_OK;
+    int grid = (s->n + 1023) / 1024;
+    if (grid > 148 * 16) grid = 148 * 16;
+    k_fill_bits<<<grid, 256, 0, s->stream>>>(reinterpret_cast<unsigned long long *>(vec), kSentinelBits, s->n);
+    s->launches++;
+    CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -195,8 +227,6 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     if (rc) return rc;
     CM_CUDA(cudaMalloc(&s->d_diag, sizeof(int) * (size_t)std::max(n, 1)));
     CM_CUDA(cudaMemcpyAsync(s->d_diag, diag.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
-    CM_CUDA(cudaMalloc(&s->d_flag, sizeof(int) * (size_t)std::max(n, 1)));
-    CM_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int) * (size_t)std::max(n, 1), s->stream));
     CM_CUDA(cudaMalloc(&s->d_ticket, 2 * sizeof(unsigned)));
     CM_CUDA(cudaMemsetAsync(s->d_ticket, 0, 2 * sizeof(unsigned), s->stream));
     s->epoch = 0;
@@ -227,22 +257,24 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     return CUDAMAT_OK;
 }
 
-int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out) {
+// rearm: vector whose cell i is reset to the sentinel by row i (the output of the NEXT sync-free sweep),
+// rearm_rhs: reset rhs[i] after reading it (rhs is the private output of the previous L sweep).
+// With the sync-free schedule `out` must be armed (all sentinel) on entry.
+int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, double *rearm, int rearm_rhs) {
     if (!s->d_M) { set_error("sptrsv: ILU0 factor not available (call cudamat_analyze with CUDAMAT_MODE_ILU0)"); return CUDAMAT_E_STATE; }
     const LevelSchedule &L = upper ? s->lvl_u : s->lvl_l;
     const int *status = s->d_sc ? &s->d_sc->status : nullptr;
     if (s->opt_sptrsv_syncfree && L.order_len > 0) {
         const int grid = (L.order_len + 255) / 256;
-        s->epoch += 1;
-        // ticket_base: the counter is monotone across launches; every launch consumes `grid` tickets
+        // the ticket counter is monotone across launches; every launch consumes `grid` tickets
         unsigned *ticket = s->d_ticket + (upper ? 1 : 0);
         unsigned &base = upper ? s->ticket_base_u : s->ticket_base_l;
         if (upper)
             k_sptrsv_syncfree<true><<<grid, 256, 0, s->stream>>>(L.d_order, L.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M,
-                                                                rhs, out, s->d_flag, s->epoch, ticket, base, status);
+                                                                rhs, out, rearm, rearm_rhs, ticket, base, status);
         else
             k_sptrsv_syncfree<false><<<grid, 256, 0, s->stream>>>(L.d_order, L.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M,
-                                                                 rhs, out, s->d_flag, s->epoch, ticket, base, status);
+                                                                 rhs, out, rearm, rearm_rhs, ticket, base, status);
         base += (unsigned)grid;
         s->launches++;
     } else {

@@ -18,9 +18,9 @@ constexpr int kTileSlabs   = 64;      // slabs per tile
 constexpr int kTile        = 2048;    // rows per tile == rows per CTA in reducing kernels
 constexpr int kGroupTiles  = 1024;    // tiles per group
 constexpr int kLongRow     = 32;      // rows longer than this use the interleaved row sum
-constexpr int kCtaThreads  = 256;
-constexpr int kCtaWarps    = 8;
-constexpr int kSlabsPerWarp = kTileSlabs / kCtaWarps;   // 8
+constexpr int kCtaThreads  = 512;
+constexpr int kCtaWarps    = 16;
+constexpr int kSlabsPerWarp = kTileSlabs / kCtaWarps;   // 4
 constexpr int kMaxQ        = 2;       // reduced quantities per kernel
 
 // solver status (device side)
@@ -78,6 +78,14 @@ struct RedCtx {
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the iteration lets its successor get scheduled while
+// it drains (launch_dependents at entry) and waits for its predecessor's results before touching
+// memory (wait). Kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ double warp_butterfly(double v) {
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, s));

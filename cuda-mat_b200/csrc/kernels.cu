@@ -20,11 +20,16 @@ __device__ __forceinline__ double rowsum_long(const SpmvArgs &a, int s, int e, i
 }
 
 template <bool HAS_D, int NDOT>
-__global__ void __launch_bounds__(kCtaThreads) k_spmv_rowlane(const SpmvArgs a) {
+__global__ void __launch_bounds__(kCtaThreads, 4) k_spmv_rowlane(const SpmvArgs a) {
+    pdl_prologue();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     __shared__ double s_slab[kMaxQ][kTileSlabs];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_base = blockIdx.x * kTile;
+    // fused-dot products of the previous slab: their butterflies are issued right after the next slab's
+    // row-pointer loads, so the shuffle latency hides under that memory round trip
+    double pp0 = 0.0, pp1 = 0.0;
+    int pslab = -1;
 #pragma unroll 1
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int slab = j * kCtaWarps + warp;
@@ -34,6 +39,10 @@ __global__ void __launch_bounds__(kCtaThreads) k_spmv_rowlane(const SpmvArgs a) 
         const bool active = row < a.n;
         int s = 0, e = 0;
         if (active) { s = __ldg(a.ia + row); e = __ldg(a.ia + row + 1); }
+        if (NDOT >= 1 && pslab >= 0) {
+            slab_deposit(s_slab, 0, pslab, pp0, lane);
+            if (NDOT >= 2) slab_deposit(s_slab, 1, pslab, pp1, lane);
+        }
         const int len = e - s;
         const int shortlen = (len <= kLongRow) ? len : 0;
         const int maxlen = __reduce_max_sync(0xffffffffu, shortlen);
@@ -62,16 +71,15 @@ __global__ void __launch_bounds__(kCtaThreads) k_spmv_rowlane(const SpmvArgs a) 
         }
         if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
         if (active) a.y[row] = sum;
-        if (NDOT >= 1) {
-            const double p0 = active ? __dmul_rn(sum, __ldg(a.u + row)) : 0.0;
-            slab_deposit(s_slab, 0, slab, p0, lane);
-        }
-        if (NDOT >= 2) {
-            const double p1 = active ? __dmul_rn(sum, sum) : 0.0;
-            slab_deposit(s_slab, 1, slab, p1, lane);
-        }
+        if (NDOT >= 1) pp0 = active ? __dmul_rn(sum, __ldg(a.u + row)) : 0.0;
+        if (NDOT >= 2) pp1 = active ? __dmul_rn(sum, sum) : 0.0;
+        pslab = slab;
     }
     if (NDOT >= 1) {
+        if (pslab >= 0) {
+            slab_deposit(s_slab, 0, pslab, pp0, lane);
+            if (NDOT >= 2) slab_deposit(s_slab, 1, pslab, pp1, lane);
+        }
         __syncthreads();
         const int rows_here = min(kTile, a.n - row_base);
         reduce_tail<(NDOT >= 1 ? NDOT : 1)>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
@@ -148,8 +156,9 @@ __device__ __forceinline__ double staged_rowsum(const double *vb, const int *cb,
 }
 
 template <bool HAS_D, int NDOT>
-__global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_staged(const StagedArgs g) {
+__global__ void __launch_bounds__(kCtaThreads, 1) k_spmv_staged(const StagedArgs g) {
     const SpmvArgs &a = g.a;
+    pdl_prologue();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_slab[kMaxQ][kTileSlabs];
@@ -283,6 +292,19 @@ int plan_staged(cudamat_solver *s) {
     return CUDAMAT_OK;
 }
 
+// launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor
+// in the stream drains; its pdl_prologue() waits for the predecessor's completion before reading.
+template <typename Kern, typename Arg>
+static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, const Arg &arg) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, arg);
+}
+
 template <bool HAS_D, int NDOT>
 static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
     const int grid = (a.n + kTile - 1) / kTile;
@@ -291,9 +313,9 @@ static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
         StagedArgs g{a, s->staged.cap_nnz, s->staged.stages, s->nnz};
         auto kern = k_spmv_staged<HAS_D, NDOT>;
         CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->staged.smem_bytes));
-        kern<<<grid, kCtaThreads, s->staged.smem_bytes, s->stream>>>(g);
+        CM_CUDA(launch_pdl(kern, grid, kCtaThreads, s->staged.smem_bytes, s->stream, g));
     } else {
-        k_spmv_rowlane<HAS_D, NDOT><<<grid, kCtaThreads, 0, s->stream>>>(a);
+        CM_CUDA(launch_pdl(k_spmv_rowlane<HAS_D, NDOT>, grid, kCtaThreads, 0, s->stream, a));
     }
     s->launches++;
     CM_CUDA(cudaGetLastError());
@@ -322,6 +344,7 @@ struct VecArgs {
 };
 
 #define VEC_PROLOGUE                                                                  \
+    pdl_prologue();                                                                   \
     if (a.sc->status != ST_RUNNING) return;                                           \
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                    \
     const int row_base = blockIdx.x * kTile;                                          \
@@ -485,6 +508,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_xr(const VecArgs a) {
 
 // spec dot product of two arbitrary vectors -> sc->red[0]
 __global__ void __launch_bounds__(kCtaThreads) k_dot(const VecArgs a) {
+    pdl_prologue();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_base = blockIdx.x * kTile;
     __shared__ double s_slab[kMaxQ][kTileSlabs];
@@ -517,7 +541,7 @@ static inline int tiles_of(int n) { return (n + kTile - 1) / kTile; }
     do {                                                                       \
         const int grid_ = tiles_of((a).n);                                     \
         if (grid_ > 0) {                                                       \
-            kern<<<grid_, kCtaThreads, 0, s->stream>>>(a);                     \
+            CM_CUDA(launch_pdl(kern, grid_, kCtaThreads, 0, s->stream, (a)));  \
             s->launches++;                                                     \
             CM_CUDA(cudaGetLastError());                                       \
         }                                                                      \

@@ -180,25 +180,28 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
 // ---- ILU0 right-preconditioned loop (gpu_pbicgstab, pbicgstab.cu:45-154) -------------------------
 static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int maxit, double tol) {
     int rc;
-    if ((rc = ensure_work(s, 8))) return rc;
+    if ((rc = ensure_work(s, 9))) return rc;
     if ((rc = ensure_hist(s, 2 * maxit + 2))) return rc;
     double *r = wv(s, 0), *rw = wv(s, 1), *p = wv(s, 2), *pw = wv(s, 3), *sv = wv(s, 4), *t = wv(s, 5), *v = wv(s, 6), *xk = wv(s, 7);
+    double *tl = wv(s, 8);          // private output of the L sweeps (carries the sync-free ready sentinel)
+    const int sf = s->opt_sptrsv_syncfree;
     const int var = s->spmv_variant;
     if ((rc = start_scalars(s, maxit, tol, 2 * maxit + 2))) return rc;
     const size_t nb = sizeof(double) * (size_t)s->n;
     if ((rc = launch_fill(s, xk, 1.0, s->n))) return rc;                                            // :306-308
     CM_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * s->work_elems, s->stream));
+    if (sf) { if ((rc = sptrsv_arm(s, tl))) return rc; if ((rc = sptrsv_arm(s, pw))) return rc; }
     if ((rc = launch_spmv(s, spmv_args(s, xk, nullptr, t, nullptr, 0, PH_NONE, 0), var))) return rc; // :67
     if ((rc = launch_init_resid(s, d_b, t, r, rw, p, PH_I_INIT))) return rc;                        // :69-74
     const int poll = std::max(1, s->opt_poll_every);
     for (int it = 0; it < maxit;) {
         if ((rc = launch_update_p(s, true, r, v, p))) return rc;                                    // :83-89 (skips i == 0)
-        if ((rc = launch_sptrsv(s, false, p, t))) return rc;                                        // :92-94
-        if ((rc = launch_sptrsv(s, true, t, pw))) return rc;                                        // :96-98
+        if ((rc = launch_sptrsv(s, false, p, tl, sf ? pw : nullptr, 0))) return rc;                 // :92-94 (+ arms pw)
+        if ((rc = launch_sptrsv(s, true, tl, pw, nullptr, sf))) return rc;                          // :96-98
         if ((rc = spmv_step(s, pw, nullptr, v, rw, 1, PH_I_A, 1))) return rc;        // :104-107
         if ((rc = launch_update_rx_ilu(s, v, pw, r, xk))) return rc;                                // :109-118
-        if ((rc = launch_sptrsv(s, false, r, t))) return rc;                                        // :121-123
-        if ((rc = launch_sptrsv(s, true, t, sv))) return rc;                                        // :125-127
+        if ((rc = launch_sptrsv(s, false, r, tl, sf ? sv : nullptr, 0))) return rc;                 // :121-123 (+ arms s)
+        if ((rc = launch_sptrsv(s, true, tl, sv, nullptr, sf))) return rc;                          // :125-127
         if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1))) return rc;         // :132-137
         if ((rc = launch_update_xr(s, true, nullptr, sv, t, rw, xk, r))) return rc;                 // :139-151, :81
         ++it;
@@ -458,7 +461,9 @@ int cudamat_sptrsv_device(cudamat_solver *s, int upper, const double *d_rhs, dou
     // kernel-level calls must not be gated by a finished solve
     int st = ST_RUNNING;
     CM_CUDA(cudaMemcpyAsync(&s->d_sc->status, &st, sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    int rc = launch_sptrsv(s, upper != 0, d_rhs, d_out);
+    int rc = CUDAMAT_OK;
+    if (s->opt_sptrsv_syncfree && (rc = sptrsv_arm(s, d_out))) return rc;
+    rc = launch_sptrsv(s, upper != 0, const_cast<double *>(d_rhs), d_out, nullptr, 0);
     if (rc) return rc;
     CM_CUDA(cudaStreamSynchronize(s->stream));
     return CUDAMAT_OK;

@@ -143,6 +143,12 @@ int cudamat_get_ilu0_host(cudamat_solver *s, double *M_out);
 int cudamat_sptrsv_device(cudamat_solver *s, int upper, const double *d_rhs, double *d_out);
 
 /* ---- multi-GPU (one process per GPU; NCCL is dlopen()ed on first use) ----------------------- */
+/* The reference is single-GPU; sharding follows BASELINE.json's north_star: contiguous row
+ * shards, halo entries of the SpMV operand exchanged point-to-point, one fused small allreduce per
+ * reduction point.  The two planners are pure host code. */
+int cudamat_partition_rows(int64_t n_global, int world, int rank, int64_t *row0, int64_t *row1);
+int cudamat_halo_plan_host(int64_t row0, int64_t row1, int64_t nnz, const int *ja_global, int world,
+                           const int64_t *row_starts, int *nhalo, int **halo_cols, int *recv_cnt);
 #define CUDAMAT_UNIQUE_ID_BYTES 128
 int cudamat_comm_unique_id(void *id128);
 int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world);
