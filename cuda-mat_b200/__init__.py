@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcudamat_b200.so")
+LIB_PATH = os.environ.get("CUDAMAT_LIB") or os.path.join(_HERE, "libcudamat_b200.so")   # CUDAMAT_LIB: A/B tuning builds
 ROOT = os.path.dirname(_HERE)
 
 MODE_PLAIN, MODE_SHIFTED, MODE_ILU0 = 0, 1, 2

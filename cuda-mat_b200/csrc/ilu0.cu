@@ -93,47 +93,48 @@ __device__ __forceinline__ double wait_value(const double *cell) {
     unsigned spins = 0;
     while (v == kSentinelBits) {
         if (++spins > (1u << 22)) __trap();            // never hang the GPU on a broken schedule
+        __nanosleep(spins < 4 ? 64 : 256);             // back off: pollers must not saturate L2
         v = ld_relaxed_u64(cell);
     }
     return __longlong_as_double((long long)v);
 }
 
+// Persistent schedule: the grid is sized to what is co-resident (occupancy API) and CTA b processes the
+// 256-row chunks b, b+G, b+2G, ... of the level-ordered row list in increasing order.  The smallest
+// unfinished chunk only depends on finished chunks and its owner is (or becomes) resident, so the
+// schedule is deadlock-free without tickets, and the look-ahead (rows that sit waiting, with their
+// matrix entries already in registers) is bounded by G*256 instead of the whole matrix.
 template <bool UPPER>
 __global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int order_len, const int *ia, const int *ja,
                                                         const int *diag, const double *M, double *rhs,
-                                                        double *out, double *rearm, int rearm_rhs, unsigned *ticket,
-                                                        unsigned ticket_base, const int *status) {
-    // every CTA takes its ticket (even when the solve already stopped) so the host-side
-    // ticket_base stays in step with the device counter
-    __shared__ unsigned s_blk;
-    if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u) - ticket_base;
-    __syncthreads();
+                                                        double *out, double *rearm, int rearm_rhs, const int *status) {
+    pdl_prologue();
     if (status && *status != ST_RUNNING) return;
-    const int t = (int)s_blk * 256 + threadIdx.x;
-    if (t >= order_len) return;
-    const int i = order[t];
-    if (i < 0) return;
-    const int pd = diag[i];
-    int p, pe;
-    if (!UPPER) { p = ia[i]; pe = pd; } else { p = pd + 1; pe = ia[i + 1]; }
-    const int cnt = pe - p;
-    int c[8]; double m[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        c[q] = (q < cnt) ? ja[p + q] : 0;
-        m[q] = (q < cnt) ? M[p + q] : 0.0;
-    }
-    const double dg = UPPER ? M[pd] : 1.0;
-    double acc = rhs[i];
     const double sentinel = __longlong_as_double((long long)kSentinelBits);
-    if (rearm_rhs) rhs[i] = sentinel;
-    if (rearm) rearm[i] = sentinel;
+    for (int t = blockIdx.x * 256 + threadIdx.x; t < order_len; t += gridDim.x * 256) {
+        const int i = order[t];
+        if (i < 0) continue;
+        const int pd = diag[i];
+        int p, pe;
+        if (!UPPER) { p = ia[i]; pe = pd; } else { p = pd + 1; pe = ia[i + 1]; }
+        const int cnt = pe - p;
+        int c[8]; double m[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-        if (q < cnt) acc = __fma_rn(-m[q], wait_value(out + c[q]), acc);
-    for (int pp = p + 8; pp < pe; ++pp) acc = __fma_rn(-M[pp], wait_value(out + ja[pp]), acc);
-    if (UPPER) acc = __ddiv_rn(acc, dg);
-    st_relaxed_f64(out + i, acc);
+        for (int q = 0; q < 8; ++q) {
+            c[q] = (q < cnt) ? ja[p + q] : 0;
+            m[q] = (q < cnt) ? M[p + q] : 0.0;
+        }
+        const double dg = UPPER ? M[pd] : 1.0;
+        double acc = rhs[i];
+        if (rearm_rhs) rhs[i] = sentinel;
+        if (rearm) rearm[i] = sentinel;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < cnt) acc = __fma_rn(-m[q], wait_value(out + c[q]), acc);
+        for (int pp = p + 8; pp < pe; ++pp) acc = __fma_rn(-M[pp], wait_value(out + ja[pp]), acc);
+        if (UPPER) acc = __ddiv_rn(acc, dg);
+        st_relaxed_f64(out + i, acc);
+    }
 }
 
 __global__ void k_fill_bits(unsigned long long *p, unsigned long long v, int64_t cnt) {
@@ -227,8 +228,6 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     if (rc) return rc;
     CM_CUDA(cudaMalloc(&s->d_diag, sizeof(int) * (size_t)std::max(n, 1)));
     CM_CUDA(cudaMemcpyAsync(s->d_diag, diag.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
-    CM_CUDA(cudaMalloc(&s->d_ticket, 2 * sizeof(unsigned)));
-    CM_CUDA(cudaMemsetAsync(s->d_ticket, 0, 2 * sizeof(unsigned), s->stream));
     s->epoch = 0;
     CM_CUDA(cudaStreamSynchronize(s->stream));
     if (st) { st->t_analysis += now_s() - t0; st->levels_l = nl; st->levels_u = nu; }
@@ -265,17 +264,28 @@ int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, doubl
     const LevelSchedule &L = upper ? s->lvl_u : s->lvl_l;
     const int *status = s->d_sc ? &s->d_sc->status : nullptr;
     if (s->opt_sptrsv_syncfree && L.order_len > 0) {
-        const int grid = (L.order_len + 255) / 256;
-        // the ticket counter is monotone across launches; every launch consumes `grid` tickets
-        unsigned *ticket = s->d_ticket + (upper ? 1 : 0);
-        unsigned &base = upper ? s->ticket_base_u : s->ticket_base_l;
+        if (s->sptrsv_grid == 0) {
+            int occ_l = 0, occ_u = 0, sms = 0;
+            CM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, k_sptrsv_syncfree<false>, 256, 0));
+            CM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_sptrsv_syncfree<true>, 256, 0));
+            CM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+            int per_sm = std::min(occ_l, occ_u);
+            if (s->opt_sptrsv_ctas_per_sm > 0) per_sm = std::min(per_sm, s->opt_sptrsv_ctas_per_sm);
+            s->sptrsv_grid = std::max(1, per_sm * sms);
+        }
+        const int grid = std::min(s->sptrsv_grid, (L.order_len + 255) / 256);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
         if (upper)
-            k_sptrsv_syncfree<true><<<grid, 256, 0, s->stream>>>(L.d_order, L.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M,
-                                                                rhs, out, rearm, rearm_rhs, ticket, base, status);
+            CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<true>, (const int *)L.d_order, L.order_len, s->d_ia, s->d_ja, (const int *)s->d_diag,
+                                       (const double *)s->d_M, rhs, out, rearm, rearm_rhs, status));
         else
-            k_sptrsv_syncfree<false><<<grid, 256, 0, s->stream>>>(L.d_order, L.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M,
-                                                                 rhs, out, rearm, rearm_rhs, ticket, base, status);
-        base += (unsigned)grid;
+            CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<false>, (const int *)L.d_order, L.order_len, s->d_ia, s->d_ja, (const int *)s->d_diag,
+                                       (const double *)s->d_M, rhs, out, rearm, rearm_rhs, status));
         s->launches++;
     } else {
         for (int l = 0; l < L.nlevels; ++l) {

@@ -19,8 +19,14 @@ __device__ __forceinline__ double rowsum_long(const SpmvArgs &a, int s, int e, i
     return warp_butterfly(acc);
 }
 
+#ifndef CUDAMAT_ROWLANE_PREFETCH
+#define CUDAMAT_ROWLANE_PREFETCH 0
+#endif
+#ifndef CUDAMAT_ROWLANE_MINB
+#define CUDAMAT_ROWLANE_MINB 4
+#endif
 template <bool HAS_D, int NDOT>
-__global__ void __launch_bounds__(kCtaThreads, 4) k_spmv_rowlane(const SpmvArgs a) {
+__global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowlane(const SpmvArgs a) {
     pdl_prologue();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     __shared__ double s_slab[kMaxQ][kTileSlabs];
@@ -30,6 +36,14 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_spmv_rowlane(const SpmvArgs 
     // row-pointer loads, so the shuffle latency hides under that memory round trip
     double pp0 = 0.0, pp1 = 0.0;
     int pslab = -1;
+#if CUDAMAT_ROWLANE_PREFETCH
+    // row bounds and dot operand of the NEXT slab are requested one slab ahead
+    int ns = 0, ne = 0; double nu = 0.0;
+    {
+        const int row = row_base + warp * kSlab + lane;
+        if (row < a.n) { ns = __ldg(a.ia + row); ne = __ldg(a.ia + row + 1); if (NDOT >= 1) nu = __ldg(a.u + row); }
+    }
+#endif
 #pragma unroll 1
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int slab = j * kCtaWarps + warp;
@@ -38,7 +52,18 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_spmv_rowlane(const SpmvArgs 
         const int row = row0 + lane;
         const bool active = row < a.n;
         int s = 0, e = 0;
-        if (active) { s = __ldg(a.ia + row); e = __ldg(a.ia + row + 1); }
+        double uval = 0.0;
+#if CUDAMAT_ROWLANE_PREFETCH
+        s = ns; e = ne; uval = nu;
+        {
+            const int nrow = row + kCtaWarps * kSlab;
+            ns = 0; ne = 0; nu = 0.0;
+            if (j + 1 < kSlabsPerWarp && nrow < a.n) { ns = __ldg(a.ia + nrow); ne = __ldg(a.ia + nrow + 1); if (NDOT >= 1) nu = __ldg(a.u + nrow); }
+        }
+#else
+        // everything that does not depend on the row's entries is requested up front
+        if (active) { s = __ldg(a.ia + row); e = __ldg(a.ia + row + 1); if (NDOT >= 1) uval = __ldg(a.u + row); }
+#endif
         if (NDOT >= 1 && pslab >= 0) {
             slab_deposit(s_slab, 0, pslab, pp0, lane);
             if (NDOT >= 2) slab_deposit(s_slab, 1, pslab, pp1, lane);
@@ -71,7 +96,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_spmv_rowlane(const SpmvArgs 
         }
         if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
         if (active) a.y[row] = sum;
-        if (NDOT >= 1) pp0 = active ? __dmul_rn(sum, __ldg(a.u + row)) : 0.0;
+        if (NDOT >= 1) pp0 = active ? __dmul_rn(sum, uval) : 0.0;
         if (NDOT >= 2) pp1 = active ? __dmul_rn(sum, sum) : 0.0;
         pslab = slab;
     }

@@ -309,6 +309,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "sptrsv_syncfree")) s->opt_sptrsv_syncfree = (int)value;
     else if (!strcmp(key, "debug")) s->opt_debug = (int)value;
     else if (!strcmp(key, "time_spmv")) s->opt_time_spmv = (int)value;
+    else if (!strcmp(key, "sptrsv_ctas_per_sm")) { s->opt_sptrsv_ctas_per_sm = (int)value; s->sptrsv_grid = 0; }
     else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
     else { set_error("unknown option '%s'", key); return CUDAMAT_E_INVALID; }
     return CUDAMAT_OK;

@@ -70,6 +70,8 @@ struct cudamat_solver {
     int opt_debug = 0;
     int opt_time_spmv = 0;
     int opt_staged_stages = 0;
+    int opt_sptrsv_ctas_per_sm = 0;
+    int sptrsv_grid = 0;
     std::vector<cudaEvent_t> ev_pool; int ev_used = 0;
     cudamat::StagedPlan staged;
     // reduction context + scalars
