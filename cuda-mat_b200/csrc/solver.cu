@@ -83,8 +83,10 @@ static SpmvArgs spmv_args(cudamat_solver *s, const double *x, const double *d, d
 }
 
 // SpMV launch bracketed by CUDA events on the launching stream when "time_spmv" is set
+// ("time_spmv" = k times the SpMVs of every k-th iteration only: event records between two kernels suspend
+// the programmatic-dependent-launch overlap at that boundary, so sparse sampling keeps the loop undisturbed)
 static int timed_spmv(cudamat_solver *s, const SpmvArgs &a, int var) {
-    const bool timed = s->opt_time_spmv && s->ev_used + 2 <= 8192;
+    const bool timed = s->opt_time_spmv > 0 && (s->loop_it % s->opt_time_spmv) == 0 && s->ev_used + 2 <= 8192;
     if (timed) {
         while ((int)s->ev_pool.size() < s->ev_used + 2) {
             cudaEvent_t e; CM_CUDA(cudaEventCreate(&e)); s->ev_pool.push_back(e);
@@ -160,6 +162,7 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
     if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
     const int poll = std::max(1, s->opt_poll_every);
     for (int it = 0; it < maxit;) {
+        s->loop_it = it;
         if ((rc = launch_update_p(s, false, r, v, p))) return rc;                                   // :668-672
         if ((rc = spmv_step(s, p, d_d, v, r0, 1, PH_U_A, 1))) return rc;                 // :675-689
         if ((rc = launch_update_s(s, r, v, sv))) return rc;                                         // :698-700
@@ -195,6 +198,7 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
     if ((rc = launch_init_resid(s, d_b, t, r, rw, p, PH_I_INIT))) return rc;                        // :69-74
     const int poll = std::max(1, s->opt_poll_every);
     for (int it = 0; it < maxit;) {
+        s->loop_it = it;
         if ((rc = launch_update_p(s, true, r, v, p))) return rc;                                    // :83-89 (skips i == 0)
         if ((rc = launch_sptrsv(s, false, p, tl, sf ? pw : nullptr, 0))) return rc;                 // :92-94 (+ arms pw)
         if ((rc = launch_sptrsv(s, true, tl, pw, nullptr, sf))) return rc;                          // :96-98

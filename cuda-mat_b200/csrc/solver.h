@@ -69,6 +69,7 @@ struct cudamat_solver {
     int opt_sptrsv_syncfree = 1;
     int opt_debug = 0;
     int opt_time_spmv = 0;
+    int loop_it = 0;
     int opt_staged_stages = 0;
     int opt_sptrsv_ctas_per_sm = 0;
     int sptrsv_grid = 0;

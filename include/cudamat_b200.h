@@ -71,7 +71,8 @@ typedef struct cudamat_stats {
     int    zero_pivot;      /* 0; <0: -(1+row) of the first exact-zero ILU0 pivot              */
     int64_t kernel_launches;/* kernels of this library launched by the call                    */
     double t_spmv;          /* seconds: sum of the SpMV kernel durations inside the loop, measured with
-                               CUDA events on the launching stream (option "time_spmv" = 1), else 0 */
+                               CUDA events on the launching stream (option "time_spmv" = k > 0: the SpMVs of every
+                               k-th iteration are timed), else 0 */
     int    n_spmv;          /* SpMV launches covered by t_spmv                                  */
     int    reserved;
 } cudamat_stats;

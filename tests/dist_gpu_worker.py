@@ -1,0 +1,84 @@
+"""torchrun worker for tests/test_gpu_multi.py: row-sharded BiCGSTAB over NCCL, one rank per GPU, checked
+bit for bit against the single-GPU solve of the same system (which the other tests pin to the oracle)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+
+def main():
+    cm = ge.load_package()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    f64 = dict(dtype=torch.float64, device="cuda")
+    grids = [int(v) for v in sys.argv[1].split(",")]
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    for N in grids:
+        n = N ** 3
+        row0, row1 = cm.partition_rows(n, world, rank)
+        nloc = row1 - row0
+        nnz = cm.poisson3d_nnz(N, row0, row1)
+        ia = torch.empty(nloc + 1, dtype=torch.int32, device="cuda")
+        ja = torch.empty(max(nnz, 1), dtype=torch.int32, device="cuda")
+        a = torch.empty(max(nnz, 1), **f64)
+        cm.gen_poisson3d_device(N, row0, row1, ia.data_ptr(), ja.data_ptr(), a.data_ptr())
+        s = cm.Solver(n, row0, row1)
+        s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr())
+        if rank == 0:
+            uid = torch.tensor(list(cm.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        cm.Comm.init(s, bytes(uid.cpu().tolist()), rank, world)
+        s.analyze(cm.MODE_PLAIN)
+        xt = torch.empty(nloc, **f64)
+        cm.gen_xtrue_device(1234, row0, nloc, xt.data_ptr())
+        b = torch.empty(nloc, **f64)
+        s.spmv(xt.data_ptr(), b.data_ptr())
+        x = torch.zeros(nloc, **f64)
+        st = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=5000, tol=1e-10)
+        dt = s.dot(x.data_ptr(), b.data_ptr())
+        torch.cuda.synchronize()
+        # gather shards on every rank (equal-size padding)
+        per = max(cm.partition_rows(n, world, r)[1] - cm.partition_rows(n, world, r)[0] for r in range(world))
+        pad = torch.zeros(per, **f64); pad[:nloc] = x
+        padb = torch.zeros(per, **f64); padb[:nloc] = b
+        xs = [torch.zeros(per, **f64) for _ in range(world)]
+        bs = [torch.zeros(per, **f64) for _ in range(world)]
+        dist.all_gather(xs, pad); dist.all_gather(bs, padb)
+        s.close()
+        if rank == 0:
+            sizes = [cm.partition_rows(n, world, r)[1] - cm.partition_rows(n, world, r)[0] for r in range(world)]
+            xg = torch.cat([xs[r][:sizes[r]] for r in range(world)])
+            bg = torch.cat([bs[r][:sizes[r]] for r in range(world)])
+            # single-GPU reference run of the same global system
+            nz = cm.poisson3d_nnz(N)
+            ia1 = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+            ja1 = torch.empty(nz, dtype=torch.int32, device="cuda")
+            a1 = torch.empty(nz, **f64)
+            cm.gen_poisson3d_device(N, 0, n, ia1.data_ptr(), ja1.data_ptr(), a1.data_ptr())
+            s1 = cm.Solver(n)
+            s1.set_csr_device(nz, a1.data_ptr(), ia1.data_ptr(), ja1.data_ptr())
+            s1.analyze(cm.MODE_PLAIN)
+            xt1 = torch.empty(n, **f64); cm.gen_xtrue_device(1234, 0, n, xt1.data_ptr())
+            b1 = torch.empty(n, **f64); s1.spmv(xt1.data_ptr(), b1.data_ptr())
+            x1 = torch.zeros(n, **f64)
+            st1 = s1.solve(cm.MODE_PLAIN, b1.data_ptr(), x1.data_ptr(), maxit=5000, tol=1e-10)
+            d1 = s1.dot(x1.data_ptr(), b1.data_ptr())
+            torch.cuda.synchronize()
+            ok = (torch.equal(bg, b1) and torch.equal(xg, x1) and st["iterations"] == st1["iterations"]
+                  and bool(st["converged"]) and dt == d1)
+            print("DIST N=%d world=%d iters=%d/%d b_equal=%s x_equal=%s dot_equal=%s loop_ms=%.2f/%.2f %s"
+                  % (N, world, st["iterations"], st1["iterations"], torch.equal(bg, b1), torch.equal(xg, x1), dt == d1,
+                     st["t_loop"] * 1e3, st1["t_loop"] * 1e3, "OK" if ok else "MISMATCH"), flush=True)
+            s1.close()
+        dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

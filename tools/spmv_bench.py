@@ -58,13 +58,19 @@ def main():
         torch.cuda.synchronize()
         plain_ms = e0.elapsed_time(e1) / 20
         s.spmv(xt.data_ptr(), b.data_ptr())
+        best = None
+        for _ in range(3):
+            st = s.solve(args.mode, b.data_ptr(), x.data_ptr(), maxit=args.iters, tol=0.0)
+            t = st["t_loop"] * 1e3 / max(st["iterations"], 1)
+            best = t if best is None else min(best, t)
+        ms_it = best
         s.set_option("time_spmv", 1)
         st = s.solve(args.mode, b.data_ptr(), x.data_ptr(), maxit=args.iters, tol=0.0)
-        ms_it = st["t_loop"] * 1e3 / max(st["iterations"], 1)
+        ms_it_timed = st["t_loop"] * 1e3 / max(st["iterations"], 1)
         sp_ms = st["t_spmv"] * 1e3 / max(st["n_spmv"], 1)
         print(json.dumps({"grid": N, "variant": sa["spmv_variant"], "stages_opt": stages, "sptrsv_ctas": tctas, "lib": os.path.basename(cm.LIB_PATH), "plain_spmv_ms": round(plain_ms, 4),
                           "plain_spmv_GBps": round(bspmv / plain_ms / 1e6, 1), "loop_spmv_ms": round(sp_ms, 4),
-                          "loop_spmv_GBps": round(bspmv / sp_ms / 1e6, 1), "ms_per_iter": round(ms_it, 4),
+                          "loop_spmv_GBps": round(bspmv / sp_ms / 1e6, 1), "ms_per_iter": round(ms_it, 4), "ms_per_iter_with_events": round(ms_it_timed, 4),
                           "iters_per_s": round(1e3 / ms_it, 1), "iter_GBps": round(biter / ms_it / 1e6, 1),
                           "iterations": st["iterations"]}))
         s.close()
