@@ -99,41 +99,100 @@ __device__ __forceinline__ double wait_value(const double *cell) {
     return __longlong_as_double((long long)v);
 }
 
-// Persistent schedule: the grid is sized to what is co-resident (occupancy API) and CTA b processes the
-// 256-row chunks b, b+G, b+2G, ... of the level-ordered row list in increasing order.  The smallest
-// unfinished chunk only depends on finished chunks and its owner is (or becomes) resident, so the
-// schedule is deadlock-free without tickets, and the look-ahead (rows that sit waiting, with their
-// matrix entries already in registers) is bounded by G*256 instead of the whole matrix.
+// Sweep plan: the rows of one triangular factor re-laid out in LEVEL ORDER so that every load of the sweep is
+// coalesced: position t holds row order[t], its number of off-diagonal entries, the first kPlanW of them
+// (column, value) in struct-of-arrays form, the CSR position of the rest, and (U) the diagonal value.
+// Built once after the factorisation (k_build_plan); values are bit copies of M, so arithmetic is unchanged.
+constexpr int kPlanW = 4;
+
 template <bool UPPER>
-__global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int order_len, const int *ia, const int *ja,
-                                                        const int *diag, const double *M, double *rhs,
+__global__ void k_build_plan(const int *order, int len, const int *ia, const int *ja, const int *diag, const double *M,
+                             int *p_cnt, int *p_ptr, int *p_col, double *p_val, double *p_dg) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len) return;
+    const int i = order[t];
+    int p = 0, pe = 0;
+    if (i >= 0) { const int pd = diag[i]; if (!UPPER) { p = ia[i]; pe = pd; } else { p = pd + 1; pe = ia[i + 1]; p_dg[t] = M[pd]; } }
+    else if (UPPER) p_dg[t] = 1.0;
+    p_cnt[t] = pe - p;
+    p_ptr[t] = p;
+#pragma unroll
+    for (int q = 0; q < kPlanW; ++q) {
+        const bool has = (p + q) < pe;
+        p_col[(size_t)q * len + t] = has ? ja[p + q] : 0;
+        p_val[(size_t)q * len + t] = has ? M[p + q] : 0.0;
+    }
+}
+
+// Persistent schedule: the grid is sized to what is co-resident (occupancy API) and CTA b processes the
+// 256-row chunks b, b+G, b+2G, ... of the level-ordered plan in increasing order.  The smallest unfinished
+// chunk only depends on finished chunks and its owner is (or becomes) resident, so the schedule is
+// deadlock-free without tickets, and the look-ahead is bounded by G*256 rows.
+// Waiting is two-phase so that pollers do not saturate L2: one representative lane per warp polls its last
+// dependency with back-off (a warp never mixes levels, so its rows become ready together), then every lane
+// verifies its own dependencies, all loads of a round issued together.
+template <bool UPPER>
+__global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int len, const int *p_cnt, const int *p_ptr,
+                                                        const int *p_col, const double *p_val, const double *p_dg,
+                                                        const int *ja, const double *M, double *rhs,
                                                         double *out, double *rearm, int rearm_rhs, const int *status) {
     pdl_prologue();
     if (status && *status != ST_RUNNING) return;
     const double sentinel = __longlong_as_double((long long)kSentinelBits);
-    for (int t = blockIdx.x * 256 + threadIdx.x; t < order_len; t += gridDim.x * 256) {
-        const int i = order[t];
-        if (i < 0) continue;
-        const int pd = diag[i];
-        int p, pe;
-        if (!UPPER) { p = ia[i]; pe = pd; } else { p = pd + 1; pe = ia[i + 1]; }
-        const int cnt = pe - p;
-        int c[8]; double m[8];
+    const int lane = threadIdx.x & 31;
+    for (int t = blockIdx.x * 256 + threadIdx.x; t - lane < len; t += gridDim.x * 256) {       // warp-uniform trip count
+        const bool inb = t < len;
+        const int i = inb ? order[t] : -1;
+        const bool act = i >= 0;
+        const int cnt = act ? p_cnt[t] : 0;
+        int c[kPlanW]; double m[kPlanW];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            c[q] = (q < cnt) ? ja[p + q] : 0;
-            m[q] = (q < cnt) ? M[p + q] : 0.0;
+        for (int q = 0; q < kPlanW; ++q) {
+            c[q] = (q < cnt) ? p_col[(size_t)q * len + t] : -1;
+            m[q] = (q < cnt) ? p_val[(size_t)q * len + t] : 0.0;
         }
-        const double dg = UPPER ? M[pd] : 1.0;
-        double acc = rhs[i];
-        if (rearm_rhs) rhs[i] = sentinel;
-        if (rearm) rearm[i] = sentinel;
+        const double dg = (UPPER && act) ? p_dg[t] : 1.0;
+        double acc = act ? rhs[i] : 0.0;
+        if (act) {
+            if (rearm_rhs) rhs[i] = sentinel;
+            if (rearm) rearm[i] = sentinel;
+        }
+        // phase 1: the first lane that has a dependency waits for its last one
+        const unsigned have = __ballot_sync(0xffffffffu, cnt > 0);
+        if (have) {
+            const int rep = __ffs(have) - 1;
+            if (lane == rep) {
+                const int last = (cnt <= kPlanW) ? c[cnt - 1] : ja[p_ptr[t] + cnt - 1];
+                unsigned spins = 0;
+                while (ld_relaxed_u64(out + last) == kSentinelBits) {
+                    if (++spins > (1u << 22)) __trap();          // never hang the GPU on a broken schedule
+                    __nanosleep(spins < 8 ? 100 : 400);
+                }
+            }
+            __syncwarp();
+        }
+        // phase 2: every lane waits for all of its first kPlanW dependencies, one round = all loads in flight
+        unsigned long long v[kPlanW];
+        unsigned spins = 0;
+        for (;;) {
+            bool ready = true;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (q < cnt) acc = __fma_rn(-m[q], wait_value(out + c[q]), acc);
-        for (int pp = p + 8; pp < pe; ++pp) acc = __fma_rn(-M[pp], wait_value(out + ja[pp]), acc);
+            for (int q = 0; q < kPlanW; ++q) v[q] = (c[q] >= 0) ? ld_relaxed_u64(out + c[q]) : 0ull;
+#pragma unroll
+            for (int q = 0; q < kPlanW; ++q) ready = ready && (v[q] != kSentinelBits);
+            if (__all_sync(0xffffffffu, ready)) break;
+            if (++spins > (1u << 22)) __trap();
+            __nanosleep(100);
+        }
+#pragma unroll
+        for (int q = 0; q < kPlanW; ++q)
+            if (q < cnt) acc = __fma_rn(-m[q], __longlong_as_double((long long)v[q]), acc);
+        if (cnt > kPlanW) {                                       // rare: the rest of a long row straight from CSR
+            const int p0 = p_ptr[t];
+            for (int pp = p0 + kPlanW; pp < p0 + cnt; ++pp) acc = __fma_rn(-M[pp], wait_value(out + ja[pp]), acc);
+        }
         if (UPPER) acc = __ddiv_rn(acc, dg);
-        st_relaxed_f64(out + i, acc);
+        if (act) st_relaxed_f64(out + i, acc);
     }
 }
 
@@ -174,8 +233,14 @@ static int build_schedule(cudamat_solver *s, const std::vector<int> &level, int 
 void ilu0_release(cudamat_solver *s) {
     if (s->d_M) cudaFree(s->d_M);
     if (s->d_diag) cudaFree(s->d_diag);
-    if (s->lvl_l.d_order) cudaFree(s->lvl_l.d_order);
-    if (s->lvl_u.d_order) cudaFree(s->lvl_u.d_order);
+    for (LevelSchedule *P : {&s->lvl_l, &s->lvl_u}) {
+        if (P->d_order) cudaFree(P->d_order);
+        if (P->d_cnt) cudaFree(P->d_cnt);
+        if (P->d_ptr) cudaFree(P->d_ptr);
+        if (P->d_col) cudaFree(P->d_col);
+        if (P->d_val) cudaFree(P->d_val);
+        if (P->d_dg) cudaFree(P->d_dg);
+    }
     if (s->d_flag) cudaFree(s->d_flag);
     if (s->d_ticket) cudaFree(s->d_ticket);
     s->d_M = nullptr; s->d_diag = nullptr; s->lvl_l = LevelSchedule(); s->lvl_u = LevelSchedule();
@@ -252,6 +317,24 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     CM_CUDA(cudaStreamSynchronize(s->stream));
     CM_CUDA(cudaFree(d_zp));
     s->zero_pivot = (zp == big) ? 0 : -(1 + zp);
+    // level-ordered sweep plans (coalesced operands for the sync-free sweeps)
+    for (int u = 0; u < 2; ++u) {
+        LevelSchedule &P = u ? s->lvl_u : s->lvl_l;
+        const size_t len = (size_t)std::max(P.order_len, 1);
+        CM_CUDA(cudaMalloc(&P.d_cnt, sizeof(int) * len));
+        CM_CUDA(cudaMalloc(&P.d_ptr, sizeof(int) * len));
+        CM_CUDA(cudaMalloc(&P.d_col, sizeof(int) * len * kPlanW));
+        CM_CUDA(cudaMalloc(&P.d_val, sizeof(double) * len * kPlanW));
+        CM_CUDA(cudaMalloc(&P.d_dg, sizeof(double) * len));
+        if (P.order_len > 0) {
+            const int grid = (P.order_len + 255) / 256;
+            if (u) k_build_plan<true><<<grid, 256, 0, s->stream>>>(P.d_order, P.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M, P.d_cnt, P.d_ptr, P.d_col, P.d_val, P.d_dg);
+            else   k_build_plan<false><<<grid, 256, 0, s->stream>>>(P.d_order, P.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M, P.d_cnt, P.d_ptr, P.d_col, P.d_val, P.d_dg);
+            s->launches++;
+        }
+    }
+    CM_CUDA(cudaGetLastError());
+    CM_CUDA(cudaStreamSynchronize(s->stream));
     if (st) { st->t_ilu0 += now_s() - t0; st->zero_pivot = s->zero_pivot; }
     return CUDAMAT_OK;
 }
@@ -281,10 +364,12 @@ int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, doubl
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         if (upper)
-            CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<true>, (const int *)L.d_order, L.order_len, s->d_ia, s->d_ja, (const int *)s->d_diag,
+            CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<true>, (const int *)L.d_order, L.order_len, (const int *)L.d_cnt, (const int *)L.d_ptr,
+                                       (const int *)L.d_col, (const double *)L.d_val, (const double *)L.d_dg, s->d_ja,
                                        (const double *)s->d_M, rhs, out, rearm, rearm_rhs, status));
         else
-            CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<false>, (const int *)L.d_order, L.order_len, s->d_ia, s->d_ja, (const int *)s->d_diag,
+            CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<false>, (const int *)L.d_order, L.order_len, (const int *)L.d_cnt, (const int *)L.d_ptr,
+                                       (const int *)L.d_col, (const double *)L.d_val, (const double *)L.d_dg, s->d_ja,
                                        (const double *)s->d_M, rhs, out, rearm, rearm_rhs, status));
         s->launches++;
     } else {

@@ -43,6 +43,8 @@ struct Comm;   // comm.cu
 struct LevelSchedule {
     int nlevels = 0;
     int *d_order = nullptr;        // rows sorted by level, each level padded to a multiple of 32 with -1
+    // level-ordered sweep plan (ilu0.cu k_build_plan)
+    int *d_cnt = nullptr, *d_ptr = nullptr, *d_col = nullptr; double *d_val = nullptr, *d_dg = nullptr;
     int order_len = 0;
     std::vector<int> level_ptr;    // host: offsets into d_order per level (padded)
 };
