@@ -353,7 +353,8 @@ int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, doubl
             CM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_sptrsv_syncfree<true>, 256, 0));
             CM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
             int per_sm = std::min(occ_l, occ_u);
-            if (s->opt_sptrsv_ctas_per_sm > 0) per_sm = std::min(per_sm, s->opt_sptrsv_ctas_per_sm);
+            // 2 CTAs/SM measured best on B200 (profiles/): enough look-ahead to hide the plan loads, few pollers
+            per_sm = std::min(per_sm, s->opt_sptrsv_ctas_per_sm > 0 ? s->opt_sptrsv_ctas_per_sm : 2);
             s->sptrsv_grid = std::max(1, per_sm * sms);
         }
         const int grid = std::min(s->sptrsv_grid, (L.order_len + 255) / 256);

@@ -78,13 +78,18 @@ struct RedCtx {
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
-// Programmatic dependent launch: every kernel of the iteration lets its successor get scheduled while
-// it drains (launch_dependents at entry) and waits for its predecessor's results before touching
-// memory (wait). Kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization.
-__device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+// Programmatic dependent launch (PDL). Every loop kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and runs
+//     [loads of operands that the IMMEDIATE predecessor does not write]  pdl_sync()  [everything else]
+// pdl_sync() = griddepcontrol.wait (predecessor complete, its writes visible) followed by
+// griddepcontrol.launch_dependents. Because a kernel releases its successor only after its own wait, a CTA
+// of kernel N+1 can start only when kernel N-1 has completed: operands last written by kernels <= N-1 may be
+// fetched before the wait, i.e. while kernel N drains — that is what hides the drain/launch/ramp bubble.
+__device__ __forceinline__ void pdl_sync() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+__device__ __forceinline__ void pdl_prologue() { pdl_sync(); }
 
 __device__ __forceinline__ double warp_butterfly(double v) {
 #pragma unroll

@@ -27,11 +27,25 @@ __device__ __forceinline__ double rowsum_long(const SpmvArgs &a, int s, int e, i
 #endif
 template <bool HAS_D, int NDOT>
 __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowlane(const SpmvArgs a) {
-    pdl_prologue();
-    if (a.check_status && a.sc->status != ST_RUNNING) return;
     __shared__ double s_slab[kMaxQ][kTileSlabs];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_base = blockIdx.x * kTile;
+    // The CSR arrays are constant during a solve, so while the predecessor kernel drains (before the PDL
+    // wait) this CTA already pulls the row bounds of its first slabs and the matrix lines behind them towards
+    // L2/L1; only the x gathers and the dot operand depend on the predecessor.
+    {
+        const int row = row_base + warp * kSlab + lane;
+        if (row < a.n) {
+            const int s0 = __ldg(a.ia + row), e0 = __ldg(a.ia + row + 1);
+            if (e0 > s0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.val + s0));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.val + e0 - 1));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ja + s0));
+            }
+        }
+    }
+    pdl_sync();
+    if (a.check_status && a.sc->status != ST_RUNNING) return;
     // fused-dot products of the previous slab: their butterflies are issued right after the next slab's
     // row-pointer loads, so the shuffle latency hides under that memory round trip
     double pp0 = 0.0, pp1 = 0.0;
@@ -368,16 +382,19 @@ struct VecArgs {
     RedCtx rc; DevScalars *sc; double *hist; int phase;
 };
 
-#define VEC_PROLOGUE                                                                  \
-    pdl_prologue();                                                                   \
-    if (a.sc->status != ST_RUNNING) return;                                           \
+#define VEC_IDS                                                                       \
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                    \
     const int row_base = blockIdx.x * kTile;                                          \
     (void)warp; (void)lane;
+// PDL: operands written by the immediate predecessor are only touched after VEC_SYNC
+#define VEC_SYNC                                                                      \
+    pdl_sync();                                                                       \
+    if (a.sc->status != ST_RUNNING) return;
 
 // r = b - y ; c1 = r ; c2 = r (optional) ; red0 = r.r          (pbicgstab.cu:67-74, 645-655)
 __global__ void __launch_bounds__(kCtaThreads) k_init_resid(const VecArgs a) {
-    VEC_PROLOGUE
+    VEC_IDS
+    VEC_SYNC
     __shared__ double s_slab[kMaxQ][kTileSlabs];
     double rv[kSlabsPerWarp];
 #pragma unroll
@@ -408,17 +425,23 @@ __global__ void __launch_bounds__(kCtaThreads) k_init_resid(const VecArgs a) {
 //   (ilu0: skipped on the first pass, i == 0, where p = r from the init)
 template <bool FMA_FORM>
 __global__ void __launch_bounds__(kCtaThreads) k_update_p(const VecArgs a) {
-    VEC_PROLOGUE
-    if (FMA_FORM && a.sc->iter == 0) return;
-    const double beta = a.sc->beta, momega = -a.sc->omega;
+    VEC_IDS
+    // v (last SpMV but one) and p (this kernel's own previous output) are not written by the predecessor
     double rr[kSlabsPerWarp], vv[kSlabsPerWarp], pp[kSlabsPerWarp];
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + j * kCtaThreads + tid;
         const bool act = row < a.n;
-        rr[j] = act ? __ldg(a.in0 + row) : 0.0;
         vv[j] = act ? __ldg(a.in1 + row) : 0.0;
         pp[j] = act ? a.out0[row] : 0.0;
+    }
+    VEC_SYNC
+    if (FMA_FORM && a.sc->iter == 0) return;
+    const double beta = a.sc->beta, momega = -a.sc->omega;
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        rr[j] = (row < a.n) ? __ldg(a.in0 + row) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -442,15 +465,19 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_p(const VecArgs a) {
 
 // s = r + fl(-alpha*v)                                            (pbicgstab.cu:698-700)
 __global__ void __launch_bounds__(kCtaThreads) k_update_s(const VecArgs a) {
-    VEC_PROLOGUE
-    const double malpha = -a.sc->alpha;
+    VEC_IDS
     double rr[kSlabsPerWarp], vv[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {          // r: written at the end of the previous iteration
+        const int row = row_base + j * kCtaThreads + tid;
+        rr[j] = (row < a.n) ? __ldg(a.in0 + row) : 0.0;
+    }
+    VEC_SYNC
+    const double malpha = -a.sc->alpha;
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + j * kCtaThreads + tid;
-        const bool act = row < a.n;
-        rr[j] = act ? __ldg(a.in0 + row) : 0.0;
-        vv[j] = act ? __ldg(a.in1 + row) : 0.0;
+        vv[j] = (row < a.n) ? __ldg(a.in1 + row) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -461,18 +488,23 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_s(const VecArgs a) {
 
 // ilu0: r = fma(-alpha,v,r) ; x = fma(alpha,pw,x) ; red0 = r.r   (pbicgstab.cu:109-111)
 __global__ void __launch_bounds__(kCtaThreads) k_update_rx_ilu(const VecArgs a) {
-    VEC_PROLOGUE
+    VEC_IDS
     __shared__ double s_slab[kMaxQ][kTileSlabs];
-    const double alpha = a.sc->alpha, malpha = -alpha;
     double vv[kSlabsPerWarp], pw[kSlabsPerWarp], rr[kSlabsPerWarp], xx[kSlabsPerWarp];
 #pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {
+    for (int j = 0; j < kSlabsPerWarp; ++j) {          // pw, r, x: not written by the preceding SpMV
         const int row = row_base + j * kCtaThreads + tid;
         const bool act = row < a.n;
-        vv[j] = act ? __ldg(a.in0 + row) : 0.0;
         pw[j] = act ? __ldg(a.in1 + row) : 0.0;
         rr[j] = act ? a.out0[row] : 0.0;
         xx[j] = act ? a.out1[row] : 0.0;
+    }
+    VEC_SYNC
+    const double alpha = a.sc->alpha, malpha = -alpha;
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        vv[j] = (row < a.n) ? __ldg(a.in0 + row) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -496,33 +528,42 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_rx_ilu(const VecArgs a) 
 // in0 = p, in1 = s, in2 = t, in3 = rhat ; out0 = x, out1 = r
 template <bool FMA_FORM>
 __global__ void __launch_bounds__(kCtaThreads) k_update_xr(const VecArgs a) {
-    VEC_PROLOGUE
+    VEC_IDS
     __shared__ double s_slab[kMaxQ][kTileSlabs];
-    const double alpha = a.sc->alpha, omega = a.sc->omega, momega = -omega;
-#pragma unroll 2
+    // only t is written by the immediate predecessor (the second SpMV): everything else is fetched before the wait
+    double pv[kSlabsPerWarp], sv[kSlabsPerWarp], rh[kSlabsPerWarp], xo[kSlabsPerWarp], ro[kSlabsPerWarp];
+#pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + j * kCtaThreads + tid;
         const bool act = row < a.n;
-        double xn = 0.0, rn = 0.0, rh = 0.0;
+        sv[j] = act ? __ldg(a.in1 + row) : 0.0;
+        rh[j] = act ? __ldg(a.in3 + row) : 0.0;
+        xo[j] = act ? a.out0[row] : 0.0;
+        pv[j] = (!FMA_FORM && act) ? __ldg(a.in0 + row) : 0.0;
+        ro[j] = (FMA_FORM && act) ? a.out1[row] : 0.0;
+    }
+    VEC_SYNC
+    const double alpha = a.sc->alpha, omega = a.sc->omega, momega = -omega;
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        const bool act = row < a.n;
+        double xn = 0.0, rn = 0.0;
         if (act) {
-            const double sv = __ldg(a.in1 + row), tv = __ldg(a.in2 + row);
-            rh = __ldg(a.in3 + row);
-            const double xo = a.out0[row];
+            const double tv = __ldg(a.in2 + row);
             if (FMA_FORM) {
-                const double ro = a.out1[row];
-                xn = __fma_rn(omega, sv, xo);
-                rn = __fma_rn(momega, tv, ro);
+                xn = __fma_rn(omega, sv[j], xo[j]);
+                rn = __fma_rn(momega, tv, ro[j]);
             } else {
-                const double pv = __ldg(a.in0 + row);
-                const double h = __dadd_rn(xo, __dmul_rn(alpha, pv));
-                xn = __dadd_rn(h, __dmul_rn(omega, sv));
-                rn = __dadd_rn(sv, __dmul_rn(momega, tv));
+                const double h = __dadd_rn(xo[j], __dmul_rn(alpha, pv[j]));
+                xn = __dadd_rn(h, __dmul_rn(omega, sv[j]));
+                rn = __dadd_rn(sv[j], __dmul_rn(momega, tv));
             }
             a.out0[row] = xn;
             a.out1[row] = rn;
         }
         if (row_base + j * kCtaThreads + warp * kSlab < a.n) {
-            slab_deposit(s_slab, 0, j * kCtaWarps + warp, act ? __dmul_rn(rh, rn) : 0.0, lane);
+            slab_deposit(s_slab, 0, j * kCtaWarps + warp, act ? __dmul_rn(rh[j], rn) : 0.0, lane);
             slab_deposit(s_slab, 1, j * kCtaWarps + warp, act ? __dmul_rn(rn, rn) : 0.0, lane);
         }
     }
