@@ -363,7 +363,7 @@ int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, doubl
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
         if (upper)
             CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<true>, (const int *)L.d_order, L.order_len, (const int *)L.d_cnt, (const int *)L.d_ptr,
                                        (const int *)L.d_col, (const double *)L.d_val, (const double *)L.d_dg, s->d_ja,

@@ -80,14 +80,19 @@ struct RedCtx {
 // ------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL). Every loop kernel is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization and runs
-//     [loads of operands that the IMMEDIATE predecessor does not write]  pdl_sync()  [everything else]
-// pdl_sync() = griddepcontrol.wait (predecessor complete, its writes visible) followed by
-// griddepcontrol.launch_dependents. Because a kernel releases its successor only after its own wait, a CTA
-// of kernel N+1 can start only when kernel N-1 has completed: operands last written by kernels <= N-1 may be
-// fetched before the wait, i.e. while kernel N drains — that is what hides the drain/launch/ramp bubble.
+//     [prefetch of operands that NO kernel of the solve writes (the CSR arrays)]  pdl_sync()  [everything else]
+// pdl_sync() = griddepcontrol.launch_dependents (the successor may be scheduled as soon as every CTA of this
+// grid has started, i.e. while this grid drains) + griddepcontrol.wait (predecessor complete, writes visible).
+// Only solve-constant data may be touched before pdl_sync(): with this order a successor can start before the
+// predecessor's predecessor has finished.
 __device__ __forceinline__ void pdl_sync() {
+#ifdef CUDAMAT_PDL_WAIT_FIRST
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#else
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ void pdl_prologue() { pdl_sync(); }
 

@@ -7,6 +7,7 @@
 // (internal.cuh) is independent of scheduling; scalars never leave the device.
 #include "solver.h"
 #include <cub/device/device_scan.cuh>
+#include <cstdlib>
 
 namespace cudamat {
 
@@ -333,6 +334,10 @@ int plan_staged(cudamat_solver *s) {
 
 // launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor
 // in the stream drains; its pdl_prologue() waits for the predecessor's completion before reading.
+bool pdl_enabled() {                      // CUDAMAT_NO_PDL=1 turns the PDL launch attribute off (tuning / debugging)
+    static const int on = [] { const char *e = getenv("CUDAMAT_NO_PDL"); return (e && *e && *e != '0') ? 0 : 1; }();
+    return on != 0;
+}
 template <typename Kern, typename Arg>
 static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, const Arg &arg) {
     cudaLaunchConfig_t cfg{};
@@ -340,7 +345,7 @@ static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaS
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, arg);
 }
 
@@ -382,19 +387,16 @@ struct VecArgs {
     RedCtx rc; DevScalars *sc; double *hist; int phase;
 };
 
-#define VEC_IDS                                                                       \
+#define VEC_PROLOGUE                                                                  \
+    pdl_prologue();                                                                   \
+    if (a.sc->status != ST_RUNNING) return;                                           \
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                    \
     const int row_base = blockIdx.x * kTile;                                          \
     (void)warp; (void)lane;
-// PDL: operands written by the immediate predecessor are only touched after VEC_SYNC
-#define VEC_SYNC                                                                      \
-    pdl_sync();                                                                       \
-    if (a.sc->status != ST_RUNNING) return;
 
 // r = b - y ; c1 = r ; c2 = r (optional) ; red0 = r.r          (pbicgstab.cu:67-74, 645-655)
 __global__ void __launch_bounds__(kCtaThreads) k_init_resid(const VecArgs a) {
-    VEC_IDS
-    VEC_SYNC
+    VEC_PROLOGUE
     __shared__ double s_slab[kMaxQ][kTileSlabs];
     double rv[kSlabsPerWarp];
 #pragma unroll
@@ -425,23 +427,17 @@ __global__ void __launch_bounds__(kCtaThreads) k_init_resid(const VecArgs a) {
 //   (ilu0: skipped on the first pass, i == 0, where p = r from the init)
 template <bool FMA_FORM>
 __global__ void __launch_bounds__(kCtaThreads) k_update_p(const VecArgs a) {
-    VEC_IDS
-    // v (last SpMV but one) and p (this kernel's own previous output) are not written by the predecessor
+    VEC_PROLOGUE
+    if (FMA_FORM && a.sc->iter == 0) return;
+    const double beta = a.sc->beta, momega = -a.sc->omega;
     double rr[kSlabsPerWarp], vv[kSlabsPerWarp], pp[kSlabsPerWarp];
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + j * kCtaThreads + tid;
         const bool act = row < a.n;
+        rr[j] = act ? __ldg(a.in0 + row) : 0.0;
         vv[j] = act ? __ldg(a.in1 + row) : 0.0;
         pp[j] = act ? a.out0[row] : 0.0;
-    }
-    VEC_SYNC
-    if (FMA_FORM && a.sc->iter == 0) return;
-    const double beta = a.sc->beta, momega = -a.sc->omega;
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {
-        const int row = row_base + j * kCtaThreads + tid;
-        rr[j] = (row < a.n) ? __ldg(a.in0 + row) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -465,19 +461,15 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_p(const VecArgs a) {
 
 // s = r + fl(-alpha*v)                                            (pbicgstab.cu:698-700)
 __global__ void __launch_bounds__(kCtaThreads) k_update_s(const VecArgs a) {
-    VEC_IDS
-    double rr[kSlabsPerWarp], vv[kSlabsPerWarp];
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {          // r: written at the end of the previous iteration
-        const int row = row_base + j * kCtaThreads + tid;
-        rr[j] = (row < a.n) ? __ldg(a.in0 + row) : 0.0;
-    }
-    VEC_SYNC
+    VEC_PROLOGUE
     const double malpha = -a.sc->alpha;
+    double rr[kSlabsPerWarp], vv[kSlabsPerWarp];
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + j * kCtaThreads + tid;
-        vv[j] = (row < a.n) ? __ldg(a.in1 + row) : 0.0;
+        const bool act = row < a.n;
+        rr[j] = act ? __ldg(a.in0 + row) : 0.0;
+        vv[j] = act ? __ldg(a.in1 + row) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -488,23 +480,18 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_s(const VecArgs a) {
 
 // ilu0: r = fma(-alpha,v,r) ; x = fma(alpha,pw,x) ; red0 = r.r   (pbicgstab.cu:109-111)
 __global__ void __launch_bounds__(kCtaThreads) k_update_rx_ilu(const VecArgs a) {
-    VEC_IDS
+    VEC_PROLOGUE
     __shared__ double s_slab[kMaxQ][kTileSlabs];
-    double vv[kSlabsPerWarp], pw[kSlabsPerWarp], rr[kSlabsPerWarp], xx[kSlabsPerWarp];
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {          // pw, r, x: not written by the preceding SpMV
-        const int row = row_base + j * kCtaThreads + tid;
-        const bool act = row < a.n;
-        pw[j] = act ? __ldg(a.in1 + row) : 0.0;
-        rr[j] = act ? a.out0[row] : 0.0;
-        xx[j] = act ? a.out1[row] : 0.0;
-    }
-    VEC_SYNC
     const double alpha = a.sc->alpha, malpha = -alpha;
+    double vv[kSlabsPerWarp], pw[kSlabsPerWarp], rr[kSlabsPerWarp], xx[kSlabsPerWarp];
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + j * kCtaThreads + tid;
-        vv[j] = (row < a.n) ? __ldg(a.in0 + row) : 0.0;
+        const bool act = row < a.n;
+        vv[j] = act ? __ldg(a.in0 + row) : 0.0;
+        pw[j] = act ? __ldg(a.in1 + row) : 0.0;
+        rr[j] = act ? a.out0[row] : 0.0;
+        xx[j] = act ? a.out1[row] : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -528,42 +515,33 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_rx_ilu(const VecArgs a) 
 // in0 = p, in1 = s, in2 = t, in3 = rhat ; out0 = x, out1 = r
 template <bool FMA_FORM>
 __global__ void __launch_bounds__(kCtaThreads) k_update_xr(const VecArgs a) {
-    VEC_IDS
+    VEC_PROLOGUE
     __shared__ double s_slab[kMaxQ][kTileSlabs];
-    // only t is written by the immediate predecessor (the second SpMV): everything else is fetched before the wait
-    double pv[kSlabsPerWarp], sv[kSlabsPerWarp], rh[kSlabsPerWarp], xo[kSlabsPerWarp], ro[kSlabsPerWarp];
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {
-        const int row = row_base + j * kCtaThreads + tid;
-        const bool act = row < a.n;
-        sv[j] = act ? __ldg(a.in1 + row) : 0.0;
-        rh[j] = act ? __ldg(a.in3 + row) : 0.0;
-        xo[j] = act ? a.out0[row] : 0.0;
-        pv[j] = (!FMA_FORM && act) ? __ldg(a.in0 + row) : 0.0;
-        ro[j] = (FMA_FORM && act) ? a.out1[row] : 0.0;
-    }
-    VEC_SYNC
     const double alpha = a.sc->alpha, omega = a.sc->omega, momega = -omega;
-#pragma unroll
+#pragma unroll 2
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + j * kCtaThreads + tid;
         const bool act = row < a.n;
-        double xn = 0.0, rn = 0.0;
+        double xn = 0.0, rn = 0.0, rh = 0.0;
         if (act) {
-            const double tv = __ldg(a.in2 + row);
+            const double sv = __ldg(a.in1 + row), tv = __ldg(a.in2 + row);
+            rh = __ldg(a.in3 + row);
+            const double xo = a.out0[row];
             if (FMA_FORM) {
-                xn = __fma_rn(omega, sv[j], xo[j]);
-                rn = __fma_rn(momega, tv, ro[j]);
+                const double ro = a.out1[row];
+                xn = __fma_rn(omega, sv, xo);
+                rn = __fma_rn(momega, tv, ro);
             } else {
-                const double h = __dadd_rn(xo[j], __dmul_rn(alpha, pv[j]));
-                xn = __dadd_rn(h, __dmul_rn(omega, sv[j]));
-                rn = __dadd_rn(sv[j], __dmul_rn(momega, tv));
+                const double pv = __ldg(a.in0 + row);
+                const double h = __dadd_rn(xo, __dmul_rn(alpha, pv));
+                xn = __dadd_rn(h, __dmul_rn(omega, sv));
+                rn = __dadd_rn(sv, __dmul_rn(momega, tv));
             }
             a.out0[row] = xn;
             a.out1[row] = rn;
         }
         if (row_base + j * kCtaThreads + warp * kSlab < a.n) {
-            slab_deposit(s_slab, 0, j * kCtaWarps + warp, act ? __dmul_rn(rh[j], rn) : 0.0, lane);
+            slab_deposit(s_slab, 0, j * kCtaWarps + warp, act ? __dmul_rn(rh, rn) : 0.0, lane);
             slab_deposit(s_slab, 1, j * kCtaWarps + warp, act ? __dmul_rn(rn, rn) : 0.0, lane);
         }
     }

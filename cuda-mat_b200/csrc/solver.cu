@@ -6,6 +6,7 @@
 // mirror.  Kernels of iterations enqueued past the stopping point return immediately.
 #include "solver.h"
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <algorithm>
@@ -193,19 +194,23 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
     const size_t nb = sizeof(double) * (size_t)s->n;
     if ((rc = launch_fill(s, xk, 1.0, s->n))) return rc;                                            // :306-308
     CM_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * s->work_elems, s->stream));
-    if (sf) { if ((rc = sptrsv_arm(s, tl))) return rc; if ((rc = sptrsv_arm(s, pw))) return rc; }
     if ((rc = launch_spmv(s, spmv_args(s, xk, nullptr, t, nullptr, 0, PH_NONE, 0), var))) return rc; // :67
     if ((rc = launch_init_resid(s, d_b, t, r, rw, p, PH_I_INIT))) return rc;                        // :69-74
     const int poll = std::max(1, s->opt_poll_every);
     for (int it = 0; it < maxit;) {
         s->loop_it = it;
         if ((rc = launch_update_p(s, true, r, v, p))) return rc;                                    // :83-89 (skips i == 0)
-        if ((rc = launch_sptrsv(s, false, p, tl, sf ? pw : nullptr, 0))) return rc;                 // :92-94 (+ arms pw)
-        if ((rc = launch_sptrsv(s, true, tl, pw, nullptr, sf))) return rc;                          // :96-98
+        // sync-free sweeps: each output vector is armed (filled with the ready sentinel) by a coalesced fill
+        // right before the sweep that produces it; re-arming through scattered stores inside the neighbouring
+        // sweep measured 7x slower for the consumer (profiles/r1_sptrsv.md)
+        if (sf && ((rc = sptrsv_arm(s, tl)) || (rc = sptrsv_arm(s, pw)))) return rc;
+        if ((rc = launch_sptrsv(s, false, p, tl, nullptr, 0))) return rc;                           // :92-94
+        if ((rc = launch_sptrsv(s, true, tl, pw, nullptr, 0))) return rc;                           // :96-98
         if ((rc = spmv_step(s, pw, nullptr, v, rw, 1, PH_I_A, 1))) return rc;        // :104-107
         if ((rc = launch_update_rx_ilu(s, v, pw, r, xk))) return rc;                                // :109-118
-        if ((rc = launch_sptrsv(s, false, r, tl, sf ? sv : nullptr, 0))) return rc;                 // :121-123 (+ arms s)
-        if ((rc = launch_sptrsv(s, true, tl, sv, nullptr, sf))) return rc;                          // :125-127
+        if (sf && ((rc = sptrsv_arm(s, tl)) || (rc = sptrsv_arm(s, sv)))) return rc;
+        if ((rc = launch_sptrsv(s, false, r, tl, nullptr, 0))) return rc;                           // :121-123
+        if ((rc = launch_sptrsv(s, true, tl, sv, nullptr, 0))) return rc;                           // :125-127
         if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1))) return rc;         // :132-137
         if ((rc = launch_update_xr(s, true, nullptr, sv, t, rw, xk, r))) return rc;                 // :139-151, :81
         ++it;

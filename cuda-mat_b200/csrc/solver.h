@@ -115,6 +115,7 @@ int launch_fill(cudamat_solver *s, double *p, double v, int64_t cnt);
 int launch_row_stats(cudamat_solver *s, int *h_out /*[max_len, n_long, max_slab_nnz]*/, double *mean);
 int launch_normalize_base(cudaStream_t st, int *ia, int64_t n1, int *ja, int64_t nnz, int base);
 int plan_staged(cudamat_solver *s);
+bool pdl_enabled();
 
 // ilu0.cu
 int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st);

@@ -45,7 +45,19 @@ def main():
                     e1.record()
                     torch.cuda.synchronize()
                     res["U" if upper else "L"] = e0.elapsed_time(e1) / args.reps
-                print(json.dumps({"grid": N, "levels": sa["levels_l"], "syncfree": syncfree, "ctas_per_sm": ctas,
+                # chained: U sweep reading the vector the L sweep has just scatter-written (as in the solver loop)
+                out2 = torch.zeros(n, **f64)
+                s.sptrsv(0, rhs.data_ptr(), out.data_ptr()); s.sptrsv(1, out.data_ptr(), out2.data_ptr())
+                torch.cuda.synchronize()
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                tl_, tu_ = 0.0, 0.0
+                for _ in range(args.reps):
+                    e0.record(); s.sptrsv(0, rhs.data_ptr(), out.data_ptr()); e1.record()
+                    s.sptrsv(1, out.data_ptr(), out2.data_ptr()); e2.record()
+                    torch.cuda.synchronize()
+                    tl_ += e0.elapsed_time(e1); tu_ += e1.elapsed_time(e2)
+                res["chainL"], res["chainU"] = tl_ / args.reps, tu_ / args.reps
+                print(json.dumps({"grid": N, "chain_L_ms": round(res["chainL"], 4), "chain_U_ms": round(res["chainU"], 4), "levels": sa["levels_l"], "syncfree": syncfree, "ctas_per_sm": ctas,
                                   "L_ms": round(res["L"], 4), "U_ms": round(res["U"], 4),
                                   "us_per_level": round(res["L"] * 1e3 / sa["levels_l"], 3),
                                   "ns_per_row": round(res["L"] * 1e6 / n, 3), "t_analysis_s": round(sa["t_analysis"], 3)}))
