@@ -128,9 +128,10 @@ __global__ void k_build_plan(const int *order, int len, const int *ia, const int
 // 256-row chunks b, b+G, b+2G, ... of the level-ordered plan in increasing order.  The smallest unfinished
 // chunk only depends on finished chunks and its owner is (or becomes) resident, so the schedule is
 // deadlock-free without tickets, and the look-ahead is bounded by G*256 rows.
-// Waiting is two-phase so that pollers do not saturate L2: one representative lane per warp polls its last
-// dependency with back-off (a warp never mixes levels, so its rows become ready together), then every lane
-// verifies its own dependencies, all loads of a round issued together.
+// Waiting is two-phase so that pollers do not saturate L2: one representative lane per warp spins on its last
+// dependency (a warp never mixes levels, so its rows become ready together; one request per L2 round trip and
+// warp — __nanosleep back-off measured 3 % slower, profiles/r1b_sptrsv_experiments.md), then every lane verifies
+// its own dependencies, all loads of a round issued together.
 template <bool UPPER>
 __global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int len, const int *p_cnt, const int *p_ptr,
                                                         const int *p_col, const double *p_val, const double *p_dg,
@@ -165,8 +166,7 @@ __global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int l
                 const int last = (cnt <= kPlanW) ? c[cnt - 1] : ja[p_ptr[t] + cnt - 1];
                 unsigned spins = 0;
                 while (ld_relaxed_u64(out + last) == kSentinelBits) {
-                    if (++spins > (1u << 22)) __trap();          // never hang the GPU on a broken schedule
-                    __nanosleep(spins < 8 ? 100 : 400);
+                    if (++spins > (1u << 24)) __trap();          // never hang the GPU on a broken schedule
                 }
             }
             __syncwarp();
@@ -181,8 +181,7 @@ __global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int l
 #pragma unroll
             for (int q = 0; q < kPlanW; ++q) ready = ready && (v[q] != kSentinelBits);
             if (__all_sync(0xffffffffu, ready)) break;
-            if (++spins > (1u << 22)) __trap();
-            __nanosleep(100);
+            if (++spins > (1u << 24)) __trap();
         }
 #pragma unroll
         for (int q = 0; q < kPlanW; ++q)
