@@ -213,56 +213,74 @@ def run_ours(args):
 
     # ---- warm-up: W iterations ----
     chunk = max(1, min(args.chunk, converge["iterations"] // 2 if converge["converged"] else args.chunk))
-    s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=max(args.warmup, 3), tol=0.0)
-
-    # ---- timed region: exactly K iterations, CUDA events on the launching stream, max over ranks ----
-    s.set_option("time_spmv", 16)          # SpMVs of every 16th iteration are event-timed
-    K = args.steps
-    plan = [chunk] * (K // chunk) + ([K % chunk] if K % chunk else [])
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = 0
-    t_spmv, n_spmv, done = 0.0, 0, 0
-    barrier()
-    with ClockSampler(local_rank) as clk:
-        e0.record()
-        for m in plan:
-            st = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=m, tol=0.0)
-            done += st["iterations"]
-            t_spmv += st["t_spmv"]; n_spmv += st["n_spmv"]
-            launches0 = st["kernel_launches"] if not launches0 else launches0
-            last_launches = st["kernel_launches"]
-        e1.record()
-        barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms[0])
-    if done != K:
-        raise SystemExit("timed region ran %d iterations instead of %d (break-down?)" % (done, K))
-    s.set_option("time_spmv", 0)
-    its_per_s = K / (ms * 1e-3)
     peak, peak_src = peaks()
-    b_spmv = bytes_spmv(n, nnz)           # whole-problem algorithmic bytes of one SpMV
+    b_spmv = bytes_spmv(n, nnz)           # whole-problem algorithmic bytes of one CSR SpMV
     b_it = bytes_iter(n, nnz)
-    spmv_ms = (t_spmv * 1e3 / n_spmv) if n_spmv else None
-    # per-GPU share of one SpMV launch on this rank
-    b_spmv_loc = 12 * nnz_loc + 4 * (nloc + 1) + 16 * nloc
-    roof = None
-    if spmv_ms:
+    b_spmv_loc = 12 * nnz_loc + 4 * (nloc + 1) + 16 * nloc      # this rank's share of one SpMV launch
+    VNAME = {1: "k_spmv_rowlane", 2: "k_spmv_staged", 3: "k_spmv_class<values from CSR>", 4: "k_spmv_class<values from dictionary>"}
+
+    def moved_bytes(variant):
+        """bytes one SpMV launch of this rank has to move in the variant's own storage format (x read once, y written
+        once, + the dot operand for the fused epilogue is not counted, as in B_spmv)"""
+        if variant == 4:
+            return 17 * nloc
+        if variant == 3:
+            return 8 * nnz_loc + 17 * nloc + 4 * (nloc // 32 + 1)
+        return b_spmv_loc
+
+    def timed_region(sol, K, W):
+        """exactly K iterations, CUDA events on the launching stream, max over ranks"""
+        sol.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=max(W, 3), tol=0.0)
+        sol.set_option("time_spmv", 32)          # the SpMVs of every 32nd iteration are event-timed
+        plan = [chunk] * (K // chunk) + ([K % chunk] if K % chunk else [])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_spmv, n_spmv, done, launches = 0.0, 0, 0, 0
+        barrier()
+        with ClockSampler(local_rank) as clk:
+            e0.record()
+            for m in plan:
+                st = sol.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=m, tol=0.0)
+                done += st["iterations"]
+                t_spmv += st["t_spmv"]; n_spmv += st["n_spmv"]
+                launches = st["kernel_launches"]
+            e1.record()
+            barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if done != K:
+            raise SystemExit("timed region ran %d iterations instead of %d (break-down?)" % (done, K))
+        sol.set_option("time_spmv", 0)
+        return float(ms[0]), (t_spmv * 1e3 / n_spmv) if n_spmv else None, n_spmv, launches, clk.summary()
+
+    def roofline(variant, ms, K, spmv_ms, n_spmv):
+        if not spmv_ms:
+            return None
+        its = K / (ms * 1e-3)
         ach = b_spmv_loc / (spmv_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch_256")
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch_256_variant%d" % variant)
             except Exception:       # noqa: BLE001
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "k_spmv_%s (fused dot epilogue)" % ("staged" if sa["spmv_variant"] == 2 else "rowlane"),
+        mv = moved_bytes(variant)
+        return {"bound": "hbm", "kernel": "%s (fused dot epilogue)" % VNAME.get(variant, "?"),
                 "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
-                "frac_of_8TBps_datasheet": ach / 8000.0, "traffic": traffic,
+                "frac_of_8TBps_datasheet": ach / 8000.0, "traffic": traffic if (N == 256 and world == 1) else None,
                 "algorithmic_bytes_per_launch": b_spmv_loc, "avg_launch_ms": spmv_ms, "launches_timed": n_spmv,
-                "iteration": {"algorithmic_bytes": b_it, "achieved_GBps": b_it / world * its_per_s / 1e9,
-                              "frac": b_it / world * its_per_s / 1e9 / peak, "spmv_share_of_step": 2 * spmv_ms / (ms / K)}}
+                "format_bytes_per_launch": mv, "format_GBps": mv / (spmv_ms * 1e-3) / 1e9, "format_frac": mv / (spmv_ms * 1e-3) / 1e9 / peak,
+                "note": "achieved/frac use the CSR algorithmic bytes of SURVEY.md 8d (12 nnz + 4(n+1) + 16 n); the dictionary variants "
+                        "(3, 4) replace index / value streams by 1 B per row, so frac can exceed 1 - format_* is what the kernel really has to move",
+                "iteration": {"algorithmic_bytes": b_it, "achieved_GBps": b_it / world * its / 1e9,
+                              "frac": b_it / world * its / 1e9 / peak, "spmv_share_of_step": 2 * spmv_ms / (ms / K)}}
+
+    # ---- timed region: the planned (AUTO) SpMV variant ----
+    K = args.steps
+    ms, spmv_ms, n_spmv, last_launches, clocks = timed_region(s, K, args.warmup)
+    its_per_s = K / (ms * 1e-3)
+    roof = roofline(sa["spmv_variant"], ms, K, spmv_ms, n_spmv)
 
     line = {"metric": METRIC, "value": its_per_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -270,21 +288,80 @@ def run_ours(args):
             "config": {"workload": "poisson3d_%d" % N, "n": n, "nnz": nnz, "mode": "unpreconditioned BiCGSTAB (pbicgstab.h:113)",
                        "x0": "ones", "b": "A*x_true, x_true=hash(1234,i) in (-1,1)", "chunk": chunk,
                        "l2": "inputs (%.1f GB CSR + vectors) larger than the 126 MB L2, no flush" % ((12 * nnz + 4 * n) / 1e9),
-                       "spmv_variant": sa["spmv_variant"], "sharding": "row slabs, %d rank(s)" % world},
-            "gpu_launches": int(last_launches - 0) if world >= 1 else 0,
-            "converge": converge, "roofline": roof, "clocks": clk.summary()}
-    line["gpu_launches"] = int(last_launches)
+                       "spmv_variant": sa["spmv_variant"], "spmv_format": VNAME.get(sa["spmv_variant"]),
+                       "sharding": "row slabs, %d rank(s)" % world},
+            "gpu_launches": int(last_launches),
+            "converge": converge, "roofline": roof, "clocks": clocks}
+
+    # ---- the same K steps with the plain CSR kernel (variant ROWLANE): the apples-to-apples roofline of SURVEY.md 8d ----
+    if sa["spmv_variant"] != 1 and not args.no_csr:
+        s1 = cm.Solver(n, row0, row1, stream=stream)
+        s1.set_csr_device(nnz_loc, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
+        if world > 1:
+            idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idbuf = torch.tensor(list(cm.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(idbuf, 0)
+            cm.Comm.init(s1, bytes(idbuf.cpu().tolist()), rank, world)
+        s1.set_option("spmv_variant", 1)
+        s1.analyze(cm.MODE_PLAIN)
+        K1 = min(K, 1000)
+        ms1, spmv_ms1, n_spmv1, _, _ = timed_region(s1, K1, args.warmup)
+        line["csr_format"] = {"value": K1 / (ms1 * 1e-3), "unit": UNIT, "steps": K1, "ms_per_step": ms1 / K1,
+                              "roofline": roofline(1, ms1, K1, spmv_ms1, n_spmv1)}
+        s1.close()
 
     if rank == 0 and world == 1 and not args.no_extras:
         line.update(single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, converge))
-    elif world > 1:
-        line["e2e"] = None
+    elif world > 1 and not args.no_extras:
+        line["e2e"] = multi_gpu_e2e(cm, torch, dist, N, n, row0, row1, nnz_loc, ia, ja, a, b, rank, world, stream, barrier)
     s.close()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def multi_gpu_e2e(cm, torch, dist, N, n, row0, row1, nnz_loc, ia, ja, a, b, rank, world, stream, barrier):
+    """e2e at N > 1: every rank holds its row shard (CSR with global columns, b) in pinned HOST memory and goes
+    through the handle API of the C ABI: cudamat_create, cudamat_set_csr_host (H2D), cudamat_comm_init (halo plan; the
+    process-wide NCCL communicator already exists), cudamat_analyze, H2D of b, cudamat_solve_device to 1e-10, D2H of x.
+    Wall clock between barriers, max over ranks."""
+    nloc = row1 - row0
+    try:
+        h_ia = torch.empty(nloc + 1, dtype=torch.int32, pin_memory=True); h_ia.copy_(ia)
+        h_ja = torch.empty(nnz_loc, dtype=torch.int32, pin_memory=True); h_ja.copy_(ja)
+        h_a = torch.empty(nnz_loc, dtype=torch.float64, pin_memory=True); h_a.copy_(a)
+        h_b = torch.empty(nloc, dtype=torch.float64, pin_memory=True); h_b.copy_(b)
+        h_x = torch.empty(nloc, dtype=torch.float64, pin_memory=True)
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idbuf = torch.tensor(list(cm.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idbuf, 0)
+        idb = bytes(idbuf.cpu().tolist())
+        barrier()
+        t0 = time.time()
+        s2 = cm.Solver(n, row0, row1, stream=stream)
+        s2.set_csr_host(h_a.numpy(), h_ia.numpy(), h_ja.numpy())
+        cm.Comm.init(s2, idb, rank, world)
+        s2.analyze(cm.MODE_PLAIN)
+        d_b = torch.empty(nloc, dtype=torch.float64, device="cuda"); d_b.copy_(h_b, non_blocking=True)
+        d_x = torch.empty(nloc, dtype=torch.float64, device="cuda")
+        st = s2.solve(cm.MODE_PLAIN, d_b.data_ptr(), d_x.data_ptr(), maxit=5000, tol=1e-10)
+        h_x.copy_(d_x)
+        barrier()
+        wall = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        wall = float(wall[0])
+        s2.close()
+        it = st["iterations"]
+        return {"value": it / wall, "unit": UNIT, "h2d_bytes_per_step": (12 * nnz_loc + 4 * (nloc + 1) + 8 * nloc) * world / max(it, 1),
+                "d2h_bytes_per_step": 8 * n / max(it, 1), "iterations": it, "wall_s": wall, "t_loop_s": st["t_loop"],
+                "converged": bool(st["converged"]),
+                "call": "per rank: cudamat_set_csr_host + cudamat_comm_init + cudamat_analyze + cudamat_solve_device(tol=1e-10) on pinned host shards"}
+    except Exception as e:      # noqa: BLE001
+        return {"value": None, "error": str(e)}
 
 
 def single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, converge):
@@ -368,6 +445,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="force an SpMV variant (1 rowlane, 2 staged)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-ilu0", action="store_true", help="skip the ILU0 extra")
+    ap.add_argument("--no-csr", action="store_true", help="skip the second timed region with the plain CSR SpMV kernel")
     ap.add_argument("--no-converge", action="store_true", help="skip the full solve to 1e-10 (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / ilu0 / mat10000 / cpu extras (profiling runs)")
     args = ap.parse_args()

@@ -29,6 +29,10 @@ struct NcclApi {
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
+// One NCCL communicator per process, created by the first cudamat_comm_init and shared by every later handle of
+// the same (rank, world): bootstrapping a communicator costs ~0.1-1 s, a solver handle should not.
+static ncclComm_t g_comm = nullptr;
+static int g_comm_rank = -1, g_comm_world = 0;
 
 static int load_nccl() {
     if (g_nccl.lib) return CUDAMAT_OK;
@@ -160,7 +164,6 @@ void comm_release(cudamat_solver *s) {
     if (c->d_ja_local) cudaFree(c->d_ja_local);
     if (c->d_exch_local) cudaFree(c->d_exch_local);
     if (c->d_exch_glob) cudaFree(c->d_exch_glob);
-    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     delete c;
     s->comm = nullptr;
 }
@@ -231,7 +234,12 @@ int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world)
     c->rank = rank; c->world = world;
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
-    CM_NCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    if (g_comm && g_comm_rank == rank && g_comm_world == world) c->comm = g_comm;       // id128 is ignored on reuse
+    else {
+        if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+        CM_NCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
+        g_comm = c->comm; g_comm_rank = rank; g_comm_world = world;
+    }
     // 1. everybody's row range
     int64_t *d_rng = nullptr;
     CM_CUDA(cudaMalloc(&d_rng, sizeof(int64_t) * 2 * (size_t)(world + 1)));

@@ -191,11 +191,11 @@ __device__ __forceinline__ void apply_phase(DevScalars *sc, double *hist, int ph
 // s_slab[q][0..63] hold the tile's slab sums (all warps done, __syncthreads() issued by caller).
 template <int NQ>
 __device__ __forceinline__ void reduce_tail(const RedCtx &rc, DevScalars *sc, double *hist, int phase,
-                                            double (*s_slab)[kTileSlabs], int nslab_tile) {
+                                            double (*s_slab)[kTileSlabs], int nslab_tile, int tile = -1) {
     __shared__ int s_flag;
     __shared__ double s_red[kMaxQ];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x;
+    if (tile < 0) tile = blockIdx.x;
     // tile partial: R() over the slab sums
     if (warp < NQ) {
         double tp = warp_reduce_values_smem(s_slab[warp], nslab_tile, lane);

@@ -8,6 +8,7 @@
 #include "solver.h"
 #include <cub/device/device_scan.cuh>
 #include <cstdlib>
+#include <algorithm>
 
 namespace cudamat {
 
@@ -119,6 +120,95 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowl
         if (pslab >= 0) {
             slab_deposit(s_slab, 0, pslab, pp0, lane);
             if (NDOT >= 2) slab_deposit(s_slab, 1, pslab, pp1, lane);
+        }
+        __syncthreads();
+        const int rows_here = min(kTile, a.n - row_base);
+        reduce_tail<(NDOT >= 1 ? NDOT : 1)>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SpMV variants PATTERN / CLASS: one row per lane like ROWLANE, but the column indices (and for CLASS the
+// values) of a row come from its class in a small dictionary held in shared memory: one byte per row is read
+// instead of 4 (12) bytes per entry (rowclass.cu).  col = row + offset, so the x gathers of a warp whose rows
+// share a class are perfectly coalesced.  Entry order = storage order: bit-identical to the CSR kernels.
+// PATTERN finds the row's first value at ia[first row of the slab] + exclusive scan of the class lengths.
+// ------------------------------------------------------------------------------------------
+#ifndef CUDAMAT_CLASS_MINB
+#define CUDAMAT_CLASS_MINB 4
+#endif
+template <bool HAS_D, int NDOT, bool CLS_VALS>
+__global__ void __launch_bounds__(kCtaThreads, CUDAMAT_CLASS_MINB) k_spmv_class(const SpmvArgs a, const ClassArgs c) {
+    __shared__ double s_slab[kMaxQ][kTileSlabs];
+    __shared__ int s_len[kDictMax];
+    __shared__ int s_off[kDictMax * kDictLen];
+    __shared__ double s_val[CLS_VALS ? kDictMax * kDictLen : 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row_base = blockIdx.x * kTile;
+    // the dictionary and the class ids are constant during a solve: fetched while the predecessor kernel drains
+    // (one tile per CTA: a persistent grid measured slower inside the loop, where many short CTAs fill the SMs
+    // as the predecessor drains — profiles/r1b_spmv_class.md)
+    for (int i = tid; i < c.ncls; i += kCtaThreads) s_len[i] = c.dict->len[i];
+    for (int i = tid; i < c.ncls * kDictLen; i += kCtaThreads) {
+        s_off[i] = c.dict->off[i];
+        if (CLS_VALS) s_val[i] = c.dict->val[i];
+    }
+    int cid[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + (j * kCtaWarps + warp) * kSlab + lane;
+        cid[j] = (row < a.n) ? (int)__ldg(c.cls + row) : -1;
+    }
+    __syncthreads();
+    pdl_sync();
+    if (a.check_status && a.sc->status != ST_RUNNING) return;
+    double pp0[kSlabsPerWarp], pp1[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        pp0[j] = 0.0; pp1[j] = 0.0;
+        const int row0 = row_base + (j * kCtaWarps + warp) * kSlab;
+        if (row0 >= a.n) continue;                                // warp-uniform
+        const int row = row0 + lane;
+        const bool active = row < a.n;
+        const int len = active ? s_len[cid[j]] : 0;
+        const int *off = s_off + max(cid[j], 0) * kDictLen;
+        const double *dv = s_val + (CLS_VALS ? max(cid[j], 0) * kDictLen : 0);
+        double uval = 0.0;
+        if (NDOT >= 1 && active) uval = __ldg(a.u + row);
+        int start = 0;
+        if (!CLS_VALS) {
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            start = __ldg(a.ia + row0) + incl - len;
+        }
+        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+        double sum = 0.0;
+        for (int k0 = 0; k0 < maxlen; k0 += 8) {
+            double av[8], xv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const bool p = (k0 + q) < len;
+                xv[q] = p ? __ldg(a.x + row + off[k0 + q]) : 0.0;
+                if (CLS_VALS) av[q] = p ? dv[k0 + q] : 0.0;
+                else av[q] = p ? __ldg(a.val + start + k0 + q) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if ((k0 + q) < len) sum = __fma_rn(av[q], xv[q], sum);
+        }
+        if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
+        if (active) a.y[row] = sum;
+        if (NDOT >= 1) pp0[j] = active ? __dmul_rn(sum, uval) : 0.0;
+        if (NDOT >= 2) pp1[j] = active ? __dmul_rn(sum, sum) : 0.0;
+    }
+    if (NDOT >= 1) {
+#pragma unroll
+        for (int j = 0; j < kSlabsPerWarp; ++j) {
+            if (row_base + (j * kCtaWarps + warp) * kSlab < a.n) {
+                slab_deposit(s_slab, 0, j * kCtaWarps + warp, pp0[j], lane);
+                if (NDOT >= 2) slab_deposit(s_slab, 1, j * kCtaWarps + warp, pp1[j], lane);
+            }
         }
         __syncthreads();
         const int rows_here = min(kTile, a.n - row_base);
@@ -349,10 +439,35 @@ static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaS
     return cudaLaunchKernelEx(&cfg, kern, arg);
 }
 
+template <typename Kern, typename A1, typename A2>
+static cudaError_t launch_pdl2(Kern kern, int grid, int block, cudaStream_t st, const A1 &a1, const A2 &a2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a1, a2);
+}
+
 template <bool HAS_D, int NDOT>
 static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
     const int grid = (a.n + kTile - 1) / kTile;
     if (grid == 0) return CUDAMAT_OK;
+    if (variant == CUDAMAT_SPMV_CLASS && s->cls[1].ncls > 0) {
+        const ClassArgs c{s->cls[1].d_cls, s->cls[1].d_dict, s->cls[1].ncls};
+        CM_CUDA(launch_pdl2(k_spmv_class<HAS_D, NDOT, true>, grid, kCtaThreads, s->stream, a, c));
+        s->launches++;
+        CM_CUDA(cudaGetLastError());
+        return CUDAMAT_OK;
+    }
+    if ((variant == CUDAMAT_SPMV_PATTERN || variant == CUDAMAT_SPMV_CLASS) && s->cls[0].ncls > 0) {
+        const ClassArgs c{s->cls[0].d_cls, s->cls[0].d_dict, s->cls[0].ncls};
+        CM_CUDA(launch_pdl2(k_spmv_class<HAS_D, NDOT, false>, grid, kCtaThreads, s->stream, a, c));
+        s->launches++;
+        CM_CUDA(cudaGetLastError());
+        return CUDAMAT_OK;
+    }
     if (variant == CUDAMAT_SPMV_STAGED && s->staged.cap_nnz > 0 && (NDOT == 0 || ((uintptr_t)a.u % 16) == 0)) {
         StagedArgs g{a, s->staged.cap_nnz, s->staged.stages, s->nnz};
         auto kern = k_spmv_staged<HAS_D, NDOT>;

@@ -1,0 +1,155 @@
+// rowclass.cu — row-class dictionaries for the compressed SpMV variants (analysis side).
+//
+// Stencil matrices (the reference's mat900 / mat10000 fixtures, the N^3 Poisson systems of BASELINE.json) have
+// only a handful of distinct rows up to translation: the column OFFSETS ja[k] - i of a row, and often its VALUES
+// too, come from a tiny set.  cudamat_analyze detects this on the device and replaces the 4-byte column index
+// (and, when the values repeat as well, the 8-byte value) of every entry by ONE byte per row:
+//   * CUDAMAT_SPMV_PATTERN: cls[i] -> (len, offsets[len]); values still streamed from CSR;
+//   * CUDAMAT_SPMV_CLASS:   cls[i] -> (len, offsets[len], values[len]); the CSR arrays are not read at all.
+// The dictionary (<= kDictMax classes of <= kDictLen entries) is exact: every row is verified against its class,
+// a single mismatch (or a hash collision) disables the variant and the CSR kernel is used.  Entry order is the
+// row's storage order, so the row sums are bit-identical to the CSR kernels.
+// This is what cusparseDcsrmv (pbicgstab.cu:67,104,132,646,676,704) cannot do: it must stream 12 B per entry.
+#include "solver.h"
+
+namespace cudamat {
+
+constexpr int kTab = 2048;                      // open-addressing table slots (power of two)
+
+__device__ __forceinline__ uint64_t mixk(uint64_t h, uint64_t v) {
+    h ^= v + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
+    h *= 0xBF58476D1CE4E5B9ULL;
+    return h ^ (h >> 29);
+}
+// key of a row: hash of (len, offsets[, value bits]); never 0
+__device__ __forceinline__ uint64_t row_key(int row, const int *ia, const int *ja, const double *a, bool with_vals, int *len_out) {
+    const int s = ia[row], e = ia[row + 1];
+    *len_out = e - s;
+    uint64_t h = mixk(0x243F6A8885A308D3ULL, (uint64_t)(e - s));
+    for (int k = s; k < e; ++k) {
+        h = mixk(h, (uint64_t)(uint32_t)(ja[k] - row));
+        if (with_vals) h = mixk(h, (uint64_t)__double_as_longlong(a[k]));
+    }
+    return h ? h : 1ull;
+}
+__device__ __forceinline__ int tab_find(const unsigned long long *tab, uint64_t key) {
+    int slot = (int)(key & (kTab - 1));
+    for (int probes = 0; probes < kTab; ++probes) {
+        const unsigned long long cur = tab[slot];
+        if (cur == key) return slot;
+        if (cur == 0ull) return -1;
+        slot = (slot + 1) & (kTab - 1);
+    }
+    return -1;
+}
+
+// pass 1: insert every row's key, remember the smallest row of each key. fail[0] != 0: not representable
+__global__ void k_cls_insert(int n, const int *ia, const int *ja, const double *a, int with_vals,
+                             unsigned long long *tab, int *rep, int *fail) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    int len;
+    const uint64_t key = row_key(row, ia, ja, a, with_vals != 0, &len);
+    if (len > kDictLen) { *fail = 1; return; }
+    int slot = (int)(key & (kTab - 1));
+    for (int probes = 0;; ++probes) {
+        if (probes >= kTab) { *fail = 1; return; }
+        unsigned long long cur = *(volatile unsigned long long *)(tab + slot);
+        if (cur == 0ull) cur = atomicCAS(tab + slot, 0ull, (unsigned long long)key);
+        if (cur == 0ull || cur == key) break;
+        slot = (slot + 1) & (kTab - 1);
+    }
+    if (row < *(volatile int *)(rep + slot)) atomicMin(rep + slot, row);
+}
+
+// pass 2 (one thread): number the classes by their first row, build the dictionary from the representatives
+__global__ void k_cls_number(const int *ia, const int *ja, const double *a, int with_vals,
+                             const unsigned long long *tab, const int *rep, int *slot_id, RowDict *dict, int *ncls_out, int *fail) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int slots[kDictMax], m = 0;
+    for (int sl = 0; sl < kTab; ++sl) {
+        slot_id[sl] = -1;
+        if (tab[sl] != 0ull) {
+            if (m >= kDictMax) { *fail = 1; *ncls_out = 0; return; }
+            int pos = m++;                                   // insertion sort by representative row
+            while (pos > 0 && rep[slots[pos - 1]] > rep[sl]) { slots[pos] = slots[pos - 1]; --pos; }
+            slots[pos] = sl;
+        }
+    }
+    for (int id = 0; id < m; ++id) {
+        const int sl = slots[id], row = rep[sl];
+        slot_id[sl] = id;
+        const int s = ia[row], len = ia[row + 1] - s;
+        dict->len[id] = len;
+        for (int k = 0; k < kDictLen; ++k) {
+            dict->off[id * kDictLen + k] = (k < len) ? ja[s + k] - row : 0;
+            dict->val[id * kDictLen + k] = (k < len && with_vals) ? a[s + k] : 0.0;
+        }
+    }
+    *ncls_out = m;
+}
+
+// pass 3: class id of every row, verified entry by entry against the dictionary
+__global__ void k_cls_assign(int n, const int *ia, const int *ja, const double *a, int with_vals,
+                             const unsigned long long *tab, const int *slot_id, const RowDict *dict, unsigned char *cls, int *fail) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    int len;
+    const uint64_t key = row_key(row, ia, ja, a, with_vals != 0, &len);
+    const int slot = tab_find(tab, key);
+    const int id = slot >= 0 ? slot_id[slot] : -1;
+    if (id < 0 || dict->len[id] != len) { *fail = 1; return; }
+    const int s = ia[row];
+    for (int k = 0; k < len; ++k) {
+        if (dict->off[id * kDictLen + k] != ja[s + k] - row) { *fail = 1; return; }
+        if (with_vals && __double_as_longlong(dict->val[id * kDictLen + k]) != __double_as_longlong(a[s + k])) { *fail = 1; return; }
+    }
+    cls[row] = (unsigned char)id;
+}
+
+void rowclass_release(cudamat_solver *s) {
+    for (int m = 0; m < 2; ++m) {
+        if (s->cls[m].d_cls) cudaFree(s->cls[m].d_cls);
+        if (s->cls[m].d_dict) cudaFree(s->cls[m].d_dict);
+        s->cls[m] = RowClasses();
+    }
+}
+
+// builds s->cls[0] (offsets only) and s->cls[1] (offsets + values) when the matrix allows it
+int rowclass_analyze(cudamat_solver *s) {
+    rowclass_release(s);
+    const int n = s->n;
+    if (n <= 0 || s->nnz <= 0 || s->max_row_len > kDictLen) return CUDAMAT_OK;
+    unsigned long long *tab = nullptr; int *rep = nullptr, *slot_id = nullptr, *flags = nullptr;
+    CM_CUDA(cudaMalloc(&tab, sizeof(unsigned long long) * kTab));
+    CM_CUDA(cudaMalloc(&rep, sizeof(int) * kTab));
+    CM_CUDA(cudaMalloc(&slot_id, sizeof(int) * kTab));
+    CM_CUDA(cudaMalloc(&flags, sizeof(int) * 2));
+    int rc = CUDAMAT_OK;
+    for (int m = 1; m >= 0 && rc == CUDAMAT_OK; --m) {          // m = 1: with values, m = 0: offsets only
+        RowClasses &C = s->cls[m];
+        cudaError_t e;
+        if ((e = cudaMalloc(&C.d_cls, (size_t)n + 16)) != cudaSuccess || (e = cudaMalloc(&C.d_dict, sizeof(RowDict))) != cudaSuccess) {
+            cuda_ok(e, "cudaMalloc(row classes)", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
+        }
+        cudaMemsetAsync(tab, 0, sizeof(unsigned long long) * kTab, s->stream);
+        cudaMemsetAsync(rep, 0x7f, sizeof(int) * kTab, s->stream);
+        cudaMemsetAsync(flags, 0, sizeof(int) * 2, s->stream);
+        const int grid = (n + 255) / 256;
+        k_cls_insert<<<grid, 256, 0, s->stream>>>(n, s->d_ia, s->d_ja, s->d_a, m, tab, rep, flags);
+        k_cls_number<<<1, 32, 0, s->stream>>>(s->d_ia, s->d_ja, s->d_a, m, tab, rep, slot_id, C.d_dict, flags + 1, flags);
+        k_cls_assign<<<grid, 256, 0, s->stream>>>(n, s->d_ia, s->d_ja, s->d_a, m, tab, slot_id, C.d_dict, C.d_cls, flags);
+        s->launches += 3;
+        int h[2] = {1, 0};
+        if ((e = cudaMemcpyAsync(h, flags, sizeof h, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
+            cuda_ok(e, "row class analysis", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
+        }
+        if (h[0] == 0 && h[1] > 0) C.ncls = h[1];
+        else { cudaFree(C.d_cls); cudaFree(C.d_dict); C = RowClasses(); }
+    }
+    cudaFree(tab); cudaFree(rep); cudaFree(slot_id); cudaFree(flags);
+    return rc;
+}
+
+}  // namespace cudamat

@@ -50,8 +50,8 @@ static int alloc_reduction(cudamat_solver *s) {
     CM_CUDA(cudaMemsetAsync(rc.done_cnt, 0, sizeof(unsigned), s->stream));
     CM_CUDA(cudaMalloc(&s->d_sc, sizeof(DevScalars)));
     CM_CUDA(cudaMemsetAsync(s->d_sc, 0, sizeof(DevScalars), s->stream));
-    CM_CUDA(cudaMallocHost(&s->h_sc, sizeof(DevScalars)));
-    memset(s->h_sc, 0, sizeof(DevScalars));
+    CM_CUDA(cudaMallocHost(&s->h_sc, 3 * sizeof(DevScalars)));        // [0] synchronous mirror, [1..2] pipelined polls
+    memset(s->h_sc, 0, 3 * sizeof(DevScalars));
     return CUDAMAT_OK;
 }
 
@@ -113,6 +113,31 @@ static int poll_status(cudamat_solver *s) {
     CM_CUDA(cudaStreamSynchronize(s->stream));
     return CUDAMAT_OK;
 }
+// Pipelined status polls: the host enqueues a copy of the scalars every `poll_every` iterations and only waits
+// for the copy enqueued one period EARLIER, so the stream always holds at least one period of work and never
+// drains while the host looks at the status.  Iterations enqueued past the stopping point return at kernel entry.
+static int poll_enqueue(cudamat_solver *s, int k) {
+    if (!s->poll_ev[k]) CM_CUDA(cudaEventCreateWithFlags(&s->poll_ev[k], cudaEventDisableTiming));
+    CM_CUDA(cudaMemcpyAsync(s->h_sc + 1 + k, s->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaEventRecord(s->poll_ev[k], s->stream));
+    return CUDAMAT_OK;
+}
+static int poll_finished(cudamat_solver *s, int k, bool *stop) {
+    CM_CUDA(cudaEventSynchronize(s->poll_ev[k]));
+    *stop = s->h_sc[1 + k].status != ST_RUNNING;
+    return CUDAMAT_OK;
+}
+// called after each enqueued iteration; *stop = true when the loop may end
+static int poll_step(cudamat_solver *s, int it, int maxit, int *npoll, bool *stop) {
+    *stop = false;
+    const int poll = std::max(1, s->opt_poll_every);
+    if (it % poll != 0 && it != maxit) return CUDAMAT_OK;
+    int rc = poll_enqueue(s, *npoll & 1);
+    if (rc) return rc;
+    if (*npoll > 0 && (rc = poll_finished(s, (*npoll - 1) & 1, stop))) return rc;
+    ++*npoll;
+    return CUDAMAT_OK;
+}
 
 static void fill_stats(cudamat_solver *s, cudamat_stats *st) {
     const DevScalars &h = *s->h_sc;
@@ -161,7 +186,7 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
     if ((rc = launch_init_resid(s, d_b, t, r, r0, nullptr, PH_U_INIT))) return rc;
     if ((rc = comm_finish_reduction(s, PH_U_INIT, 1))) return rc;
     if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
-    const int poll = std::max(1, s->opt_poll_every);
+    int npoll = 0; bool stop = false;
     for (int it = 0; it < maxit;) {
         s->loop_it = it;
         if ((rc = launch_update_p(s, false, r, v, p))) return rc;                                   // :668-672
@@ -171,10 +196,8 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
         if ((rc = launch_update_xr(s, false, p, sv, t, r0, xk, r))) return rc;                      // :694-696,714-747
         if ((rc = comm_finish_reduction(s, PH_U_C, 2))) return rc;
         ++it;
-        if (it % poll == 0 || it == maxit) {
-            if ((rc = poll_status(s))) return rc;
-            if (s->h_sc->status != ST_RUNNING) break;
-        }
+        if ((rc = poll_step(s, it, maxit, &npoll, &stop))) return rc;
+        if (stop) break;
     }
     if ((rc = poll_status(s))) return rc;
     CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
@@ -196,7 +219,7 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
     CM_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * s->work_elems, s->stream));
     if ((rc = launch_spmv(s, spmv_args(s, xk, nullptr, t, nullptr, 0, PH_NONE, 0), var))) return rc; // :67
     if ((rc = launch_init_resid(s, d_b, t, r, rw, p, PH_I_INIT))) return rc;                        // :69-74
-    const int poll = std::max(1, s->opt_poll_every);
+    int npoll = 0; bool stop = false;
     for (int it = 0; it < maxit;) {
         s->loop_it = it;
         if ((rc = launch_update_p(s, true, r, v, p))) return rc;                                    // :83-89 (skips i == 0)
@@ -214,10 +237,8 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
         if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1))) return rc;         // :132-137
         if ((rc = launch_update_xr(s, true, nullptr, sv, t, rw, xk, r))) return rc;                 // :139-151, :81
         ++it;
-        if (it % poll == 0 || it == maxit) {
-            if ((rc = poll_status(s))) return rc;
-            if (s->h_sc->status != ST_RUNNING) break;
-        }
+        if ((rc = poll_step(s, it, maxit, &npoll, &stop))) return rc;
+        if (stop) break;
     }
     if ((rc = poll_status(s))) return rc;
     CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
@@ -295,6 +316,7 @@ int cudamat_destroy(cudamat_solver *s) {
     cudaStreamSynchronize(s->stream);
     comm_release(s);
     ilu0_release(s);
+    rowclass_release(s);
     if (s->own_ia) cudaFree(s->own_ia);
     if (s->own_ja) cudaFree(s->own_ja);
     if (s->own_a) cudaFree(s->own_a);
@@ -307,6 +329,7 @@ int cudamat_destroy(cudamat_solver *s) {
     if (s->d_hist) cudaFree(s->d_hist);
     if (s->work) cudaFree(s->work);
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->poll_ev) if (e) cudaEventDestroy(e);
     delete s;
     return CUDAMAT_OK;
 }
@@ -319,6 +342,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "debug")) s->opt_debug = (int)value;
     else if (!strcmp(key, "time_spmv")) s->opt_time_spmv = (int)value;
     else if (!strcmp(key, "sptrsv_ctas_per_sm")) { s->opt_sptrsv_ctas_per_sm = (int)value; s->sptrsv_grid = 0; }
+    else if (!strcmp(key, "class_ctas_per_sm")) s->opt_class_ctas_per_sm = (int)value;
     else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
     else { set_error("unknown option '%s'", key); return CUDAMAT_E_INVALID; }
     return CUDAMAT_OK;
@@ -374,12 +398,17 @@ int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
     if ((rc = plan_staged(s))) return rc;
     const bool aligned = (((uintptr_t)s->d_a) % 16 == 0) && (((uintptr_t)s->d_ja) % 16 == 0);
     if (!aligned) s->staged = StagedPlan();
-    // variant choice from row-length statistics. Measured on B200 (profiles/r1_spmv_variants.md): with
-    // <= 32 entries per row the direct row-per-lane kernel already streams at ~95% of the copy roofline
-    // (full occupancy hides the strided val/col loads behind L1), ahead of the TMA-staged kernel whose
-    // shared-memory ring caps occupancy; it is therefore the default and the staged kernel is opt-in.
+    // Variant choice from the row statistics.  Measured on B200 (profiles/): with <= 32 entries per row the direct
+    // row-per-lane kernel streams CSR at ~99 % of the copy roofline, ahead of the TMA-staged kernel whose
+    // shared-memory ring caps occupancy (opt-in).  When the rows fall into a few classes up to translation
+    // (stencil matrices) the dictionary variants move far fewer bytes and win outright: CLASS (offsets and
+    // values from the dictionary) > PATTERN (offsets only) > ROWLANE.
+    if ((rc = rowclass_analyze(s))) return rc;
     int variant = s->opt_spmv_variant;
-    if (variant == CUDAMAT_SPMV_AUTO) variant = CUDAMAT_SPMV_ROWLANE;
+    if (variant == CUDAMAT_SPMV_AUTO)
+        variant = s->cls[1].ncls > 0 ? CUDAMAT_SPMV_CLASS : s->cls[0].ncls > 0 ? CUDAMAT_SPMV_PATTERN : CUDAMAT_SPMV_ROWLANE;
+    if (variant == CUDAMAT_SPMV_CLASS && s->cls[1].ncls == 0) variant = CUDAMAT_SPMV_PATTERN;
+    if (variant == CUDAMAT_SPMV_PATTERN && s->cls[0].ncls == 0) variant = CUDAMAT_SPMV_ROWLANE;
     if (variant == CUDAMAT_SPMV_STAGED && s->staged.cap_nnz == 0) variant = CUDAMAT_SPMV_ROWLANE;
     s->spmv_variant = variant;
     if (st) st->t_analysis += now_s() - t0;

@@ -38,6 +38,17 @@ struct StagedPlan {
     size_t smem_bytes = 0;
 };
 
+// row-class dictionaries of the compressed SpMV variants (rowclass.cu)
+constexpr int kDictMax = 128;      // classes
+constexpr int kDictLen = 16;       // entries per class
+struct RowDict { int len[kDictMax]; int off[kDictMax * kDictLen]; double val[kDictMax * kDictLen]; };
+struct RowClasses {
+    unsigned char *d_cls = nullptr;    // class id per row
+    RowDict *d_dict = nullptr;
+    int ncls = 0;                      // 0 = not available
+};
+struct ClassArgs { const unsigned char *cls; const RowDict *dict; int ncls; };
+
 struct Comm;   // comm.cu
 
 struct LevelSchedule {
@@ -73,15 +84,18 @@ struct cudamat_solver {
     int opt_time_spmv = 0;
     int loop_it = 0;
     int opt_staged_stages = 0;
+    int opt_class_ctas_per_sm = 0;
     int opt_sptrsv_ctas_per_sm = 0;
     int sptrsv_grid = 0;
     std::vector<cudaEvent_t> ev_pool; int ev_used = 0;
     cudamat::StagedPlan staged;
+    cudamat::RowClasses cls[2];            // [0] offsets only (PATTERN), [1] offsets + values (CLASS)
     // reduction context + scalars
     cudamat::RedCtx rc{};
     double *slots_own = nullptr;           // the allocation behind rc.slots (rc.slots may be redirected by comm)
     cudamat::DevScalars *d_sc = nullptr;
-    cudamat::DevScalars *h_sc = nullptr;   // pinned mirror
+    cudamat::DevScalars *h_sc = nullptr;   // pinned mirrors: [0] synchronous, [1..2] pipelined polls
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     double *d_hist = nullptr; int hist_cap = 0;
     // work vectors (n + nhalo each)
     double *work = nullptr; size_t work_elems = 0; int work_nvec = 0;
@@ -116,6 +130,10 @@ int launch_row_stats(cudamat_solver *s, int *h_out /*[max_len, n_long, max_slab_
 int launch_normalize_base(cudaStream_t st, int *ia, int64_t n1, int *ja, int64_t nnz, int base);
 int plan_staged(cudamat_solver *s);
 bool pdl_enabled();
+
+// rowclass.cu
+int rowclass_analyze(cudamat_solver *s);
+void rowclass_release(cudamat_solver *s);
 
 // ilu0.cu
 int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st);

@@ -52,6 +52,8 @@ extern "C" {
 #define CUDAMAT_SPMV_AUTO      0    /* chosen from row-length statistics at analyze time     */
 #define CUDAMAT_SPMV_ROWLANE   1    /* thread-per-row, direct global loads                   */
 #define CUDAMAT_SPMV_STAGED    2    /* row-block staged through shared memory by TMA bulk copies */
+#define CUDAMAT_SPMV_PATTERN   3    /* column offsets from a per-row class dictionary (1 B/row), values from CSR */
+#define CUDAMAT_SPMV_CLASS     4    /* offsets AND values from the class dictionary: CSR arrays are not read   */
 
 typedef struct cudamat_stats {
     int    iterations;      /* the reference's loop counter i at exit                          */

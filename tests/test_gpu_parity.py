@@ -15,7 +15,7 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 2]   # ROWLANE, STAGED
+VARIANTS = [1, 2, 3, 4]   # ROWLANE, STAGED, PATTERN, CLASS (the dictionary variants fall back to ROWLANE when a matrix has no small row-class dictionary)
 
 
 def dev(torch, a, dtype=None):
@@ -97,11 +97,15 @@ def test_spmv_linearity_and_variants_agree_large(cm, torch_cuda):
     cm.gen_xtrue_device(1234, 0, n, x.data_ptr())
     cm.gen_xtrue_device(99, 0, n, y.data_ptr())
     ax1, ax2, ay = (torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3))
+    st = s.analyze(0)
+    assert st["spmv_variant"] == cm.SPMV_CLASS          # a constant-coefficient stencil: the class dictionary is chosen
     s.spmv(x.data_ptr(), ax1.data_ptr(), variant=1)
-    s.spmv(x.data_ptr(), ax2.data_ptr(), variant=2)
+    for v in (2, 3, 4):
+        s.spmv(x.data_ptr(), ax2.data_ptr(), variant=v)
+        torch.cuda.synchronize()
+        assert torch.equal(ax1, ax2), v
     s.spmv(y.data_ptr(), ay.data_ptr())
     torch.cuda.synchronize()
-    assert torch.equal(ax1, ax2)
     ones = torch.ones(n, dtype=torch.float64, device="cuda")
     r = torch.empty_like(ones)
     s.spmv(ones.data_ptr(), r.data_ptr())
@@ -334,7 +338,8 @@ def test_full_size_properties_poisson128(cm, torch_cuda):
         assert len(h) == st["iterations"] + 1 and h[0] == st["nrm_r0"] and h[-1] == st["nrm_r"] and h[-1] < 1e-10 * h[0]
         results.append((st["iterations"], x.clone()))
         s.close()
-    assert results[0][0] == results[1][0] and torch.equal(results[0][1], results[1][1])
+    for k in range(1, len(results)):
+        assert results[0][0] == results[k][0] and torch.equal(results[0][1], results[k][1])
     # ILU0 on the same system: fewer iterations, same answer to 1e-8
     s = cm.Solver(n)
     s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))

@@ -36,14 +36,16 @@ def main():
     bspmv = 12 * nnz + 4 * (n + 1) + 16 * n
     biter = 2 * bspmv + 120 * n
     for cfg in args.configs.split(","):
-        parts = [int(v) for v in cfg.split(":")] + [0, 0]
-        variant, stages, tctas = parts[0], parts[1], parts[2]
+        parts = [int(v) for v in cfg.split(":")] + [0, 0, 0]
+        variant, stages, tctas, cctas = parts[0], parts[1], parts[2], parts[3]
         s = cm.Solver(n)
         s.set_option("spmv_variant", variant)
         if stages:
             s.set_option("staged_stages", stages)
         if tctas:
             s.set_option("sptrsv_ctas_per_sm", tctas)
+        if cctas:
+            s.set_option("class_ctas_per_sm", cctas)
         s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr())
         sa = s.analyze(args.mode)
         s.spmv(xt.data_ptr(), b.data_ptr())
@@ -68,7 +70,7 @@ def main():
         st = s.solve(args.mode, b.data_ptr(), x.data_ptr(), maxit=args.iters, tol=0.0)
         ms_it_timed = st["t_loop"] * 1e3 / max(st["iterations"], 1)
         sp_ms = st["t_spmv"] * 1e3 / max(st["n_spmv"], 1)
-        print(json.dumps({"grid": N, "variant": sa["spmv_variant"], "stages_opt": stages, "sptrsv_ctas": tctas, "lib": os.path.basename(cm.LIB_PATH), "plain_spmv_ms": round(plain_ms, 4),
+        print(json.dumps({"grid": N, "variant": sa["spmv_variant"], "stages_opt": stages, "sptrsv_ctas": tctas, "class_ctas": cctas, "lib": os.path.basename(cm.LIB_PATH), "plain_spmv_ms": round(plain_ms, 4),
                           "plain_spmv_GBps": round(bspmv / plain_ms / 1e6, 1), "loop_spmv_ms": round(sp_ms, 4),
                           "loop_spmv_GBps": round(bspmv / sp_ms / 1e6, 1), "ms_per_iter": round(ms_it, 4), "ms_per_iter_with_events": round(ms_it_timed, 4),
                           "iters_per_s": round(1e3 / ms_it, 1), "iter_GBps": round(biter / ms_it / 1e6, 1),
