@@ -289,7 +289,9 @@ def run_ours(args):
                        "x0": "ones", "b": "A*x_true, x_true=hash(1234,i) in (-1,1)", "chunk": chunk,
                        "l2": "inputs (%.1f GB CSR + vectors) larger than the 126 MB L2, no flush" % ((12 * nnz + 4 * n) / 1e9),
                        "spmv_variant": sa["spmv_variant"], "spmv_format": VNAME.get(sa["spmv_variant"]),
-                       "sharding": "row slabs, %d rank(s)" % world},
+                       "sharding": "row slabs, %d rank(s)" % world,
+                       "comm": ("none" if world == 1 else ("peer memory over NVLink (CUDA IPC): fused halo pushes + in-kernel gather of the partial sums, no NCCL call per iteration"
+                                                            if cm.Comm.p2p_enabled(s) else "NCCL send/recv halo + allreduce of the partial sums"))},
             "gpu_launches": int(last_launches),
             "converge": converge, "roofline": roof, "clocks": clocks}
 

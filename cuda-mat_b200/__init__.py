@@ -55,7 +55,7 @@ EXPORTS = [
     "cudamat_ilu0_host", "cudamat_create", "cudamat_destroy", "cudamat_set_option",
     "cudamat_set_csr_host", "cudamat_set_csr_device", "cudamat_analyze", "cudamat_solve_device",
     "cudamat_get_history", "cudamat_spmv_device", "cudamat_dot_device", "cudamat_get_ilu0_host",
-    "cudamat_sptrsv_device", "cudamat_comm_unique_id", "cudamat_comm_init", "cudamat_partition_rows",
+    "cudamat_sptrsv_device", "cudamat_comm_p2p_enabled", "cudamat_comm_unique_id", "cudamat_comm_init", "cudamat_partition_rows",
     "cudamat_halo_plan_host",
     "cudamat_gen_poisson3d_device", "cudamat_poisson3d_nnz", "cudamat_gen_xtrue_device",
     "cudamat_gen_random_dd_device", "cudamat_load_mm", "cudamat_free",
@@ -88,6 +88,7 @@ lib.cudamat_halo_plan_host.argtypes = [C.c_int64, C.c_int64, C.c_int64, c_ip, C.
                                        C.POINTER(c_ip), c_ip]
 lib.cudamat_comm_unique_id.argtypes = [C.c_void_p]
 lib.cudamat_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+lib.cudamat_comm_p2p_enabled.argtypes = [C.c_void_p]
 lib.cudamat_gen_poisson3d_device.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.cudamat_poisson3d_nnz.restype = C.c_int64
 lib.cudamat_poisson3d_nnz.argtypes = [C.c_int, C.c_int64, C.c_int64]
@@ -292,6 +293,10 @@ class Comm:
     def init(solver, uid, rank, world):
         raw = (C.c_ubyte * 128)(*uid)
         _check(lib.cudamat_comm_init(solver.h, raw, rank, world))
+
+    @staticmethod
+    def p2p_enabled(solver):
+        return bool(lib.cudamat_comm_p2p_enabled(solver.h))
 
 
 def gen_poisson3d_device(N, row0, row1, d_ia, d_ja, d_a, stream=0):

@@ -12,6 +12,7 @@
 #include <nccl.h>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 namespace cudamat {
 
@@ -54,7 +55,27 @@ static int load_nccl() {
         if (r_ != ncclSuccess) { set_error("NCCL error %d (%s) at %s:%d", (int)r_, g_nccl.GetErrorString(r_), __FILE__, __LINE__); return CUDAMAT_E_COMM; } \
     } while (0)
 
+// peer-memory path (CUDA IPC over NVLink), see internal.cuh
+struct P2P {
+    bool on = false;
+    unsigned char *arena = nullptr;            // [flags 4 KB][gather parity 0][gather parity 1]
+    unsigned long long *flags = nullptr;       // [0, kMaxWorld): reduction arrival per source rank; [kMaxWorld*(1+slot) + src]: halo slot
+    double *gather[2] = {nullptr, nullptr};
+    std::vector<unsigned char *> peer_arena;   // per rank (self: own pointer)
+    std::vector<double *> peer_work;           // per rank, nullptr unless a halo neighbour
+    std::vector<unsigned long long> peer_work_elems;
+    std::vector<long long> peer_n;
+    std::vector<int> peer_recv_off_me;         // offset of MY rows inside rank r's halo region
+    PeerRed *d_peers = nullptr;
+    unsigned *d_local_cnt = nullptr;           // [2 slots][kMaxPeer]
+    unsigned char *d_tile_wait = nullptr;
+    unsigned long long red_epoch = 0, halo_epoch[2] = {0, 0};
+    std::vector<int> nbr;                      // ranks I exchange halo rows with (send side)
+    std::vector<int> src;                      // ranks I receive halo rows from
+};
+
 struct Comm {
+    P2P p2p;
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
     std::vector<int64_t> row_starts;
@@ -88,8 +109,18 @@ __global__ void k_pack(const double *vec, const int *idx, double *out, int cnt) 
 
 // finish a reduction after the cross-rank exchange: (level 1) tiles -> groups -> final, (level 2) groups -> final
 __global__ void __launch_bounds__(kCtaThreads) k_finalize(const double *exch, int level, int count, int stride, int nq,
-                                                          DevScalars *sc, double *hist, int phase) {
+                                                          DevScalars *sc, double *hist, int phase,
+                                                          const unsigned long long *flags, int world, unsigned long long epoch) {
+    pdl_sync();
     if (sc->status != ST_RUNNING && phase != PH_STORE) return;
+    if (flags) {                                   // peer-memory path: every rank's partial sums must have arrived
+        if ((int)threadIdx.x < world) {
+            unsigned spins = 0;
+            while (ld_acquire_sys_u64(flags + threadIdx.x) < epoch)
+                if (++spins > (1u << 26)) __trap();
+        }
+        __syncthreads();
+    }
     __shared__ double s_grp[kMaxQ][64];
     __shared__ double s_red[kMaxQ];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,18 +178,184 @@ int comm_halo_exchange(cudamat_solver *s, double *vec) {
 int comm_finish_reduction(cudamat_solver *s, int phase, int nq) {
     Comm *c = s->comm;
     if (!c || c->world == 1) return CUDAMAT_OK;
-    CM_NCCL(g_nccl.AllReduce(c->d_exch_local, c->d_exch_glob, (size_t)c->exch_count, ncclDouble, ncclSum, c->comm, s->stream));
     const int stride = c->exch_count / kMaxQ;
-    k_finalize<<<1, kCtaThreads, 0, s->stream>>>(c->d_exch_glob, c->exch_level, c->exch_level == 1 ? c->ntile_global : s->rc.nslots,
-                                                 stride, nq, s->d_sc, s->d_hist, phase);
+    const int count = c->exch_level == 1 ? c->ntile_global : s->rc.nslots;
+    if (c->p2p.on) {
+        // the reducing kernel's last CTA has pushed this rank's partial sums to every rank (reduce_tail/p2p_push);
+        // one small kernel waits for all arrivals and finishes the fixed-order tree — no NCCL call in the loop
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(kCtaThreads); cfg.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        const unsigned long long ep = c->p2p.red_epoch;
+        CM_CUDA(cudaLaunchKernelEx(&cfg, k_finalize, (const double *)c->p2p.gather[ep & 1], c->exch_level, count, stride, nq, s->d_sc, s->d_hist,
+                                   phase, (const unsigned long long *)c->p2p.flags, c->world, ep));
+    } else {
+        CM_NCCL(g_nccl.AllReduce(c->d_exch_local, c->d_exch_glob, (size_t)c->exch_count, ncclDouble, ncclSum, c->comm, s->stream));
+        k_finalize<<<1, kCtaThreads, 0, s->stream>>>(c->d_exch_glob, c->exch_level, count, stride, nq, s->d_sc, s->d_hist, phase,
+                                                     nullptr, 0, 0ull);
+    }
     s->launches++;
     CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
+bool comm_p2p(const cudamat_solver *s) { return s->comm && s->comm->world > 1 && s->comm->p2p.on; }
+
+void comm_begin_reduction(cudamat_solver *s, RedCtx &rc) {
+    if (!comm_p2p(s)) return;
+    rc.p2p.epoch = ++s->comm->p2p.red_epoch;
+}
+
+// kernel that writes `vec` (one of the work vectors): where its halo rows go. slot 0 / 1 = the two vectors pushed
+// per iteration (p, s); returns false when the peer-memory path is off
+bool comm_halo_push(cudamat_solver *s, double *vec, int slot, HaloPush *hp) {
+    *hp = HaloPush{};
+    if (!comm_p2p(s)) return false;
+    Comm *c = s->comm; P2P &P = c->p2p;
+    const size_t k = (size_t)(vec - s->work) / s->work_elems;            // which work vector
+    hp->epoch = ++P.halo_epoch[slot];
+    hp->local_cnt = P.d_local_cnt + slot * kMaxPeer;
+    for (int r : P.nbr) {
+        const int q = hp->npeer++;
+        hp->dst[q] = P.peer_work[r] + k * P.peer_work_elems[r] + P.peer_n[r] + P.peer_recv_off_me[r];
+        hp->first[q] = c->send_contig[r];
+        hp->cnt[q] = c->send_cnt[r];
+        hp->ntiles[q] = (hp->first[q] + hp->cnt[q] - 1) / kTile - hp->first[q] / kTile + 1;
+        hp->flag[q] = reinterpret_cast<unsigned long long *>(P.peer_arena[r]) + (size_t)kMaxWorld * (1 + slot) + c->rank;
+    }
+    return true;
+}
+void comm_halo_wait(cudamat_solver *s, int slot, HaloWait *hw) {
+    *hw = HaloWait{};
+    if (!comm_p2p(s)) return;
+    P2P &P = s->comm->p2p;
+    for (int r : P.src) hw->flag[hw->nsrc++] = P.flags + (size_t)kMaxWorld * (1 + slot) + r;
+    hw->tile_wait = P.d_tile_wait;
+    hw->epoch = P.halo_epoch[slot];
+}
+
+__global__ void k_tile_wait(int n, const int *ia, const int *ja, unsigned char *tile_wait) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    for (int k = ia[row]; k < ia[row + 1]; ++k)
+        if (ja[k] >= n) { tile_wait[row / kTile] = 1; return; }
+}
+
+static void p2p_release(Comm *c) {
+    P2P &P = c->p2p;
+    for (size_t r = 0; r < P.peer_arena.size(); ++r)
+        if ((int)r != c->rank && P.peer_arena[r]) cudaIpcCloseMemHandle(P.peer_arena[r]);
+    for (size_t r = 0; r < P.peer_work.size(); ++r)
+        if ((int)r != c->rank && P.peer_work[r]) cudaIpcCloseMemHandle(P.peer_work[r]);
+    if (P.arena) cudaFree(P.arena);
+    if (P.d_peers) cudaFree(P.d_peers);
+    if (P.d_local_cnt) cudaFree(P.d_local_cnt);
+    if (P.d_tile_wait) cudaFree(P.d_tile_wait);
+    P = P2P();
+}
+
+// Peer-memory set-up (collective). Any failure on any rank switches the path off everywhere (NCCL path stays).
+static int p2p_setup(cudamat_solver *s, const std::vector<int> &W) {
+    Comm *c = s->comm; P2P &P = c->p2p;
+    const int world = c->world, rank = c->rank;
+    const char *env = getenv("CUDAMAT_NO_P2P");
+    int ok = !(env && *env && *env != '0') && world <= kMaxWorld;
+    // halo sends must be contiguous row ranges (row slabs of a banded matrix are), at most kMaxPeer neighbours each way
+    for (int r = 0; r < world && ok; ++r) {
+        if (c->send_cnt[r] > 0) { if (c->send_contig[r] < 0) ok = 0; P.nbr.push_back(r); }
+        if (c->recv_cnt[r] > 0) P.src.push_back(r);
+    }
+    if ((int)P.nbr.size() > kMaxPeer || (int)P.src.size() > kMaxPeer) ok = 0;
+    struct Xchg { cudaIpcMemHandle_t work, arena; unsigned long long work_elems; long long n; int ok; int pad; };
+    Xchg mine{}; memset(&mine, 0, sizeof mine);
+    const size_t gbytes = sizeof(double) * (size_t)c->exch_count;
+    const size_t abytes = 4096 + 2 * ((gbytes + 255) / 256) * 256;
+    if (ok && ensure_work(s, 9) != CUDAMAT_OK) ok = 0;
+    if (ok && cudaMalloc(&P.arena, abytes) != cudaSuccess) { ok = 0; P.arena = nullptr; }
+    if (ok) {
+        cudaMemsetAsync(P.arena, 0, abytes, s->stream);
+        P.flags = reinterpret_cast<unsigned long long *>(P.arena);
+        P.gather[0] = reinterpret_cast<double *>(P.arena + 4096);
+        P.gather[1] = reinterpret_cast<double *>(P.arena + 4096 + ((gbytes + 255) / 256) * 256);
+        if (cudaIpcGetMemHandle(&mine.work, s->work) != cudaSuccess || cudaIpcGetMemHandle(&mine.arena, P.arena) != cudaSuccess) ok = 0;
+        mine.work_elems = s->work_elems; mine.n = s->n;
+    }
+    cudaGetLastError();
+    mine.ok = ok;
+    // all-gather the handles
+    unsigned char *d_x = nullptr;
+    CM_CUDA(cudaMalloc(&d_x, sizeof(Xchg) * (size_t)(world + 1)));
+    CM_CUDA(cudaMemcpyAsync(d_x + sizeof(Xchg) * (size_t)world, &mine, sizeof mine, cudaMemcpyHostToDevice, s->stream));
+    CM_NCCL(g_nccl.AllGather(d_x + sizeof(Xchg) * (size_t)world, d_x, sizeof(Xchg), ncclUint8, c->comm, s->stream));
+    std::vector<Xchg> all((size_t)world);
+    CM_CUDA(cudaMemcpyAsync(all.data(), d_x, sizeof(Xchg) * (size_t)world, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    for (int r = 0; r < world; ++r) if (!all[r].ok) ok = 0;
+    int opened = ok;
+    if (ok) {
+        P.peer_arena.assign(world, nullptr); P.peer_work.assign(world, nullptr);
+        P.peer_work_elems.assign(world, 0); P.peer_n.assign(world, 0); P.peer_recv_off_me.assign(world, 0);
+        for (int r = 0; r < world && opened; ++r) {
+            P.peer_work_elems[r] = all[r].work_elems; P.peer_n[r] = all[r].n;
+            int off = 0;                                           // rank r's halo region: sources in rank order
+            for (int q = 0; q < rank; ++q) off += W[(size_t)r * world + q];
+            P.peer_recv_off_me[r] = off;
+            if (r == rank) { P.peer_arena[r] = P.arena; P.peer_work[r] = s->work; continue; }
+            void *pa = nullptr;
+            if (cudaIpcOpenMemHandle(&pa, all[r].arena, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened = 0; break; }
+            P.peer_arena[r] = (unsigned char *)pa;
+            if (c->send_cnt[r] > 0) {
+                void *pw = nullptr;
+                if (cudaIpcOpenMemHandle(&pw, all[r].work, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened = 0; break; }
+                P.peer_work[r] = (double *)pw;
+            }
+        }
+        cudaGetLastError();
+    }
+    // agree on the outcome
+    int *d_ok = reinterpret_cast<int *>(d_x);
+    CM_CUDA(cudaMemcpyAsync(d_ok, &opened, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CM_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, s->stream));
+    CM_CUDA(cudaMemcpyAsync(&opened, d_ok, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    CM_CUDA(cudaFree(d_x));
+    if (!opened) { p2p_release(c); return CUDAMAT_OK; }
+    // device tables
+    std::vector<PeerRed> pr((size_t)world);
+    for (int r = 0; r < world; ++r) {
+        unsigned char *pa = P.peer_arena[r];
+        pr[r].gather[0] = reinterpret_cast<double *>(pa + 4096);
+        pr[r].gather[1] = reinterpret_cast<double *>(pa + 4096 + ((gbytes + 255) / 256) * 256);
+        pr[r].flag = reinterpret_cast<unsigned long long *>(pa) + rank;
+    }
+    CM_CUDA(cudaMalloc(&P.d_peers, sizeof(PeerRed) * (size_t)world));
+    CM_CUDA(cudaMemcpyAsync(P.d_peers, pr.data(), sizeof(PeerRed) * (size_t)world, cudaMemcpyHostToDevice, s->stream));
+    CM_CUDA(cudaMalloc(&P.d_local_cnt, sizeof(unsigned) * 2 * kMaxPeer));
+    CM_CUDA(cudaMemsetAsync(P.d_local_cnt, 0, sizeof(unsigned) * 2 * kMaxPeer, s->stream));
+    const int ntile = (s->n + kTile - 1) / kTile;
+    CM_CUDA(cudaMalloc(&P.d_tile_wait, (size_t)std::max(ntile, 1)));
+    CM_CUDA(cudaMemsetAsync(P.d_tile_wait, 0, (size_t)std::max(ntile, 1), s->stream));
+    if (s->n > 0) k_tile_wait<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->n, s->d_ia, s->d_ja, P.d_tile_wait);
+    CM_CUDA(cudaGetLastError());
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    RedCtx &rcx = s->rc;
+    rcx.p2p.world = world;
+    rcx.p2p.peers = P.d_peers;
+    rcx.p2p.stride = c->exch_count / kMaxQ;
+    if (c->exch_level == 2) { rcx.p2p.my_off = rcx.group0; rcx.p2p.my_cnt = rcx.ngroup_loc; }
+    else { rcx.p2p.my_off = rcx.tile0; rcx.p2p.my_cnt = rcx.ntile; }
+    P.on = true;
     return CUDAMAT_OK;
 }
 
 void comm_release(cudamat_solver *s) {
     Comm *c = s->comm;
     if (!c) return;
+    p2p_release(c);
+    s->rc.p2p = P2PRed{};
     if (c->d_send_idx) cudaFree(c->d_send_idx);
     if (c->d_sendbuf) cudaFree(c->d_sendbuf);
     if (c->d_ja_local) cudaFree(c->d_ja_local);
@@ -210,6 +407,8 @@ int cudamat_halo_plan_host(int64_t row0, int64_t row1, int64_t nnz, const int *j
     std::copy(halo.begin(), halo.end(), *halo_cols);
     return CUDAMAT_OK;
 }
+
+int cudamat_comm_p2p_enabled(cudamat_solver *s) { return (s && comm_p2p(s)) ? 1 : 0; }
 
 int cudamat_comm_unique_id(void *id128) {
     if (!id128) return CUDAMAT_E_INVALID;
@@ -348,7 +547,8 @@ int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world)
     }
     CM_CUDA(cudaStreamSynchronize(s->stream));
     s->analyzed = false;
-    return CUDAMAT_OK;
+    // 7. peer-memory path (CUDA IPC): fused halo pushes and reduction gathers without NCCL calls in the loop
+    return p2p_setup(s, W);
 }
 
 }  // extern "C"

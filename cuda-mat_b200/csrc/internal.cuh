@@ -55,6 +55,39 @@ struct DevScalars {
     int pad;
 };
 
+// ---- multi-GPU peer-memory plumbing (comm.cu) ---------------------------------------------
+// Every rank maps its neighbours' work-vector arena and every rank's small exchange arena (CUDA IPC) and the
+// kernels talk to them directly over NVLink: no NCCL call inside the iteration.
+constexpr int kMaxPeer = 4;        // halo neighbours of one shard (row slabs: 2)
+constexpr int kMaxWorld = 64;      // ranks
+struct PeerRed {                   // where rank r keeps the partial sums gathered from all ranks
+    double *gather[2];             // [parity][kMaxQ * stride]
+    unsigned long long *flag;      // r's arrival flag of THIS rank's contribution (value = epoch)
+};
+struct P2PRed {                    // part of RedCtx; world == 0: disabled
+    int world, my_off, my_cnt, stride;
+    const PeerRed *peers;          // device array [world]
+    unsigned long long epoch;      // of the reduction this kernel feeds; parity = epoch & 1
+};
+// halo rows of a vector are stored straight into the neighbours' copy of that vector by the kernel that
+// produces it; the last boundary CTA of the grid then raises the neighbour's flag to `epoch`
+struct HaloPush {
+    int npeer;
+    double *dst[kMaxPeer];                 // neighbour's halo slot for this rank's rows
+    int first[kMaxPeer], cnt[kMaxPeer];    // local rows [first, first + cnt) go to dst[0 .. cnt)
+    int ntiles[kMaxPeer];                  // CTAs (tiles) that overlap the range
+    unsigned long long *flag[kMaxPeer];
+    unsigned *local_cnt;                   // [kMaxPeer] boundary CTAs finished
+    unsigned long long epoch;
+};
+// the consuming SpMV: CTAs whose rows reference halo columns wait until every neighbour's flag reached `epoch`
+struct HaloWait {
+    int nsrc;
+    const unsigned long long *flag[kMaxPeer];
+    const unsigned char *tile_wait;        // [tiles] 1: the tile has halo columns
+    unsigned long long epoch;
+};
+
 // reduction context of one shard
 struct RedCtx {
     double   *tile_part;   // [kMaxQ][tile_stride]  tile partials, indexed by LOCAL tile
@@ -73,6 +106,7 @@ struct RedCtx {
     int tile0;             // global index of the first local tile
     int exch_stride;
     double *exch;          // level 1: [kMaxQ][exch_stride] indexed by global tile
+    P2PRed p2p;            // peer-memory all-gather of the partials instead of an NCCL allreduce
 };
 
 // ------------------------------------------------------------------------------------------
@@ -95,6 +129,44 @@ __device__ __forceinline__ void pdl_sync() {
 #endif
 }
 __device__ __forceinline__ void pdl_prologue() { pdl_sync(); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void halo_store(const HaloPush &hp, int row, double v) {
+#pragma unroll
+    for (int p = 0; p < kMaxPeer; ++p)
+        if (p < hp.npeer && row >= hp.first[p] && row < hp.first[p] + hp.cnt[p]) hp.dst[p][row - hp.first[p]] = v;
+}
+// end of a producing CTA (all threads): publish this tile's halo stores; the last boundary CTA raises the flag
+__device__ __forceinline__ void halo_signal(const HaloPush &hp, int row_base, int rows_here) {
+    if (hp.npeer == 0) return;
+    __syncthreads();
+    const int p = threadIdx.x;
+    if (p < hp.npeer && row_base < hp.first[p] + hp.cnt[p] && row_base + rows_here > hp.first[p]) {
+        __threadfence_system();
+        const unsigned old = atomicAdd(hp.local_cnt + p, 1u);
+        if (old == (unsigned)(hp.ntiles[p] - 1)) {
+            hp.local_cnt[p] = 0u;
+            __threadfence_system();
+            st_release_sys_u64(hp.flag[p], hp.epoch);
+        }
+    }
+}
+__device__ __forceinline__ void halo_wait(const HaloWait &hw, int tile) {
+    if (hw.nsrc == 0 || !hw.tile_wait[tile]) return;
+    if ((int)threadIdx.x < hw.nsrc) {
+        unsigned spins = 0;
+        while (ld_acquire_sys_u64(hw.flag[threadIdx.x]) < hw.epoch)
+            if (++spins > (1u << 26)) __trap();         // a lost neighbour must not hang the GPU
+    }
+    __syncthreads();
+}
 
 __device__ __forceinline__ double warp_butterfly(double v) {
 #pragma unroll
@@ -187,6 +259,26 @@ __device__ __forceinline__ void apply_phase(DevScalars *sc, double *hist, int ph
     }
 }
 
+// last CTA of a reducing kernel on a sharded handle: copy this rank's partial sums (its tiles or groups) into
+// every rank's gather array over NVLink, then raise this rank's arrival flag there
+template <int NQ>
+__device__ __forceinline__ void p2p_push(const RedCtx &rc, const double *local) {
+    const P2PRed &pp = rc.p2p;
+    __threadfence();
+    const int par = (int)(pp.epoch & 1ull);
+    for (int r = 0; r < pp.world; ++r) {
+        double *dst = pp.peers[r].gather[par];
+        for (int q = 0; q < NQ; ++q)
+            for (int i = threadIdx.x; i < pp.my_cnt; i += blockDim.x)
+                dst[(size_t)q * pp.stride + pp.my_off + i] = __ldcg(local + (size_t)q * pp.stride + pp.my_off + i);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < pp.world) {
+        __threadfence_system();
+        st_release_sys_u64(pp.peers[threadIdx.x].flag, pp.epoch);
+    }
+}
+
 // Grid-level tail of a reducing kernel. Contract: gridDim.x == rc.ntile, CTA b owns local tile b,
 // s_slab[q][0..63] hold the tile's slab sums (all warps done, __syncthreads() issued by caller).
 template <int NQ>
@@ -205,7 +297,18 @@ __device__ __forceinline__ void reduce_tail(const RedCtx &rc, DevScalars *sc, do
             __threadfence();
         }
     }
-    if (rc.exch_level == 1) return;      // groups and final are formed after the cross-rank exchange
+    if (rc.exch_level == 1) {            // groups and final are formed after the cross-rank exchange
+        if (rc.p2p.world == 0) return;
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned old = atomicAdd(rc.done_cnt, 1u);
+            s_flag = (old == (unsigned)(rc.ntile - 1));
+            if (s_flag) *rc.done_cnt = 0u;
+        }
+        __syncthreads();
+        if (s_flag) p2p_push<NQ>(rc, rc.exch);
+        return;
+    }
     __syncthreads();
     const int g = tile / kGroupTiles;
     if (tid == 0) {
@@ -233,6 +336,7 @@ __device__ __forceinline__ void reduce_tail(const RedCtx &rc, DevScalars *sc, do
         if (s_flag) *rc.done_cnt = 0u;
     }
     __syncthreads();
+    if (s_flag && rc.p2p.world > 0) { p2p_push<NQ>(rc, rc.slots); return; }
     if (!s_flag || !rc.do_final) return;
     __threadfence();
     if (warp < NQ) {

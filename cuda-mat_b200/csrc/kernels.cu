@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowl
     }
     pdl_sync();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
+    halo_wait(a.hw, blockIdx.x);
     // fused-dot products of the previous slab: their butterflies are issued right after the next slab's
     // row-pointer loads, so the shuffle latency hides under that memory round trip
     double pp0 = 0.0, pp1 = 0.0;
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_CLASS_MINB) k_spmv_class(
     __syncthreads();
     pdl_sync();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
+    halo_wait(a.hw, blockIdx.x);
     double pp0[kSlabsPerWarp], pp1[kSlabsPerWarp];
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_spmv_staged(const StagedArgs
     const SpmvArgs &a = g.a;
     pdl_prologue();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
+    halo_wait(a.hw, blockIdx.x);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_slab[kMaxQ][kTileSlabs];
     __shared__ uint64_t s_bar[kCtaWarps][8];
@@ -500,6 +503,7 @@ struct VecArgs {
     const double *in0, *in1, *in2, *in3, *in4;
     double *out0, *out1, *out2;
     RedCtx rc; DevScalars *sc; double *hist; int phase;
+    HaloPush hp;           // multi-GPU peer-memory path: out0's halo rows go straight to the neighbours (npeer == 0: off)
 };
 
 #define VEC_PROLOGUE                                                                  \
@@ -570,8 +574,10 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_p(const VecArgs a) {
                 q = __dadd_rn(rr[j], q);
             }
             a.out0[row] = q;
+            halo_store(a.hp, row, q);
         }
     }
+    halo_signal(a.hp, row_base, min(kTile, a.n - row_base));
 }
 
 // s = r + fl(-alpha*v)                                            (pbicgstab.cu:698-700)
@@ -589,8 +595,13 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_s(const VecArgs a) {
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + j * kCtaThreads + tid;
-        if (row < a.n) a.out0[row] = __dadd_rn(rr[j], __dmul_rn(malpha, vv[j]));
+        if (row < a.n) {
+            const double q = __dadd_rn(rr[j], __dmul_rn(malpha, vv[j]));
+            a.out0[row] = q;
+            halo_store(a.hp, row, q);
+        }
     }
+    halo_signal(a.hp, row_base, min(kTile, a.n - row_base));
 }
 
 // ilu0: r = fma(-alpha,v,r) ; x = fma(alpha,pw,x) ; red0 = r.r   (pbicgstab.cu:109-111)
@@ -692,6 +703,7 @@ __global__ void k_fill(double *p, double v, int64_t cnt) {
 static VecArgs vec_args(cudamat_solver *s, int phase) {
     VecArgs a{};
     a.n = s->n; a.rc = s->rc; a.sc = s->d_sc; a.hist = s->d_hist; a.phase = phase;
+    if (phase != PH_NONE) comm_begin_reduction(s, a.rc);       // reducing kernel: stamp the reduction epoch (p2p)
     return a;
 }
 static inline int tiles_of(int n) { return (n + kTile - 1) / kTile; }
@@ -712,15 +724,17 @@ int launch_init_resid(cudamat_solver *s, const double *b, const double *y, doubl
     LAUNCH_VEC(k_init_resid, a);
     return CUDAMAT_OK;
 }
-int launch_update_p(cudamat_solver *s, bool fma_form, const double *r, const double *v, double *p) {
+int launch_update_p(cudamat_solver *s, bool fma_form, const double *r, const double *v, double *p, const HaloPush *hp) {
     VecArgs a = vec_args(s, PH_NONE);
     a.in0 = r; a.in1 = v; a.out0 = p;
+    if (hp) a.hp = *hp;
     if (fma_form) LAUNCH_VEC(k_update_p<true>, a); else LAUNCH_VEC(k_update_p<false>, a);
     return CUDAMAT_OK;
 }
-int launch_update_s(cudamat_solver *s, const double *r, const double *v, double *sv) {
+int launch_update_s(cudamat_solver *s, const double *r, const double *v, double *sv, const HaloPush *hp) {
     VecArgs a = vec_args(s, PH_NONE);
     a.in0 = r; a.in1 = v; a.out0 = sv;
+    if (hp) a.hp = *hp;
     LAUNCH_VEC(k_update_s, a);
     return CUDAMAT_OK;
 }
@@ -799,6 +813,32 @@ int launch_normalize_base(cudaStream_t st, int *ia, int64_t n1, int *ja, int64_t
     k_sub_base<<<1184, 256, 0, st>>>(ia, n1, base);
     k_sub_base<<<1184, 256, 0, st>>>(ja, nnz, base);
     CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
+// first offending row (row pointers not monotone) / entry (column outside [0, ncols)), or INT_MAX
+__global__ void k_validate_csr(const int *ia, int n, const int *ja, int64_t nnz, int64_t ncols, int *bad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = i; k < nnz; k += stride) {
+        const int c = ja[k];
+        if (c < 0 || c >= ncols) atomicMin(bad + 1, (int)k);
+    }
+    for (int64_t r = i; r < n; r += stride)
+        if (ia[r + 1] < ia[r]) atomicMin(bad + 0, (int)r);
+}
+int launch_validate_csr(cudaStream_t st, const int *ia, int n, const int *ja, int64_t nnz, int64_t ncols, int *h_bad) {
+    int *d_bad = nullptr;
+    CM_CUDA(cudaMalloc(&d_bad, 2 * sizeof(int)));
+    CM_CUDA(cudaMemsetAsync(d_bad, 0x7f, 2 * sizeof(int), st));
+    k_validate_csr<<<1184, 256, 0, st>>>(ia, n, ja, nnz, ncols, d_bad);
+    CM_CUDA(cudaGetLastError());
+    int h[2];
+    CM_CUDA(cudaMemcpyAsync(h, d_bad, sizeof h, cudaMemcpyDeviceToHost, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    CM_CUDA(cudaFree(d_bad));
+    h_bad[0] = h[0] == 0x7f7f7f7f ? -1 : h[0];
+    h_bad[1] = h[1] == 0x7f7f7f7f ? -1 : h[1];
     return CUDAMAT_OK;
 }
 

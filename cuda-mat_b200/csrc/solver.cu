@@ -55,7 +55,7 @@ static int alloc_reduction(cudamat_solver *s) {
     return CUDAMAT_OK;
 }
 
-static int ensure_work(cudamat_solver *s, int nvec) {
+int ensure_work(cudamat_solver *s, int nvec) {
     const size_t elems = (size_t)s->n + (size_t)s->nhalo;
     // keep each vector 256-byte aligned
     const size_t stride = ((elems + 31) / 32) * 32;
@@ -80,6 +80,7 @@ static SpmvArgs spmv_args(cudamat_solver *s, const double *x, const double *d, d
     SpmvArgs a{};
     a.n = s->n; a.ia = s->d_ia; a.ja = s->d_ja; a.val = s->d_a; a.x = x; a.d = d; a.y = y; a.u = u;
     a.ndot = ndot; a.phase = phase; a.rc = s->rc; a.sc = s->d_sc; a.hist = s->d_hist; a.check_status = check;
+    if (ndot > 0) comm_begin_reduction(s, a.rc);
     return a;
 }
 
@@ -102,10 +103,14 @@ static int timed_spmv(cudamat_solver *s, const SpmvArgs &a, int var) {
 }
 // SpMV step of the loop: halo exchange of the operand (multi-GPU), the kernel, then the cross-rank
 // part of its fused reductions
-static int spmv_step(cudamat_solver *s, double *x, const double *d, double *y, const double *u, int ndot, int phase, int check) {
-    int rc = comm_halo_exchange(s, x);
-    if (rc) return rc;
-    return timed_spmv(s, spmv_args(s, x, d, y, u, ndot, phase, check), s->spmv_variant);
+// (pushed_slot >= 0: the kernel that produced x has already stored its halo rows into the neighbours' copies over
+// NVLink — the SpMV's boundary CTAs wait for the neighbours' flags instead of an NCCL exchange)
+static int spmv_step(cudamat_solver *s, double *x, const double *d, double *y, const double *u, int ndot, int phase, int check,
+                     int pushed_slot = -1) {
+    SpmvArgs a = spmv_args(s, x, d, y, u, ndot, phase, check);
+    if (pushed_slot >= 0 && comm_p2p(s)) comm_halo_wait(s, pushed_slot, &a.hw);
+    else { int rc = comm_halo_exchange(s, x); if (rc) return rc; }
+    return timed_spmv(s, a, s->spmv_variant);
 }
 
 static int poll_status(cudamat_solver *s) {
@@ -189,10 +194,13 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
     int npoll = 0; bool stop = false;
     for (int it = 0; it < maxit;) {
         s->loop_it = it;
-        if ((rc = launch_update_p(s, false, r, v, p))) return rc;                                   // :668-672
-        if ((rc = spmv_step(s, p, d_d, v, r0, 1, PH_U_A, 1))) return rc;                 // :675-689
-        if ((rc = launch_update_s(s, r, v, sv))) return rc;                                         // :698-700
-        if ((rc = spmv_step(s, sv, d_d, t, sv, 2, PH_U_B, 1))) return rc;               // :703-710
+        HaloPush hp;
+        int slot = comm_halo_push(s, p, 0, &hp) ? 0 : -1;
+        if ((rc = launch_update_p(s, false, r, v, p, &hp))) return rc;                              // :668-672
+        if ((rc = spmv_step(s, p, d_d, v, r0, 1, PH_U_A, 1, slot))) return rc;           // :675-689
+        slot = comm_halo_push(s, sv, 1, &hp) ? 1 : -1;
+        if ((rc = launch_update_s(s, r, v, sv, &hp))) return rc;                                    // :698-700
+        if ((rc = spmv_step(s, sv, d_d, t, sv, 2, PH_U_B, 1, slot))) return rc;         // :703-710
         if ((rc = launch_update_xr(s, false, p, sv, t, r0, xk, r))) return rc;                      // :694-696,714-747
         if ((rc = comm_finish_reduction(s, PH_U_C, 2))) return rc;
         ++it;
@@ -354,10 +362,6 @@ int cudamat_set_csr_host(cudamat_solver *s, int nnz, const double *A, const int 
     const int base = iA[0];
     if (base != 0 && base != 1) { set_error("set_csr_host: index base %d is neither 0 nor 1 (pbicgstab.cu:201)", base); return CUDAMAT_E_INVALID; }
     if (iA[n] - base != nnz) { set_error("set_csr_host: iA[n]-iA[0]=%d != nnz=%d", iA[n] - base, nnz); return CUDAMAT_E_INVALID; }
-    for (int i = 0; i < n; ++i)
-        if (iA[i + 1] < iA[i]) { set_error("set_csr_host: row pointers not monotone at row %d", i); return CUDAMAT_E_INVALID; }
-    for (int k = 0; k < nnz; ++k)
-        if (jA[k] - base < 0 || jA[k] - base >= s->n_global) { set_error("set_csr_host: column index out of range at entry %d", k); return CUDAMAT_E_INVALID; }
     if (s->own_ia) { cudaFree(s->own_ia); cudaFree(s->own_ja); cudaFree(s->own_a); s->own_ia = nullptr; s->own_ja = nullptr; s->own_a = nullptr; }
     // +16 bytes of slack so aligned bulk copies of the last slab stay inside the allocation
     CM_CUDA(cudaMalloc(&s->own_ia, sizeof(int) * (size_t)(n + 1)));
@@ -370,7 +374,12 @@ int cudamat_set_csr_host(cudamat_solver *s, int nnz, const double *A, const int 
     }
     int rc = launch_normalize_base(s->stream, s->own_ia, n + 1, s->own_ja, nnz, base);
     if (rc) return rc;
-    CM_CUDA(cudaStreamSynchronize(s->stream));
+    // structure checks run on the device over the uploaded arrays (a host pass over nnz entries would cost as much
+    // as the upload itself): monotone row pointers, column indices inside [0, n_global)
+    int bad[2] = {-1, -1};
+    if ((rc = launch_validate_csr(s->stream, s->own_ia, n, s->own_ja, nnz, s->n_global, bad))) return rc;
+    if (bad[0] >= 0) { set_error("set_csr_host: row pointers not monotone at row %d", bad[0]); return CUDAMAT_E_INVALID; }
+    if (bad[1] >= 0) { set_error("set_csr_host: column index out of range at entry %d", bad[1]); return CUDAMAT_E_INVALID; }
     s->d_ia = s->own_ia; s->d_ja = s->own_ja; s->d_a = s->own_a; s->d_ja_global = s->own_ja;
     s->nnz = nnz; s->analyzed = false;
     return CUDAMAT_OK;

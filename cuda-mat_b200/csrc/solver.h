@@ -29,6 +29,7 @@ struct SpmvArgs {
     DevScalars *sc;        // may be nullptr when ndot == 0 and status is not checked
     double *hist;
     int check_status;      // 1: return immediately unless sc->status == ST_RUNNING
+    HaloWait hw;           // multi-GPU peer-memory path: wait for the neighbours' halo rows of x (nsrc == 0: none)
 };
 
 // staged (TMA bulk copy) SpMV plan
@@ -119,8 +120,8 @@ namespace cudamat {
 // kernels.cu
 int launch_spmv(cudamat_solver *s, const SpmvArgs &a, int variant);
 int launch_init_resid(cudamat_solver *s, const double *b, const double *y, double *r, double *c1, double *c2, int phase);
-int launch_update_p(cudamat_solver *s, bool fma_form, const double *r, const double *v, double *p);
-int launch_update_s(cudamat_solver *s, const double *r, const double *v, double *sv);
+int launch_update_p(cudamat_solver *s, bool fma_form, const double *r, const double *v, double *p, const HaloPush *hp = nullptr);
+int launch_update_s(cudamat_solver *s, const double *r, const double *v, double *sv, const HaloPush *hp = nullptr);
 int launch_update_rx_ilu(cudamat_solver *s, const double *v, const double *pw, double *r, double *x);
 int launch_update_xr(cudamat_solver *s, bool fma_form, const double *p, const double *sv, const double *t,
                      const double *rhat, double *x, double *r);
@@ -128,6 +129,7 @@ int launch_dot(cudamat_solver *s, const double *a, const double *b);
 int launch_fill(cudamat_solver *s, double *p, double v, int64_t cnt);
 int launch_row_stats(cudamat_solver *s, int *h_out /*[max_len, n_long, max_slab_nnz]*/, double *mean);
 int launch_normalize_base(cudaStream_t st, int *ia, int64_t n1, int *ja, int64_t nnz, int base);
+int launch_validate_csr(cudaStream_t st, const int *ia, int n, const int *ja, int64_t nnz, int64_t ncols, int *h_bad /*[row, entry] or -1*/);
 int plan_staged(cudamat_solver *s);
 bool pdl_enabled();
 
@@ -144,6 +146,11 @@ void ilu0_release(cudamat_solver *s);
 // comm.cu
 int comm_halo_exchange(cudamat_solver *s, double *vec);
 int comm_finish_reduction(cudamat_solver *s, int phase, int nq);
+bool comm_p2p(const cudamat_solver *s);                           // peer-memory path active
+void comm_begin_reduction(cudamat_solver *s, RedCtx &rc);          // stamps the next reduction epoch into rc (p2p)
+bool comm_halo_push(cudamat_solver *s, double *vec, int slot, HaloPush *hp);   // fills hp for the kernel that writes vec
+void comm_halo_wait(cudamat_solver *s, int slot, HaloWait *hw);    // fills hw for the SpMV that reads the pushed vector
+int ensure_work(cudamat_solver *s, int nvec);
 void comm_release(cudamat_solver *s);
 
 // generators (kernels.cu)

@@ -155,6 +155,10 @@ int cudamat_halo_plan_host(int64_t row0, int64_t row1, int64_t nnz, const int *j
 #define CUDAMAT_UNIQUE_ID_BYTES 128
 int cudamat_comm_unique_id(void *id128);
 int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world);
+/* 1 when the handle uses the peer-memory path (CUDA IPC over NVLink: halo rows stored into the neighbours' vectors
+ * by the producing kernels, partial sums gathered by the reducing kernels — no NCCL call inside the iteration),
+ * 0 when it uses ncclSend/Recv + ncclAllReduce (CUDAMAT_NO_P2P=1, IPC unavailable, non-contiguous halo sends). */
+int cudamat_comm_p2p_enabled(cudamat_solver *s);
 
 /* ---- device-side synthetic inputs ------------------------------- */
 /* rows [row0,row1) of the N^3 7-point Dirichlet Poisson matrix, base-0, global column ids.

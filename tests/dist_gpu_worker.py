@@ -34,6 +34,7 @@ def main():
             uid = torch.tensor(list(cm.Comm.unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         cm.Comm.init(s, bytes(uid.cpu().tolist()), rank, world)
+        p2p = cm.Comm.p2p_enabled(s)
         s.analyze(cm.MODE_PLAIN)
         xt = torch.empty(nloc, **f64)
         cm.gen_xtrue_device(1234, row0, nloc, xt.data_ptr())
@@ -72,8 +73,8 @@ def main():
             torch.cuda.synchronize()
             ok = (torch.equal(bg, b1) and torch.equal(xg, x1) and st["iterations"] == st1["iterations"]
                   and bool(st["converged"]) and dt == d1)
-            print("DIST N=%d world=%d iters=%d/%d b_equal=%s x_equal=%s dot_equal=%s loop_ms=%.2f/%.2f %s"
-                  % (N, world, st["iterations"], st1["iterations"], torch.equal(bg, b1), torch.equal(xg, x1), dt == d1,
+            print("DIST N=%d world=%d p2p=%d iters=%d/%d b_equal=%s x_equal=%s dot_equal=%s loop_ms=%.2f/%.2f %s"
+                  % (N, world, int(p2p), st["iterations"], st1["iterations"], torch.equal(bg, b1), torch.equal(xg, x1), dt == d1,
                      st["t_loop"] * 1e3, st1["t_loop"] * 1e3, "OK" if ok else "MISMATCH"), flush=True)
             s1.close()
         dist.barrier()
