@@ -318,11 +318,67 @@ def run_ours(args):
     elif world > 1 and not args.no_extras:
         line["e2e"] = multi_gpu_e2e(cm, torch, dist, N, n, row0, row1, nnz_loc, ia, ja, a, b, rank, world, stream, barrier)
     s.close()
+    # ---- BASELINE config 5: the 512^3 system (134 M rows) on the same ranks, short timed region ----
+    del ia, ja, a
+    torch.cuda.empty_cache()
+    if not args.no_512 and N != 512:
+        try:
+            line["poisson512"] = big_grid_run(cm, torch, dist, 512, world, rank, stream, barrier, steps=200)
+        except Exception as e:      # noqa: BLE001
+            line["poisson512"] = {"error": str(e)}
+
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def big_grid_run(cm, torch, dist, N, world, rank, stream, barrier, steps=200):
+    """iterations/s of the unpreconditioned loop on Poisson N^3 row-sharded over the ranks of this run (config 5 of
+    BASELINE.json: 512^3 on 1/2/4/8 GPUs; it fits one B200).  CUDA events, max over ranks."""
+    n = N ** 3
+    row0, row1 = cm.partition_rows(n, world, rank)
+    nloc = row1 - row0
+    nnz_loc = cm.poisson3d_nnz(N, row0, row1)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    ia = torch.empty(nloc + 1, dtype=torch.int32, device="cuda")
+    ja = torch.empty(nnz_loc, dtype=torch.int32, device="cuda")
+    a = torch.empty(nnz_loc, **f64)
+    cm.gen_poisson3d_device(N, row0, row1, ia.data_ptr(), ja.data_ptr(), a.data_ptr(), stream)
+    s = cm.Solver(n, row0, row1, stream=stream)
+    s.set_csr_device(nnz_loc, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idbuf = torch.tensor(list(cm.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idbuf, 0)
+        cm.Comm.init(s, bytes(idbuf.cpu().tolist()), rank, world)
+    sa = s.analyze(cm.MODE_PLAIN)
+    xt = torch.empty(nloc, **f64)
+    cm.gen_xtrue_device(1234, row0, nloc, xt.data_ptr(), stream)
+    b = torch.empty(nloc, **f64)
+    s.spmv(xt.data_ptr(), b.data_ptr())
+    x = torch.zeros(nloc, **f64)
+    s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=5, tol=0.0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    st = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=steps, tol=0.0)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    nnz = cm.poisson3d_nnz(N)
+    s.close()
+    del ia, ja, a, xt, b, x
+    torch.cuda.empty_cache()
+    return {"workload": "poisson3d_%d" % N, "n": n, "nnz": nnz, "steps": st["iterations"], "ms_per_step": ms / max(st["iterations"], 1),
+            "iters_per_s": st["iterations"] / (ms * 1e-3), "spmv_variant": sa["spmv_variant"],
+            "iteration_csr_GBps_per_gpu": bytes_iter(n, nnz) / world * st["iterations"] / (ms * 1e-3) / 1e9,
+            "note": "strong scaling of the SAME 512^3 system over the ranks of this run; includes the 1 SpMV residual set-up of the restart"}
 
 
 def multi_gpu_e2e(cm, torch, dist, N, n, row0, row1, nnz_loc, ia, ja, a, b, rank, world, stream, barrier):
@@ -447,6 +503,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="force an SpMV variant (1 rowlane, 2 staged)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-ilu0", action="store_true", help="skip the ILU0 extra")
+    ap.add_argument("--no-512", action="store_true", help="skip the 512^3 extra (BASELINE config 5)")
     ap.add_argument("--no-csr", action="store_true", help="skip the second timed region with the plain CSR SpMV kernel")
     ap.add_argument("--no-converge", action="store_true", help="skip the full solve to 1e-10 (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / ilu0 / mat10000 / cpu extras (profiling runs)")

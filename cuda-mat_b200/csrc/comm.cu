@@ -102,6 +102,23 @@ __global__ void k_remap_cols(int64_t nnz, const int *ja_global, int *ja_local, i
         ja_local[k] = n + lo;
     }
 }
+// out-of-shard column ids: warp-aggregated append (out == nullptr: count only)
+__global__ void k_collect_halo(int64_t nnz, const int *ja_global, int64_t row0, int64_t row1, int *out, unsigned long long *cnt) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (int64_t k0 = k - lane; k0 < nnz; k0 += stride) {             // warp-uniform trip count
+        const int64_t kk = k0 + lane;
+        const int c = kk < nnz ? ja_global[kk] : 0;
+        const bool outside = kk < nnz && (c < row0 || c >= row1);
+        const unsigned m = __ballot_sync(0xffffffffu, outside);
+        if (!m) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cnt, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (outside && out) out[base + __popc(m & ((1u << lane) - 1u))] = c;
+    }
+}
 __global__ void k_pack(const double *vec, const int *idx, double *out, int cnt) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < cnt) out[k] = vec[idx[k]];
@@ -273,6 +290,9 @@ static int p2p_setup(cudamat_solver *s, const std::vector<int> &W) {
     Xchg mine{}; memset(&mine, 0, sizeof mine);
     const size_t gbytes = sizeof(double) * (size_t)c->exch_count;
     const size_t abytes = 4096 + 2 * ((gbytes + 255) / 256) * 256;
+    if (s->work && s->work_pooled) {                  // an arena from the memory pool cannot be shared over IPC
+        cudaStreamSynchronize(s->stream); dev_free(s->work); s->work = nullptr; s->work_nvec = 0;
+    }
     if (ok && ensure_work(s, 9) != CUDAMAT_OK) ok = 0;
     if (ok && cudaMalloc(&P.arena, abytes) != cudaSuccess) { ok = 0; P.arena = nullptr; }
     if (ok) {
@@ -457,13 +477,29 @@ int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world)
     }
     c->row_starts[world] = rng[2 * world - 1];
     if (c->row_starts[0] != 0 || c->row_starts[world] != s->n_global) { set_error("comm_init: shards do not cover [0,n)"); return CUDAMAT_E_INVALID; }
-    // 2. halo columns of this shard (host pass over the global column ids)
-    std::vector<int> ja((size_t)s->nnz);
-    CM_CUDA(cudaMemcpyAsync(ja.data(), s->d_ja_global, sizeof(int) * (size_t)s->nnz, cudaMemcpyDeviceToHost, s->stream));
+    // 2. halo columns of this shard: the out-of-range column ids are collected on the device (two passes: count,
+    //    append), only that short list travels to the host where cudamat_halo_plan_host sorts / uniquifies it
+    unsigned long long *d_cntx = nullptr;
+    CM_CUDA(cudaMalloc(&d_cntx, sizeof(unsigned long long)));
+    CM_CUDA(cudaMemsetAsync(d_cntx, 0, sizeof(unsigned long long), s->stream));
+    if (s->nnz > 0) k_collect_halo<<<1184, 256, 0, s->stream>>>(s->nnz, s->d_ja_global, s->row0, s->row1, nullptr, d_cntx);
+    unsigned long long nout = 0;
+    CM_CUDA(cudaMemcpyAsync(&nout, d_cntx, sizeof nout, cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<int> ja((size_t)nout);
+    if (nout > 0) {
+        int *d_out = nullptr;
+        CM_CUDA(cudaMalloc(&d_out, sizeof(int) * (size_t)nout));
+        CM_CUDA(cudaMemsetAsync(d_cntx, 0, sizeof(unsigned long long), s->stream));
+        k_collect_halo<<<1184, 256, 0, s->stream>>>(s->nnz, s->d_ja_global, s->row0, s->row1, d_out, d_cntx);
+        CM_CUDA(cudaMemcpyAsync(ja.data(), d_out, sizeof(int) * (size_t)nout, cudaMemcpyDeviceToHost, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+        CM_CUDA(cudaFree(d_out));
+    }
+    CM_CUDA(cudaFree(d_cntx));
     int nhalo = 0; int *halo_raw = nullptr;
     c->recv_cnt.assign(world, 0); c->recv_off.assign(world, 0);
-    int prc = cudamat_halo_plan_host(s->row0, s->row1, s->nnz, ja.data(), world, c->row_starts.data(), &nhalo, &halo_raw, c->recv_cnt.data());
+    int prc = cudamat_halo_plan_host(s->row0, s->row1, (int64_t)nout, ja.data(), world, c->row_starts.data(), &nhalo, &halo_raw, c->recv_cnt.data());
     if (prc) return prc;
     std::vector<int> halo(halo_raw, halo_raw + nhalo);
     free(halo_raw);

@@ -109,7 +109,7 @@ __global__ void k_cls_assign(int n, const int *ia, const int *ja, const double *
 
 void rowclass_release(cudamat_solver *s) {
     for (int m = 0; m < 2; ++m) {
-        if (s->cls[m].d_cls) cudaFree(s->cls[m].d_cls);
+        dev_free(s->cls[m].d_cls);
         if (s->cls[m].d_dict) cudaFree(s->cls[m].d_dict);
         s->cls[m] = RowClasses();
     }
@@ -129,7 +129,7 @@ int rowclass_analyze(cudamat_solver *s) {
     for (int m = 1; m >= 0 && rc == CUDAMAT_OK; --m) {          // m = 1: with values, m = 0: offsets only
         RowClasses &C = s->cls[m];
         cudaError_t e;
-        if ((e = cudaMalloc(&C.d_cls, (size_t)n + 16)) != cudaSuccess || (e = cudaMalloc(&C.d_dict, sizeof(RowDict))) != cudaSuccess) {
+        if ((e = dev_alloc((void **)&C.d_cls, (size_t)n + 16)) != cudaSuccess || (e = cudaMalloc(&C.d_dict, sizeof(RowDict))) != cudaSuccess) {
             cuda_ok(e, "cudaMalloc(row classes)", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
         }
         cudaMemsetAsync(tab, 0, sizeof(unsigned long long) * kTab, s->stream);
@@ -146,7 +146,7 @@ int rowclass_analyze(cudamat_solver *s) {
             cuda_ok(e, "row class analysis", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
         }
         if (h[0] == 0 && h[1] > 0) C.ncls = h[1];
-        else { cudaFree(C.d_cls); cudaFree(C.d_dict); C = RowClasses(); }
+        else { dev_free(C.d_cls); cudaFree(C.d_dict); C = RowClasses(); }
     }
     cudaFree(tab); cudaFree(rep); cudaFree(slot_id); cudaFree(flags);
     return rc;

@@ -30,6 +30,43 @@ static double now_s() {
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+// Large buffers of the one-shot host entry points come from a stream-ordered memory pool that keeps freed memory
+// mapped: cudaFree of the 2.5 GB a 256^3 solve holds costs ~0.4 s of page unmapping, more than the solve itself.
+// (IPC-shared buffers of the multi-GPU path cannot live in the default pool and stay with cudaMalloc.)
+static cudaStream_t g_pool_stream = nullptr;
+static bool pool_ready() {
+    static int state = 0;                       // 0 untried, 1 ok, -1 unavailable
+    if (state == 0) {
+        state = -1;
+        const char *off = getenv("CUDAMAT_NO_POOL");
+        int dev = 0, supported = 0;
+        if (!(off && *off && *off != '0') && cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && supported) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&g_pool_stream, cudaStreamNonBlocking) == cudaSuccess) {
+                const char *mb = getenv("CUDAMAT_POOL_KEEP_MB");
+                unsigned long long keep = (mb ? strtoull(mb, nullptr, 10) : 8192ull) << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                state = 1;
+            }
+        }
+        cudaGetLastError();
+    }
+    return state == 1;
+}
+cudaError_t dev_alloc(void **p, size_t bytes) {
+    if (!pool_ready()) return cudaMalloc(p, bytes);
+    cudaError_t e = cudaMallocAsync(p, bytes, g_pool_stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(g_pool_stream);    // usable from any stream on return
+}
+void dev_free(void *p) {                            // no work may still use p (callers synchronise their stream first)
+    if (!p) return;
+    if (!pool_ready()) { cudaFree(p); return; }
+    cudaFreeAsync(p, g_pool_stream);
+}
+
 static int alloc_reduction(cudamat_solver *s) {
     RedCtx &rc = s->rc;
     rc.ntile = (s->n + kTile - 1) / kTile;
@@ -60,8 +97,10 @@ int ensure_work(cudamat_solver *s, int nvec) {
     // keep each vector 256-byte aligned
     const size_t stride = ((elems + 31) / 32) * 32;
     if (s->work && s->work_nvec >= nvec && s->work_elems == stride) return CUDAMAT_OK;
-    if (s->work) { cudaFree(s->work); s->work = nullptr; }
-    CM_CUDA(cudaMalloc(&s->work, sizeof(double) * std::max<size_t>(stride * nvec, 32)));
+    if (s->work) { cudaStreamSynchronize(s->stream); if (s->work_pooled) dev_free(s->work); else cudaFree(s->work); s->work = nullptr; }
+    s->work_pooled = (s->comm == nullptr);          // sharded handles share the arena over CUDA IPC: plain cudaMalloc
+    if (s->work_pooled) CM_CUDA(dev_alloc((void **)&s->work, sizeof(double) * std::max<size_t>(stride * nvec, 32)));
+    else CM_CUDA(cudaMalloc(&s->work, sizeof(double) * std::max<size_t>(stride * nvec, 32)));
     s->work_elems = stride; s->work_nvec = nvec;
     return CUDAMAT_OK;
 }
@@ -325,9 +364,7 @@ int cudamat_destroy(cudamat_solver *s) {
     comm_release(s);
     ilu0_release(s);
     rowclass_release(s);
-    if (s->own_ia) cudaFree(s->own_ia);
-    if (s->own_ja) cudaFree(s->own_ja);
-    if (s->own_a) cudaFree(s->own_a);
+    dev_free(s->own_ia); dev_free(s->own_ja); dev_free(s->own_a);
     if (s->rc.tile_part) cudaFree(s->rc.tile_part);
     if (s->slots_own) cudaFree(s->slots_own);
     if (s->rc.group_cnt) cudaFree(s->rc.group_cnt);
@@ -335,7 +372,7 @@ int cudamat_destroy(cudamat_solver *s) {
     if (s->d_sc) cudaFree(s->d_sc);
     if (s->h_sc) cudaFreeHost(s->h_sc);
     if (s->d_hist) cudaFree(s->d_hist);
-    if (s->work) cudaFree(s->work);
+    if (s->work) { if (s->work_pooled) dev_free(s->work); else cudaFree(s->work); }
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : s->poll_ev) if (e) cudaEventDestroy(e);
     delete s;
@@ -362,11 +399,11 @@ int cudamat_set_csr_host(cudamat_solver *s, int nnz, const double *A, const int 
     const int base = iA[0];
     if (base != 0 && base != 1) { set_error("set_csr_host: index base %d is neither 0 nor 1 (pbicgstab.cu:201)", base); return CUDAMAT_E_INVALID; }
     if (iA[n] - base != nnz) { set_error("set_csr_host: iA[n]-iA[0]=%d != nnz=%d", iA[n] - base, nnz); return CUDAMAT_E_INVALID; }
-    if (s->own_ia) { cudaFree(s->own_ia); cudaFree(s->own_ja); cudaFree(s->own_a); s->own_ia = nullptr; s->own_ja = nullptr; s->own_a = nullptr; }
+    if (s->own_ia) { cudaStreamSynchronize(s->stream); dev_free(s->own_ia); dev_free(s->own_ja); dev_free(s->own_a); s->own_ia = nullptr; s->own_ja = nullptr; s->own_a = nullptr; }
     // +16 bytes of slack so aligned bulk copies of the last slab stay inside the allocation
-    CM_CUDA(cudaMalloc(&s->own_ia, sizeof(int) * (size_t)(n + 1)));
-    CM_CUDA(cudaMalloc(&s->own_ja, sizeof(int) * (size_t)std::max(nnz, 1) + 16));
-    CM_CUDA(cudaMalloc(&s->own_a, sizeof(double) * (size_t)std::max(nnz, 1) + 16));
+    CM_CUDA(dev_alloc((void **)&s->own_ia, sizeof(int) * (size_t)(n + 1)));
+    CM_CUDA(dev_alloc((void **)&s->own_ja, sizeof(int) * (size_t)std::max(nnz, 1) + 16));
+    CM_CUDA(dev_alloc((void **)&s->own_a, sizeof(double) * (size_t)std::max(nnz, 1) + 16));
     CM_CUDA(cudaMemcpyAsync(s->own_ia, iA, sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, s->stream));
     if (nnz > 0) {
         CM_CUDA(cudaMemcpyAsync(s->own_ja, jA, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
@@ -525,16 +562,16 @@ int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *
     if (mode == CUDAMAT_MODE_SHIFTED && (!d || !x0)) { set_error("bicgstab_host: shifted mode needs d and x0"); return CUDAMAT_E_INVALID; }
     cudamat_stats st{};
     cudamat_solver *s = nullptr;
+    const bool tm = getenv("CUDAMAT_TIMING") != nullptr;      // stderr breakdown of the host entry point
+    const double tt0 = now_s();
     int rc = cudamat_create(&s, n, 0, n, nullptr);
     if (rc) return rc;
     s->opt_debug = debug;
     if (debug) printf("N=%d, nnz=%d\n", n, nnz);                                  // pbicgstab.cu:203
     double *d_b = nullptr, *d_x = nullptr, *d_x0 = nullptr, *d_d = nullptr;
     auto cleanup = [&]() {
-        if (d_b) cudaFree(d_b);
-        if (d_x) cudaFree(d_x);
-        if (d_x0) cudaFree(d_x0);
-        if (d_d) cudaFree(d_d);
+        cudaDeviceSynchronize();
+        dev_free(d_b); dev_free(d_x); dev_free(d_x0); dev_free(d_d);
         cudamat_destroy(s);
     };
 #define HOST_TRY(expr) do { rc = (expr); if (rc) { cleanup(); return rc; } } while (0)
@@ -542,19 +579,21 @@ int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *
     double t0 = now_s();
     HOST_TRY(cudamat_set_csr_host(s, nnz, A, iA, jA));
     const size_t nb = sizeof(double) * (size_t)std::max(n, 1);
-    HOST_CUDA(cudaMalloc(&d_b, nb));
-    HOST_CUDA(cudaMalloc(&d_x, nb));
+    HOST_CUDA(dev_alloc((void **)&d_b, nb));
+    HOST_CUDA(dev_alloc((void **)&d_x, nb));
     HOST_CUDA(cudaMemcpy(d_b, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
     if (mode == CUDAMAT_MODE_SHIFTED || (mode == CUDAMAT_MODE_PLAIN && x0)) {
-        HOST_CUDA(cudaMalloc(&d_x0, nb));
+        HOST_CUDA(dev_alloc((void **)&d_x0, nb));
         HOST_CUDA(cudaMemcpy(d_x0, x0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
     }
     if (mode != CUDAMAT_MODE_ILU0 && d) {
-        HOST_CUDA(cudaMalloc(&d_d, nb));
+        HOST_CUDA(dev_alloc((void **)&d_d, nb));
         HOST_CUDA(cudaMemcpy(d_d, d, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
     }
     st.t_h2d = now_s() - t0;
+    const double tt1 = now_s();
     HOST_TRY(cudamat_analyze(s, mode, &st));
+    const double tt2 = now_s();
     if (debug && mode == CUDAMAT_MODE_ILU0) {
         printf("analysis lower+upper %f (s), levels %d / %d\n", st.t_analysis, st.levels_l, st.levels_u);   // cf. pbicgstab.cu:349
         printf("ILU0 factorisation time(s) = %10.8f \n", st.t_ilu0);                                         // cf. :354-363
@@ -566,7 +605,10 @@ int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *
     st.kernel_launches = s->launches;
     if (dtAlg) *dtAlg = st.t_loop;
     if (st_out) *st_out = st;
+    const double tt3 = now_s();
     cleanup();
+    if (tm) fprintf(stderr, "cudamat_bicgstab_host: create+upload %.4f s, analyze %.4f s, solve+download %.4f s, cleanup %.4f s\n",
+                    tt1 - tt0, tt2 - tt1, tt3 - tt2, now_s() - tt3);
 #undef HOST_TRY
 #undef HOST_CUDA
     return CUDAMAT_OK;

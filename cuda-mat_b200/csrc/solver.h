@@ -8,6 +8,8 @@
 namespace cudamat {
 
 void set_error(const char *fmt, ...);
+cudaError_t dev_alloc(void **p, size_t bytes);     // solver.cu: pooled allocation for large buffers
+void dev_free(void *p);
 bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
 #define CM_CUDA(call)                                                       \
     do {                                                                    \
@@ -99,7 +101,7 @@ struct cudamat_solver {
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     double *d_hist = nullptr; int hist_cap = 0;
     // work vectors (n + nhalo each)
-    double *work = nullptr; size_t work_elems = 0; int work_nvec = 0;
+    double *work = nullptr; size_t work_elems = 0; int work_nvec = 0; bool work_pooled = false;
     // ILU0
     double *d_M = nullptr; int *d_diag = nullptr;
     cudamat::LevelSchedule lvl_l, lvl_u;
