@@ -124,48 +124,6 @@ __global__ void k_pack(const double *vec, const int *idx, double *out, int cnt) 
     if (k < cnt) out[k] = vec[idx[k]];
 }
 
-// finish a reduction after the cross-rank exchange: (level 1) tiles -> groups -> final, (level 2) groups -> final
-__global__ void __launch_bounds__(kCtaThreads) k_finalize(const double *exch, int level, int count, int stride, int nq,
-                                                          DevScalars *sc, double *hist, int phase,
-                                                          const unsigned long long *flags, int world, unsigned long long epoch) {
-    pdl_sync();
-    if (sc->status != ST_RUNNING && phase != PH_STORE) return;
-    if (flags) {                                   // peer-memory path: every rank's partial sums must have arrived
-        if ((int)threadIdx.x < world) {
-            unsigned spins = 0;
-            while (ld_acquire_sys_u64(flags + threadIdx.x) < epoch)
-                if (++spins > (1u << 26)) __trap();
-        }
-        __syncthreads();
-    }
-    __shared__ double s_grp[kMaxQ][64];
-    __shared__ double s_red[kMaxQ];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int nfinal = count;
-    if (level == 1) {
-        const int ngroups = (count + kGroupTiles - 1) / kGroupTiles;     // <= 64 (checked on the host)
-        for (int w = warp; w < nq * ngroups; w += kCtaWarps) {
-            const int q = w / ngroups, g = w % ngroups;
-            const double v = warp_reduce_values_cg(exch + (size_t)q * stride + (size_t)g * kGroupTiles,
-                                                   min(kGroupTiles, count - g * kGroupTiles), lane);
-            if (lane == 0) s_grp[q][g] = v;
-        }
-        __syncthreads();
-        nfinal = ngroups;
-    }
-    if (warp < nq) {
-        const double f = (level == 1) ? warp_reduce_values_smem(s_grp[warp], nfinal, lane)
-                                      : warp_reduce_values_cg(exch + (size_t)warp * stride, nfinal, lane);
-        if (lane == 0) s_red[warp] = f;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double red[kMaxQ] = {0.0, 0.0};
-        for (int q = 0; q < nq; ++q) red[q] = s_red[q];
-        apply_phase(sc, hist, phase, red);
-    }
-}
-
 // ---- hooks used by solver.cu ---------------------------------------------------------------------
 int comm_halo_exchange(cudamat_solver *s, double *vec) {
     Comm *c = s->comm;
@@ -192,31 +150,18 @@ int comm_halo_exchange(cudamat_solver *s, double *vec) {
     return CUDAMAT_OK;
 }
 
-int comm_finish_reduction(cudamat_solver *s, int phase, int nq) {
+// Every reducing kernel is followed by this: groups, cross-rank exchange (if sharded), final sum, recurrence.
+// `rc` is the reduction context the reducing kernel was launched with (it carries the p2p epoch).
+int finish_reduction(cudamat_solver *s, const RedCtx &rc, int phase, int nq) {
     Comm *c = s->comm;
-    if (!c || c->world == 1) return CUDAMAT_OK;
-    const int stride = c->exch_count / kMaxQ;
-    const int count = c->exch_level == 1 ? c->ntile_global : s->rc.nslots;
-    if (c->p2p.on) {
-        // the reducing kernel's last CTA has pushed this rank's partial sums to every rank (reduce_tail/p2p_push);
-        // one small kernel waits for all arrivals and finishes the fixed-order tree — no NCCL call in the loop
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(1); cfg.blockDim = dim3(kCtaThreads); cfg.stream = s->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-        const unsigned long long ep = c->p2p.red_epoch;
-        CM_CUDA(cudaLaunchKernelEx(&cfg, k_finalize, (const double *)c->p2p.gather[ep & 1], c->exch_level, count, stride, nq, s->d_sc, s->d_hist,
-                                   phase, (const unsigned long long *)c->p2p.flags, c->world, ep));
-    } else {
-        CM_NCCL(g_nccl.AllReduce(c->d_exch_local, c->d_exch_glob, (size_t)c->exch_count, ncclDouble, ncclSum, c->comm, s->stream));
-        k_finalize<<<1, kCtaThreads, 0, s->stream>>>(c->d_exch_glob, c->exch_level, count, stride, nq, s->d_sc, s->d_hist, phase,
-                                                     nullptr, 0, 0ull);
-    }
-    s->launches++;
-    CM_CUDA(cudaGetLastError());
-    return CUDAMAT_OK;
+    if (s->n == 0 && (!c || c->world == 1)) return CUDAMAT_OK;
+    if (!c || c->world == 1 || c->p2p.on)
+        return launch_reduce_finish(s, rc, nq, phase, 0, nullptr, c ? c->p2p.flags : nullptr);
+    // NCCL path: local groups -> allreduce of the zero-padded partials -> final
+    int r;
+    if (c->exch_level == 2 && (r = launch_reduce_finish(s, rc, nq, phase, 1, nullptr, nullptr))) return r;
+    CM_NCCL(g_nccl.AllReduce(c->d_exch_local, c->d_exch_glob, (size_t)c->exch_count, ncclDouble, ncclSum, c->comm, s->stream));
+    return launch_reduce_finish(s, rc, nq, phase, 2, c->d_exch_glob, nullptr);
 }
 
 bool comm_p2p(const cudamat_solver *s) { return s->comm && s->comm->world > 1 && s->comm->p2p.on; }
@@ -363,6 +308,7 @@ static int p2p_setup(cudamat_solver *s, const std::vector<int> &W) {
     CM_CUDA(cudaStreamSynchronize(s->stream));
     RedCtx &rcx = s->rc;
     rcx.p2p.world = world;
+    rcx.p2p.me = rank;
     rcx.p2p.peers = P.d_peers;
     rcx.p2p.stride = c->exch_count / kMaxQ;
     if (c->exch_level == 2) { rcx.p2p.my_off = rcx.group0; rcx.p2p.my_cnt = rcx.ngroup_loc; }
@@ -570,7 +516,6 @@ int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world)
     CM_CUDA(cudaMalloc(&c->d_exch_glob, sizeof(double) * (size_t)c->exch_count));
     CM_CUDA(cudaMemsetAsync(c->d_exch_local, 0, sizeof(double) * (size_t)c->exch_count, s->stream));
     CM_CUDA(cudaMemsetAsync(c->d_exch_glob, 0, sizeof(double) * (size_t)c->exch_count, s->stream));
-    rcx.do_final = 0;
     rcx.exch_level = c->exch_level;
     rcx.tile0 = (int)(s->row0 / kTile);
     if (c->exch_level == 2) {

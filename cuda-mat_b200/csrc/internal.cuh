@@ -65,7 +65,7 @@ struct PeerRed {                   // where rank r keeps the partial sums gather
     unsigned long long *flag;      // r's arrival flag of THIS rank's contribution (value = epoch)
 };
 struct P2PRed {                    // part of RedCtx; world == 0: disabled
-    int world, my_off, my_cnt, stride;
+    int world, me, my_off, my_cnt, stride;
     const PeerRed *peers;          // device array [world]
     unsigned long long epoch;      // of the reduction this kernel feeds; parity = epoch & 1
 };
@@ -92,15 +92,13 @@ struct HaloWait {
 struct RedCtx {
     double   *tile_part;   // [kMaxQ][tile_stride]  tile partials, indexed by LOCAL tile
     double   *slots;       // [kMaxQ][slot_stride]  group partials, indexed by GLOBAL group
-    unsigned *group_cnt;   // [local groups]
-    unsigned *done_cnt;    // [1]
     int ntile;             // local tiles
     int tile_stride;
     int slot_stride;
     int ngroup_loc;        // local groups
     int group0;            // global index of the first local group
     int nslots;            // global number of groups
-    int do_final;          // 1: last CTA reduces slots and runs the phase (single shard)
+    int ntile_global;      // global number of tiles (exch_level 1)
     // multi-GPU: where this shard deposits its contribution for the zero-padded allreduce
     int exch_level;        // 0 none; 1 tile partials (global tile index); 2 group partials (== slots)
     int tile0;             // global index of the first local tile
@@ -259,16 +257,14 @@ __device__ __forceinline__ void apply_phase(DevScalars *sc, double *hist, int ph
     }
 }
 
-// last CTA of a reducing kernel on a sharded handle: copy this rank's partial sums (its tiles or groups) into
-// every rank's gather array over NVLink, then raise this rank's arrival flag there
-template <int NQ>
-__device__ __forceinline__ void p2p_push(const RedCtx &rc, const double *local) {
+// Finishing kernel, sharded handle: copy this rank's partial sums (its tiles or groups) into every rank's gather
+// array over NVLink, then raise this rank's arrival flag there (all threads of the CTA call)
+__device__ __forceinline__ void p2p_push(const RedCtx &rc, const double *local, int nq) {
     const P2PRed &pp = rc.p2p;
-    __threadfence();
     const int par = (int)(pp.epoch & 1ull);
     for (int r = 0; r < pp.world; ++r) {
         double *dst = pp.peers[r].gather[par];
-        for (int q = 0; q < NQ; ++q)
+        for (int q = 0; q < nq; ++q)
             for (int i = threadIdx.x; i < pp.my_cnt; i += blockDim.x)
                 dst[(size_t)q * pp.stride + pp.my_off + i] = __ldcg(local + (size_t)q * pp.stride + pp.my_off + i);
     }
@@ -279,75 +275,23 @@ __device__ __forceinline__ void p2p_push(const RedCtx &rc, const double *local) 
     }
 }
 
-// Grid-level tail of a reducing kernel. Contract: gridDim.x == rc.ntile, CTA b owns local tile b,
-// s_slab[q][0..63] hold the tile's slab sums (all warps done, __syncthreads() issued by caller).
+// Tail of a reducing kernel. Contract: CTA `tile` owns local tile `tile`, s_slab[q][0..63] hold the tile's slab
+// sums (all warps done, __syncthreads() issued by caller).  The CTA only forms its TILE partial R(slab sums) and
+// stores it; groups, the final sum and the scalar recurrence are done by k_reduce_finish, launched right behind
+// (programmatic dependent launch).  No fence and no atomic here: a gpu-scope fence in each of the 8192 CTAs
+// invalidates the SM's L1 (CCTL.IVALL) under the co-resident CTAs' x gathers — measured +45 % SpMV time.
 template <int NQ>
 __device__ __forceinline__ void reduce_tail(const RedCtx &rc, DevScalars *sc, double *hist, int phase,
                                             double (*s_slab)[kTileSlabs], int nslab_tile, int tile = -1) {
-    __shared__ int s_flag;
-    __shared__ double s_red[kMaxQ];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (tile < 0) tile = blockIdx.x;
-    // tile partial: R() over the slab sums
+    (void)sc; (void)hist; (void)phase;
     if (warp < NQ) {
-        double tp = warp_reduce_values_smem(s_slab[warp], nslab_tile, lane);
+        const double tp = warp_reduce_values_smem(s_slab[warp], nslab_tile, lane);
         if (lane == 0) {
-            if (rc.exch_level == 1) rc.exch[(size_t)warp * rc.exch_stride + rc.tile0 + tile] = tp;
+            if (rc.exch_level == 1) __stcg(rc.exch + (size_t)warp * rc.exch_stride + rc.tile0 + tile, tp);
             __stcg(rc.tile_part + (size_t)warp * rc.tile_stride + tile, tp);
-            __threadfence();
         }
-    }
-    if (rc.exch_level == 1) {            // groups and final are formed after the cross-rank exchange
-        if (rc.p2p.world == 0) return;
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned old = atomicAdd(rc.done_cnt, 1u);
-            s_flag = (old == (unsigned)(rc.ntile - 1));
-            if (s_flag) *rc.done_cnt = 0u;
-        }
-        __syncthreads();
-        if (s_flag) p2p_push<NQ>(rc, rc.exch);
-        return;
-    }
-    __syncthreads();
-    const int g = tile / kGroupTiles;
-    if (tid == 0) {
-        int in_group = min(kGroupTiles, rc.ntile - g * kGroupTiles);
-        unsigned old = atomicAdd(rc.group_cnt + g, 1u);
-        s_flag = (old == (unsigned)(in_group - 1));
-    }
-    __syncthreads();
-    if (!s_flag) return;
-    __threadfence();
-    if (warp < NQ) {
-        int in_group = min(kGroupTiles, rc.ntile - g * kGroupTiles);
-        double gp = warp_reduce_values_cg(rc.tile_part + (size_t)warp * rc.tile_stride + (size_t)g * kGroupTiles,
-                                          in_group, lane);
-        if (lane == 0) {
-            __stcg(rc.slots + (size_t)warp * rc.slot_stride + rc.group0 + g, gp);
-            __threadfence();
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        rc.group_cnt[g] = 0u;
-        unsigned old = atomicAdd(rc.done_cnt, 1u);
-        s_flag = (old == (unsigned)(rc.ngroup_loc - 1));
-        if (s_flag) *rc.done_cnt = 0u;
-    }
-    __syncthreads();
-    if (s_flag && rc.p2p.world > 0) { p2p_push<NQ>(rc, rc.slots); return; }
-    if (!s_flag || !rc.do_final) return;
-    __threadfence();
-    if (warp < NQ) {
-        double f = warp_reduce_values_cg(rc.slots + (size_t)warp * rc.slot_stride, rc.nslots, lane);
-        if (lane == 0) s_red[warp] = f;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double red[kMaxQ] = {0.0, 0.0};
-        for (int q = 0; q < NQ; ++q) red[q] = s_red[q];
-        apply_phase(sc, hist, phase, red);
     }
 }
 

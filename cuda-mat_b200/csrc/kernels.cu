@@ -135,6 +135,54 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowl
 // share a class are perfectly coalesced.  Entry order = storage order: bit-identical to the CSR kernels.
 // PATTERN finds the row's first value at ia[first row of the slab] + exclusive scan of the class lengths.
 // ------------------------------------------------------------------------------------------
+// rows of a slab with mixed classes (domain boundaries, ragged last slab): per-lane lengths and offsets
+template <bool CLS_VALS>
+__device__ __noinline__ double class_row_general(const double *x, const double *val, const int *ia, int cid, int row0, int row,
+                                                 bool active, int lane, const int *s_len, const int *s_off, const double *s_val) {
+    const int len = active ? s_len[cid] : 0;
+    const int *off = s_off + cid * kDictLen;
+    const double *dv = s_val + (CLS_VALS ? cid * kDictLen : 0);
+    int start = 0;
+    if (!CLS_VALS) {
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        start = __ldg(ia + row0) + incl - len;
+    }
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    double sum = 0.0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < maxlen; k0 += 4) {
+        double av[4], xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool p = (k0 + q) < len;
+            xv[q] = p ? __ldg(x + row + off[k0 + q]) : 0.0;
+            if (CLS_VALS) av[q] = p ? dv[k0 + q] : 0.0;
+            else av[q] = p ? __ldg(val + start + k0 + q) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if ((k0 + q) < len) sum = __fma_rn(av[q], xv[q], sum);
+    }
+    return sum;
+}
+// a slab whose 32 rows share one class of LEN entries (the interior of a stencil): offsets and values are
+// warp-uniform shared-memory broadcasts, no predication, LEN coalesced gathers in flight per lane
+template <int LEN, bool CLS_VALS>
+__device__ __forceinline__ double class_row_uniform(const double *xrow, const double *vrow, const int *off, const double *dv) {
+    double xv[LEN], av[CLS_VALS ? 1 : LEN];
+#pragma unroll
+    for (int q = 0; q < LEN; ++q) {
+        xv[q] = __ldg(xrow + off[q]);
+        if (!CLS_VALS) av[q] = __ldg(vrow + q);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < LEN; ++q) sum = __fma_rn(CLS_VALS ? dv[q] : av[q], xv[q], sum);
+    return sum;
+}
+
 #ifndef CUDAMAT_CLASS_MINB
 #define CUDAMAT_CLASS_MINB 4
 #endif
@@ -158,7 +206,7 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_CLASS_MINB) k_spmv_class(
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + (j * kCtaWarps + warp) * kSlab + lane;
-        cid[j] = (row < a.n) ? (int)__ldg(c.cls + row) : -1;
+        cid[j] = (row < a.n) ? (int)__ldg(c.cls + row) : 0xff;
     }
     __syncthreads();
     pdl_sync();
@@ -172,32 +220,19 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_CLASS_MINB) k_spmv_class(
         if (row0 >= a.n) continue;                                // warp-uniform
         const int row = row0 + lane;
         const bool active = row < a.n;
-        const int len = active ? s_len[cid[j]] : 0;
-        const int *off = s_off + max(cid[j], 0) * kDictLen;
-        const double *dv = s_val + (CLS_VALS ? max(cid[j], 0) * kDictLen : 0);
         double uval = 0.0;
         if (NDOT >= 1 && active) uval = __ldg(a.u + row);
-        int start = 0;
-        if (!CLS_VALS) {
-            int incl = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            start = __ldg(a.ia + row0) + incl - len;
-        }
-        const int maxlen = __reduce_max_sync(0xffffffffu, len);
-        double sum = 0.0;
-        for (int k0 = 0; k0 < maxlen; k0 += 8) {
-            double av[8], xv[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const bool p = (k0 + q) < len;
-                xv[q] = p ? __ldg(a.x + row + off[k0 + q]) : 0.0;
-                if (CLS_VALS) av[q] = p ? dv[k0 + q] : 0.0;
-                else av[q] = p ? __ldg(a.val + start + k0 + q) : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if ((k0 + q) < len) sum = __fma_rn(av[q], xv[q], sum);
+        double sum;
+        const int c0 = __shfl_sync(0xffffffffu, cid[j], 0);
+        const int len0 = (c0 != 0xff) ? s_len[c0] : 0;
+        if (__all_sync(0xffffffffu, cid[j] == c0) && (len0 == 7 || len0 == 5)) {
+            const int *off = s_off + c0 * kDictLen;
+            const double *dv = s_val + (CLS_VALS ? c0 * kDictLen : 0);
+            const double *vrow = CLS_VALS ? nullptr : a.val + (__ldg(a.ia + row0) + lane * len0);
+            if (len0 == 7) sum = class_row_uniform<7, CLS_VALS>(a.x + row, vrow, off, dv);
+            else           sum = class_row_uniform<5, CLS_VALS>(a.x + row, vrow, off, dv);
+        } else {
+            sum = class_row_general<CLS_VALS>(a.x, a.val, a.ia, active ? cid[j] : 0, row0, row, active, lane, s_len, s_off, s_val);
         }
         if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
         if (active) a.y[row] = sum;
@@ -694,6 +729,82 @@ __global__ void __launch_bounds__(kCtaThreads) k_dot(const VecArgs a) {
     reduce_tail<1>(a.rc, a.sc, a.hist, PH_STORE, s_slab, (rows_here + kSlab - 1) / kSlab);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_reduce_finish: one CTA, launched right behind every reducing kernel.  Spec tree (internal.cuh): tile partials
+// (written by the reducing kernel) -> group partials R(1024 tiles) -> result R(groups) -> scalar recurrence.
+//   stage 0: everything; on a sharded handle with the peer-memory path the group (or tile) partials of this rank
+//            are pushed to every rank and the kernel waits for all arrivals before the final sum;
+//   stage 1: local group partials only (NCCL path, before the allreduce);
+//   stage 2: final sum + recurrence from `glob` (NCCL path, after the allreduce).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtaThreads) k_reduce_finish(const RedCtx rc, int nq, DevScalars *sc, double *hist, int phase,
+                                                               int stage, const double *glob, const unsigned long long *flags) {
+    pdl_sync();
+    if (phase != PH_STORE && sc->status != ST_RUNNING) return;
+    __shared__ double s_grp[kMaxQ][64];
+    __shared__ double s_red[kMaxQ];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (stage != 2 && rc.exch_level != 1) {                    // local groups into the slots array (global group index)
+        for (int w = warp; w < nq * rc.ngroup_loc; w += kCtaWarps) {
+            const int q = w / rc.ngroup_loc, g = w % rc.ngroup_loc;
+            const int in_group = min(kGroupTiles, rc.ntile - g * kGroupTiles);
+            const double gp = warp_reduce_values_cg(rc.tile_part + (size_t)q * rc.tile_stride + (size_t)g * kGroupTiles, in_group, lane);
+            if (lane == 0) __stcg(rc.slots + (size_t)q * rc.slot_stride + rc.group0 + g, gp);
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+    if (stage == 1) return;
+    const double *src = (stage == 2) ? glob : (rc.exch_level == 1 ? rc.exch : rc.slots);
+    const int stride = (rc.exch_level == 1) ? rc.exch_stride : rc.slot_stride;
+    if (stage == 0 && rc.p2p.world > 0) {
+        p2p_push(rc, src, nq);
+        if ((int)threadIdx.x < rc.p2p.world) {                 // every rank's partial sums must have arrived
+            unsigned spins = 0;
+            while (ld_acquire_sys_u64(flags + threadIdx.x) < rc.p2p.epoch)
+                if (++spins > (1u << 26)) __trap();            // a lost rank must not hang the GPU
+        }
+        __syncthreads();
+        src = rc.p2p.peers[rc.p2p.me].gather[rc.p2p.epoch & 1ull];
+    }
+    int nfinal = rc.nslots;
+    if (rc.exch_level == 1) {                                  // unaligned shards: groups over the GLOBAL tile index
+        const int ngroups = (rc.ntile_global + kGroupTiles - 1) / kGroupTiles;     // <= 64 (checked on the host)
+        for (int w = warp; w < nq * ngroups; w += kCtaWarps) {
+            const int q = w / ngroups, g = w % ngroups;
+            const double v = warp_reduce_values_cg(src + (size_t)q * stride + (size_t)g * kGroupTiles,
+                                                   min(kGroupTiles, rc.ntile_global - g * kGroupTiles), lane);
+            if (lane == 0) s_grp[q][g] = v;
+        }
+        __syncthreads();
+        nfinal = ngroups;
+    }
+    if (warp < nq) {
+        const double f = (rc.exch_level == 1) ? warp_reduce_values_smem(s_grp[warp], nfinal, lane)
+                                              : warp_reduce_values_cg(src + (size_t)warp * stride, nfinal, lane);
+        if (lane == 0) s_red[warp] = f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double red[kMaxQ] = {0.0, 0.0};
+        for (int q = 0; q < nq; ++q) red[q] = s_red[q];
+        apply_phase(sc, hist, phase, red);
+    }
+}
+int launch_reduce_finish(cudamat_solver *s, const RedCtx &rc, int nq, int phase, int stage, const double *glob,
+                         const unsigned long long *flags) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(kCtaThreads); cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CM_CUDA(cudaLaunchKernelEx(&cfg, k_reduce_finish, rc, nq, s->d_sc, s->d_hist, phase, stage, glob, flags));
+    s->launches++;
+    CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
 __global__ void k_fill(double *p, double v, int64_t cnt) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -722,7 +833,7 @@ int launch_init_resid(cudamat_solver *s, const double *b, const double *y, doubl
     VecArgs a = vec_args(s, phase);
     a.in0 = b; a.in1 = y; a.out0 = r; a.out1 = c1; a.out2 = c2;
     LAUNCH_VEC(k_init_resid, a);
-    return CUDAMAT_OK;
+    return finish_reduction(s, a.rc, phase, 1);
 }
 int launch_update_p(cudamat_solver *s, bool fma_form, const double *r, const double *v, double *p, const HaloPush *hp) {
     VecArgs a = vec_args(s, PH_NONE);
@@ -742,20 +853,20 @@ int launch_update_rx_ilu(cudamat_solver *s, const double *v, const double *pw, d
     VecArgs a = vec_args(s, PH_I_A2);
     a.in0 = v; a.in1 = pw; a.out0 = r; a.out1 = x;
     LAUNCH_VEC(k_update_rx_ilu, a);
-    return CUDAMAT_OK;
+    return finish_reduction(s, a.rc, PH_I_A2, 1);
 }
 int launch_update_xr(cudamat_solver *s, bool fma_form, const double *p, const double *sv, const double *t,
                      const double *rhat, double *x, double *r) {
     VecArgs a = vec_args(s, fma_form ? PH_I_C : PH_U_C);
     a.in0 = p; a.in1 = sv; a.in2 = t; a.in3 = rhat; a.out0 = x; a.out1 = r;
     if (fma_form) LAUNCH_VEC(k_update_xr<true>, a); else LAUNCH_VEC(k_update_xr<false>, a);
-    return CUDAMAT_OK;
+    return finish_reduction(s, a.rc, a.phase, 2);
 }
 int launch_dot(cudamat_solver *s, const double *x, const double *y) {
     VecArgs a = vec_args(s, PH_STORE);
     a.in0 = x; a.in1 = y;
     LAUNCH_VEC(k_dot, a);
-    return CUDAMAT_OK;
+    return finish_reduction(s, a.rc, PH_STORE, 1);
 }
 int launch_fill(cudamat_solver *s, double *p, double v, int64_t cnt) {
     if (cnt <= 0) return CUDAMAT_OK;

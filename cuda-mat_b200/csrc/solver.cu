@@ -76,15 +76,12 @@ static int alloc_reduction(cudamat_solver *s) {
     rc.nslots = (int)((tiles_global + kGroupTiles - 1) / kGroupTiles);
     rc.slot_stride = std::max(rc.nslots, 1);
     rc.group0 = (int)(s->row0 / ((int64_t)kTile * kGroupTiles));
-    rc.do_final = 1;
+    rc.exch_level = 2;
+    rc.ntile_global = (int)tiles_global;
     CM_CUDA(cudaMalloc(&rc.tile_part, sizeof(double) * kMaxQ * (size_t)rc.tile_stride));
     CM_CUDA(cudaMalloc(&rc.slots, sizeof(double) * kMaxQ * (size_t)rc.slot_stride));
     s->slots_own = rc.slots;
     CM_CUDA(cudaMemsetAsync(rc.slots, 0, sizeof(double) * kMaxQ * (size_t)rc.slot_stride, s->stream));
-    CM_CUDA(cudaMalloc(&rc.group_cnt, sizeof(unsigned) * (size_t)std::max(rc.ngroup_loc, 1)));
-    CM_CUDA(cudaMemsetAsync(rc.group_cnt, 0, sizeof(unsigned) * (size_t)std::max(rc.ngroup_loc, 1), s->stream));
-    CM_CUDA(cudaMalloc(&rc.done_cnt, sizeof(unsigned)));
-    CM_CUDA(cudaMemsetAsync(rc.done_cnt, 0, sizeof(unsigned), s->stream));
     CM_CUDA(cudaMalloc(&s->d_sc, sizeof(DevScalars)));
     CM_CUDA(cudaMemsetAsync(s->d_sc, 0, sizeof(DevScalars), s->stream));
     CM_CUDA(cudaMallocHost(&s->h_sc, 3 * sizeof(DevScalars)));        // [0] synchronous mirror, [1..2] pipelined polls
@@ -137,7 +134,7 @@ static int timed_spmv(cudamat_solver *s, const SpmvArgs &a, int var) {
     int rc = launch_spmv(s, a, var);
     if (rc) return rc;
     if (timed) { CM_CUDA(cudaEventRecord(s->ev_pool[s->ev_used + 1], s->stream)); s->ev_used += 2; }
-    if (a.ndot > 0) return comm_finish_reduction(s, a.phase, a.ndot);
+    if (a.ndot > 0) return finish_reduction(s, a.rc, a.phase, a.ndot);
     return CUDAMAT_OK;
 }
 // SpMV step of the loop: halo exchange of the operand (multi-GPU), the kernel, then the cross-rank
@@ -228,7 +225,6 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
     if ((rc = comm_halo_exchange(s, xk))) return rc;
     if ((rc = launch_spmv(s, spmv_args(s, xk, d_d, t, nullptr, 0, PH_NONE, 0), var))) return rc;
     if ((rc = launch_init_resid(s, d_b, t, r, r0, nullptr, PH_U_INIT))) return rc;
-    if ((rc = comm_finish_reduction(s, PH_U_INIT, 1))) return rc;
     if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
     int npoll = 0; bool stop = false;
     for (int it = 0; it < maxit;) {
@@ -241,7 +237,6 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
         if ((rc = launch_update_s(s, r, v, sv, &hp))) return rc;                                    // :698-700
         if ((rc = spmv_step(s, sv, d_d, t, sv, 2, PH_U_B, 1, slot))) return rc;         // :703-710
         if ((rc = launch_update_xr(s, false, p, sv, t, r0, xk, r))) return rc;                      // :694-696,714-747
-        if ((rc = comm_finish_reduction(s, PH_U_C, 2))) return rc;
         ++it;
         if ((rc = poll_step(s, it, maxit, &npoll, &stop))) return rc;
         if (stop) break;
@@ -367,8 +362,6 @@ int cudamat_destroy(cudamat_solver *s) {
     dev_free(s->own_ia); dev_free(s->own_ja); dev_free(s->own_a);
     if (s->rc.tile_part) cudaFree(s->rc.tile_part);
     if (s->slots_own) cudaFree(s->slots_own);
-    if (s->rc.group_cnt) cudaFree(s->rc.group_cnt);
-    if (s->rc.done_cnt) cudaFree(s->rc.done_cnt);
     if (s->d_sc) cudaFree(s->d_sc);
     if (s->h_sc) cudaFreeHost(s->h_sc);
     if (s->d_hist) cudaFree(s->d_hist);
@@ -527,7 +520,6 @@ int cudamat_dot_device(cudamat_solver *s, const double *d_a, const double *d_b, 
     if (s->n == 0) { *result = 0.0; return CUDAMAT_OK; }
     int rc = launch_dot(s, d_a, d_b);
     if (rc) return rc;
-    if ((rc = comm_finish_reduction(s, PH_STORE, 1))) return rc;
     if ((rc = poll_status(s))) return rc;
     *result = s->h_sc->red[0];
     return CUDAMAT_OK;

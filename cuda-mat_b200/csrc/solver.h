@@ -147,7 +147,9 @@ void ilu0_release(cudamat_solver *s);
 
 // comm.cu
 int comm_halo_exchange(cudamat_solver *s, double *vec);
-int comm_finish_reduction(cudamat_solver *s, int phase, int nq);
+int finish_reduction(cudamat_solver *s, const RedCtx &rc, int phase, int nq);   // groups + cross-rank exchange + final + scalar recurrence
+int launch_reduce_finish(cudamat_solver *s, const RedCtx &rc, int nq, int phase, int stage, const double *glob,
+                         const unsigned long long *flags);               // kernels.cu
 bool comm_p2p(const cudamat_solver *s);                           // peer-memory path active
 void comm_begin_reduction(cudamat_solver *s, RedCtx &rc);          // stamps the next reduction epoch into rc (p2p)
 bool comm_halo_push(cudamat_solver *s, double *vec, int slot, HaloPush *hp);   // fills hp for the kernel that writes vec
