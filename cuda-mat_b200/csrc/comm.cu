@@ -157,9 +157,9 @@ int finish_reduction(cudamat_solver *s, const RedCtx &rc, int phase, int nq) {
     if (s->n == 0 && (!c || c->world == 1)) return CUDAMAT_OK;
     if (!c || c->world == 1 || c->p2p.on)
         return launch_reduce_finish(s, rc, nq, phase, 0, nullptr, c ? c->p2p.flags : nullptr);
-    // NCCL path: local groups -> allreduce of the zero-padded partials -> final
+    // NCCL path: local tile (and group) partials -> allreduce of the zero-padded partials -> final
     int r;
-    if (c->exch_level == 2 && (r = launch_reduce_finish(s, rc, nq, phase, 1, nullptr, nullptr))) return r;
+    if ((r = launch_reduce_finish(s, rc, nq, phase, 1, nullptr, nullptr))) return r;
     CM_NCCL(g_nccl.AllReduce(c->d_exch_local, c->d_exch_glob, (size_t)c->exch_count, ncclDouble, ncclSum, c->comm, s->stream));
     return launch_reduce_finish(s, rc, nq, phase, 2, c->d_exch_glob, nullptr);
 }

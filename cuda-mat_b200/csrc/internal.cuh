@@ -90,6 +90,10 @@ struct HaloWait {
 
 // reduction context of one shard
 struct RedCtx {
+    double   *slab_part;   // [kMaxQ][slab_stride]  slab sums, indexed by LOCAL slab
+    int slab_stride;
+    int n_local;           // rows of this shard
+    unsigned *done_cnt;    // [1] CTAs of k_reduce_finish that have finished their tiles
     double   *tile_part;   // [kMaxQ][tile_stride]  tile partials, indexed by LOCAL tile
     double   *slots;       // [kMaxQ][slot_stride]  group partials, indexed by GLOBAL group
     int ntile;             // local tiles
@@ -275,30 +279,14 @@ __device__ __forceinline__ void p2p_push(const RedCtx &rc, const double *local, 
     }
 }
 
-// Tail of a reducing kernel. Contract: CTA `tile` owns local tile `tile`, s_slab[q][0..63] hold the tile's slab
-// sums (all warps done, __syncthreads() issued by caller).  The CTA only forms its TILE partial R(slab sums) and
-// stores it; groups, the final sum and the scalar recurrence are done by k_reduce_finish, launched right behind
-// (programmatic dependent launch).  No fence and no atomic here: a gpu-scope fence in each of the 8192 CTAs
-// invalidates the SM's L1 (CCTL.IVALL) under the co-resident CTAs' x gathers — measured +45 % SpMV time.
-template <int NQ>
-__device__ __forceinline__ void reduce_tail(const RedCtx &rc, DevScalars *sc, double *hist, int phase,
-                                            double (*s_slab)[kTileSlabs], int nslab_tile, int tile = -1) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (tile < 0) tile = blockIdx.x;
-    (void)sc; (void)hist; (void)phase;
-    if (warp < NQ) {
-        const double tp = warp_reduce_values_smem(s_slab[warp], nslab_tile, lane);
-        if (lane == 0) {
-            if (rc.exch_level == 1) __stcg(rc.exch + (size_t)warp * rc.exch_stride + rc.tile0 + tile, tp);
-            __stcg(rc.tile_part + (size_t)warp * rc.tile_stride + tile, tp);
-        }
-    }
-}
-
-// slab sum of one product per lane (inactive lanes pass +0.0) deposited for the tile tail
-__device__ __forceinline__ void slab_deposit(double (*s_slab)[kTileSlabs], int q, int slab_in_tile, double prod, int lane) {
-    double s = warp_butterfly(prod);
-    if (lane == 0) s_slab[q][slab_in_tile] = s;
+// Reducing kernels only publish SLAB sums: one product per lane (inactive lanes pass +0.0), butterfly, lane 0
+// stores the sum at the slab's LOCAL index (tile * 64 + slab in tile).  No CTA barrier, no fence, no atomic in
+// the bandwidth kernels: a gpu-scope fence per CTA invalidates the SM's L1 under the co-resident CTAs' x gathers
+// and the barrier in front of a CTA-level tail parked 27 % of the warp samples (profiles/r1c_*).  Tiles, groups,
+// the final sum and the scalar recurrence are formed by k_reduce_finish, launched right behind.
+__device__ __forceinline__ void slab_deposit(const RedCtx &rc, int q, int slab_local, double prod, int lane) {
+    const double s = warp_butterfly(prod);
+    if (lane == 0) __stcg(rc.slab_part + (size_t)q * rc.slab_stride + slab_local, s);
 }
 
 }  // namespace cudamat

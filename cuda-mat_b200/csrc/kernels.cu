@@ -29,7 +29,6 @@ __device__ __forceinline__ double rowsum_long(const SpmvArgs &a, int s, int e, i
 #endif
 template <bool HAS_D, int NDOT>
 __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowlane(const SpmvArgs a) {
-    __shared__ double s_slab[kMaxQ][kTileSlabs];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_base = blockIdx.x * kTile;
     // The CSR arrays are constant during a solve, so while the predecessor kernel drains (before the PDL
@@ -82,8 +81,8 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowl
         if (active) { s = __ldg(a.ia + row); e = __ldg(a.ia + row + 1); if (NDOT >= 1) uval = __ldg(a.u + row); }
 #endif
         if (NDOT >= 1 && pslab >= 0) {
-            slab_deposit(s_slab, 0, pslab, pp0, lane);
-            if (NDOT >= 2) slab_deposit(s_slab, 1, pslab, pp1, lane);
+            slab_deposit(a.rc, 0, blockIdx.x * kTileSlabs + (pslab), pp0, lane);
+            if (NDOT >= 2) slab_deposit(a.rc, 1, blockIdx.x * kTileSlabs + (pslab), pp1, lane);
         }
         const int len = e - s;
         const int shortlen = (len <= kLongRow) ? len : 0;
@@ -119,12 +118,9 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowl
     }
     if (NDOT >= 1) {
         if (pslab >= 0) {
-            slab_deposit(s_slab, 0, pslab, pp0, lane);
-            if (NDOT >= 2) slab_deposit(s_slab, 1, pslab, pp1, lane);
+            slab_deposit(a.rc, 0, blockIdx.x * kTileSlabs + (pslab), pp0, lane);
+            if (NDOT >= 2) slab_deposit(a.rc, 1, blockIdx.x * kTileSlabs + (pslab), pp1, lane);
         }
-        __syncthreads();
-        const int rows_here = min(kTile, a.n - row_base);
-        reduce_tail<(NDOT >= 1 ? NDOT : 1)>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
     }
 }
 
@@ -138,10 +134,10 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowl
 // rows of a slab with mixed classes (domain boundaries, ragged last slab): per-lane lengths and offsets
 template <bool CLS_VALS>
 __device__ __noinline__ double class_row_general(const double *x, const double *val, const int *ia, int cid, int row0, int row,
-                                                 bool active, int lane, const int *s_len, const int *s_off, const double *s_val) {
-    const int len = active ? s_len[cid] : 0;
-    const int *off = s_off + cid * kDictLen;
-    const double *dv = s_val + (CLS_VALS ? cid * kDictLen : 0);
+                                                 bool active, int lane, const DictParam &D) {
+    const int len = active ? D.len[cid] : 0;
+    const int *off = D.off + cid * kDictLen;
+    const double *dv = D.val + cid * kDictLen;
     int start = 0;
     if (!CLS_VALS) {
         int incl = len;
@@ -167,15 +163,23 @@ __device__ __noinline__ double class_row_general(const double *x, const double *
     }
     return sum;
 }
-// a slab whose 32 rows share one class of LEN entries (the interior of a stencil): offsets and values are
-// warp-uniform shared-memory broadcasts, no predication, LEN coalesced gathers in flight per lane
-template <int LEN, bool CLS_VALS>
-__device__ __forceinline__ double class_row_uniform(const double *xrow, const double *vrow, const int *off, const double *dv) {
+// A slab whose 32 rows share one class of LEN entries (the interior of a stencil): offsets and values are
+// warp-uniform constant-bank reads, no predication.  RP >= 0: the class holds the offsets (-1, 0, +1) at positions
+// RP..RP+2 — x[row] is loaded once and the two neighbours come from the adjacent lanes by shuffle (the edge lanes
+// load theirs), which removes the two misaligned gathers (3 L1 wavefronts each) of a 5/7-point row.
+template <int LEN, int RP, bool CLS_VALS>
+__device__ __forceinline__ double class_row_uniform(const double *xrow, const double *vrow, const int *off, const double *dv, int lane) {
     double xv[LEN], av[CLS_VALS ? 1 : LEN];
 #pragma unroll
     for (int q = 0; q < LEN; ++q) {
-        xv[q] = __ldg(xrow + off[q]);
+        if (RP < 0 || q < RP || q > RP + 2 || q == RP + 1) xv[q] = __ldg(xrow + off[q]);
         if (!CLS_VALS) av[q] = __ldg(vrow + q);
+    }
+    if (RP >= 0) {
+        double xl = __shfl_up_sync(0xffffffffu, xv[RP + 1], 1), xr = __shfl_down_sync(0xffffffffu, xv[RP + 1], 1);
+        if (lane == 0) xl = __ldg(xrow - 1);
+        if (lane == 31) xr = __ldg(xrow + 1);
+        xv[RP] = xl; xv[RP + 2] = xr;
     }
     double sum = 0.0;
 #pragma unroll
@@ -187,69 +191,58 @@ __device__ __forceinline__ double class_row_uniform(const double *xrow, const do
 #define CUDAMAT_CLASS_MINB 4
 #endif
 template <bool HAS_D, int NDOT, bool CLS_VALS>
-__global__ void __launch_bounds__(kCtaThreads, CUDAMAT_CLASS_MINB) k_spmv_class(const SpmvArgs a, const ClassArgs c) {
-    __shared__ double s_slab[kMaxQ][kTileSlabs];
-    __shared__ int s_len[kDictMax];
-    __shared__ int s_off[kDictMax * kDictLen];
-    __shared__ double s_val[CLS_VALS ? kDictMax * kDictLen : 1];
+__global__ void __launch_bounds__(kCtaThreads, CUDAMAT_CLASS_MINB) k_spmv_class(const SpmvArgs a, const ClassArgs c,
+                                                                                const __grid_constant__ DictParam D) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row_base = blockIdx.x * kTile;
-    // the dictionary and the class ids are constant during a solve: fetched while the predecessor kernel drains
-    // (one tile per CTA: a persistent grid measured slower inside the loop, where many short CTAs fill the SMs
-    // as the predecessor drains — profiles/r1b_spmv_class.md)
-    for (int i = tid; i < c.ncls; i += kCtaThreads) s_len[i] = c.dict->len[i];
-    for (int i = tid; i < c.ncls * kDictLen; i += kCtaThreads) {
-        s_off[i] = c.dict->off[i];
-        if (CLS_VALS) s_val[i] = c.dict->val[i];
-    }
-    int cid[kSlabsPerWarp];
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {
-        const int row = row_base + (j * kCtaWarps + warp) * kSlab + lane;
-        cid[j] = (row < a.n) ? (int)__ldg(c.cls + row) : 0xff;
-    }
-    __syncthreads();
-    pdl_sync();
-    if (a.check_status && a.sc->status != ST_RUNNING) return;
-    halo_wait(a.hw, blockIdx.x);
-    double pp0[kSlabsPerWarp], pp1[kSlabsPerWarp];
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {
-        pp0[j] = 0.0; pp1[j] = 0.0;
-        const int row0 = row_base + (j * kCtaWarps + warp) * kSlab;
-        if (row0 >= a.n) continue;                                // warp-uniform
-        const int row = row0 + lane;
-        const bool active = row < a.n;
-        double uval = 0.0;
-        if (NDOT >= 1 && active) uval = __ldg(a.u + row);
-        double sum;
-        const int c0 = __shfl_sync(0xffffffffu, cid[j], 0);
-        const int len0 = (c0 != 0xff) ? s_len[c0] : 0;
-        if (__all_sync(0xffffffffu, cid[j] == c0) && (len0 == 7 || len0 == 5)) {
-            const int *off = s_off + c0 * kDictLen;
-            const double *dv = s_val + (CLS_VALS ? c0 * kDictLen : 0);
-            const double *vrow = CLS_VALS ? nullptr : a.val + (__ldg(a.ia + row0) + lane * len0);
-            if (len0 == 7) sum = class_row_uniform<7, CLS_VALS>(a.x + row, vrow, off, dv);
-            else           sum = class_row_uniform<5, CLS_VALS>(a.x + row, vrow, off, dv);
-        } else {
-            sum = class_row_general<CLS_VALS>(a.x, a.val, a.ia, active ? cid[j] : 0, row0, row, active, lane, s_len, s_off, s_val);
-        }
-        if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
-        if (active) a.y[row] = sum;
-        if (NDOT >= 1) pp0[j] = active ? __dmul_rn(sum, uval) : 0.0;
-        if (NDOT >= 2) pp1[j] = active ? __dmul_rn(sum, sum) : 0.0;
-    }
-    if (NDOT >= 1) {
+    const int ntile = (a.n + kTile - 1) / kTile;
+    const int tile_end = min(ntile, (int)(blockIdx.x + 1) * c.tiles_per_cta);
+    // The class ids are constant during a solve: those of the first tile are fetched while the predecessor kernel
+    // drains.  There is no CTA-level step in this kernel (slab sums go straight to global memory), so a CTA can walk
+    // several consecutive tiles: fewer, longer-lived CTAs.
+    int cid[kSlabsPerWarp], nid[kSlabsPerWarp];
+    auto load_ids = [&](int tile, int (&id)[kSlabsPerWarp]) {
 #pragma unroll
         for (int j = 0; j < kSlabsPerWarp; ++j) {
-            if (row_base + (j * kCtaWarps + warp) * kSlab < a.n) {
-                slab_deposit(s_slab, 0, j * kCtaWarps + warp, pp0[j], lane);
-                if (NDOT >= 2) slab_deposit(s_slab, 1, j * kCtaWarps + warp, pp1[j], lane);
-            }
+            const int row = tile * kTile + (j * kCtaWarps + warp) * kSlab + lane;
+            id[j] = (tile < tile_end && row < a.n) ? (int)__ldg(c.cls + row) : 0xff;
         }
-        __syncthreads();
-        const int rows_here = min(kTile, a.n - row_base);
-        reduce_tail<(NDOT >= 1 ? NDOT : 1)>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
+    };
+    load_ids(blockIdx.x * c.tiles_per_cta, cid);
+    pdl_sync();
+    if (a.check_status && a.sc->status != ST_RUNNING) return;
+    for (int tile = blockIdx.x * c.tiles_per_cta; tile < tile_end; ++tile) {
+        const int row_base = tile * kTile;
+        halo_wait(a.hw, tile);
+        load_ids(tile + 1, nid);
+#pragma unroll
+        for (int j = 0; j < kSlabsPerWarp; ++j) {
+            const int row0 = row_base + (j * kCtaWarps + warp) * kSlab;
+            if (row0 >= a.n) continue;                                // warp-uniform
+            const int row = row0 + lane;
+            const bool active = row < a.n;
+            double uval = 0.0;
+            if (NDOT >= 1 && active) uval = __ldg(a.u + row);
+            double sum;
+            const int c0 = __shfl_sync(0xffffffffu, cid[j], 0);
+            const bool uni = __all_sync(0xffffffffu, cid[j] == c0) && c0 != 0xff;
+            const int len0 = uni ? D.len[c0] : 0, rp = uni ? D.run[c0] : -1;
+            if ((len0 == 7 && rp == 2) || (len0 == 5 && rp == 1)) {
+                const int *off = D.off + c0 * kDictLen;
+                const double *dv = D.val + c0 * kDictLen;
+                const double *vrow = CLS_VALS ? nullptr : a.val + (__ldg(a.ia + row0) + lane * len0);
+                if (len0 == 7) sum = class_row_uniform<7, 2, CLS_VALS>(a.x + row, vrow, off, dv, lane);
+                else           sum = class_row_uniform<5, 1, CLS_VALS>(a.x + row, vrow, off, dv, lane);
+            } else {
+                sum = class_row_general<CLS_VALS>(a.x, a.val, a.ia, active ? cid[j] : 0, row0, row, active, lane, D);
+            }
+            if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
+            if (active) a.y[row] = sum;
+            const int slab = tile * kTileSlabs + j * kCtaWarps + warp;
+            if (NDOT >= 1) slab_deposit(a.rc, 0, slab, active ? __dmul_rn(sum, uval) : 0.0, lane);
+            if (NDOT >= 2) slab_deposit(a.rc, 1, slab, active ? __dmul_rn(sum, sum) : 0.0, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < kSlabsPerWarp; ++j) cid[j] = nid[j];
     }
 }
 
@@ -329,7 +322,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_spmv_staged(const StagedArgs
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     halo_wait(a.hw, blockIdx.x);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double s_slab[kMaxQ][kTileSlabs];
     __shared__ uint64_t s_bar[kCtaWarps][8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_base = blockIdx.x * kTile;
@@ -430,15 +422,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_spmv_staged(const StagedArgs
         }
         if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
         if (active) a.y[row] = sum;
-        if (NDOT >= 1) slab_deposit(s_slab, 0, slab, active ? __dmul_rn(sum, uval) : 0.0, lane);
-        if (NDOT >= 2) slab_deposit(s_slab, 1, slab, active ? __dmul_rn(sum, sum) : 0.0, lane);
+        if (NDOT >= 1) slab_deposit(a.rc, 0, blockIdx.x * kTileSlabs + (slab), active ? __dmul_rn(sum, uval) : 0.0, lane);
+        if (NDOT >= 2) slab_deposit(a.rc, 1, blockIdx.x * kTileSlabs + (slab), active ? __dmul_rn(sum, sum) : 0.0, lane);
         cs_ = ns_; ce_ = ne_;
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) cxv[q8] = nxv[q8];
     }
     if (NDOT >= 1) {
-        __syncthreads();
-        reduce_tail<(NDOT >= 1 ? NDOT : 1)>(a.rc, a.sc, a.hist, a.phase, s_slab, nslab_tile);
     }
 }
 
@@ -477,15 +467,15 @@ static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaS
     return cudaLaunchKernelEx(&cfg, kern, arg);
 }
 
-template <typename Kern, typename A1, typename A2>
-static cudaError_t launch_pdl2(Kern kern, int grid, int block, cudaStream_t st, const A1 &a1, const A2 &a2) {
+template <typename Kern, typename A1, typename A2, typename A3>
+static cudaError_t launch_pdl2(Kern kern, int grid, int block, cudaStream_t st, const A1 &a1, const A2 &a2, const A3 &a3) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, a1, a2);
+    return cudaLaunchKernelEx(&cfg, kern, a1, a2, a3);
 }
 
 template <bool HAS_D, int NDOT>
@@ -493,15 +483,17 @@ static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
     const int grid = (a.n + kTile - 1) / kTile;
     if (grid == 0) return CUDAMAT_OK;
     if (variant == CUDAMAT_SPMV_CLASS && s->cls[1].ncls > 0) {
-        const ClassArgs c{s->cls[1].d_cls, s->cls[1].d_dict, s->cls[1].ncls};
-        CM_CUDA(launch_pdl2(k_spmv_class<HAS_D, NDOT, true>, grid, kCtaThreads, s->stream, a, c));
+        const int T = std::max(1, s->opt_class_tiles_per_cta);
+        const ClassArgs c{s->cls[1].d_cls, s->cls[1].ncls, T};
+        CM_CUDA(launch_pdl2(k_spmv_class<HAS_D, NDOT, true>, (grid + T - 1) / T, kCtaThreads, s->stream, a, c, *s->cls[1].h_dict));
         s->launches++;
         CM_CUDA(cudaGetLastError());
         return CUDAMAT_OK;
     }
     if ((variant == CUDAMAT_SPMV_PATTERN || variant == CUDAMAT_SPMV_CLASS) && s->cls[0].ncls > 0) {
-        const ClassArgs c{s->cls[0].d_cls, s->cls[0].d_dict, s->cls[0].ncls};
-        CM_CUDA(launch_pdl2(k_spmv_class<HAS_D, NDOT, false>, grid, kCtaThreads, s->stream, a, c));
+        const int T = std::max(1, s->opt_class_tiles_per_cta);
+        const ClassArgs c{s->cls[0].d_cls, s->cls[0].ncls, T};
+        CM_CUDA(launch_pdl2(k_spmv_class<HAS_D, NDOT, false>, (grid + T - 1) / T, kCtaThreads, s->stream, a, c, *s->cls[0].h_dict));
         s->launches++;
         CM_CUDA(cudaGetLastError());
         return CUDAMAT_OK;
@@ -551,7 +543,6 @@ struct VecArgs {
 // r = b - y ; c1 = r ; c2 = r (optional) ; red0 = r.r          (pbicgstab.cu:67-74, 645-655)
 __global__ void __launch_bounds__(kCtaThreads) k_init_resid(const VecArgs a) {
     VEC_PROLOGUE
-    __shared__ double s_slab[kMaxQ][kTileSlabs];
     double rv[kSlabsPerWarp];
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -568,11 +559,8 @@ __global__ void __launch_bounds__(kCtaThreads) k_init_resid(const VecArgs a) {
             if (a.out2) a.out2[row] = rv[j];
         }
         if (row_base + j * kCtaThreads + warp * kSlab < a.n)
-            slab_deposit(s_slab, 0, j * kCtaWarps + warp, active ? __dmul_rn(rv[j], rv[j]) : 0.0, lane);
+            slab_deposit(a.rc, 0, blockIdx.x * kTileSlabs + (j * kCtaWarps + warp), active ? __dmul_rn(rv[j], rv[j]) : 0.0, lane);
     }
-    __syncthreads();
-    const int rows_here = min(kTile, a.n - row_base);
-    reduce_tail<1>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
 }
 
 // p' = r + beta*(p - omega*v)
@@ -642,7 +630,6 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_s(const VecArgs a) {
 // ilu0: r = fma(-alpha,v,r) ; x = fma(alpha,pw,x) ; red0 = r.r   (pbicgstab.cu:109-111)
 __global__ void __launch_bounds__(kCtaThreads) k_update_rx_ilu(const VecArgs a) {
     VEC_PROLOGUE
-    __shared__ double s_slab[kMaxQ][kTileSlabs];
     const double alpha = a.sc->alpha, malpha = -alpha;
     double vv[kSlabsPerWarp], pw[kSlabsPerWarp], rr[kSlabsPerWarp], xx[kSlabsPerWarp];
 #pragma unroll
@@ -662,11 +649,8 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_rx_ilu(const VecArgs a) 
         const double xn = __fma_rn(alpha, pw[j], xx[j]);
         if (act) { a.out0[row] = rn; a.out1[row] = xn; }
         if (row_base + j * kCtaThreads + warp * kSlab < a.n)
-            slab_deposit(s_slab, 0, j * kCtaWarps + warp, act ? __dmul_rn(rn, rn) : 0.0, lane);
+            slab_deposit(a.rc, 0, blockIdx.x * kTileSlabs + (j * kCtaWarps + warp), act ? __dmul_rn(rn, rn) : 0.0, lane);
     }
-    __syncthreads();
-    const int rows_here = min(kTile, a.n - row_base);
-    reduce_tail<1>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
 }
 
 // end-of-iteration update with the two fused dots.
@@ -677,7 +661,6 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_rx_ilu(const VecArgs a) 
 template <bool FMA_FORM>
 __global__ void __launch_bounds__(kCtaThreads) k_update_xr(const VecArgs a) {
     VEC_PROLOGUE
-    __shared__ double s_slab[kMaxQ][kTileSlabs];
     const double alpha = a.sc->alpha, omega = a.sc->omega, momega = -omega;
 #pragma unroll 2
     for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -702,13 +685,10 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_xr(const VecArgs a) {
             a.out1[row] = rn;
         }
         if (row_base + j * kCtaThreads + warp * kSlab < a.n) {
-            slab_deposit(s_slab, 0, j * kCtaWarps + warp, act ? __dmul_rn(rh, rn) : 0.0, lane);
-            slab_deposit(s_slab, 1, j * kCtaWarps + warp, act ? __dmul_rn(rn, rn) : 0.0, lane);
+            slab_deposit(a.rc, 0, blockIdx.x * kTileSlabs + (j * kCtaWarps + warp), act ? __dmul_rn(rh, rn) : 0.0, lane);
+            slab_deposit(a.rc, 1, blockIdx.x * kTileSlabs + (j * kCtaWarps + warp), act ? __dmul_rn(rn, rn) : 0.0, lane);
         }
     }
-    __syncthreads();
-    const int rows_here = min(kTile, a.n - row_base);
-    reduce_tail<2>(a.rc, a.sc, a.hist, a.phase, s_slab, (rows_here + kSlab - 1) / kSlab);
 }
 
 // spec dot product of two arbitrary vectors -> sc->red[0]
@@ -716,26 +696,24 @@ __global__ void __launch_bounds__(kCtaThreads) k_dot(const VecArgs a) {
     pdl_prologue();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_base = blockIdx.x * kTile;
-    __shared__ double s_slab[kMaxQ][kTileSlabs];
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + j * kCtaThreads + tid;
         const bool act = row < a.n;
         const double p = act ? __dmul_rn(__ldg(a.in0 + row), __ldg(a.in1 + row)) : 0.0;
-        if (row_base + j * kCtaThreads + warp * kSlab < a.n) slab_deposit(s_slab, 0, j * kCtaWarps + warp, p, lane);
+        if (row_base + j * kCtaThreads + warp * kSlab < a.n) slab_deposit(a.rc, 0, blockIdx.x * kTileSlabs + (j * kCtaWarps + warp), p, lane);
     }
-    __syncthreads();
-    const int rows_here = min(kTile, a.n - row_base);
-    reduce_tail<1>(a.rc, a.sc, a.hist, PH_STORE, s_slab, (rows_here + kSlab - 1) / kSlab);
 }
 
 // ------------------------------------------------------------------------------------------
-// k_reduce_finish: one CTA, launched right behind every reducing kernel.  Spec tree (internal.cuh): tile partials
-// (written by the reducing kernel) -> group partials R(1024 tiles) -> result R(groups) -> scalar recurrence.
+// k_reduce_finish: launched right behind every reducing kernel (PDL).  Spec tree: slab sums
+// (written by the reducing kernel) -> tile partials R(64 slabs) -> group partials R(1024 tiles) -> result
+// R(groups) -> scalar recurrence.  Every warp of the grid forms tile partials; the last CTA to finish (ticket)
+// does the rest:
 //   stage 0: everything; on a sharded handle with the peer-memory path the group (or tile) partials of this rank
-//            are pushed to every rank and the kernel waits for all arrivals before the final sum;
-//   stage 1: local group partials only (NCCL path, before the allreduce);
-//   stage 2: final sum + recurrence from `glob` (NCCL path, after the allreduce).
+//            are pushed to every rank and the CTA waits for all arrivals before the final sum;
+//   stage 1: up to the local group partials (NCCL path, before the allreduce);
+//   stage 2: final sum + recurrence from `glob` (NCCL path, after the allreduce; one CTA).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads) k_reduce_finish(const RedCtx rc, int nq, DevScalars *sc, double *hist, int phase,
                                                                int stage, const double *glob, const unsigned long long *flags) {
@@ -743,16 +721,41 @@ __global__ void __launch_bounds__(kCtaThreads) k_reduce_finish(const RedCtx rc, 
     if (phase != PH_STORE && sc->status != ST_RUNNING) return;
     __shared__ double s_grp[kMaxQ][64];
     __shared__ double s_red[kMaxQ];
+    __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (stage != 2 && rc.exch_level != 1) {                    // local groups into the slots array (global group index)
-        for (int w = warp; w < nq * rc.ngroup_loc; w += kCtaWarps) {
-            const int q = w / rc.ngroup_loc, g = w % rc.ngroup_loc;
-            const int in_group = min(kGroupTiles, rc.ntile - g * kGroupTiles);
-            const double gp = warp_reduce_values_cg(rc.tile_part + (size_t)q * rc.tile_stride + (size_t)g * kGroupTiles, in_group, lane);
-            if (lane == 0) __stcg(rc.slots + (size_t)q * rc.slot_stride + rc.group0 + g, gp);
+    if (stage != 2) {
+        // tile partials: job = (q, local tile), one warp each
+        const int njobs = nq * rc.ntile;
+        for (int w = blockIdx.x * kCtaWarps + warp; w < njobs; w += gridDim.x * kCtaWarps) {
+            const int q = w / rc.ntile, tile = w % rc.ntile;
+            const int nslab = min(kTileSlabs, (rc.n_local - tile * kTile + kSlab - 1) / kSlab);
+            const double tp = warp_reduce_values_cg(rc.slab_part + (size_t)q * rc.slab_stride + (size_t)tile * kTileSlabs, nslab, lane);
+            if (lane == 0) {
+                if (rc.exch_level == 1) __stcg(rc.exch + (size_t)q * rc.exch_stride + rc.tile0 + tile, tp);
+                __stcg(rc.tile_part + (size_t)q * rc.tile_stride + tile, tp);
+            }
         }
-        __threadfence_block();
+        // last CTA of this (small) grid continues
+        __threadfence();
         __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned old = atomicAdd(rc.done_cnt, 1u);
+            s_last = (old == gridDim.x - 1);
+            if (s_last) *rc.done_cnt = 0u;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (rc.exch_level != 1) {                              // local groups into the slots array (global group index)
+            for (int w = warp; w < nq * rc.ngroup_loc; w += kCtaWarps) {
+                const int q = w / rc.ngroup_loc, g = w % rc.ngroup_loc;
+                const int in_group = min(kGroupTiles, rc.ntile - g * kGroupTiles);
+                const double gp = warp_reduce_values_cg(rc.tile_part + (size_t)q * rc.tile_stride + (size_t)g * kGroupTiles, in_group, lane);
+                if (lane == 0) __stcg(rc.slots + (size_t)q * rc.slot_stride + rc.group0 + g, gp);
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
     }
     if (stage == 1) return;
     const double *src = (stage == 2) ? glob : (rc.exch_level == 1 ? rc.exch : rc.slots);
@@ -794,7 +797,10 @@ __global__ void __launch_bounds__(kCtaThreads) k_reduce_finish(const RedCtx rc, 
 int launch_reduce_finish(cudamat_solver *s, const RedCtx &rc, int nq, int phase, int stage, const double *glob,
                          const unsigned long long *flags) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(1); cfg.blockDim = dim3(kCtaThreads); cfg.stream = s->stream;
+    // one warp per (quantity, tile); a few hundred CTAs at most, so the ticket / fence cost stays negligible
+    int grid = 1;
+    if (stage != 2) grid = std::max(1, std::min((nq * rc.ntile + kCtaWarps - 1) / kCtaWarps, 296));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCtaThreads); cfg.stream = s->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;

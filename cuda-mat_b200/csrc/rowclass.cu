@@ -11,6 +11,7 @@
 // row's storage order, so the row sums are bit-identical to the CSR kernels.
 // This is what cusparseDcsrmv (pbicgstab.cu:67,104,132,646,676,704) cannot do: it must stream 12 B per entry.
 #include "solver.h"
+#include <cstring>
 
 namespace cudamat {
 
@@ -110,6 +111,7 @@ __global__ void k_cls_assign(int n, const int *ia, const int *ja, const double *
 void rowclass_release(cudamat_solver *s) {
     for (int m = 0; m < 2; ++m) {
         dev_free(s->cls[m].d_cls);
+        delete s->cls[m].h_dict;
         if (s->cls[m].d_dict) cudaFree(s->cls[m].d_dict);
         s->cls[m] = RowClasses();
     }
@@ -145,8 +147,25 @@ int rowclass_analyze(cudamat_solver *s) {
             (e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
             cuda_ok(e, "row class analysis", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
         }
-        if (h[0] == 0 && h[1] > 0) C.ncls = h[1];
-        else { dev_free(C.d_cls); cudaFree(C.d_dict); C = RowClasses(); }
+        if (h[0] == 0 && h[1] > 0) {
+            RowDict hd;
+            if ((e = cudaMemcpy(&hd, C.d_dict, sizeof hd, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+                cuda_ok(e, "row class dictionary download", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
+            }
+            C.ncls = h[1];
+            C.h_dict = new DictParam();
+            memset(C.h_dict, 0, sizeof(DictParam));
+            for (int id = 0; id < C.ncls; ++id) {
+                C.h_dict->len[id] = hd.len[id];
+                C.h_dict->run[id] = -1;
+                for (int k = 0; k < kDictLen; ++k) {
+                    C.h_dict->off[id * kDictLen + k] = hd.off[id * kDictLen + k];
+                    C.h_dict->val[id * kDictLen + k] = hd.val[id * kDictLen + k];
+                }
+                for (int k = 0; k + 2 < hd.len[id]; ++k)
+                    if (hd.off[id * kDictLen + k] == -1 && hd.off[id * kDictLen + k + 1] == 0 && hd.off[id * kDictLen + k + 2] == 1) { C.h_dict->run[id] = k; break; }
+            }
+        } else { dev_free(C.d_cls); cudaFree(C.d_dict); C = RowClasses(); }
     }
     cudaFree(tab); cudaFree(rep); cudaFree(slot_id); cudaFree(flags);
     return rc;

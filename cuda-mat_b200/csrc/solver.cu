@@ -79,6 +79,11 @@ static int alloc_reduction(cudamat_solver *s) {
     rc.exch_level = 2;
     rc.ntile_global = (int)tiles_global;
     CM_CUDA(cudaMalloc(&rc.tile_part, sizeof(double) * kMaxQ * (size_t)rc.tile_stride));
+    rc.n_local = s->n;
+    rc.slab_stride = std::max((s->n + kSlab - 1) / kSlab, 1);
+    CM_CUDA(cudaMalloc(&rc.slab_part, sizeof(double) * kMaxQ * (size_t)rc.slab_stride));
+    CM_CUDA(cudaMalloc(&rc.done_cnt, sizeof(unsigned)));
+    CM_CUDA(cudaMemsetAsync(rc.done_cnt, 0, sizeof(unsigned), s->stream));
     CM_CUDA(cudaMalloc(&rc.slots, sizeof(double) * kMaxQ * (size_t)rc.slot_stride));
     s->slots_own = rc.slots;
     CM_CUDA(cudaMemsetAsync(rc.slots, 0, sizeof(double) * kMaxQ * (size_t)rc.slot_stride, s->stream));
@@ -361,6 +366,8 @@ int cudamat_destroy(cudamat_solver *s) {
     rowclass_release(s);
     dev_free(s->own_ia); dev_free(s->own_ja); dev_free(s->own_a);
     if (s->rc.tile_part) cudaFree(s->rc.tile_part);
+    if (s->rc.slab_part) cudaFree(s->rc.slab_part);
+    if (s->rc.done_cnt) cudaFree(s->rc.done_cnt);
     if (s->slots_own) cudaFree(s->slots_own);
     if (s->d_sc) cudaFree(s->d_sc);
     if (s->h_sc) cudaFreeHost(s->h_sc);
@@ -380,7 +387,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "debug")) s->opt_debug = (int)value;
     else if (!strcmp(key, "time_spmv")) s->opt_time_spmv = (int)value;
     else if (!strcmp(key, "sptrsv_ctas_per_sm")) { s->opt_sptrsv_ctas_per_sm = (int)value; s->sptrsv_grid = 0; }
-    else if (!strcmp(key, "class_ctas_per_sm")) s->opt_class_ctas_per_sm = (int)value;
+    else if (!strcmp(key, "class_tiles_per_cta")) s->opt_class_tiles_per_cta = (int)value;
     else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
     else { set_error("unknown option '%s'", key); return CUDAMAT_E_INVALID; }
     return CUDAMAT_OK;

@@ -42,15 +42,24 @@ struct StagedPlan {
 };
 
 // row-class dictionaries of the compressed SpMV variants (rowclass.cu)
-constexpr int kDictMax = 128;      // classes
+constexpr int kDictMax = 64;       // classes
 constexpr int kDictLen = 16;       // entries per class
 struct RowDict { int len[kDictMax]; int off[kDictMax * kDictLen]; double val[kDictMax * kDictLen]; };
+// The dictionary travels to the SpMV kernel as a KERNEL PARAMETER (12.6 KB of the 32 KB parameter space): it is
+// read through the constant cache (LDC), not through L1/shared memory, which is the busiest unit of that kernel.
+struct DictParam {
+    int len[kDictMax];
+    int run[kDictMax];                 // position of offset -1 when the class holds (-1, 0, +1) consecutively, else -1
+    int off[kDictMax * kDictLen];
+    double val[kDictMax * kDictLen];
+};
 struct RowClasses {
     unsigned char *d_cls = nullptr;    // class id per row
     RowDict *d_dict = nullptr;
+    DictParam *h_dict = nullptr;       // host copy handed to the kernel launches
     int ncls = 0;                      // 0 = not available
 };
-struct ClassArgs { const unsigned char *cls; const RowDict *dict; int ncls; };
+struct ClassArgs { const unsigned char *cls; int ncls; int tiles_per_cta; };
 
 struct Comm;   // comm.cu
 
@@ -87,7 +96,7 @@ struct cudamat_solver {
     int opt_time_spmv = 0;
     int loop_it = 0;
     int opt_staged_stages = 0;
-    int opt_class_ctas_per_sm = 0;
+    int opt_class_tiles_per_cta = 1;
     int opt_sptrsv_ctas_per_sm = 0;
     int sptrsv_grid = 0;
     std::vector<cudaEvent_t> ev_pool; int ev_used = 0;

@@ -45,7 +45,7 @@ def main():
         if tctas:
             s.set_option("sptrsv_ctas_per_sm", tctas)
         if cctas:
-            s.set_option("class_ctas_per_sm", cctas)
+            s.set_option("class_tiles_per_cta", cctas)
         s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr())
         sa = s.analyze(args.mode)
         s.spmv(xt.data_ptr(), b.data_ptr())
