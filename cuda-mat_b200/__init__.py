@@ -55,7 +55,7 @@ EXPORTS = [
     "cudamat_ilu0_host", "cudamat_create", "cudamat_destroy", "cudamat_set_option",
     "cudamat_set_csr_host", "cudamat_set_csr_device", "cudamat_analyze", "cudamat_solve_device",
     "cudamat_get_history", "cudamat_spmv_device", "cudamat_dot_device", "cudamat_get_ilu0_host",
-    "cudamat_sptrsv_device", "cudamat_comm_p2p_enabled", "cudamat_comm_unique_id", "cudamat_comm_init", "cudamat_partition_rows",
+    "cudamat_sptrsv_device", "cudamat_comm_p2p_enabled", "cudamat_write_mm", "cudamat_write_mm_vector", "cudamat_comm_unique_id", "cudamat_comm_init", "cudamat_partition_rows",
     "cudamat_halo_plan_host",
     "cudamat_gen_poisson3d_device", "cudamat_poisson3d_nnz", "cudamat_gen_xtrue_device",
     "cudamat_gen_random_dd_device", "cudamat_load_mm", "cudamat_free",
@@ -97,6 +97,8 @@ lib.cudamat_gen_random_dd_device.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.
                                              C.POINTER(C.c_int64), C.c_void_p]
 lib.cudamat_load_mm.argtypes = [C.c_char_p, C.c_int, c_ip, c_ip, c_ip, C.POINTER(c_dp), C.POINTER(c_ip), C.POINTER(c_ip)]
 lib.cudamat_free.argtypes = [C.c_void_p]
+lib.cudamat_write_mm.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_ip, C.c_int, C.c_char_p]
+lib.cudamat_write_mm_vector.argtypes = [C.c_char_p, C.c_int, c_dp, C.c_char_p]
 
 
 def last_error():
@@ -180,6 +182,19 @@ def load_mm(path, csr=True):
     for p in (av, ai, aj):
         lib.cudamat_free(C.cast(p, C.c_void_p))
     return m.value, n.value, ptr, ind, val
+
+
+def write_mm(path, m, n, ptr, ind, val, symmetric=False, comment=None):
+    """CSR -> Matrix Market coordinate file (replaces mm_write_mtx_crd, mmio.c:405-445)."""
+    ptr, ind, val = _i32(ptr), _i32(ind), _f64(val)
+    _check(lib.cudamat_write_mm(path.encode(), m, n, len(val), _dp(val), _ip(ptr), _ip(ind), int(symmetric),
+                                comment.encode() if comment else None))
+
+
+def write_mm_vector(path, x, comment=None):
+    """dense vector -> n x 1 coordinate file (the reference's -V input, example.cpp:310-336)."""
+    x = _f64(x)
+    _check(lib.cudamat_write_mm_vector(path.encode(), len(x), _dp(x), comment.encode() if comment else None))
 
 
 def to_dense_vector(n, A, IA):

@@ -1,6 +1,7 @@
 // cudamat_example.cpp — demo CLI with the reference's switches (example.cpp:185-223):
 //   -M<matrix.mtx> -V<vector.mtx> -D (debug trace) -R<prob of zero> -N<dim> -P (print x) device=<n>
-// plus -T<tol> -I<maxit> -U (unpreconditioned instead of ILU0).  Unlike the reference's main
+// plus -T<tol> -I<maxit> -U (unpreconditioned instead of ILU0) -O<x.mtx> (write the solution as an n x 1 Matrix
+// Market file, the format -V reads) -W<A.mtx> (write the system matrix, e.g. the random default problem).  Unlike the reference's main
 // (example.cpp:169,377) the exit status is 0 on success.
 #include <cstdio>
 #include <cstdlib>
@@ -14,9 +15,10 @@
 #include "helper_cusolver.h"
 #include "mmio_wrapper.h"
 #include "pbicgstab.h"
+#include "../../include/cudamat_b200.h"
 
 int main(int argc, char *argv[]) {
-    const char *matrix_file = nullptr, *vector_file = nullptr;
+    const char *matrix_file = nullptr, *vector_file = nullptr, *out_file = nullptr, *mat_out_file = nullptr;
     bool debug = false, print = false, unprec = false;
     double p_zero_mat = 0.99, p_zero_vec = 0.2, tol = 1e-6;
     int dim = 10000, maxit = 2000;
@@ -33,6 +35,8 @@ int main(int argc, char *argv[]) {
         case 'N': dim = std::stoi(a + 2); break;
         case 'T': tol = std::stod(a + 2); break;
         case 'I': maxit = std::stoi(a + 2); break;
+        case 'O': out_file = a + 2; break;
+        case 'W': mat_out_file = a + 2; break;
         case 'd': break;                                 // -device=<n>
         default: fprintf(stderr, "Unknown switch '-%s'\n", a + 1); return EXIT_FAILURE;
         }
@@ -80,6 +84,10 @@ int main(int argc, char *argv[]) {
     } else {
         gen_rand_vector(n, b, p_zero_vec, 1, 5.0);       // example.cpp:338-340
     }
+    if (mat_out_file && cudamat_write_mm(mat_out_file, n, n, nnz, A, iA, jA, 0, "written by cudamat_example")) {
+        fprintf(stderr, "%s\n", cudamat_last_error());
+        return EXIT_FAILURE;
+    }
     double *x = (double *)malloc(sizeof(double) * n);
     std::cout << "nnz=" << nnz << std::endl;
     double dtAlg = 0.0;
@@ -93,6 +101,10 @@ int main(int argc, char *argv[]) {
             std::ostringstream s;
             dump_vector(s, n, x);
             std::cout << "result:" << std::endl << s.str() << std::endl;
+        }
+        if (out_file && cudamat_write_mm_vector(out_file, n, x, "solution written by cudamat_example")) {
+            fprintf(stderr, "%s\n", cudamat_last_error());
+            return EXIT_FAILURE;
         }
         std::cout << "algorithm delta time = " << dtAlg << " s" << std::endl;
         std::cout << "total delta time = " << t2 - t1 << " s" << std::endl;

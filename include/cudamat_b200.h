@@ -176,6 +176,13 @@ int cudamat_gen_random_dd_device(int n, uint64_t seed, int *d_ia, int *d_ja, dou
 int  cudamat_load_mm(const char *filename, int csr_format, int *m, int *n, int *nnz,
                      double **aVal, int **aRowInd, int **aColInd);
 void cudamat_free(void *p);
+/* ---- Matrix Market writing (replaces mm_write_banner / mm_write_mtx_crd, mmio.c:405-445,447-510) ----
+ * CSR (index base = rowptr[0], 0 or 1) -> coordinate real general, or (symmetric != 0) the lower triangle as
+ * coordinate real symmetric; 1-based, %.17g (exact round trip).  comment may be NULL. */
+int  cudamat_write_mm(const char *filename, int m, int n, int nnz, const double *val, const int *rowptr,
+                      const int *colind, int symmetric, const char *comment);
+/* dense vector as the n x 1 coordinate matrix the reference's -V switch reads (example.cpp:310-336) */
+int  cudamat_write_mm_vector(const char *filename, int n, const double *x, const char *comment);
 
 #ifdef __cplusplus
 }

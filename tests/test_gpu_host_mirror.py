@@ -28,6 +28,16 @@ def test_cudamat_example_cli(torch_cuda):
     assert rc != 0 and "no structural diagonal" in err
     rc, out, err = run("cudamat_example", "-N300", "-R0.9", "-U")                            # random default problem
     assert "nnz=" in out
+    # -O / -W: solution and matrix export in the format -V / -M read back (Matrix Market I/O either side of the path)
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        xo, ao = os.path.join(td, "x.mtx"), os.path.join(td, "a.mtx")
+        rc, out, err = run("cudamat_example", "-Mmat3.mtx", "-Vvec3.mtx", "-U", "-T1e-10", "-O" + xo, "-W" + ao)
+        assert rc == 0, err[-300:]
+        xs = [float(l.split()[2]) for l in open(xo).read().splitlines()[3:]]
+        assert len(xs) == 3 and abs(xs[0] - 7.0 / 6.0) < 1e-9 and abs(xs[2] + 23.0 / 6.0) < 1e-9
+        rc, out, err = run("cudamat_example", "-M" + ao, "-Vvec3.mtx", "-U", "-P", "-T1e-10")
+        assert rc == 0 and "(1.166667 5.666667 -3.833333 )" in out
     rc, out, err = run("cudamat_example", "-Zfoo")
     assert rc != 0 and "Unknown switch" in err
 

@@ -50,6 +50,69 @@ def test_loader_rejects(cm, tmp_path, text, why):
         cm.load_mm(str(tmp_path / "missing.mtx"))
 
 
+def test_writer_round_trip_and_large_parallel_parse(cm, O, pin, tmp_path):
+    """cudamat_write_mm / cudamat_write_mm_vector (mm_write_mtx_crd, mmio.c:405) round-trip exactly through the loader,
+    general and symmetric-lower; a > 1 MiB file goes through the multi-threaded parser and must agree with the oracle's CSR."""
+    ia, ja, a = csr = (pin["mat900_ia"], pin["mat900_ja"], pin["mat900_a"])
+    for sym in (False, True):
+        p = str(tmp_path / ("w%d.mtx" % sym))
+        cm.write_mm(p, 900, 900, ia, ja, a, symmetric=sym, comment="round trip")
+        m, n, ia2, ja2, a2 = cm.load_mm(p)
+        assert (m, n) == (900, 900) and np.array_equal(ia2, ia) and np.array_equal(ja2, ja) and np.array_equal(a2, a)
+    # base-0 CSR with awkward values
+    pia, pja, pa = O.poisson3d(40)                       # 64000 rows, 438400 entries: ~9 MB of text -> parallel parse
+    rng = np.random.default_rng(3)
+    pa = pa * rng.standard_normal(len(pa)) * 10.0 ** rng.integers(-30, 30, len(pa))
+    p = str(tmp_path / "big.mtx")
+    cm.write_mm(p, 64000, 64000, pia, pja, pa)
+    assert os.path.getsize(p) > (1 << 20)
+    m, n, ia2, ja2, a2 = cm.load_mm(p)
+    assert np.array_equal(ia2 - 1, pia) and np.array_equal(ja2 - 1, pja) and np.array_equal(a2, pa)
+    x = rng.standard_normal(777); x[5] = 0.0; x[776] = 0.0
+    p = str(tmp_path / "v.mtx")
+    cm.write_mm_vector(p, x)
+    m, n, vi, vj, va = cm.load_mm(p)
+    assert (m, n) == (777, 1) and np.array_equal(cm.to_dense_vector(777, va, vi), x)
+    with pytest.raises(cm.CudamatError):
+        cm.write_mm(str(tmp_path / "nodir" / "x.mtx"), 900, 900, ia, ja, a)
+
+
+def test_loader_agrees_with_reference_loader_on_generated_files(cm, O, tmp_path):
+    """property test against the REFERENCE's loader (oracle/_ref, only where the reference checkout was compiled):
+    random real / integer files, general / symmetric / skew-symmetric / hermitian, base-1."""
+    if not O.ref_available("mmio"):
+        pytest.skip("oracle/_ref/libref_mmio.so not built (needs /root/reference)")
+    rng = np.random.default_rng(11)
+    for field in ("real", "integer"):
+        for sym in ("general", "symmetric", "skew-symmetric", "hermitian"):
+            n = int(rng.integers(5, 40))
+            ents = {}
+            for _ in range(4 * n):
+                i, j = int(rng.integers(1, n + 1)), int(rng.integers(1, n + 1))
+                if sym != "general" and j > i:
+                    i, j = j, i
+                if sym == "skew-symmetric" and i == j:
+                    continue
+                ents[(i, j)] = int(rng.integers(-9, 10)) if field == "integer" else float(rng.standard_normal())
+            ents[(n, n if sym != "skew-symmetric" else 1)] = 3 if field == "integer" else 3.5      # makes the file base-1
+            p = tmp_path / ("%s_%s.mtx" % (field, sym))
+            with open(p, "w") as f:
+                f.write("%%%%MatrixMarket matrix coordinate %s %s\n%% generated\n%d %d %d\n" % (field, sym, n, n, len(ents)))
+                for (i, j), v in ents.items():
+                    f.write(("%d %d %d\n" if field == "integer" else "%d %d %.17g\n") % (i, j, v))
+            if sym == "hermitian" and field == "real":   # mm_is_valid (mmio.c:96) rejects real hermitian: both loaders must fail
+                with pytest.raises(cm.CudamatError):
+                    cm.load_mm(str(p))
+                with pytest.raises(RuntimeError):
+                    O.ref_load_mm(str(p))
+                continue
+            got = cm.load_mm(str(p))
+            ref = O.ref_load_mm(str(p))
+            assert got[0] == ref[0] and got[1] == ref[1], (field, sym)
+            for g, r in zip(got[2:], ref[2:]):
+                assert np.array_equal(g, r), (field, sym)
+
+
 def test_to_dense_vector(cm, O, pin):
     for nm in ("vec3", "vec3_d"):
         got = cm.to_dense_vector(3, pin[nm + "_a"], pin[nm + "_ia"])
