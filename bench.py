@@ -381,6 +381,49 @@ def big_grid_run(cm, torch, dist, N, world, rank, stream, barrier, steps=200):
             "note": "strong scaling of the SAME 512^3 system over the ranks of this run; includes the 1 SpMV residual set-up of the restart"}
 
 
+def random_dd_run(cm, torch, n):
+    """n rows, row lengths from a 90/9/1 % mixture (mean 8.5 off-diagonals, up to ~190), columns uniform
+    over [0, n) (x = 400 MB does not fit L2: sector over-fetch on the gathers), values U(-10,10), dominant diagonal.
+    Reports the SpMV rate (plain + inside the loop) and a full solve of A x = A x_true to 1e-10."""
+    f64 = dict(dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    ia = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    nnz = cm.gen_random_dd_device(n, 20240, ia.data_ptr(), stream=stream)
+    ja = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    a = torch.empty(nnz, **f64)
+    cm.gen_random_dd_device(n, 20240, ia.data_ptr(), ja.data_ptr(), a.data_ptr(), stream=stream)
+    s = cm.Solver(n, stream=stream)
+    s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
+    sa = s.analyze(cm.MODE_PLAIN)
+    xt = torch.empty(n, **f64)
+    cm.gen_xtrue_device(1234, 0, n, xt.data_ptr(), stream)
+    b = torch.empty(n, **f64)
+    s.spmv(xt.data_ptr(), b.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        s.spmv(xt.data_ptr(), b.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    spmv_ms = e0.elapsed_time(e1) / 10
+    x = torch.zeros(n, **f64)
+    st = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=2000, tol=1e-10)
+    relerr = float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt))
+    bs = bytes_spmv(n, nnz)
+    peak, _ = peaks()
+    out = {"n": n, "nnz": nnz, "max_row_len_class": "irregular (mixture 90/9/1 %)", "spmv_variant": sa["spmv_variant"],
+           "spmv_ms": spmv_ms, "spmv_GBps": bs / spmv_ms / 1e6, "spmv_frac_of_measured_peak": bs / spmv_ms / 1e6 / peak,
+           "iterations": st["iterations"], "converged": bool(st["converged"]), "t_loop_s": st["t_loop"],
+           "iters_per_s": st["iterations"] / max(st["t_loop"], 1e-9), "relres": st["nrm_r"] / st["nrm_r0"], "rel_err_vs_xtrue": relerr,
+           "iteration_GBps": bytes_iter(n, nnz) * st["iterations"] / max(st["t_loop"], 1e-9) / 1e9,
+           "note": "x gathers are random over 400 MB: 32-byte sectors fetched per 8 useful bytes, the algorithmic roofline is not reachable (SURVEY.md H5)"}
+    s.close()
+    del ia, ja, a, xt, b, x
+    torch.cuda.empty_cache()
+    return out
+
+
 def multi_gpu_e2e(cm, torch, dist, N, n, row0, row1, nnz_loc, ia, ja, a, b, rank, world, stream, barrier):
     """e2e at N > 1: every rank holds its row shard (CSR with global columns, b) in pinned HOST memory and goes
     through the handle API of the C ABI: cudamat_create, cudamat_set_csr_host (H2D), cudamat_comm_init (halo plan; the
@@ -487,6 +530,13 @@ def single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, conver
     except Exception as e:      # noqa: BLE001
         out["mat10000_ilu0"] = {"error": str(e)}
 
+    # ---- BASELINE config 4: generator.cpp-style random nonsymmetric diagonally dominant CSR, 50 M rows, irregular rows ----
+    if not args.no_random:
+        try:
+            out["random_dd_50M"] = random_dd_run(cm, torch, args.random_rows)
+        except Exception as e:      # noqa: BLE001
+            out["random_dd_50M"] = {"error": str(e)}
+
     # ---- CPU baseline (reported, not the target): reference bicstab_omp on the host cores ----
     if not args.no_cpu:
         try:
@@ -508,6 +558,8 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="force an SpMV variant (1 rowlane, 2 staged)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-ilu0", action="store_true", help="skip the ILU0 extra")
+    ap.add_argument("--no-random", action="store_true", help="skip the 50 M-row random matrix extra (BASELINE config 4)")
+    ap.add_argument("--random-rows", type=int, default=50_000_000)
     ap.add_argument("--no-512", action="store_true", help="skip the 512^3 extra (BASELINE config 5)")
     ap.add_argument("--no-csr", action="store_true", help="skip the second timed region with the plain CSR SpMV kernel")
     ap.add_argument("--no-converge", action="store_true", help="skip the full solve to 1e-10 (profiling runs)")

@@ -907,7 +907,7 @@ __global__ void k_row_stats(int n, const int *ia, int *out /*max_len, n_long, ma
 
 int launch_row_stats(cudamat_solver *s, int *h_out, double *mean) {
     int *d_out = nullptr;
-    CM_CUDA(cudaMalloc(&d_out, 3 * sizeof(int)));
+    CM_CUDA(dev_alloc((void **)&d_out, 3 * sizeof(int)));
     CM_CUDA(cudaMemsetAsync(d_out, 0, 3 * sizeof(int), s->stream));
     if (s->n > 0) {
         k_row_stats<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->n, s->d_ia, d_out);
@@ -915,7 +915,7 @@ int launch_row_stats(cudamat_solver *s, int *h_out, double *mean) {
     }
     CM_CUDA(cudaMemcpyAsync(h_out, d_out, 3 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));
-    CM_CUDA(cudaFree(d_out));
+    dev_free(d_out);
     *mean = s->n > 0 ? (double)s->nnz / s->n : 0.0;
     return CUDAMAT_OK;
 }
@@ -946,14 +946,14 @@ __global__ void k_validate_csr(const int *ia, int n, const int *ja, int64_t nnz,
 }
 int launch_validate_csr(cudaStream_t st, const int *ia, int n, const int *ja, int64_t nnz, int64_t ncols, int *h_bad) {
     int *d_bad = nullptr;
-    CM_CUDA(cudaMalloc(&d_bad, 2 * sizeof(int)));
+    CM_CUDA(dev_alloc((void **)&d_bad, 2 * sizeof(int)));
     CM_CUDA(cudaMemsetAsync(d_bad, 0x7f, 2 * sizeof(int), st));
     k_validate_csr<<<1184, 256, 0, st>>>(ia, n, ja, nnz, ncols, d_bad);
     CM_CUDA(cudaGetLastError());
     int h[2];
     CM_CUDA(cudaMemcpyAsync(h, d_bad, sizeof h, cudaMemcpyDeviceToHost, st));
     CM_CUDA(cudaStreamSynchronize(st));
-    CM_CUDA(cudaFree(d_bad));
+    dev_free(d_bad);
     h_bad[0] = h[0] == 0x7f7f7f7f ? -1 : h[0];
     h_bad[1] = h[1] == 0x7f7f7f7f ? -1 : h[1];
     return CUDAMAT_OK;

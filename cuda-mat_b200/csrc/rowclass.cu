@@ -112,7 +112,7 @@ void rowclass_release(cudamat_solver *s) {
     for (int m = 0; m < 2; ++m) {
         dev_free(s->cls[m].d_cls);
         delete s->cls[m].h_dict;
-        if (s->cls[m].d_dict) cudaFree(s->cls[m].d_dict);
+        dev_free(s->cls[m].d_dict);
         s->cls[m] = RowClasses();
     }
 }
@@ -123,15 +123,15 @@ int rowclass_analyze(cudamat_solver *s) {
     const int n = s->n;
     if (n <= 0 || s->nnz <= 0 || s->max_row_len > kDictLen) return CUDAMAT_OK;
     unsigned long long *tab = nullptr; int *rep = nullptr, *slot_id = nullptr, *flags = nullptr;
-    CM_CUDA(cudaMalloc(&tab, sizeof(unsigned long long) * kTab));
-    CM_CUDA(cudaMalloc(&rep, sizeof(int) * kTab));
-    CM_CUDA(cudaMalloc(&slot_id, sizeof(int) * kTab));
-    CM_CUDA(cudaMalloc(&flags, sizeof(int) * 2));
+    CM_CUDA(dev_alloc((void **)&tab, sizeof(unsigned long long) * kTab));
+    CM_CUDA(dev_alloc((void **)&rep, sizeof(int) * kTab));
+    CM_CUDA(dev_alloc((void **)&slot_id, sizeof(int) * kTab));
+    CM_CUDA(dev_alloc((void **)&flags, sizeof(int) * 2));
     int rc = CUDAMAT_OK;
     for (int m = 1; m >= 0 && rc == CUDAMAT_OK; --m) {          // m = 1: with values, m = 0: offsets only
         RowClasses &C = s->cls[m];
         cudaError_t e;
-        if ((e = dev_alloc((void **)&C.d_cls, (size_t)n + 16)) != cudaSuccess || (e = cudaMalloc(&C.d_dict, sizeof(RowDict))) != cudaSuccess) {
+        if ((e = dev_alloc((void **)&C.d_cls, (size_t)n + 16)) != cudaSuccess || (e = dev_alloc((void **)&C.d_dict, sizeof(RowDict))) != cudaSuccess) {
             cuda_ok(e, "cudaMalloc(row classes)", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
         }
         cudaMemsetAsync(tab, 0, sizeof(unsigned long long) * kTab, s->stream);
@@ -165,9 +165,10 @@ int rowclass_analyze(cudamat_solver *s) {
                 for (int k = 0; k + 2 < hd.len[id]; ++k)
                     if (hd.off[id * kDictLen + k] == -1 && hd.off[id * kDictLen + k + 1] == 0 && hd.off[id * kDictLen + k + 2] == 1) { C.h_dict->run[id] = k; break; }
             }
-        } else { dev_free(C.d_cls); cudaFree(C.d_dict); C = RowClasses(); }
+        } else { dev_free(C.d_cls); dev_free(C.d_dict); C = RowClasses(); }
     }
-    cudaFree(tab); cudaFree(rep); cudaFree(slot_id); cudaFree(flags);
+    cudaStreamSynchronize(s->stream);
+    dev_free(tab); dev_free(rep); dev_free(slot_id); dev_free(flags);
     return rc;
 }
 

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <cmath>
 #include <algorithm>
+#include <mutex>
+#include <vector>
 #include <time.h>
 
 namespace cudamat {
@@ -67,6 +69,25 @@ void dev_free(void *p) {                            // no work may still use p (
     cudaFreeAsync(p, g_pool_stream);
 }
 
+// pinned status mirrors are recycled process-wide: cudaMallocHost / cudaFreeHost cost up to 0.1-0.4 s when other
+// large pinned regions exist (page-locking + device-wide synchronisation)
+static std::vector<DevScalars *> g_pinned_free;
+static std::mutex g_pinned_mu;
+static DevScalars *pinned_scalars_get() {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        if (!g_pinned_free.empty()) { DevScalars *p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
+    }
+    DevScalars *p = nullptr;
+    if (cudaMallocHost(&p, 3 * sizeof(DevScalars)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+static void pinned_scalars_put(DevScalars *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned_free.push_back(p);
+}
+
 static int alloc_reduction(cudamat_solver *s) {
     RedCtx &rc = s->rc;
     rc.ntile = (s->n + kTile - 1) / kTile;
@@ -78,18 +99,19 @@ static int alloc_reduction(cudamat_solver *s) {
     rc.group0 = (int)(s->row0 / ((int64_t)kTile * kGroupTiles));
     rc.exch_level = 2;
     rc.ntile_global = (int)tiles_global;
-    CM_CUDA(cudaMalloc(&rc.tile_part, sizeof(double) * kMaxQ * (size_t)rc.tile_stride));
+    CM_CUDA(dev_alloc((void **)&rc.tile_part, sizeof(double) * kMaxQ * (size_t)rc.tile_stride));
     rc.n_local = s->n;
     rc.slab_stride = std::max((s->n + kSlab - 1) / kSlab, 1);
-    CM_CUDA(cudaMalloc(&rc.slab_part, sizeof(double) * kMaxQ * (size_t)rc.slab_stride));
-    CM_CUDA(cudaMalloc(&rc.done_cnt, sizeof(unsigned)));
+    CM_CUDA(dev_alloc((void **)&rc.slab_part, sizeof(double) * kMaxQ * (size_t)rc.slab_stride));
+    CM_CUDA(dev_alloc((void **)&rc.done_cnt, sizeof(unsigned)));
     CM_CUDA(cudaMemsetAsync(rc.done_cnt, 0, sizeof(unsigned), s->stream));
-    CM_CUDA(cudaMalloc(&rc.slots, sizeof(double) * kMaxQ * (size_t)rc.slot_stride));
+    CM_CUDA(dev_alloc((void **)&rc.slots, sizeof(double) * kMaxQ * (size_t)rc.slot_stride));
     s->slots_own = rc.slots;
     CM_CUDA(cudaMemsetAsync(rc.slots, 0, sizeof(double) * kMaxQ * (size_t)rc.slot_stride, s->stream));
-    CM_CUDA(cudaMalloc(&s->d_sc, sizeof(DevScalars)));
+    CM_CUDA(dev_alloc((void **)&s->d_sc, sizeof(DevScalars)));
     CM_CUDA(cudaMemsetAsync(s->d_sc, 0, sizeof(DevScalars), s->stream));
-    CM_CUDA(cudaMallocHost(&s->h_sc, 3 * sizeof(DevScalars)));        // [0] synchronous mirror, [1..2] pipelined polls
+    s->h_sc = pinned_scalars_get();                                    // [0] synchronous mirror, [1..2] pipelined polls
+    if (!s->h_sc) { set_error("cudaMallocHost failed for the status mirror"); return CUDAMAT_E_CUDA; }
     memset(s->h_sc, 0, 3 * sizeof(DevScalars));
     return CUDAMAT_OK;
 }
@@ -110,9 +132,9 @@ static inline double *wv(cudamat_solver *s, int k) { return s->work + (size_t)k 
 
 static int ensure_hist(cudamat_solver *s, int cap) {
     if (s->d_hist && s->hist_cap >= cap) return CUDAMAT_OK;
-    if (s->d_hist) cudaFree(s->d_hist);
+    if (s->d_hist) { cudaStreamSynchronize(s->stream); dev_free(s->d_hist); }
     s->d_hist = nullptr;
-    CM_CUDA(cudaMalloc(&s->d_hist, sizeof(double) * (size_t)std::max(cap, 1)));
+    CM_CUDA(dev_alloc((void **)&s->d_hist, sizeof(double) * (size_t)std::max(cap, 1)));
     s->hist_cap = cap;
     return CUDAMAT_OK;
 }
@@ -360,21 +382,23 @@ int cudamat_create(cudamat_solver **out, int64_t n_global, int64_t row0, int64_t
 
 int cudamat_destroy(cudamat_solver *s) {
     if (!s) return CUDAMAT_OK;
+    const bool tm = getenv("CUDAMAT_TIMING") != nullptr;
+    const double t0 = now_s();
     cudaStreamSynchronize(s->stream);
     comm_release(s);
     ilu0_release(s);
     rowclass_release(s);
+    const double t1 = now_s();
     dev_free(s->own_ia); dev_free(s->own_ja); dev_free(s->own_a);
-    if (s->rc.tile_part) cudaFree(s->rc.tile_part);
-    if (s->rc.slab_part) cudaFree(s->rc.slab_part);
-    if (s->rc.done_cnt) cudaFree(s->rc.done_cnt);
-    if (s->slots_own) cudaFree(s->slots_own);
-    if (s->d_sc) cudaFree(s->d_sc);
-    if (s->h_sc) cudaFreeHost(s->h_sc);
-    if (s->d_hist) cudaFree(s->d_hist);
+    dev_free(s->rc.tile_part); dev_free(s->rc.slab_part); dev_free(s->rc.done_cnt);
+    dev_free(s->slots_own);
+    dev_free(s->d_sc);
+    pinned_scalars_put(s->h_sc);
+    dev_free(s->d_hist);
     if (s->work) { if (s->work_pooled) dev_free(s->work); else cudaFree(s->work); }
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : s->poll_ev) if (e) cudaEventDestroy(e);
+    if (tm) fprintf(stderr, "cudamat_destroy: sync+release %.4f s, frees %.4f s\n", t1 - t0, now_s() - t1);
     delete s;
     return CUDAMAT_OK;
 }

@@ -301,6 +301,41 @@ def test_breakdown_maxit_and_edge_cases(cm, O, pin):
     assert st["converged"] and x[0] == 0.5
 
 
+def test_spmv_agrees_with_cusparse_through_torch(cm, torch_cuda):
+    """Independent on-box comparator: torch's CSR mat-vec calls modern cuSPARSE (cusparseSpMV). Summation
+    orders differ, so the check is a tight tolerance, not bits: |y - y_cusparse| <= 1e-13 * (|A| |x|) row by row."""
+    torch = torch_cuda
+    for N, gen in ((96, "poisson"), (200000, "random")):
+        if gen == "poisson":
+            n = N ** 3
+            nnz = cm.poisson3d_nnz(N)
+            ia = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+            ja = torch.empty(nnz, dtype=torch.int32, device="cuda")
+            a = torch.empty(nnz, dtype=torch.float64, device="cuda")
+            cm.gen_poisson3d_device(N, 0, n, ia.data_ptr(), ja.data_ptr(), a.data_ptr())
+        else:
+            n = N
+            ia = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+            nnz = cm.gen_random_dd_device(n, 7, ia.data_ptr())
+            ja = torch.empty(nnz, dtype=torch.int32, device="cuda")
+            a = torch.empty(nnz, dtype=torch.float64, device="cuda")
+            cm.gen_random_dd_device(n, 7, ia.data_ptr(), ja.data_ptr(), a.data_ptr())
+        x = torch.empty(n, dtype=torch.float64, device="cuda")
+        cm.gen_xtrue_device(5, 0, n, x.data_ptr())
+        s = cm.Solver(n)
+        s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
+        s.analyze(0)
+        y = torch.empty(n, dtype=torch.float64, device="cuda")
+        s.spmv(x.data_ptr(), y.data_ptr())
+        A = torch.sparse_csr_tensor(ia.long(), ja.long(), a, size=(n, n))
+        yc = A @ x
+        Aabs = torch.sparse_csr_tensor(ia.long(), ja.long(), a.abs(), size=(n, n))
+        scale = Aabs @ x.abs()
+        torch.cuda.synchronize()
+        assert float(((y - yc).abs() / scale.clamp_min(1e-300)).max()) <= 1e-13, gen
+        s.close()
+
+
 def test_full_size_properties_poisson128(cm, torch_cuda):
     """At a size the oracle does not finish in seconds: solve Poisson 128^3 (2.1 M rows) on device and check the
     domain's size-independent properties: true residual <= tol*||r0||, solution error vs x_true, residual
