@@ -240,6 +240,10 @@ void ilu0_release(cudamat_solver *s) {
         if (P->d_val) cudaFree(P->d_val);
         if (P->d_dg) cudaFree(P->d_dg);
     }
+    if (s->blk_ia) cudaFree(s->blk_ia);
+    if (s->blk_ja) cudaFree(s->blk_ja);
+    if (s->blk_a) cudaFree(s->blk_a);
+    s->blk_ia = nullptr; s->blk_ja = nullptr; s->blk_a = nullptr; s->blk_nnz = 0;
     if (s->d_flag) cudaFree(s->d_flag);
     if (s->d_ticket) cudaFree(s->d_ticket);
     s->d_M = nullptr; s->d_diag = nullptr; s->lvl_l = LevelSchedule(); s->lvl_u = LevelSchedule();
@@ -252,18 +256,61 @@ static double now_s() {
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+// Sharded handles: the preconditioner is block-Jacobi ILU(0) — each rank factors the diagonal block of its row
+// shard (entries whose column lives on another rank are left out), so the sweeps need no communication.  It is a
+// different (weaker) preconditioner than the global ILU(0) of the single-GPU run: iteration counts differ, the
+// solution does not (SURVEY.md §8e "ILU0 across GPUs", option block-Jacobi).
+__global__ void k_block_count(int n, const int *ia, const int *ja, int *cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { cnt[n] = 0; return; }
+    int c = 0;
+    for (int p = ia[i]; p < ia[i + 1]; ++p) c += (ja[p] < n) ? 1 : 0;
+    cnt[i] = c;
+}
+__global__ void k_block_fill(int n, const int *ia, const int *ja, const double *a, const int *bia, int *bja, double *ba) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int q = bia[i];
+    for (int p = ia[i]; p < ia[i + 1]; ++p)
+        if (ja[p] < n) { bja[q] = ja[p]; ba[q] = a[p]; ++q; }
+}
+int exclusive_scan_inplace(int *d, int64_t cnt, cudaStream_t st);      // kernels.cu
+
+static int build_local_block(cudamat_solver *s) {
+    const int n = s->n;
+    CM_CUDA(cudaMalloc(&s->blk_ia, sizeof(int) * (size_t)(n + 1)));
+    k_block_count<<<(n + 1 + 255) / 256, 256, 0, s->stream>>>(n, s->d_ia, s->d_ja, s->blk_ia);
+    CM_CUDA(cudaGetLastError());
+    int rc = exclusive_scan_inplace(s->blk_ia, (int64_t)n + 1, s->stream);
+    if (rc) return rc;
+    int last = 0;
+    CM_CUDA(cudaMemcpyAsync(&last, s->blk_ia + n, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    s->blk_nnz = last;
+    CM_CUDA(cudaMalloc(&s->blk_ja, sizeof(int) * (size_t)std::max(last, 1)));
+    CM_CUDA(cudaMalloc(&s->blk_a, sizeof(double) * (size_t)std::max(last, 1)));
+    if (n > 0) k_block_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->d_ia, s->d_ja, s->d_a, s->blk_ia, s->blk_ja, s->blk_a);
+    CM_CUDA(cudaGetLastError());
+    s->launches += 2;
+    return CUDAMAT_OK;
+}
+
 int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
-    if (s->row0 != 0 || s->row1 != s->n_global) {
-        set_error("ILU0 is only available on a single shard (multi-GPU ILU0 is out of scope, SURVEY.md §8e)");
-        return CUDAMAT_E_INVALID;
-    }
     ilu0_release(s);
     const int n = s->n;
-    const int64_t nnz = s->nnz;
+    // the matrix the preconditioner is built from: the whole matrix, or the local diagonal block of a shard
+    s->pre_ia = s->d_ia; s->pre_ja = s->d_ja; s->pre_a = s->d_a; s->pre_nnz = s->nnz;
+    if (s->nhalo > 0 || s->row0 != 0 || s->row1 != s->n_global) {
+        int rcb = build_local_block(s);
+        if (rcb) return rcb;
+        s->pre_ia = s->blk_ia; s->pre_ja = s->blk_ja; s->pre_a = s->blk_a; s->pre_nnz = s->blk_nnz;
+    }
+    const int64_t nnz = s->pre_nnz;
     double t0 = now_s();
     std::vector<int> ia(n + 1), ja((size_t)nnz);
-    CM_CUDA(cudaMemcpyAsync(ia.data(), s->d_ia, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, s->stream));
-    CM_CUDA(cudaMemcpyAsync(ja.data(), s->d_ja, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaMemcpyAsync(ia.data(), s->pre_ia, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaMemcpyAsync(ja.data(), s->pre_ja, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));
     std::vector<int> diag(n), lvl(n);
     for (int i = 0; i < n; ++i) {
@@ -299,7 +346,7 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     // factorisation on a copy of A (pbicgstab.cu:316,359)
     t0 = now_s();
     CM_CUDA(cudaMalloc(&s->d_M, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
-    CM_CUDA(cudaMemcpyAsync(s->d_M, s->d_a, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, s->stream));
+    CM_CUDA(cudaMemcpyAsync(s->d_M, s->pre_a, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, s->stream));
     int *d_zp = nullptr;
     CM_CUDA(cudaMalloc(&d_zp, sizeof(int)));
     const int big = 0x7fffffff;
@@ -307,7 +354,7 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     for (int l = 0; l < nl; ++l) {
         const int off = s->lvl_l.level_ptr[l], cnt = s->lvl_l.level_ptr[l + 1] - off;
         if (cnt == 0) continue;
-        k_ilu0_level<<<(cnt + 127) / 128, 128, 0, s->stream>>>(s->lvl_l.d_order + off, cnt, s->d_ia, s->d_ja, s->d_diag, s->d_M, d_zp);
+        k_ilu0_level<<<(cnt + 127) / 128, 128, 0, s->stream>>>(s->lvl_l.d_order + off, cnt, s->pre_ia, s->pre_ja, s->d_diag, s->d_M, d_zp);
         s->launches++;
     }
     CM_CUDA(cudaGetLastError());
@@ -327,8 +374,8 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
         CM_CUDA(cudaMalloc(&P.d_dg, sizeof(double) * len));
         if (P.order_len > 0) {
             const int grid = (P.order_len + 255) / 256;
-            if (u) k_build_plan<true><<<grid, 256, 0, s->stream>>>(P.d_order, P.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M, P.d_cnt, P.d_ptr, P.d_col, P.d_val, P.d_dg);
-            else   k_build_plan<false><<<grid, 256, 0, s->stream>>>(P.d_order, P.order_len, s->d_ia, s->d_ja, s->d_diag, s->d_M, P.d_cnt, P.d_ptr, P.d_col, P.d_val, P.d_dg);
+            if (u) k_build_plan<true><<<grid, 256, 0, s->stream>>>(P.d_order, P.order_len, s->pre_ia, s->pre_ja, s->d_diag, s->d_M, P.d_cnt, P.d_ptr, P.d_col, P.d_val, P.d_dg);
+            else   k_build_plan<false><<<grid, 256, 0, s->stream>>>(P.d_order, P.order_len, s->pre_ia, s->pre_ja, s->d_diag, s->d_M, P.d_cnt, P.d_ptr, P.d_col, P.d_val, P.d_dg);
             s->launches++;
         }
     }
@@ -365,11 +412,11 @@ int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, doubl
         cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
         if (upper)
             CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<true>, (const int *)L.d_order, L.order_len, (const int *)L.d_cnt, (const int *)L.d_ptr,
-                                       (const int *)L.d_col, (const double *)L.d_val, (const double *)L.d_dg, s->d_ja,
+                                       (const int *)L.d_col, (const double *)L.d_val, (const double *)L.d_dg, s->pre_ja,
                                        (const double *)s->d_M, rhs, out, rearm, rearm_rhs, status));
         else
             CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<false>, (const int *)L.d_order, L.order_len, (const int *)L.d_cnt, (const int *)L.d_ptr,
-                                       (const int *)L.d_col, (const double *)L.d_val, (const double *)L.d_dg, s->d_ja,
+                                       (const int *)L.d_col, (const double *)L.d_val, (const double *)L.d_dg, s->pre_ja,
                                        (const double *)s->d_M, rhs, out, rearm, rearm_rhs, status));
         s->launches++;
     } else {
@@ -377,9 +424,9 @@ int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, doubl
             const int off = L.level_ptr[l], cnt = L.level_ptr[l + 1] - off;
             if (cnt == 0) continue;
             if (upper)
-                k_sptrsv_level<true><<<(cnt + 127) / 128, 128, 0, s->stream>>>(L.d_order + off, cnt, s->d_ia, s->d_ja, s->d_diag, s->d_M, rhs, out, status);
+                k_sptrsv_level<true><<<(cnt + 127) / 128, 128, 0, s->stream>>>(L.d_order + off, cnt, s->pre_ia, s->pre_ja, s->d_diag, s->d_M, rhs, out, status);
             else
-                k_sptrsv_level<false><<<(cnt + 127) / 128, 128, 0, s->stream>>>(L.d_order + off, cnt, s->d_ia, s->d_ja, s->d_diag, s->d_M, rhs, out, status);
+                k_sptrsv_level<false><<<(cnt + 127) / 128, 128, 0, s->stream>>>(L.d_order + off, cnt, s->pre_ia, s->pre_ja, s->d_diag, s->d_M, rhs, out, status);
             s->launches++;
         }
     }

@@ -985,7 +985,7 @@ __global__ void k_poisson_fill(int N, int64_t row0, int64_t row1, const int *ia,
     if (k < N - 1) { ja[p] = (int)(r + nn); a[p++] = -1.0; }
 }
 
-static int exclusive_scan_inplace(int *d, int64_t cnt, cudaStream_t st) {
+int exclusive_scan_inplace(int *d, int64_t cnt, cudaStream_t st) {
     void *tmp = nullptr; size_t bytes = 0;
     CM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, d, d, cnt, st));
     CM_CUDA(cudaMalloc(&tmp, bytes ? bytes : 16));

@@ -286,6 +286,7 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
     const size_t nb = sizeof(double) * (size_t)s->n;
     if ((rc = launch_fill(s, xk, 1.0, s->n))) return rc;                                            // :306-308
     CM_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * s->work_elems, s->stream));
+    if ((rc = comm_halo_exchange(s, xk))) return rc;
     if ((rc = launch_spmv(s, spmv_args(s, xk, nullptr, t, nullptr, 0, PH_NONE, 0), var))) return rc; // :67
     if ((rc = launch_init_resid(s, d_b, t, r, rw, p, PH_I_INIT))) return rc;                        // :69-74
     int npoll = 0; bool stop = false;
@@ -559,6 +560,7 @@ int cudamat_dot_device(cudamat_solver *s, const double *d_a, const double *d_b, 
 int cudamat_get_ilu0_host(cudamat_solver *s, double *M_out) {
     if (!s || !M_out) return CUDAMAT_E_INVALID;
     if (!s->d_M) { set_error("get_ilu0_host: no factor (analyze with CUDAMAT_MODE_ILU0)"); return CUDAMAT_E_STATE; }
+    if (s->pre_nnz != s->nnz) { set_error("get_ilu0_host: sharded handles hold a block-Jacobi factor of the local block (%lld entries), not A's pattern", (long long)s->pre_nnz); return CUDAMAT_E_STATE; }
     CM_CUDA(cudaMemcpyAsync(M_out, s->d_M, sizeof(double) * (size_t)s->nnz, cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));
     return CUDAMAT_OK;

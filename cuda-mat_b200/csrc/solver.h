@@ -113,6 +113,9 @@ struct cudamat_solver {
     double *work = nullptr; size_t work_elems = 0; int work_nvec = 0; bool work_pooled = false;
     // ILU0
     double *d_M = nullptr; int *d_diag = nullptr;
+    // matrix behind the preconditioner: the CSR itself, or (sharded handles) the local diagonal block blk_*
+    const int *pre_ia = nullptr; const int *pre_ja = nullptr; const double *pre_a = nullptr; int64_t pre_nnz = 0;
+    int *blk_ia = nullptr; int *blk_ja = nullptr; double *blk_a = nullptr; int64_t blk_nnz = 0;
     cudamat::LevelSchedule lvl_l, lvl_u;
     int *d_flag = nullptr;                 // sync-free epoch flags (n)
     unsigned *d_ticket = nullptr;          // sync-free CTA ticket

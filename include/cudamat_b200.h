@@ -125,7 +125,8 @@ int cudamat_set_csr_host(cudamat_solver *s, int nnz, const double *A, const int 
 int cudamat_set_csr_device(cudamat_solver *s, int64_t nnz, const double *dA, const int *dIA, const int *dJA);
 
 /* SpMV plan from row-length statistics; for CUDAMAT_MODE_ILU0 also level analysis + factorisation
- * (cusparseDcsrsv_analysis pbicgstab.cu:338,345; cusparseDcsrilu0 :359). */
+ * (cusparseDcsrsv_analysis pbicgstab.cu:338,345; cusparseDcsrilu0 :359).  On a sharded handle (after
+ * cudamat_comm_init) MODE_ILU0 builds a block-Jacobi ILU(0) of the shard's diagonal block. */
 int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st);
 
 /* the iteration (gpu_pbicgstab pbicgstab.cu:45-154 / gpu_pbicgstab2 :581-754) on device vectors of
