@@ -195,6 +195,81 @@ __global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int l
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// triangular sweeps, variant C: small systems (the output vector fits in shared memory, e.g. mat900 / mat10000:
+// 88 / 199 levels of <= 15 / 100 rows).  ONE CTA walks the levels of the level-ordered plan with a CTA barrier
+// between levels; solved values are read from shared memory, the operands of the next level are fetched before the
+// barrier.  A level costs a barrier + a few shared-memory reads (~0.1 us) instead of an L2 round trip per
+// dependent hop (~1.1 us) or a kernel launch.  Same per-row operation order as the other variants.
+// ------------------------------------------------------------------------------------------
+#ifndef CUDAMAT_SMEM_SWEEP_THREADS
+#define CUDAMAT_SMEM_SWEEP_THREADS 1024
+#endif
+constexpr int kSmemSweepThreads = CUDAMAT_SMEM_SWEEP_THREADS;
+template <bool UPPER>
+__global__ void __launch_bounds__(kSmemSweepThreads) k_sptrsv_smem(const int *order, const int *level_ptr, int nlevels, int len, int n,
+                                                                   const int *p_cnt, const int *p_ptr, const int *p_col, const double *p_val,
+                                                                   const double *p_dg, const int *ja, const double *M,
+                                                                   const double *rhs, double *out, const int *status) {
+    extern __shared__ double y[];                                  // n entries
+    pdl_prologue();
+    if (status && *status != ST_RUNNING) return;
+    const int tid = threadIdx.x;
+    struct Row { int i, cnt, c[kPlanW]; double m[kPlanW], dg, rhs; };
+    auto fetch = [&](int t, Row &r) {
+        r.i = (t >= 0) ? order[t] : -1;
+        r.cnt = 0; r.dg = 1.0; r.rhs = 0.0;
+        if (r.i >= 0) {
+            r.cnt = p_cnt[t];
+#pragma unroll
+            for (int q = 0; q < kPlanW; ++q) { r.c[q] = p_col[(size_t)q * len + t]; r.m[q] = p_val[(size_t)q * len + t]; }
+            if (UPPER) r.dg = p_dg[t];
+            r.rhs = rhs[r.i];
+        }
+    };
+    auto solve = [&](int t, const Row &r) {
+        if (r.i < 0) return;
+        double acc = r.rhs;
+#pragma unroll
+        for (int q = 0; q < kPlanW; ++q)
+            if (q < r.cnt) acc = __fma_rn(-r.m[q], y[r.c[q]], acc);
+        if (r.cnt > kPlanW) {
+            const int p0 = p_ptr[t];
+            for (int pp = p0 + kPlanW; pp < p0 + r.cnt; ++pp) acc = __fma_rn(-M[pp], y[ja[pp]], acc);
+        }
+        if (UPPER) acc = __ddiv_rn(acc, r.dg);
+        y[r.i] = acc;
+        out[r.i] = acc;
+    };
+    // The CTA is split into kGroups groups of 128 threads; group g owns the levels g, g + kGroups, ... and fetches
+    // the operands of its next level a whole round (kGroups levels) before they are needed, so neither the plan
+    // loads nor the dependent rhs[order[t]] load sit on the level-to-level chain.
+    constexpr int kGroups = kSmemSweepThreads / 128;
+    const int g = tid >> 7, lt = tid & 127;
+    int tcur = -1, tnxt = -1;
+    Row cur, nxt;
+    auto fetch_level = [&](int l, Row &r, int &t) {
+        t = -1;
+        if (l < nlevels) { const int tt = level_ptr[l] + lt; if (tt < level_ptr[l + 1]) t = tt; }
+        fetch(t, r);
+    };
+    fetch_level(g, cur, tcur);
+    for (int l0 = 0; l0 < nlevels; l0 += kGroups) {
+        fetch_level(l0 + kGroups + g, nxt, tnxt);
+#pragma unroll 1
+        for (int k = 0; k < kGroups; ++k) {
+            const int l = l0 + k;
+            if (l >= nlevels) break;                               // uniform
+            if (k == g) {
+                solve(tcur, cur);
+                for (int t = level_ptr[l] + lt + 128; t < level_ptr[l + 1]; t += 128) { Row r; fetch(t, r); solve(t, r); }   // wide levels
+            }
+            __syncthreads();
+        }
+        cur = nxt; tcur = tnxt;
+    }
+}
+
 __global__ void k_fill_bits(unsigned long long *p, unsigned long long v, int64_t cnt) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -202,6 +277,7 @@ __global__ void k_fill_bits(unsigned long long *p, unsigned long long v, int64_t
 }
 int sptrsv_arm(cudamat_solver *s, double *vec) {
     if (s->n <= 0) return CUDAMAT_OK;
+    if (sizeof(double) * (size_t)s->n <= 200 * 1024 && !s->opt_sptrsv_no_smem) return CUDAMAT_OK;   // single-CTA sweep: no sentinel
     int grid = (s->n + 1023) / 1024;
     if (grid > 148 * 16) grid = 148 * 16;
     k_fill_bits<<<grid, 256, 0, s->stream>>>(reinterpret_cast<unsigned long long *>(vec), kSentinelBits, s->n);
@@ -225,7 +301,13 @@ static int build_schedule(cudamat_solver *s, const std::vector<int> &level, int 
     out.nlevels = nlevels;
     CM_CUDA(cudaMalloc(&out.d_order, sizeof(int) * (size_t)std::max(out.order_len, 1)));
     CM_CUDA(cudaMemcpyAsync(out.d_order, order.data(), sizeof(int) * (size_t)out.order_len, cudaMemcpyHostToDevice, s->stream));
-    CM_CUDA(cudaStreamSynchronize(s->stream));
+    CM_CUDA(cudaMalloc(&out.d_level_ptr, sizeof(int) * (size_t)(nlevels + 2)));
+    {
+        std::vector<int> lp(out.level_ptr);
+        lp.push_back(out.order_len);                       // level_ptr[nlevels + 1]: lets the kernel look one level ahead
+        CM_CUDA(cudaMemcpyAsync(out.d_level_ptr, lp.data(), sizeof(int) * (size_t)(nlevels + 2), cudaMemcpyHostToDevice, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+    }
     return CUDAMAT_OK;
 }
 
@@ -234,6 +316,7 @@ void ilu0_release(cudamat_solver *s) {
     if (s->d_diag) cudaFree(s->d_diag);
     for (LevelSchedule *P : {&s->lvl_l, &s->lvl_u}) {
         if (P->d_order) cudaFree(P->d_order);
+        if (P->d_level_ptr) cudaFree(P->d_level_ptr);
         if (P->d_cnt) cudaFree(P->d_cnt);
         if (P->d_ptr) cudaFree(P->d_ptr);
         if (P->d_col) cudaFree(P->d_col);
@@ -392,7 +475,28 @@ int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, doubl
     if (!s->d_M) { set_error("sptrsv: ILU0 factor not available (call cudamat_analyze with CUDAMAT_MODE_ILU0)"); return CUDAMAT_E_STATE; }
     const LevelSchedule &L = upper ? s->lvl_u : s->lvl_l;
     const int *status = s->d_sc ? &s->d_sc->status : nullptr;
-    if (s->opt_sptrsv_syncfree && L.order_len > 0) {
+    const size_t smem_y = sizeof(double) * (size_t)s->n;
+    if (s->opt_sptrsv_syncfree && L.order_len > 0 && smem_y <= 200 * 1024 && !s->opt_sptrsv_no_smem) {
+        // small system: one CTA, solved values in shared memory, a CTA barrier per level
+        const void *kern = upper ? (const void *)k_sptrsv_smem<true> : (const void *)k_sptrsv_smem<false>;
+        if (!s->sptrsv_smem_ready) {
+            CM_CUDA(cudaFuncSetAttribute(k_sptrsv_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CM_CUDA(cudaFuncSetAttribute(k_sptrsv_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            s->sptrsv_smem_ready = true;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(kSmemSweepThreads); cfg.stream = s->stream; cfg.dynamicSmemBytes = smem_y;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        const int *a_order = L.d_order, *a_lp = L.d_level_ptr, *a_cnt = L.d_cnt, *a_ptr = L.d_ptr, *a_col = L.d_col, *a_ja = s->pre_ja;
+        int a_nl = L.nlevels, a_len = L.order_len, a_n = s->n;
+        const double *a_val = L.d_val, *a_dg = L.d_dg, *a_M = s->d_M, *a_rhs = rhs;
+        void *args[] = {&a_order, &a_lp, &a_nl, &a_len, &a_n, &a_cnt, &a_ptr, &a_col, &a_val, &a_dg, &a_ja, &a_M, &a_rhs, &out, &status};
+        CM_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+        s->launches++;
+    } else if (s->opt_sptrsv_syncfree && L.order_len > 0) {
         if (s->sptrsv_grid == 0) {
             int occ_l = 0, occ_u = 0, sms = 0;
             CM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, k_sptrsv_syncfree<false>, 256, 0));

@@ -66,6 +66,7 @@ struct Comm;   // comm.cu
 struct LevelSchedule {
     int nlevels = 0;
     int *d_order = nullptr;        // rows sorted by level, each level padded to a multiple of 32 with -1
+    int *d_level_ptr = nullptr;    // device copy of level_ptr (+ one extra entry) for the single-CTA sweep
     // level-ordered sweep plan (ilu0.cu k_build_plan)
     int *d_cnt = nullptr, *d_ptr = nullptr, *d_col = nullptr; double *d_val = nullptr, *d_dg = nullptr;
     int order_len = 0;
@@ -98,6 +99,8 @@ struct cudamat_solver {
     int opt_staged_stages = 0;
     int opt_class_tiles_per_cta = 1;
     int opt_sptrsv_ctas_per_sm = 0;
+    int opt_sptrsv_no_smem = 0;            // 1: never use the single-CTA shared-memory sweep
+    bool sptrsv_smem_ready = false;
     int sptrsv_grid = 0;
     std::vector<cudaEvent_t> ev_pool; int ev_used = 0;
     cudamat::StagedPlan staged;
