@@ -499,6 +499,38 @@ def single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, conver
     except Exception as e:      # noqa: BLE001
         out["e2e"] = {"value": None, "error": str(e)}
 
+    # ---- same-box bar: modern cuSPARSE SpMV (cusparseSpMV through torch's CSR mat-vec) on the same matrix; library
+    #      comparator only, never on the product path ----
+    try:
+        A = torch.sparse_csr_tensor(ia, ja, a, size=(n, n))
+        y = A @ xt
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            y = A @ xt
+        e1.record()
+        torch.cuda.synchronize()
+        cms = e0.elapsed_time(e1) / 20
+        e0.record()
+        for _ in range(20):
+            s.spmv(xt.data_ptr(), y.data_ptr(), variant=1)
+        e1.record()
+        torch.cuda.synchronize()
+        oms = e0.elapsed_time(e1) / 20
+        e0.record()
+        for _ in range(20):
+            s.spmv(xt.data_ptr(), y.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        ams = e0.elapsed_time(e1) / 20
+        out["cusparse_spmv"] = {"cusparse_ms": cms, "cusparse_GBps": bytes_spmv(n, nnz) / cms / 1e6,
+                                "ours_csr_ms": oms, "ours_csr_GBps": bytes_spmv(n, nnz) / oms / 1e6,
+                                "ours_auto_ms": ams, "note": "plain y = A x, 20 back-to-back launches, CSR-algorithmic bytes; torch CSR mat-vec = cusparseSpMV"}
+        del A, y
+    except Exception as e:      # noqa: BLE001
+        out["cusparse_spmv"] = {"error": str(e)}
+
     # ---- ILU0 mode on the same system (BASELINE config 3, second mode) ----
     if not args.no_ilu0:
         try:
