@@ -33,7 +33,7 @@ class Stats(C.Structure):
                 ("t_loop", C.c_double), ("t_d2h", C.c_double), ("levels_l", C.c_int),
                 ("levels_u", C.c_int), ("spmv_variant", C.c_int), ("zero_pivot", C.c_int),
                 ("kernel_launches", C.c_int64), ("t_spmv", C.c_double), ("n_spmv", C.c_int),
-                ("reserved", C.c_int)]
+                ("graph_replay", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -222,6 +222,7 @@ static void fill_stats(cudamat_solver *s, cudamat_stats *st) {
     st->levels_u = s->lvl_u.nlevels;
     st->zero_pivot = s->zero_pivot;
     st->kernel_launches = s->launches;
+    st->graph_replay = s->graph_used ? 1 : 0;
 }
 
 static int start_scalars(cudamat_solver *s, int maxit, double tol, int hist_cap) {
@@ -231,6 +232,51 @@ static int start_scalars(cudamat_solver *s, int maxit, double tol, int hist_cap)
     *s->h_sc = h;
     CM_CUDA(cudaMemcpyAsync(s->d_sc, s->h_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));
+    return CUDAMAT_OK;
+}
+
+// Runs the iteration loop. Small single-GPU systems are launch-bound (8-19 kernels of a few microseconds per
+// iteration): there one batch of `poll_every` iterations is captured ONCE into a CUDA graph (the kernels' arguments do
+// not change between iterations — every scalar lives on the device) and replayed; the programmatic-dependent-launch
+// edges are kept by the capture.  Large systems and sharded handles (per-launch epochs) launch directly.
+template <typename Iter>
+static int run_iterations(cudamat_solver *s, int maxit, Iter &&one_iteration) {
+    int rc, npoll = 0, it = 0;
+    bool stop = false;
+    const int poll = std::max(1, s->opt_poll_every);
+    static const bool no_graph = [] { const char *e = getenv("CUDAMAT_NO_GRAPH"); return e && *e && *e != '0'; }();
+    const bool use_graph = !no_graph && s->opt_graph != 0 && !s->comm && s->opt_time_spmv == 0 && s->stream != nullptr &&
+                           s->stream != cudaStreamLegacy && s->stream != cudaStreamPerThread &&
+                           (s->opt_graph > 0 || s->n <= (1 << 22)) && maxit >= 2 * poll;
+    if (use_graph) {
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        const int64_t l0 = s->launches;
+        bool ok = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            rc = CUDAMAT_OK;
+            for (int k = 0; k < poll && rc == CUDAMAT_OK; ++k) { s->loop_it = k; rc = one_iteration(); }
+            ok = cudaStreamEndCapture(s->stream, &graph) == cudaSuccess && rc == CUDAMAT_OK && graph != nullptr;
+        }
+        const int64_t per_batch = s->launches - l0;
+        s->launches = l0;
+        if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        while (ok && !stop && it + poll <= maxit) {
+            CM_CUDA(cudaGraphLaunch(exec, s->stream));
+            s->launches += per_batch;
+            it += poll;
+            if ((rc = poll_step(s, it, maxit, &npoll, &stop))) { cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); return rc; }
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        s->graph_used = ok;
+    }
+    while (!stop && it < maxit) {
+        s->loop_it = it;
+        if ((rc = one_iteration())) return rc;
+        ++it;
+        if ((rc = poll_step(s, it, maxit, &npoll, &stop))) return rc;
+    }
     return CUDAMAT_OK;
 }
 
@@ -253,21 +299,18 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
     if ((rc = launch_spmv(s, spmv_args(s, xk, d_d, t, nullptr, 0, PH_NONE, 0), var))) return rc;
     if ((rc = launch_init_resid(s, d_b, t, r, r0, nullptr, PH_U_INIT))) return rc;
     if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
-    int npoll = 0; bool stop = false;
-    for (int it = 0; it < maxit;) {
-        s->loop_it = it;
+    rc = run_iterations(s, maxit, [&]() -> int {
+        int r2;
         HaloPush hp;
         int slot = comm_halo_push(s, p, 0, &hp) ? 0 : -1;
-        if ((rc = launch_update_p(s, false, r, v, p, &hp))) return rc;                              // :668-672
-        if ((rc = spmv_step(s, p, d_d, v, r0, 1, PH_U_A, 1, slot))) return rc;           // :675-689
+        if ((r2 = launch_update_p(s, false, r, v, p, &hp))) return r2;                              // :668-672
+        if ((r2 = spmv_step(s, p, d_d, v, r0, 1, PH_U_A, 1, slot))) return r2;           // :675-689
         slot = comm_halo_push(s, sv, 1, &hp) ? 1 : -1;
-        if ((rc = launch_update_s(s, r, v, sv, &hp))) return rc;                                    // :698-700
-        if ((rc = spmv_step(s, sv, d_d, t, sv, 2, PH_U_B, 1, slot))) return rc;         // :703-710
-        if ((rc = launch_update_xr(s, false, p, sv, t, r0, xk, r))) return rc;                      // :694-696,714-747
-        ++it;
-        if ((rc = poll_step(s, it, maxit, &npoll, &stop))) return rc;
-        if (stop) break;
-    }
+        if ((r2 = launch_update_s(s, r, v, sv, &hp))) return r2;                                    // :698-700
+        if ((r2 = spmv_step(s, sv, d_d, t, sv, 2, PH_U_B, 1, slot))) return r2;         // :703-710
+        return launch_update_xr(s, false, p, sv, t, r0, xk, r);                                     // :694-696,714-747
+    });
+    if (rc) return rc;
     if ((rc = poll_status(s))) return rc;
     CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
     return CUDAMAT_OK;
@@ -289,9 +332,8 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
     if ((rc = comm_halo_exchange(s, xk))) return rc;
     if ((rc = launch_spmv(s, spmv_args(s, xk, nullptr, t, nullptr, 0, PH_NONE, 0), var))) return rc; // :67
     if ((rc = launch_init_resid(s, d_b, t, r, rw, p, PH_I_INIT))) return rc;                        // :69-74
-    int npoll = 0; bool stop = false;
-    for (int it = 0; it < maxit;) {
-        s->loop_it = it;
+    rc = run_iterations(s, maxit, [&]() -> int {
+        int rc;
         if ((rc = launch_update_p(s, true, r, v, p))) return rc;                                    // :83-89 (skips i == 0)
         // sync-free sweeps: each output vector is armed (filled with the ready sentinel) by a coalesced fill
         // right before the sweep that produces it; re-arming through scattered stores inside the neighbouring
@@ -305,11 +347,9 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
         if ((rc = launch_sptrsv(s, false, r, tl, nullptr, 0))) return rc;                           // :121-123
         if ((rc = launch_sptrsv(s, true, tl, sv, nullptr, 0))) return rc;                           // :125-127
         if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1))) return rc;         // :132-137
-        if ((rc = launch_update_xr(s, true, nullptr, sv, t, rw, xk, r))) return rc;                 // :139-151, :81
-        ++it;
-        if ((rc = poll_step(s, it, maxit, &npoll, &stop))) return rc;
-        if (stop) break;
-    }
+        return launch_update_xr(s, true, nullptr, sv, t, rw, xk, r);                                // :139-151, :81
+    });
+    if (rc) return rc;
     if ((rc = poll_status(s))) return rc;
     CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
     return CUDAMAT_OK;
@@ -412,6 +452,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "debug")) s->opt_debug = (int)value;
     else if (!strcmp(key, "time_spmv")) s->opt_time_spmv = (int)value;
     else if (!strcmp(key, "sptrsv_ctas_per_sm")) { s->opt_sptrsv_ctas_per_sm = (int)value; s->sptrsv_grid = 0; }
+    else if (!strcmp(key, "graph")) s->opt_graph = (int)value;          // -1 auto (small systems), 0 off, 1 force
     else if (!strcmp(key, "sptrsv_no_smem")) s->opt_sptrsv_no_smem = (int)value;
     else if (!strcmp(key, "class_tiles_per_cta")) s->opt_class_tiles_per_cta = (int)value;
     else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
@@ -590,7 +631,13 @@ int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *
     cudamat_solver *s = nullptr;
     const bool tm = getenv("CUDAMAT_TIMING") != nullptr;      // stderr breakdown of the host entry point
     const double tt0 = now_s();
-    int rc = cudamat_create(&s, n, 0, n, nullptr);
+    int rc = require_device();
+    if (rc) return rc;
+    // one private non-blocking stream per thread for the one-shot entry points (CUDA graphs cannot be captured on the
+    // legacy default stream); every operation of the call is enqueued on it or is synchronous
+    static thread_local cudaStream_t host_stream = nullptr;
+    if (!host_stream && cudaStreamCreateWithFlags(&host_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); host_stream = nullptr; }
+    rc = cudamat_create(&s, n, 0, n, host_stream);
     if (rc) return rc;
     s->opt_debug = debug;
     if (debug) printf("N=%d, nnz=%d\n", n, nnz);                                  // pbicgstab.cu:203

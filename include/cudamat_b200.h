@@ -76,7 +76,7 @@ typedef struct cudamat_stats {
                                CUDA events on the launching stream (option "time_spmv" = k > 0: the SpMVs of every
                                k-th iteration are timed), else 0 */
     int    n_spmv;          /* SpMV launches covered by t_spmv                                  */
-    int    reserved;
+    int    graph_replay;    /* 1 iff the iteration loop ran as CUDA-graph replays of poll_every-iteration batches */
 } cudamat_stats;
 
 typedef struct cudamat_solver cudamat_solver;   /* opaque per-matrix handle */

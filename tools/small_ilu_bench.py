@@ -15,4 +15,4 @@ for nm in ("mat900", "mat10000"):
         for _ in range(5):
             x, dt, st = fn(a, ia, ja, b, maxit=2000, tol=1e-6)
             best = dt if best is None else min(best, dt)
-        print("%s %s: iterations=%d loop=%.3f ms  %.1f us/iteration launches=%d" % (nm, mode, st["iterations"], best * 1e3, best * 1e6 / max(st["iterations"], 1), st["kernel_launches"]))
+        print("%s %s: iterations=%d loop=%.3f ms  %.1f us/iteration launches=%d graph=%d" % (nm, mode, st["iterations"], best * 1e3, best * 1e6 / max(st["iterations"], 1), st["kernel_launches"], st["graph_replay"]))
