@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CUDAMAT_LIB") or os.path.join(_HERE, "libcudamat_b200
 ROOT = os.path.dirname(_HERE)
 
 MODE_PLAIN, MODE_SHIFTED, MODE_ILU0 = 0, 1, 2
-SPMV_AUTO, SPMV_ROWLANE, SPMV_STAGED, SPMV_PATTERN, SPMV_CLASS = 0, 1, 2, 3, 4
+SPMV_AUTO, SPMV_ROWLANE, SPMV_STAGED, SPMV_PATTERN, SPMV_CLASS, SPMV_TILED = 0, 1, 2, 3, 4, 5
 E_NO_DEVICE = -2
 
 c_dp = C.POINTER(C.c_double)

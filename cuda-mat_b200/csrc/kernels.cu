@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowl
 // PATTERN finds the row's first value at ia[first row of the slab] + exclusive scan of the class lengths.
 // ------------------------------------------------------------------------------------------
 // rows of a slab with mixed classes (domain boundaries, ragged last slab): per-lane lengths and offsets
-template <bool CLS_VALS>
+template <bool CLS_VALS, typename DICT>
 __device__ __noinline__ double class_row_general(const double *x, const double *val, const int *ia, int cid, int row0, int row,
-                                                 bool active, int lane, const DictParam &D) {
+                                                 bool active, int lane, const DICT &D) {
     const int len = active ? D.len[cid] : 0;
     const int *off = D.off + cid * kDictLen;
     const double *dv = D.val + cid * kDictLen;
@@ -268,6 +268,134 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// SpMV variant TILED: CLASS + shared-memory staging of x.  The column offsets of the frequent classes cluster into
+// a few windows (7-point stencil: {-N^2}, {-N..N}, {+N^2}); for a 2048-row tile each window is ONE contiguous range of
+// x, copied into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier complete_tx) — 3 copies per CTA replace
+// 7 x 2048 per-thread gathers, every tap becomes a conflict-free shared-memory read at row + disp[class][entry], and
+// the global traffic is full lines regardless of the L1 hit rate.  Tiles with a row whose class does not fit the
+// windows (halo columns of a shard, irregular rows) take the gather path of the CLASS kernel inside the same launch.
+// Entry order = storage order: bit-identical to every other variant.
+// ------------------------------------------------------------------------------------------
+template <int LEN>
+__device__ __forceinline__ double tiled_row_uniform(const double *xrow, const int *disp, const double *dv) {
+    double xv[LEN];
+#pragma unroll
+    for (int q = 0; q < LEN; ++q) xv[q] = xrow[disp[q]];
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < LEN; ++q) sum = __fma_rn(dv[q], xv[q], sum);
+    return sum;
+}
+#ifndef CUDAMAT_TILED_MINB
+#define CUDAMAT_TILED_MINB 3
+#endif
+template <bool HAS_D, int NDOT>
+__global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(const SpmvArgs a, const TiledArgs c,
+                                                                                const __grid_constant__ TiledDict D) {
+    extern __shared__ __align__(128) double xs[];
+    __shared__ uint64_t s_bar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int row_base = tile * kTile;
+    int cid[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + (j * kCtaWarps + warp) * kSlab + lane;
+        cid[j] = (row < a.n) ? (int)__ldg(c.cls + row) : 0xff;
+    }
+    const bool tiled = __ldg(c.tile_ok + tile) != 0;               // CTA-uniform, solve-constant
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_sync();
+    if (a.check_status && a.sc->status != ST_RUNNING) return;
+    halo_wait(a.hw, tile);
+    if (tiled) {
+        if (tid == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int g = 0; g < kMaxSeg; ++g) {
+                if (g < D.nseg) {
+                    const long long gs = (long long)row_base + D.seg_lo[g];
+                    const long long cs = max(gs, 0LL), ce = min(gs + D.seg_len[g], (long long)c.nx);
+                    const long long cnt = ce - cs;
+                    if (cnt > 0) {
+                        total += (uint32_t)(cnt & ~1LL) * 8u;
+                        if (cnt & 1) xs[D.seg_base[g] + (int)(ce - 1 - gs)] = a.x[ce - 1];      // odd tail element
+                    }
+                }
+            }
+            mbar_expect_tx(&s_bar, total);
+#pragma unroll
+            for (int g = 0; g < kMaxSeg; ++g) {
+                if (g < D.nseg) {
+                    const long long gs = (long long)row_base + D.seg_lo[g];
+                    const long long cs = max(gs, 0LL), ce = min(gs + D.seg_len[g], (long long)c.nx);
+                    const long long cnt = (ce - cs) & ~1LL;
+                    if (cnt > 0) tma_bulk_g2s(xs + D.seg_base[g] + (int)(cs - gs), a.x + cs, (uint32_t)cnt * 8u, &s_bar);
+                }
+            }
+        }
+        unsigned spins = 0;
+        while (!mbar_try_wait(&s_bar, 0)) { if (++spins > (1u << 26)) __trap(); }
+    }
+    double pp0[kSlabsPerWarp], pp1[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        pp0[j] = 0.0; pp1[j] = 0.0;
+        const int row0 = row_base + (j * kCtaWarps + warp) * kSlab;
+        if (row0 >= a.n) continue;                                // warp-uniform
+        const int row = row0 + lane;
+        const bool active = row < a.n;
+        double uval = 0.0;
+        if (NDOT >= 1 && active) uval = __ldg(a.u + row);
+        double sum;
+        if (tiled) {
+            const double *xrow = xs + (row - row_base);
+            const int c0 = __shfl_sync(0xffffffffu, cid[j], 0);
+            const bool uni = __all_sync(0xffffffffu, cid[j] == c0) && c0 != 0xff;
+            const int len0 = uni ? D.len[c0] : 0;
+            if (len0 == 7) sum = tiled_row_uniform<7>(xrow, D.disp + c0 * kDictLen, D.val + c0 * kDictLen);
+            else if (len0 == 5) sum = tiled_row_uniform<5>(xrow, D.disp + c0 * kDictLen, D.val + c0 * kDictLen);
+            else {
+                const int cc = active ? cid[j] : 0;
+                const int len = active ? D.len[cc] : 0;
+                const int *dp = D.disp + cc * kDictLen;
+                const double *dv = D.val + cc * kDictLen;
+                const int maxlen = __reduce_max_sync(0xffffffffu, len);
+                sum = 0.0;
+#pragma unroll 1
+                for (int k0 = 0; k0 < maxlen; k0 += 4) {
+                    double xv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) xv[q] = (k0 + q < len) ? xrow[dp[k0 + q]] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (k0 + q < len) sum = __fma_rn(dv[k0 + q], xv[q], sum);
+                }
+            }
+        } else {
+            sum = class_row_general<true>(a.x, a.val, a.ia, active ? cid[j] : 0, row0, row, active, lane, D);
+        }
+        if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
+        if (active) a.y[row] = sum;
+        if (NDOT >= 1) pp0[j] = active ? __dmul_rn(sum, uval) : 0.0;
+        if (NDOT >= 2) pp1[j] = active ? __dmul_rn(sum, sum) : 0.0;
+    }
+    if (NDOT >= 1) {
+#pragma unroll
+        for (int j = 0; j < kSlabsPerWarp; ++j) {
+            if (row_base + (j * kCtaWarps + warp) * kSlab < a.n) {
+                slab_deposit(a.rc, 0, tile * kTileSlabs + j * kCtaWarps + warp, pp0[j], lane);
+                if (NDOT >= 2) slab_deposit(a.rc, 1, tile * kTileSlabs + j * kCtaWarps + warp, pp1[j], lane);
+            }
+        }
+    }
 }
 
 struct StagedArgs {
@@ -482,6 +610,23 @@ template <bool HAS_D, int NDOT>
 static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
     const int grid = (a.n + kTile - 1) / kTile;
     if (grid == 0) return CUDAMAT_OK;
+    if (variant == CUDAMAT_SPMV_TILED && s->cls[1].h_tdict && ((uintptr_t)a.x % 16) == 0) {
+        const TiledArgs c{s->cls[1].d_cls, s->cls[1].d_tile_ok, s->cls[1].ncls, s->n + s->nhalo};
+        auto kern = k_spmv_tiled<HAS_D, NDOT>;
+        static bool attr_set = false;
+        if (!attr_set) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = true; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCtaThreads); cfg.dynamicSmemBytes = s->cls[1].tiled_smem; cfg.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        CM_CUDA(cudaLaunchKernelEx(&cfg, kern, a, c, *s->cls[1].h_tdict));
+        s->launches++;
+        CM_CUDA(cudaGetLastError());
+        return CUDAMAT_OK;
+    }
+    if (variant == CUDAMAT_SPMV_TILED) variant = CUDAMAT_SPMV_CLASS;
     if (variant == CUDAMAT_SPMV_CLASS && s->cls[1].ncls > 0) {
         const int T = std::max(1, s->opt_class_tiles_per_cta);
         const ClassArgs c{s->cls[1].d_cls, s->cls[1].ncls, T};

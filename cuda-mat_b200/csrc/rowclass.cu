@@ -12,6 +12,8 @@
 // This is what cusparseDcsrmv (pbicgstab.cu:67,104,132,646,676,704) cannot do: it must stream 12 B per entry.
 #include "solver.h"
 #include <cstring>
+#include <algorithm>
+#include <vector>
 
 namespace cudamat {
 
@@ -108,10 +110,105 @@ __global__ void k_cls_assign(int n, const int *ia, const int *ja, const double *
     cls[row] = (unsigned char)id;
 }
 
+__global__ void k_cls_hist(int n, const unsigned char *cls, unsigned *hist) {
+    __shared__ unsigned h[kDictMax];
+    for (int i = threadIdx.x; i < kDictMax; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&h[cls[i] & (kDictMax - 1)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kDictMax; i += blockDim.x) if (h[i]) atomicAdd(hist + i, h[i]);
+}
+// tile_ok[t] = every row of tile t belongs to a class whose offsets all fall into the staged windows
+__global__ void k_tile_ok(int n, const unsigned char *cls, unsigned long long ok_mask, unsigned char *tile_ok) {
+    const int tile = blockIdx.x;
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int r = tile * kTile + threadIdx.x; r < min(n, (tile + 1) * kTile); r += blockDim.x)
+        if (!((ok_mask >> (cls[r] & 63)) & 1ull)) bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) tile_ok[tile] = bad ? 0 : 1;
+}
+
+// TILED plan for the offsets+values dictionary: windows = clusters of the column offsets of the frequent classes
+static int tiled_plan(cudamat_solver *s, RowClasses &C) {
+    const int n = s->n;
+    unsigned *d_hist = nullptr;
+    CM_CUDA(dev_alloc((void **)&d_hist, sizeof(unsigned) * kDictMax));
+    CM_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * kDictMax, s->stream));
+    k_cls_hist<<<296, 256, 0, s->stream>>>(n, C.d_cls, d_hist);
+    unsigned hist[kDictMax];
+    CM_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    dev_free(d_hist);
+    s->launches++;
+    const DictParam &D = *C.h_dict;
+    // offsets of the frequent classes (>= 1/64 of the rows, or the most frequent one)
+    int top = 0;
+    for (int c = 1; c < C.ncls; ++c) if (hist[c] > hist[top]) top = c;
+    std::vector<int> offs;
+    for (int c = 0; c < C.ncls; ++c)
+        if (c == top || hist[c] >= (unsigned)std::max(1, n / 64))
+            for (int k = 0; k < D.len[c]; ++k) offs.push_back(D.off[c * kDictLen + k]);
+    if (offs.empty()) return CUDAMAT_OK;
+    std::sort(offs.begin(), offs.end());
+    offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+    TiledDict *T = new TiledDict();
+    memset(T, 0, sizeof(TiledDict));
+    int nseg = 0, base = 0;
+    size_t k = 0;
+    bool fits = true;
+    while (k < offs.size()) {
+        int lo = offs[k], hi = offs[k];
+        while (k + 1 < offs.size() && (long long)offs[k + 1] - hi <= 4096) hi = offs[++k];
+        ++k;
+        if (nseg == kMaxSeg) { fits = false; break; }
+        lo &= ~1;                                              // 16-byte aligned bulk copies (tile starts are even)
+        int len = kTile + (hi - lo) + 1;
+        len = (len + 1) & ~1;
+        T->seg_lo[nseg] = lo; T->seg_len[nseg] = len; T->seg_base[nseg] = base;
+        base += len;
+        ++nseg;
+    }
+    const size_t smem = sizeof(double) * (size_t)base;
+    if (!fits || smem > 100 * 1024) { delete T; return CUDAMAT_OK; }
+    T->nseg = nseg;
+    unsigned long long ok_mask = 0;
+    for (int c = 0; c < C.ncls; ++c) {
+        T->len[c] = D.len[c];
+        bool ok = true;
+        for (int q = 0; q < kDictLen; ++q) {
+            const int o = D.off[c * kDictLen + q];
+            T->off[c * kDictLen + q] = o;
+            T->val[c * kDictLen + q] = D.val[c * kDictLen + q];
+            int disp = 0;
+            if (q < D.len[c]) {
+                int sg = -1;
+                for (int g = 0; g < nseg; ++g)
+                    if (o >= T->seg_lo[g] && o + kTile <= T->seg_lo[g] + T->seg_len[g]) { sg = g; break; }
+                if (sg < 0) ok = false; else disp = T->seg_base[sg] + (o - T->seg_lo[sg]);
+            }
+            T->disp[c * kDictLen + q] = disp;
+        }
+        if (ok) ok_mask |= 1ull << c;
+    }
+    const int ntile = (n + kTile - 1) / kTile;
+    CM_CUDA(dev_alloc((void **)&C.d_tile_ok, (size_t)std::max(ntile, 1)));
+    k_tile_ok<<<ntile, 256, 0, s->stream>>>(n, C.d_cls, ok_mask, C.d_tile_ok);
+    CM_CUDA(cudaGetLastError());
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    s->launches++;
+    C.h_tdict = T;
+    C.tiled_smem = smem;
+    return CUDAMAT_OK;
+}
+
 void rowclass_release(cudamat_solver *s) {
     for (int m = 0; m < 2; ++m) {
         dev_free(s->cls[m].d_cls);
         delete s->cls[m].h_dict;
+        delete s->cls[m].h_tdict;
+        dev_free(s->cls[m].d_tile_ok);
         dev_free(s->cls[m].d_dict);
         s->cls[m] = RowClasses();
     }
@@ -169,6 +266,7 @@ int rowclass_analyze(cudamat_solver *s) {
     }
     cudaStreamSynchronize(s->stream);
     dev_free(tab); dev_free(rep); dev_free(slot_id); dev_free(flags);
+    if (rc == CUDAMAT_OK && s->cls[1].ncls > 0) rc = tiled_plan(s, s->cls[1]);
     return rc;
 }
 

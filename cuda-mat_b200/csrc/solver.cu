@@ -520,6 +520,7 @@ int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
     int variant = s->opt_spmv_variant;
     if (variant == CUDAMAT_SPMV_AUTO)
         variant = s->cls[1].ncls > 0 ? CUDAMAT_SPMV_CLASS : s->cls[0].ncls > 0 ? CUDAMAT_SPMV_PATTERN : CUDAMAT_SPMV_ROWLANE;
+    if (variant == CUDAMAT_SPMV_TILED && !s->cls[1].h_tdict) variant = CUDAMAT_SPMV_CLASS;
     if (variant == CUDAMAT_SPMV_CLASS && s->cls[1].ncls == 0) variant = CUDAMAT_SPMV_PATTERN;
     if (variant == CUDAMAT_SPMV_PATTERN && s->cls[0].ncls == 0) variant = CUDAMAT_SPMV_ROWLANE;
     if (variant == CUDAMAT_SPMV_STAGED && s->staged.cap_nnz == 0) variant = CUDAMAT_SPMV_ROWLANE;

@@ -53,10 +53,26 @@ struct DictParam {
     int off[kDictMax * kDictLen];
     double val[kDictMax * kDictLen];
 };
+// TILED variant: x windows of a tile staged in shared memory by TMA bulk copies (rowclass.cu tiled_plan)
+constexpr int kMaxSeg = 4;
+struct TiledDict {                     // kernel parameter (16.9 KB)
+    int len[kDictMax];
+    int off[kDictMax * kDictLen];      // column offsets (fallback path: tiles that are not eligible)
+    int disp[kDictMax * kDictLen];     // shared-memory index of the entry relative to the row's position in the tile
+    double val[kDictMax * kDictLen];
+    int nseg;
+    int seg_lo[kMaxSeg];               // first column offset of the window (even)
+    int seg_len[kMaxSeg];              // window length in elements = kTile + span (even)
+    int seg_base[kMaxSeg];             // start of the window in shared memory (elements)
+};
+struct TiledArgs { const unsigned char *cls; const unsigned char *tile_ok; int ncls; int nx; };
 struct RowClasses {
     unsigned char *d_cls = nullptr;    // class id per row
     RowDict *d_dict = nullptr;
     DictParam *h_dict = nullptr;       // host copy handed to the kernel launches
+    TiledDict *h_tdict = nullptr;      // TILED plan (only for the offsets+values dictionary), nullptr = unavailable
+    unsigned char *d_tile_ok = nullptr;
+    size_t tiled_smem = 0;
     int ncls = 0;                      // 0 = not available
 };
 struct ClassArgs { const unsigned char *cls; int ncls; int tiles_per_cta; };

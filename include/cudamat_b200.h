@@ -54,6 +54,7 @@ extern "C" {
 #define CUDAMAT_SPMV_STAGED    2    /* row-block staged through shared memory by TMA bulk copies */
 #define CUDAMAT_SPMV_PATTERN   3    /* column offsets from a per-row class dictionary (1 B/row), values from CSR */
 #define CUDAMAT_SPMV_CLASS     4    /* offsets AND values from the class dictionary: CSR arrays are not read   */
+#define CUDAMAT_SPMV_TILED     5    /* CLASS + the x windows of a 2048-row tile staged in shared memory by TMA  */
 
 typedef struct cudamat_stats {
     int    iterations;      /* the reference's loop counter i at exit                          */

@@ -15,7 +15,7 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 2, 3, 4]   # ROWLANE, STAGED, PATTERN, CLASS (the dictionary variants fall back to ROWLANE when a matrix has no small row-class dictionary)
+VARIANTS = [1, 2, 3, 4, 5]   # ROWLANE, STAGED, PATTERN, CLASS, TILED (the dictionary variants fall back to ROWLANE when a matrix has no small row-class dictionary)
 
 
 def dev(torch, a, dtype=None):
@@ -100,7 +100,7 @@ def test_spmv_linearity_and_variants_agree_large(cm, torch_cuda):
     st = s.analyze(0)
     assert st["spmv_variant"] == cm.SPMV_CLASS          # a constant-coefficient stencil: the class dictionary is chosen
     s.spmv(x.data_ptr(), ax1.data_ptr(), variant=1)
-    for v in (2, 3, 4):
+    for v in (2, 3, 4, 5):
         s.spmv(x.data_ptr(), ax2.data_ptr(), variant=v)
         torch.cuda.synchronize()
         assert torch.equal(ax1, ax2), v
