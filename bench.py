@@ -217,12 +217,13 @@ def run_ours(args):
     b_spmv = bytes_spmv(n, nnz)           # whole-problem algorithmic bytes of one CSR SpMV
     b_it = bytes_iter(n, nnz)
     b_spmv_loc = 12 * nnz_loc + 4 * (nloc + 1) + 16 * nloc      # this rank's share of one SpMV launch
-    VNAME = {1: "k_spmv_rowlane", 2: "k_spmv_staged", 3: "k_spmv_class<values from CSR>", 4: "k_spmv_class<values from dictionary>"}
+    VNAME = {1: "k_spmv_rowlane", 2: "k_spmv_staged", 3: "k_spmv_class<values from CSR>", 4: "k_spmv_class<values from dictionary>",
+             5: "k_spmv_tiled<class dictionary, x windows staged by TMA>"}
 
     def moved_bytes(variant):
         """bytes one SpMV launch of this rank has to move in the variant's own storage format (x read once, y written
         once, + the dot operand for the fused epilogue is not counted, as in B_spmv)"""
-        if variant == 4:
+        if variant in (4, 5):
             return 17 * nloc
         if variant == 3:
             return 8 * nnz_loc + 17 * nloc + 4 * (nloc // 32 + 1)
@@ -272,7 +273,7 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": b_spmv_loc, "avg_launch_ms": spmv_ms, "launches_timed": n_spmv,
                 "format_bytes_per_launch": mv, "format_GBps": mv / (spmv_ms * 1e-3) / 1e9, "format_frac": mv / (spmv_ms * 1e-3) / 1e9 / peak,
                 "note": "achieved/frac use the CSR algorithmic bytes of SURVEY.md 8d (12 nnz + 4(n+1) + 16 n); the dictionary variants "
-                        "(3, 4) replace index / value streams by 1 B per row, so frac can exceed 1 - format_* is what the kernel really has to move",
+                        "(3, 4, 5) replace index / value streams by 1 B per row, so frac can exceed 1 - format_* is what the kernel really has to move",
                 "iteration": {"algorithmic_bytes": b_it, "achieved_GBps": b_it / world * its / 1e9,
                               "frac": b_it / world * its / 1e9 / peak, "spmv_share_of_step": 2 * spmv_ms / (ms / K)}}
 

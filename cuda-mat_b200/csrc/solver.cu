@@ -514,12 +514,13 @@ int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
     // Variant choice from the row statistics.  Measured on B200 (profiles/): with <= 32 entries per row the direct
     // row-per-lane kernel streams CSR at ~99 % of the copy roofline, ahead of the TMA-staged kernel whose
     // shared-memory ring caps occupancy (opt-in).  When the rows fall into a few classes up to translation
-    // (stencil matrices) the dictionary variants move far fewer bytes and win outright: CLASS (offsets and
-    // values from the dictionary) > PATTERN (offsets only) > ROWLANE.
+    // (stencil matrices) the dictionary variants move far fewer bytes and win outright: TILED (CLASS + x windows staged
+    // in shared memory by TMA) > CLASS (offsets and values from the dictionary) > PATTERN (offsets only) > ROWLANE.
     if ((rc = rowclass_analyze(s))) return rc;
     int variant = s->opt_spmv_variant;
     if (variant == CUDAMAT_SPMV_AUTO)
-        variant = s->cls[1].ncls > 0 ? CUDAMAT_SPMV_CLASS : s->cls[0].ncls > 0 ? CUDAMAT_SPMV_PATTERN : CUDAMAT_SPMV_ROWLANE;
+        variant = s->cls[1].h_tdict ? CUDAMAT_SPMV_TILED : s->cls[1].ncls > 0 ? CUDAMAT_SPMV_CLASS
+                : s->cls[0].ncls > 0 ? CUDAMAT_SPMV_PATTERN : CUDAMAT_SPMV_ROWLANE;
     if (variant == CUDAMAT_SPMV_TILED && !s->cls[1].h_tdict) variant = CUDAMAT_SPMV_CLASS;
     if (variant == CUDAMAT_SPMV_CLASS && s->cls[1].ncls == 0) variant = CUDAMAT_SPMV_PATTERN;
     if (variant == CUDAMAT_SPMV_PATTERN && s->cls[0].ncls == 0) variant = CUDAMAT_SPMV_ROWLANE;

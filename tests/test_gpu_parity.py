@@ -98,7 +98,7 @@ def test_spmv_linearity_and_variants_agree_large(cm, torch_cuda):
     cm.gen_xtrue_device(99, 0, n, y.data_ptr())
     ax1, ax2, ay = (torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3))
     st = s.analyze(0)
-    assert st["spmv_variant"] == cm.SPMV_CLASS          # a constant-coefficient stencil: the class dictionary is chosen
+    assert st["spmv_variant"] == cm.SPMV_TILED          # a constant-coefficient stencil: class dictionary + staged x windows
     s.spmv(x.data_ptr(), ax1.data_ptr(), variant=1)
     for v in (2, 3, 4, 5):
         s.spmv(x.data_ptr(), ax2.data_ptr(), variant=v)
