@@ -9,6 +9,7 @@
 // The parallel schedule (levels / sync-free flags) never changes the per-row operation order.
 #include "solver.h"
 #include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace cudamat {
 
@@ -289,6 +290,160 @@ int sptrsv_arm(cudamat_solver *s, double *vec) {
 // ------------------------------------------------------------------------------------------
 // host-side analysis (v1): level sets from the CSR pattern on the host
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Level analysis on the device (replaces cusparseDcsrsv_analysis, pbicgstab.cu:338,345; the first version of this
+// file downloaded the pattern and walked it on the host: 0.9 s at 256^3).
+//   k_find_diag        : position of the diagonal entry of every row (missing -> smallest such row)
+//   k_levels_syncfree  : level(i) = 1 + max level of its dependencies, one launch per factor.  A warp owns 32
+//                        consecutive positions of the sweep order (ticketed, so earlier positions always started);
+//                        dependencies outside the warp are polled (level array pre-filled with -1), dependencies
+//                        inside the warp are resolved by 32 shuffle steps over a per-lane dependency mask.
+//   radix sort by level (stable: ascending rows inside a level) + k_level_starts + k_scatter_order build the padded
+//   level-ordered row list.
+// ------------------------------------------------------------------------------------------
+__global__ void k_find_diag(int n, const int *ia, const int *ja, int *diag, int *bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int dp = -1;
+    for (int p = ia[i]; p < ia[i + 1]; ++p) if (ja[p] == i) { dp = p; break; }
+    diag[i] = dp;
+    if (dp < 0) atomicMin(bad, i);
+}
+__device__ __forceinline__ int ld_relaxed_i32(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <bool UPPER>
+__global__ void __launch_bounds__(256) k_levels_syncfree(int n, const int *ia, const int *ja, const int *diag, int *level,
+                                                        unsigned *ticket, int *maxlevel) {
+    __shared__ unsigned s_chunk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunk = (n + 255) / 256;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned chunk = s_chunk;
+        if (chunk >= (unsigned)nchunk) break;
+        const int pbase = (int)chunk * 256 + warp * 32;            // first position of this warp
+        const int pos = pbase + lane;
+        const bool act = pos < n;
+        const int i = act ? (UPPER ? n - 1 - pos : pos) : 0;
+        int lv = 0;
+        unsigned mask = 0;
+        if (act) {
+            const int p0 = UPPER ? diag[i] + 1 : ia[i], p1 = UPPER ? ia[i + 1] : diag[i];
+            for (int p = p0; p < p1; ++p) {
+                const int c = ja[p];
+                const int cpos = UPPER ? n - 1 - c : c;
+                if (cpos >= pbase) { mask |= 1u << (cpos - pbase); continue; }     // inside this warp (cpos < pos)
+                int v = ld_relaxed_i32(level + c);
+                unsigned spins = 0;
+                while (v < 0) { if (++spins > (1u << 24)) __trap(); v = ld_relaxed_i32(level + c); }
+                lv = max(lv, v + 1);
+            }
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, mask != 0);
+        if (any) {
+#pragma unroll 1
+            for (int t = 0; t < 31; ++t) {                         // lane t is final once lanes < t are
+                const int lt = __shfl_sync(0xffffffffu, lv, t);
+                if ((mask >> t) & 1u) lv = max(lv, lt + 1);
+            }
+        }
+        if (act) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(level + i), "r"(lv) : "memory");
+        const int wmax = __reduce_max_sync(0xffffffffu, act ? lv : 0);
+        if (lane == 0) atomicMax(maxlevel, wmax);
+    }
+}
+__global__ void k_iota(int n, int *v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+__global__ void k_level_starts(int n, const int *sorted_level, int *start /*[nlevels + 1]*/, int nlevels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = sorted_level[i];
+    if (i == 0) { for (int q = 0; q <= l; ++q) start[q] = 0; }
+    else { const int lp = sorted_level[i - 1]; for (int q = lp + 1; q <= l; ++q) start[q] = i; }
+    if (i == n - 1) { for (int q = l + 1; q <= nlevels; ++q) start[q] = n; }
+}
+__global__ void k_scatter_order(int n, const int *sorted_level, const int *sorted_row, const int *start, const int *padded_ptr, int *order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = sorted_level[i];
+    order[padded_ptr[l] + (i - start[l])] = sorted_row[i];
+}
+
+// level set of one factor entirely on the device; fills out.{nlevels, level_ptr, order_len, d_order, d_level_ptr}
+static int device_schedule(cudamat_solver *s, bool upper, LevelSchedule &out) {
+    const int n = s->n;
+    int *d_level = nullptr, *d_rows = nullptr, *d_level2 = nullptr, *d_rows2 = nullptr, *d_misc = nullptr;
+    CM_CUDA(dev_alloc((void **)&d_level, sizeof(int) * (size_t)std::max(n, 1)));
+    CM_CUDA(dev_alloc((void **)&d_misc, sizeof(int) * 4));
+    CM_CUDA(cudaMemsetAsync(d_level, 0xff, sizeof(int) * (size_t)std::max(n, 1), s->stream));
+    CM_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 4, s->stream));
+    if (n > 0) {
+        int occ = 0, sms = 0;
+        if (upper) CM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_levels_syncfree<true>, 256, 0));
+        else CM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_levels_syncfree<false>, 256, 0));
+        CM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+        const int grid = std::max(1, std::min(occ * sms, (n + 255) / 256));       // co-resident: a polling CTA never starves a producer
+        if (upper) k_levels_syncfree<true><<<grid, 256, 0, s->stream>>>(n, s->pre_ia, s->pre_ja, s->d_diag, d_level, (unsigned *)d_misc, d_misc + 1);
+        else k_levels_syncfree<false><<<grid, 256, 0, s->stream>>>(n, s->pre_ia, s->pre_ja, s->d_diag, d_level, (unsigned *)d_misc, d_misc + 1);
+        CM_CUDA(cudaGetLastError());
+        s->launches++;
+    }
+    int maxl = 0;
+    CM_CUDA(cudaMemcpyAsync(&maxl, d_misc + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    const int nlevels = n > 0 ? maxl + 1 : 0;
+    out.nlevels = nlevels;
+    out.level_ptr.assign((size_t)nlevels + 1, 0);
+    std::vector<int> start((size_t)nlevels + 1, 0);
+    int *d_start = nullptr, *d_pad = nullptr;
+    if (n > 0) {
+        CM_CUDA(dev_alloc((void **)&d_rows, sizeof(int) * (size_t)n));
+        CM_CUDA(dev_alloc((void **)&d_level2, sizeof(int) * (size_t)n));
+        CM_CUDA(dev_alloc((void **)&d_rows2, sizeof(int) * (size_t)n));
+        k_iota<<<(n + 255) / 256, 256, 0, s->stream>>>(n, d_rows);
+        int bits = 1;
+        while ((1 << bits) < nlevels + 1 && bits < 31) ++bits;
+        size_t tmp_bytes = 0;
+        CM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_level, d_level2, d_rows, d_rows2, n, 0, bits, s->stream));
+        void *d_tmp = nullptr;
+        CM_CUDA(dev_alloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        CM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_level, d_level2, d_rows, d_rows2, n, 0, bits, s->stream));
+        CM_CUDA(dev_alloc((void **)&d_start, sizeof(int) * (size_t)(nlevels + 1)));
+        CM_CUDA(dev_alloc((void **)&d_pad, sizeof(int) * (size_t)(nlevels + 1)));
+        k_level_starts<<<(n + 255) / 256, 256, 0, s->stream>>>(n, d_level2, d_start, nlevels);
+        CM_CUDA(cudaMemcpyAsync(start.data(), d_start, sizeof(int) * (size_t)(nlevels + 1), cudaMemcpyDeviceToHost, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+        dev_free(d_tmp);
+        s->launches += 3;
+    }
+    for (int l = 0; l < nlevels; ++l) out.level_ptr[l + 1] = out.level_ptr[l] + ((start[l + 1] - start[l] + 31) / 32) * 32;
+    out.order_len = nlevels > 0 ? out.level_ptr[nlevels] : 0;
+    CM_CUDA(cudaMalloc(&out.d_order, sizeof(int) * (size_t)std::max(out.order_len, 1)));
+    CM_CUDA(cudaMemsetAsync(out.d_order, 0xff, sizeof(int) * (size_t)std::max(out.order_len, 1), s->stream));
+    CM_CUDA(cudaMalloc(&out.d_level_ptr, sizeof(int) * (size_t)(nlevels + 2)));
+    {
+        std::vector<int> lp(out.level_ptr);
+        lp.push_back(out.order_len);                       // level_ptr[nlevels + 1]: lets the kernel look one level ahead
+        CM_CUDA(cudaMemcpyAsync(out.d_level_ptr, lp.data(), sizeof(int) * (size_t)(nlevels + 2), cudaMemcpyHostToDevice, s->stream));
+        if (n > 0) {
+            CM_CUDA(cudaMemcpyAsync(d_pad, out.level_ptr.data(), sizeof(int) * (size_t)(nlevels + 1), cudaMemcpyHostToDevice, s->stream));
+            k_scatter_order<<<(n + 255) / 256, 256, 0, s->stream>>>(n, d_level2, d_rows2, d_start, d_pad, out.d_order);
+            s->launches++;
+        }
+        CM_CUDA(cudaGetLastError());
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    dev_free(d_level); dev_free(d_misc); dev_free(d_rows); dev_free(d_level2); dev_free(d_rows2); dev_free(d_start); dev_free(d_pad);
+    return CUDAMAT_OK;
+}
+
 static int build_schedule(cudamat_solver *s, const std::vector<int> &level, int nlevels, LevelSchedule &out) {
     const int n = s->n;
     std::vector<int> cnt(nlevels + 1, 0);
@@ -391,37 +546,55 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     }
     const int64_t nnz = s->pre_nnz;
     double t0 = now_s();
-    std::vector<int> ia(n + 1), ja((size_t)nnz);
-    CM_CUDA(cudaMemcpyAsync(ia.data(), s->pre_ia, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, s->stream));
-    CM_CUDA(cudaMemcpyAsync(ja.data(), s->pre_ja, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, s->stream));
-    CM_CUDA(cudaStreamSynchronize(s->stream));
-    std::vector<int> diag(n), lvl(n);
-    for (int i = 0; i < n; ++i) {
-        int dp = -1;
-        for (int p = ia[i]; p < ia[i + 1]; ++p) if (ja[p] == i) { dp = p; break; }
-        if (dp < 0) {
-            set_error("ILU0: row %d has no structural diagonal entry (precondition pbicgstab.h:118)", i);
+    int nl = 0, nu = 0, rc;
+    CM_CUDA(cudaMalloc(&s->d_diag, sizeof(int) * (size_t)std::max(n, 1)));
+    if (!s->opt_host_analysis) {
+        int *d_bad = nullptr;
+        CM_CUDA(dev_alloc((void **)&d_bad, sizeof(int)));
+        CM_CUDA(cudaMemsetAsync(d_bad, 0x7f, sizeof(int), s->stream));
+        if (n > 0) k_find_diag<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->pre_ia, s->pre_ja, s->d_diag, d_bad);
+        int bad = 0;
+        CM_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+        dev_free(d_bad);
+        s->launches++;
+        if (bad != 0x7f7f7f7f) {
+            set_error("ILU0: row %d has no structural diagonal entry (precondition pbicgstab.h:118)", bad);
             return CUDAMAT_E_NO_DIAGONAL;
         }
-        diag[i] = dp;
+        if ((rc = device_schedule(s, false, s->lvl_l))) return rc;
+        if ((rc = device_schedule(s, true, s->lvl_u))) return rc;
+        nl = s->lvl_l.nlevels; nu = s->lvl_u.nlevels;
+    } else {
+        // host cross-check path ("host_analysis" option): download the pattern and walk it serially
+        std::vector<int> ia(n + 1), ja((size_t)nnz);
+        CM_CUDA(cudaMemcpyAsync(ia.data(), s->pre_ia, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, s->stream));
+        CM_CUDA(cudaMemcpyAsync(ja.data(), s->pre_ja, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+        std::vector<int> diag(n), lvl(n);
+        for (int i = 0; i < n; ++i) {
+            int dp = -1;
+            for (int p = ia[i]; p < ia[i + 1]; ++p) if (ja[p] == i) { dp = p; break; }
+            if (dp < 0) {
+                set_error("ILU0: row %d has no structural diagonal entry (precondition pbicgstab.h:118)", i);
+                return CUDAMAT_E_NO_DIAGONAL;
+            }
+            diag[i] = dp;
+        }
+        for (int i = 0; i < n; ++i) {
+            int lv = 0;
+            for (int p = ia[i]; p < diag[i]; ++p) lv = std::max(lv, lvl[ja[p]] + 1);
+            lvl[i] = lv; nl = std::max(nl, lv + 1);
+        }
+        if ((rc = build_schedule(s, lvl, nl, s->lvl_l))) return rc;
+        for (int i = n - 1; i >= 0; --i) {
+            int lv = 0;
+            for (int p = diag[i] + 1; p < ia[i + 1]; ++p) lv = std::max(lv, lvl[ja[p]] + 1);
+            lvl[i] = lv; nu = std::max(nu, lv + 1);
+        }
+        if ((rc = build_schedule(s, lvl, nu, s->lvl_u))) return rc;
+        CM_CUDA(cudaMemcpyAsync(s->d_diag, diag.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
     }
-    int nl = 0, nu = 0;
-    for (int i = 0; i < n; ++i) {
-        int lv = 0;
-        for (int p = ia[i]; p < diag[i]; ++p) lv = std::max(lv, lvl[ja[p]] + 1);
-        lvl[i] = lv; nl = std::max(nl, lv + 1);
-    }
-    int rc = build_schedule(s, lvl, nl, s->lvl_l);
-    if (rc) return rc;
-    for (int i = n - 1; i >= 0; --i) {
-        int lv = 0;
-        for (int p = diag[i] + 1; p < ia[i + 1]; ++p) lv = std::max(lv, lvl[ja[p]] + 1);
-        lvl[i] = lv; nu = std::max(nu, lv + 1);
-    }
-    rc = build_schedule(s, lvl, nu, s->lvl_u);
-    if (rc) return rc;
-    CM_CUDA(cudaMalloc(&s->d_diag, sizeof(int) * (size_t)std::max(n, 1)));
-    CM_CUDA(cudaMemcpyAsync(s->d_diag, diag.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
     s->epoch = 0;
     CM_CUDA(cudaStreamSynchronize(s->stream));
     if (st) { st->t_analysis += now_s() - t0; st->levels_l = nl; st->levels_u = nu; }

@@ -115,6 +115,7 @@ struct cudamat_solver {
     int opt_staged_stages = 0;
     int opt_class_tiles_per_cta = 1;
     int opt_sptrsv_ctas_per_sm = 0;
+    int opt_host_analysis = 0;             // 1: ILU0 level analysis on the host (cross-check of the device analysis)
     int opt_graph = -1;                    // CUDA-graph replay of iteration batches: -1 auto, 0 off, 1 force
     bool graph_used = false;
     int opt_sptrsv_no_smem = 0;            // 1: never use the single-CTA shared-memory sweep

@@ -301,6 +301,29 @@ def test_breakdown_maxit_and_edge_cases(cm, O, pin):
     assert st["converged"] and x[0] == 0.5
 
 
+def test_device_level_analysis_matches_host_walk(cm, O, pin, torch_cuda):
+    """the sync-free device level analysis (k_levels_syncfree + radix sort) and the serial host walk of the pattern give the
+    same level counts, the same ILU(0) factor and bit-identical solves"""
+    torch = torch_cuda
+    for nm, (ia, ja, a) in (("mat10000", csr(pin, "mat10000")), ("poisson20", O.poisson3d(20)), ("random_dd", O.random_dd(5000, 20240))):
+        n = len(ia) - 1
+        b = np.random.default_rng(2).standard_normal(n)
+        res = []
+        for host in (0, 1):
+            s = cm.Solver(n)
+            s.set_option("host_analysis", host)
+            s.set_csr_host(a, ia, ja)
+            st = s.analyze(cm.MODE_ILU0)
+            db, dx = dev(torch, b), torch.zeros(n, dtype=torch.float64, device="cuda")
+            so = s.solve(cm.MODE_ILU0, db.data_ptr(), dx.data_ptr(), maxit=500, tol=1e-10)
+            res.append((st["levels_l"], st["levels_u"], s.ilu0_values(len(a)), so["iterations"], dx.cpu().numpy()))
+            s.close()
+        assert res[0][0] == res[1][0] and res[0][1] == res[1][1], nm
+        assert np.array_equal(res[0][2], res[1][2]) and res[0][3] == res[1][3] and np.array_equal(res[0][4], res[1][4]), nm
+        lo, nl = O.levels(ia - ia[0], ja - ia[0], upper=False)
+        assert nl == res[0][0], nm
+
+
 def test_spmv_agrees_with_cusparse_through_torch(cm, torch_cuda):
     """Independent on-box comparator: torch's CSR mat-vec calls modern cuSPARSE (cusparseSpMV). Summation
     orders differ, so the check is a tight tolerance, not bits: |y - y_cusparse| <= 1e-13 * (|A| |x|) row by row."""
