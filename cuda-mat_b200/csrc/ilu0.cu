@@ -76,8 +76,7 @@ __global__ void k_sptrsv_level(const int *order, int cnt, const int *ia, const i
 //     no fence;
 //   * the row's matrix entries are loaded before the first wait, so the dependent chain per level is
 //     just poll -> fma -> store.
-//   The sentinel is re-armed for free: the L sweep clears the output cell of the following U sweep, the
-//   U sweep clears the cell of its right-hand side (the L sweep's private output) after reading it.
+//   The output vector is armed (filled with the sentinel) by a coalesced fill right before the sweep (sptrsv_arm).
 // ------------------------------------------------------------------------------------------
 constexpr unsigned long long kSentinelBits = 0xFFF8B200C0DEFACEull;
 
@@ -136,11 +135,10 @@ __global__ void k_build_plan(const int *order, int len, const int *ia, const int
 template <bool UPPER>
 __global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int len, const int *p_cnt, const int *p_ptr,
                                                         const int *p_col, const double *p_val, const double *p_dg,
-                                                        const int *ja, const double *M, double *rhs,
-                                                        double *out, double *rearm, int rearm_rhs, const int *status) {
+                                                        const int *ja, const double *M, const double *rhs,
+                                                        double *out, const int *status) {
     pdl_prologue();
     if (status && *status != ST_RUNNING) return;
-    const double sentinel = __longlong_as_double((long long)kSentinelBits);
     const int lane = threadIdx.x & 31;
     for (int t = blockIdx.x * 256 + threadIdx.x; t - lane < len; t += gridDim.x * 256) {       // warp-uniform trip count
         const bool inb = t < len;
@@ -155,10 +153,6 @@ __global__ void __launch_bounds__(256) k_sptrsv_syncfree(const int *order, int l
         }
         const double dg = (UPPER && act) ? p_dg[t] : 1.0;
         double acc = act ? rhs[i] : 0.0;
-        if (act) {
-            if (rearm_rhs) rhs[i] = sentinel;
-            if (rearm) rearm[i] = sentinel;
-        }
         // phase 1: the first lane that has a dependency waits for its last one
         const unsigned have = __ballot_sync(0xffffffffu, cnt > 0);
         if (have) {
@@ -641,10 +635,8 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     return CUDAMAT_OK;
 }
 
-// rearm: vector whose cell i is reset to the sentinel by row i (the output of the NEXT sync-free sweep),
-// rearm_rhs: reset rhs[i] after reading it (rhs is the private output of the previous L sweep).
 // With the sync-free schedule `out` must be armed (all sentinel) on entry.
-int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, double *rearm, int rearm_rhs) {
+int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out) {
     if (!s->d_M) { set_error("sptrsv: ILU0 factor not available (call cudamat_analyze with CUDAMAT_MODE_ILU0)"); return CUDAMAT_E_STATE; }
     const LevelSchedule &L = upper ? s->lvl_u : s->lvl_l;
     const int *status = s->d_sc ? &s->d_sc->status : nullptr;
@@ -690,11 +682,11 @@ int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, doubl
         if (upper)
             CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<true>, (const int *)L.d_order, L.order_len, (const int *)L.d_cnt, (const int *)L.d_ptr,
                                        (const int *)L.d_col, (const double *)L.d_val, (const double *)L.d_dg, s->pre_ja,
-                                       (const double *)s->d_M, rhs, out, rearm, rearm_rhs, status));
+                                       (const double *)s->d_M, rhs, out, status));
         else
             CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_syncfree<false>, (const int *)L.d_order, L.order_len, (const int *)L.d_cnt, (const int *)L.d_ptr,
                                        (const int *)L.d_col, (const double *)L.d_val, (const double *)L.d_dg, s->pre_ja,
-                                       (const double *)s->d_M, rhs, out, rearm, rearm_rhs, status));
+                                       (const double *)s->d_M, rhs, out, status));
         s->launches++;
     } else {
         for (int l = 0; l < L.nlevels; ++l) {

@@ -339,13 +339,13 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
         // right before the sweep that produces it; re-arming through scattered stores inside the neighbouring
         // sweep measured 7x slower for the consumer (profiles/r1_sptrsv.md)
         if (sf && ((rc = sptrsv_arm(s, tl)) || (rc = sptrsv_arm(s, pw)))) return rc;
-        if ((rc = launch_sptrsv(s, false, p, tl, nullptr, 0))) return rc;                           // :92-94
-        if ((rc = launch_sptrsv(s, true, tl, pw, nullptr, 0))) return rc;                           // :96-98
+        if ((rc = launch_sptrsv(s, false, p, tl))) return rc;                           // :92-94
+        if ((rc = launch_sptrsv(s, true, tl, pw))) return rc;                           // :96-98
         if ((rc = spmv_step(s, pw, nullptr, v, rw, 1, PH_I_A, 1))) return rc;        // :104-107
         if ((rc = launch_update_rx_ilu(s, v, pw, r, xk))) return rc;                                // :109-118
         if (sf && ((rc = sptrsv_arm(s, tl)) || (rc = sptrsv_arm(s, sv)))) return rc;
-        if ((rc = launch_sptrsv(s, false, r, tl, nullptr, 0))) return rc;                           // :121-123
-        if ((rc = launch_sptrsv(s, true, tl, sv, nullptr, 0))) return rc;                           // :125-127
+        if ((rc = launch_sptrsv(s, false, r, tl))) return rc;                           // :121-123
+        if ((rc = launch_sptrsv(s, true, tl, sv))) return rc;                           // :125-127
         if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1))) return rc;         // :132-137
         return launch_update_xr(s, true, nullptr, sv, t, rw, xk, r);                                // :139-151, :81
     });
@@ -618,7 +618,7 @@ int cudamat_sptrsv_device(cudamat_solver *s, int upper, const double *d_rhs, dou
     CM_CUDA(cudaMemcpyAsync(&s->d_sc->status, &st, sizeof(int), cudaMemcpyHostToDevice, s->stream));
     int rc = CUDAMAT_OK;
     if (s->opt_sptrsv_syncfree && (rc = sptrsv_arm(s, d_out))) return rc;
-    rc = launch_sptrsv(s, upper != 0, const_cast<double *>(d_rhs), d_out, nullptr, 0);
+    rc = launch_sptrsv(s, upper != 0, d_rhs, d_out);
     if (rc) return rc;
     CM_CUDA(cudaStreamSynchronize(s->stream));
     return CUDAMAT_OK;

@@ -175,7 +175,7 @@ void rowclass_release(cudamat_solver *s);
 
 // ilu0.cu
 int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st);
-int launch_sptrsv(cudamat_solver *s, bool upper, double *rhs, double *out, double *rearm, int rearm_rhs);
+int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out);
 int sptrsv_arm(cudamat_solver *s, double *vec);
 void ilu0_release(cudamat_solver *s);
 
