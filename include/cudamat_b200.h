@@ -116,7 +116,10 @@ int cudamat_ilu0_host(int n, int nnz, const double *A, const int *iA, const int 
  * ------------------------------------------------------------------------------------------- */
 int cudamat_create(cudamat_solver **out, int64_t n_global, int64_t row0, int64_t row1, void *stream);
 int cudamat_destroy(cudamat_solver *s);
-/* option keys: "spmv_variant", "poll_every", "sptrsv_syncfree", "debug", "time_spmv" */
+/* option keys: "spmv_variant" (CUDAMAT_SPMV_*), "poll_every" (iterations between status polls), "sptrsv_syncfree" (0: one
+ * launch per level), "sptrsv_no_smem" (1: never use the single-CTA shared-memory sweep), "sptrsv_ctas_per_sm",
+ * "host_analysis" (1: ILU0 level analysis on the host, cross-check), "graph" (-1 auto, 0 off, 1 force CUDA-graph replay),
+ * "debug", "time_spmv" (k: event-time the SpMVs of every k-th iteration) */
 int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value);
 
 /* CSR rows of this shard with GLOBAL column indices (cusparseDcsrmv operand pbicgstab.cu:67).
