@@ -270,9 +270,17 @@ __global__ void k_fill_bits(unsigned long long *p, unsigned long long v, int64_t
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < cnt; i += stride) p[i] = v;
 }
+// which sweep kernel a handle uses: 0 one launch per level (also: few levels, e.g. the multicolour ordering — every level
+// is a full-occupancy bandwidth-bound launch), 1 single-CTA shared-memory sweep (small systems), 2 sync-free persistent sweep
+static int sweep_mode(const cudamat_solver *s) {
+    if (!s->opt_sptrsv_syncfree) return 0;
+    if (sizeof(double) * (size_t)s->n <= 200 * 1024 && !s->opt_sptrsv_no_smem) return 1;
+    if (std::max(s->lvl_l.nlevels, s->lvl_u.nlevels) <= 32) return 0;
+    return 2;
+}
 int sptrsv_arm(cudamat_solver *s, double *vec) {
     if (s->n <= 0) return CUDAMAT_OK;
-    if (sizeof(double) * (size_t)s->n <= 200 * 1024 && !s->opt_sptrsv_no_smem) return CUDAMAT_OK;   // single-CTA sweep: no sentinel
+    if (sweep_mode(s) != 2) return CUDAMAT_OK;                 // only the sync-free sweep needs the sentinel
     int grid = (s->n + 1023) / 1024;
     if (grid > 148 * 16) grid = 148 * 16;
     k_fill_bits<<<grid, 256, 0, s->stream>>>(reinterpret_cast<unsigned long long *>(vec), kSentinelBits, s->n);
@@ -349,6 +357,48 @@ __global__ void __launch_bounds__(256) k_levels_syncfree(int n, const int *ia, c
         if (act) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(level + i), "r"(lv) : "memory");
         const int wmax = __reduce_max_sync(0xffffffffu, act ? lv : 0);
         if (lane == 0) atomicMax(maxlevel, wmax);
+    }
+}
+// natural-order greedy colouring, same sync-free scheme as the level kernel: colour(i) = smallest colour not used by
+// the neighbours that precede i (lower part of the row).  On a 5/7-point grid this is the red-black colouring: two
+// colours with a perfectly regular layout, so the permuted sweeps stay coalesced.
+__global__ void __launch_bounds__(256) k_greedy_color_syncfree(int n, const int *ia, const int *ja, int *color, unsigned *ticket, int *overflow) {
+    __shared__ unsigned s_chunk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunk = (n + 255) / 256;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned chunk = s_chunk;
+        if (chunk >= (unsigned)nchunk) break;
+        const int pbase = (int)chunk * 256 + warp * 32;
+        const int i = pbase + lane;
+        const bool act = i < n;
+        unsigned long long used = 0ull;
+        unsigned mask = 0;
+        if (act) {
+            for (int p = ia[i]; p < ia[i + 1]; ++p) {
+                const int c = ja[p];
+                if (c >= i) continue;                                  // later rows avoid this row's colour themselves
+                if (c >= pbase) { mask |= 1u << (c - pbase); continue; }
+                int v = ld_relaxed_i32(color + c);
+                unsigned spins = 0;
+                while (v < 0) { if (++spins > (1u << 24)) __trap(); v = ld_relaxed_i32(color + c); }
+                if (v < 64) used |= 1ull << v;
+            }
+        }
+        int myc = 0;
+#pragma unroll 1
+        for (int t = 0; t < 32; ++t) {                                 // lane t is final once lanes < t are
+            if (lane == t) myc = __ffsll((long long)~used) - 1;
+            const int ct = __shfl_sync(0xffffffffu, myc, t);
+            if ((mask >> t) & 1u) { if (ct >= 0 && ct < 64) used |= 1ull << ct; }
+        }
+        if (act) {
+            if (myc < 0) { *overflow = 1; myc = 63; }
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(color + i), "r"(myc) : "memory");
+        }
     }
 }
 __global__ void k_iota(int n, int *v) {
@@ -472,6 +522,11 @@ void ilu0_release(cudamat_solver *s) {
         if (P->d_val) cudaFree(P->d_val);
         if (P->d_dg) cudaFree(P->d_dg);
     }
+    if (s->d_perm) cudaFree(s->d_perm);
+    if (s->prm_ia) cudaFree(s->prm_ia);
+    if (s->prm_ja) cudaFree(s->prm_ja);
+    if (s->prm_a) cudaFree(s->prm_a);
+    s->d_perm = nullptr; s->prm_ia = nullptr; s->prm_ja = nullptr; s->prm_a = nullptr;
     if (s->blk_ia) cudaFree(s->blk_ia);
     if (s->blk_ja) cudaFree(s->blk_ja);
     if (s->blk_a) cudaFree(s->blk_a);
@@ -528,6 +583,112 @@ static int build_local_block(cudamat_solver *s) {
     return CUDAMAT_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Opt-in multicolour reordering of the preconditioner matrix ("ilu0_reorder" = 1; SURVEY.md 8f-4, hard part H3).
+// The natural ordering of a 7-point grid gives 3N-2 dependent levels per sweep; a colouring of the adjacency graph
+// gives (number of colours) levels, i.e. bandwidth-bound sweeps.  ILU(0) of the permuted matrix P A P^T is a DIFFERENT
+// (usually weaker) preconditioner, so iteration counts differ from the reference ordering — hence opt-in; the solution
+// is the same.  Natural-order greedy colouring (sync-free kernel, red-black on 5/7-point grids), rows stably sorted by
+// colour, the permuted CSR is rebuilt with ascending columns, and the usual analysis / factorisation / sweeps run on it;
+// M^-1 v = P^T (LU)^-1 P v costs one gather and one scatter around each sweep pair.
+// ------------------------------------------------------------------------------------------
+__global__ void k_perm_count(int n, const int *perm, const int *ia, int *cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { cnt[n] = 0; return; }
+    const int o = perm[i];
+    cnt[i] = ia[o + 1] - ia[o];
+}
+__global__ void k_perm_fill(int n, const int *perm, const int *inv, const int *ia, const int *ja, const double *a,
+                            const int *pia, int *pja, double *pa) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int o = perm[i];
+    const int q0 = pia[i];
+    int m = 0;
+    for (int p = ia[o]; p < ia[o + 1]; ++p) {                      // insertion sort by the new column index
+        const int c = inv[ja[p]];
+        const double v = a[p];
+        int pos = m;
+        while (pos > 0 && pja[q0 + pos - 1] > c) { pja[q0 + pos] = pja[q0 + pos - 1]; pa[q0 + pos] = pa[q0 + pos - 1]; --pos; }
+        pja[q0 + pos] = c; pa[q0 + pos] = v;
+        ++m;
+    }
+}
+__global__ void k_invert_perm(int n, const int *perm, int *inv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = i;
+}
+__global__ void k_gather_perm(int n, const int *perm, const double *in, double *out, const int *status) {
+    if (status && *status != ST_RUNNING) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+__global__ void k_scatter_perm(int n, const int *perm, const double *in, double *out, const int *status) {
+    if (status && *status != ST_RUNNING) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[perm[i]] = in[i];
+}
+int launch_permute(cudamat_solver *s, bool scatter, const double *in, double *out) {
+    if (s->n <= 0) return CUDAMAT_OK;
+    const int *status = s->d_sc ? &s->d_sc->status : nullptr;
+    if (scatter) k_scatter_perm<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->n, s->d_perm, in, out, status);
+    else k_gather_perm<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->n, s->d_perm, in, out, status);
+    s->launches++;
+    CM_CUDA(cudaGetLastError());
+    return CUDAMAT_OK;
+}
+
+// replaces pre_* by the multicolour-permuted matrix; on failure (more than 64 colours) keeps the original ordering
+static int build_multicolor(cudamat_solver *s) {
+    const int n = s->n;
+    if (n <= 0) return CUDAMAT_OK;
+    int *d_color = nullptr, *d_misc = nullptr, *d_color2 = nullptr, *d_iota = nullptr, *d_inv = nullptr;
+    CM_CUDA(dev_alloc((void **)&d_color, sizeof(int) * (size_t)n));
+    CM_CUDA(dev_alloc((void **)&d_misc, sizeof(int) * 2));
+    CM_CUDA(cudaMemsetAsync(d_color, 0xff, sizeof(int) * (size_t)n, s->stream));
+    CM_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 2, s->stream));
+    int h[2] = {0, 0};
+    {
+        int occ = 0, sms = 0;
+        CM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy_color_syncfree, 256, 0));
+        CM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+        const int grid = std::max(1, std::min(occ * sms, (n + 255) / 256));
+        k_greedy_color_syncfree<<<grid, 256, 0, s->stream>>>(n, s->pre_ia, s->pre_ja, d_color, (unsigned *)d_misc, d_misc + 1);
+        CM_CUDA(cudaMemcpyAsync(h, d_misc, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+        s->launches++;
+        h[0] = 0;
+    }
+    if (h[1]) { dev_free(d_color); dev_free(d_misc); return CUDAMAT_OK; }                   // > 64 colours: keep the reference ordering
+    // perm[new] = old: stable sort of the rows by colour
+    CM_CUDA(dev_alloc((void **)&d_color2, sizeof(int) * (size_t)n));
+    CM_CUDA(dev_alloc((void **)&d_iota, sizeof(int) * (size_t)n));
+    CM_CUDA(cudaMalloc(&s->d_perm, sizeof(int) * (size_t)n));
+    CM_CUDA(dev_alloc((void **)&d_inv, sizeof(int) * (size_t)n));
+    k_iota<<<(n + 255) / 256, 256, 0, s->stream>>>(n, d_iota);
+    size_t tmp_bytes = 0;
+    CM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_color, d_color2, d_iota, s->d_perm, n, 0, 6, s->stream));
+    void *d_tmp = nullptr;
+    CM_CUDA(dev_alloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    CM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_color, d_color2, d_iota, s->d_perm, n, 0, 6, s->stream));
+    k_invert_perm<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->d_perm, d_inv);
+    // permuted CSR with ascending columns
+    CM_CUDA(cudaMalloc(&s->prm_ia, sizeof(int) * (size_t)(n + 1)));
+    k_perm_count<<<(n + 1 + 255) / 256, 256, 0, s->stream>>>(n, s->d_perm, s->pre_ia, s->prm_ia);
+    int rc = exclusive_scan_inplace(s->prm_ia, (int64_t)n + 1, s->stream);
+    if (rc) return rc;
+    CM_CUDA(cudaMalloc(&s->prm_ja, sizeof(int) * (size_t)std::max<int64_t>(s->pre_nnz, 1)));
+    CM_CUDA(cudaMalloc(&s->prm_a, sizeof(double) * (size_t)std::max<int64_t>(s->pre_nnz, 1)));
+    k_perm_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->d_perm, d_inv, s->pre_ia, s->pre_ja, s->pre_a, s->prm_ia, s->prm_ja, s->prm_a);
+    CM_CUDA(cudaGetLastError());
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    s->launches += 5;
+    dev_free(d_tmp); dev_free(d_color); dev_free(d_color2); dev_free(d_iota); dev_free(d_inv); dev_free(d_misc);
+    s->pre_ia = s->prm_ia; s->pre_ja = s->prm_ja; s->pre_a = s->prm_a;
+    return CUDAMAT_OK;
+}
+
 int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     ilu0_release(s);
     const int n = s->n;
@@ -538,8 +699,9 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
         if (rcb) return rcb;
         s->pre_ia = s->blk_ia; s->pre_ja = s->blk_ja; s->pre_a = s->blk_a; s->pre_nnz = s->blk_nnz;
     }
-    const int64_t nnz = s->pre_nnz;
     double t0 = now_s();
+    if (s->opt_ilu0_reorder) { int rcm = build_multicolor(s); if (rcm) return rcm; }
+    const int64_t nnz = s->pre_nnz;
     int nl = 0, nu = 0, rc;
     CM_CUDA(cudaMalloc(&s->d_diag, sizeof(int) * (size_t)std::max(n, 1)));
     if (!s->opt_host_analysis) {
@@ -641,7 +803,8 @@ int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out)
     const LevelSchedule &L = upper ? s->lvl_u : s->lvl_l;
     const int *status = s->d_sc ? &s->d_sc->status : nullptr;
     const size_t smem_y = sizeof(double) * (size_t)s->n;
-    if (s->opt_sptrsv_syncfree && L.order_len > 0 && smem_y <= 200 * 1024 && !s->opt_sptrsv_no_smem) {
+    const int mode = sweep_mode(s);
+    if (mode == 1 && L.order_len > 0) {
         // small system: one CTA, solved values in shared memory, a CTA barrier per level
         const void *kern = upper ? (const void *)k_sptrsv_smem<true> : (const void *)k_sptrsv_smem<false>;
         if (!s->sptrsv_smem_ready) {
@@ -661,7 +824,7 @@ int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out)
         void *args[] = {&a_order, &a_lp, &a_nl, &a_len, &a_n, &a_cnt, &a_ptr, &a_col, &a_val, &a_dg, &a_ja, &a_M, &a_rhs, &out, &status};
         CM_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
         s->launches++;
-    } else if (s->opt_sptrsv_syncfree && L.order_len > 0) {
+    } else if (mode == 2 && L.order_len > 0) {
         if (s->sptrsv_grid == 0) {
             int occ_l = 0, occ_u = 0, sms = 0;
             CM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, k_sptrsv_syncfree<false>, 256, 0));

@@ -319,11 +319,29 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
 // ---- ILU0 right-preconditioned loop (gpu_pbicgstab, pbicgstab.cu:45-154) -------------------------
 static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int maxit, double tol) {
     int rc;
-    if ((rc = ensure_work(s, 9))) return rc;
+    if ((rc = ensure_work(s, s->d_perm ? 10 : 9))) return rc;
     if ((rc = ensure_hist(s, 2 * maxit + 2))) return rc;
     double *r = wv(s, 0), *rw = wv(s, 1), *p = wv(s, 2), *pw = wv(s, 3), *sv = wv(s, 4), *t = wv(s, 5), *v = wv(s, 6), *xk = wv(s, 7);
     double *tl = wv(s, 8);          // private output of the L sweeps (carries the sync-free ready sentinel)
+    double *tp = s->d_perm ? wv(s, 9) : nullptr;      // multicolour ordering: permuted right-hand side / permuted solution
     const int sf = s->opt_sptrsv_syncfree;
+    // out = M^-1 in (pbicgstab.cu:92-98, 121-127); with the multicolour ordering M^-1 = P^T (LU)^-1 P
+    auto precond = [&](const double *in, double *out) -> int {
+        int rc;
+        if (!tp) {
+            // sync-free sweeps: each output vector is armed (filled with the ready sentinel) by a coalesced fill
+            // right before the sweep that produces it
+            if (sf && ((rc = sptrsv_arm(s, tl)) || (rc = sptrsv_arm(s, out)))) return rc;
+            if ((rc = launch_sptrsv(s, false, in, tl))) return rc;
+            return launch_sptrsv(s, true, tl, out);
+        }
+        if (sf && (rc = sptrsv_arm(s, tl))) return rc;
+        if ((rc = launch_permute(s, false, in, tp))) return rc;
+        if ((rc = launch_sptrsv(s, false, tp, tl))) return rc;
+        if (sf && (rc = sptrsv_arm(s, tp))) return rc;
+        if ((rc = launch_sptrsv(s, true, tl, tp))) return rc;
+        return launch_permute(s, true, tp, out);
+    };
     const int var = s->spmv_variant;
     if ((rc = start_scalars(s, maxit, tol, 2 * maxit + 2))) return rc;
     const size_t nb = sizeof(double) * (size_t)s->n;
@@ -335,17 +353,10 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
     rc = run_iterations(s, maxit, [&]() -> int {
         int rc;
         if ((rc = launch_update_p(s, true, r, v, p))) return rc;                                    // :83-89 (skips i == 0)
-        // sync-free sweeps: each output vector is armed (filled with the ready sentinel) by a coalesced fill
-        // right before the sweep that produces it; re-arming through scattered stores inside the neighbouring
-        // sweep measured 7x slower for the consumer (profiles/r1_sptrsv.md)
-        if (sf && ((rc = sptrsv_arm(s, tl)) || (rc = sptrsv_arm(s, pw)))) return rc;
-        if ((rc = launch_sptrsv(s, false, p, tl))) return rc;                           // :92-94
-        if ((rc = launch_sptrsv(s, true, tl, pw))) return rc;                           // :96-98
+        if ((rc = precond(p, pw))) return rc;                                                      // :92-98
         if ((rc = spmv_step(s, pw, nullptr, v, rw, 1, PH_I_A, 1))) return rc;        // :104-107
         if ((rc = launch_update_rx_ilu(s, v, pw, r, xk))) return rc;                                // :109-118
-        if (sf && ((rc = sptrsv_arm(s, tl)) || (rc = sptrsv_arm(s, sv)))) return rc;
-        if ((rc = launch_sptrsv(s, false, r, tl))) return rc;                           // :121-123
-        if ((rc = launch_sptrsv(s, true, tl, sv))) return rc;                           // :125-127
+        if ((rc = precond(r, sv))) return rc;                                                      // :121-127
         if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1))) return rc;         // :132-137
         return launch_update_xr(s, true, nullptr, sv, t, rw, xk, r);                                // :139-151, :81
     });
@@ -452,6 +463,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "debug")) s->opt_debug = (int)value;
     else if (!strcmp(key, "time_spmv")) s->opt_time_spmv = (int)value;
     else if (!strcmp(key, "sptrsv_ctas_per_sm")) { s->opt_sptrsv_ctas_per_sm = (int)value; s->sptrsv_grid = 0; }
+    else if (!strcmp(key, "ilu0_reorder")) { s->opt_ilu0_reorder = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "host_analysis")) { s->opt_host_analysis = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "graph")) s->opt_graph = (int)value;          // -1 auto (small systems), 0 off, 1 force
     else if (!strcmp(key, "sptrsv_no_smem")) s->opt_sptrsv_no_smem = (int)value;
@@ -605,6 +617,7 @@ int cudamat_dot_device(cudamat_solver *s, const double *d_a, const double *d_b, 
 int cudamat_get_ilu0_host(cudamat_solver *s, double *M_out) {
     if (!s || !M_out) return CUDAMAT_E_INVALID;
     if (!s->d_M) { set_error("get_ilu0_host: no factor (analyze with CUDAMAT_MODE_ILU0)"); return CUDAMAT_E_STATE; }
+    if (s->d_perm) { set_error("get_ilu0_host: the factor belongs to the multicolour-permuted matrix (option ilu0_reorder)"); return CUDAMAT_E_STATE; }
     if (s->pre_nnz != s->nnz) { set_error("get_ilu0_host: sharded handles hold a block-Jacobi factor of the local block (%lld entries), not A's pattern", (long long)s->pre_nnz); return CUDAMAT_E_STATE; }
     CM_CUDA(cudaMemcpyAsync(M_out, s->d_M, sizeof(double) * (size_t)s->nnz, cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));

@@ -138,6 +138,9 @@ struct cudamat_solver {
     // matrix behind the preconditioner: the CSR itself, or (sharded handles) the local diagonal block blk_*
     const int *pre_ia = nullptr; const int *pre_ja = nullptr; const double *pre_a = nullptr; int64_t pre_nnz = 0;
     int *blk_ia = nullptr; int *blk_ja = nullptr; double *blk_a = nullptr; int64_t blk_nnz = 0;
+    // opt-in multicolour reordering of the preconditioner matrix: perm[new] = old, permuted CSR prm_*
+    int opt_ilu0_reorder = 0;
+    int *d_perm = nullptr; int *prm_ia = nullptr; int *prm_ja = nullptr; double *prm_a = nullptr;
     cudamat::LevelSchedule lvl_l, lvl_u;
     int *d_flag = nullptr;                 // sync-free epoch flags (n)
     unsigned *d_ticket = nullptr;          // sync-free CTA ticket
@@ -177,6 +180,7 @@ void rowclass_release(cudamat_solver *s);
 int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st);
 int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out);
 int sptrsv_arm(cudamat_solver *s, double *vec);
+int launch_permute(cudamat_solver *s, bool scatter, const double *in, double *out);
 void ilu0_release(cudamat_solver *s);
 
 // comm.cu

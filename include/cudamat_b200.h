@@ -118,6 +118,7 @@ int cudamat_create(cudamat_solver **out, int64_t n_global, int64_t row0, int64_t
 int cudamat_destroy(cudamat_solver *s);
 /* option keys: "spmv_variant" (CUDAMAT_SPMV_*), "poll_every" (iterations between status polls), "sptrsv_syncfree" (0: one
  * launch per level), "sptrsv_no_smem" (1: never use the single-CTA shared-memory sweep), "sptrsv_ctas_per_sm",
+ * "ilu0_reorder" (1: multicolour ordering of the preconditioner matrix — few sweep levels, a different ILU(0), opt-in),
  * "host_analysis" (1: ILU0 level analysis on the host, cross-check), "graph" (-1 auto, 0 off, 1 force CUDA-graph replay),
  * "debug", "time_spmv" (k: event-time the SpMVs of every k-th iteration) */
 int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value);
