@@ -344,6 +344,41 @@ def test_ilu0_multicolor_reordering_option(cm, O, pin, torch_cuda):
         s.close()
 
 
+def test_tiled_spmv_mixed_tiles_periodic_stencil(cm, O, torch_cuda):
+    """TILED variant on a PERIODIC 2-D 5-point stencil: the wrap-around rows have column offsets of +-(n - N) that do not fit the
+    staged x windows, so their tiles take the gather path inside the same launch while interior tiles use shared memory; odd n
+    exercises the odd-tail element of the bulk copies.  Every variant must agree bit for bit with the oracle."""
+    torch = torch_cuda
+    import scipy.sparse as sp
+    for N in (128, 99):
+        n = N * N
+        idx = np.arange(n).reshape(N, N)
+        rows, cols, vals = [], [], []
+        for dj, di, v in ((0, 0, 4.5), (0, 1, -1.0), (0, -1, -1.25), (1, 0, -0.75), (-1, 0, -1.0)):
+            rows.append(idx.ravel()); cols.append(np.roll(np.roll(idx, -dj, axis=0), -di, axis=1).ravel()); vals.append(np.full(n, v))
+        A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+        A.sort_indices()
+        ia, ja, a = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+        x = np.random.default_rng(N).standard_normal(n)
+        want = O.spmv(ia, ja, a, x)
+        for v in (1, 3, 4, 5):
+            s, st = make_solver(cm, torch, ia, ja, a, variant=v)
+            if v == 5:
+                assert st["spmv_variant"] == 5, st            # the plan exists (frequent classes fit the windows)
+            dx, dy = dev(torch, x), torch.zeros(n, dtype=torch.float64, device="cuda")
+            s.spmv(dx.data_ptr(), dy.data_ptr(), variant=v)
+            torch.cuda.synchronize()
+            assert np.array_equal(dy.cpu().numpy(), want), (N, v)
+            b = dev(torch, want)
+            xs = torch.zeros(n, dtype=torch.float64, device="cuda")
+            r = s.solve(0, b.data_ptr(), xs.data_ptr(), maxit=400, tol=1e-10)
+            if v == 1:
+                ref = (r["iterations"], xs.clone())
+            else:
+                assert r["iterations"] == ref[0] and torch.equal(xs, ref[1]), (N, v)
+            s.close()
+
+
 def test_spmv_agrees_with_cusparse_through_torch(cm, torch_cuda):
     """Independent on-box comparator: torch's CSR mat-vec calls modern cuSPARSE (cusparseSpMV). Summation
     orders differ, so the check is a tight tolerance, not bits: |y - y_cusparse| <= 1e-13 * (|A| |x|) row by row."""
