@@ -36,6 +36,7 @@ static double now_s() {
 // mapped: cudaFree of the 2.5 GB a 256^3 solve holds costs ~0.4 s of page unmapping, more than the solve itself.
 // (IPC-shared buffers of the multi-GPU path cannot live in the default pool and stay with cudaMalloc.)
 static cudaStream_t g_pool_stream = nullptr;
+static cudaMemPool_t g_pool = nullptr;            // the library's OWN pool: the device's default pool is left untouched
 static bool pool_ready() {
     static int state = 0;                       // 0 untried, 1 ok, -1 unavailable
     if (state == 0) {
@@ -44,12 +45,16 @@ static bool pool_ready() {
         int dev = 0, supported = 0;
         if (!(off && *off && *off != '0') && cudaGetDevice(&dev) == cudaSuccess &&
             cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && supported) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            if (cudaMemPoolCreate(&g_pool, &props) == cudaSuccess &&
                 cudaStreamCreateWithFlags(&g_pool_stream, cudaStreamNonBlocking) == cudaSuccess) {
                 const char *mb = getenv("CUDAMAT_POOL_KEEP_MB");
                 unsigned long long keep = (mb ? strtoull(mb, nullptr, 10) : 8192ull) << 20;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                cudaMemPoolSetAttribute(g_pool, cudaMemPoolAttrReleaseThreshold, &keep);
                 state = 1;
             }
         }
@@ -59,7 +64,7 @@ static bool pool_ready() {
 }
 cudaError_t dev_alloc(void **p, size_t bytes) {
     if (!pool_ready()) return cudaMalloc(p, bytes);
-    cudaError_t e = cudaMallocAsync(p, bytes, g_pool_stream);
+    cudaError_t e = cudaMallocFromPoolAsync(p, bytes, g_pool, g_pool_stream);
     if (e != cudaSuccess) return e;
     return cudaStreamSynchronize(g_pool_stream);    // usable from any stream on return
 }
