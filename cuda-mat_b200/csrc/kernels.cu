@@ -341,8 +341,11 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
                 }
             }
         }
-        unsigned spins = 0;
-        while (!mbar_try_wait(&s_bar, 0)) { if (++spins > (1u << 26)) __trap(); }
+        if (warp == 0) {                                           // one warp probes the barrier, the others sleep at bar.sync
+            unsigned spins = 0;
+            while (!mbar_try_wait(&s_bar, 0)) { if (++spins > (1u << 26)) __trap(); }
+        }
+        __syncthreads();
     }
     double pp0[kSlabsPerWarp], pp1[kSlabsPerWarp];
 #pragma unroll
