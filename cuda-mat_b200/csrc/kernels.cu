@@ -279,20 +279,23 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 // windows (halo columns of a shard, irregular rows) take the gather path of the CLASS kernel inside the same launch.
 // Entry order = storage order: bit-identical to every other variant.
 // ------------------------------------------------------------------------------------------
-template <int LEN>
-__device__ __forceinline__ double tiled_row_uniform(const double *xrow, const int *disp, const double *dv) {
-    double xv[LEN];
+template <int LEN, bool CLS_VALS>
+__device__ __forceinline__ double tiled_row_uniform(const double *xrow, const int *disp, const double *dv, const double *vrow) {
+    double xv[LEN], av[CLS_VALS ? 1 : LEN];
 #pragma unroll
-    for (int q = 0; q < LEN; ++q) xv[q] = xrow[disp[q]];
+    for (int q = 0; q < LEN; ++q) {
+        xv[q] = xrow[disp[q]];
+        if (!CLS_VALS) av[q] = __ldg(vrow + q);
+    }
     double sum = 0.0;
 #pragma unroll
-    for (int q = 0; q < LEN; ++q) sum = __fma_rn(dv[q], xv[q], sum);
+    for (int q = 0; q < LEN; ++q) sum = __fma_rn(CLS_VALS ? dv[q] : av[q], xv[q], sum);
     return sum;
 }
 #ifndef CUDAMAT_TILED_MINB
 #define CUDAMAT_TILED_MINB 3
 #endif
-template <bool HAS_D, int NDOT>
+template <bool HAS_D, int NDOT, bool CLS_VALS>
 __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(const SpmvArgs a, const TiledArgs c,
                                                                                 const __grid_constant__ TiledDict D) {
     extern __shared__ __align__(128) double xs[];
@@ -363,27 +366,39 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
             const int c0 = __shfl_sync(0xffffffffu, cid[j], 0);
             const bool uni = __all_sync(0xffffffffu, cid[j] == c0) && c0 != 0xff;
             const int len0 = uni ? D.len[c0] : 0;
-            if (len0 == 7) sum = tiled_row_uniform<7>(xrow, D.disp + c0 * kDictLen, D.val + c0 * kDictLen);
-            else if (len0 == 5) sum = tiled_row_uniform<5>(xrow, D.disp + c0 * kDictLen, D.val + c0 * kDictLen);
+            const double *vrow = CLS_VALS ? nullptr : a.val + (__ldg(a.ia + row0) + lane * len0);   // uniform length: no scan
+            if (len0 == 7) sum = tiled_row_uniform<7, CLS_VALS>(xrow, D.disp + c0 * kDictLen, D.val + c0 * kDictLen, vrow);
+            else if (len0 == 5) sum = tiled_row_uniform<5, CLS_VALS>(xrow, D.disp + c0 * kDictLen, D.val + c0 * kDictLen, vrow);
             else {
                 const int cc = active ? cid[j] : 0;
                 const int len = active ? D.len[cc] : 0;
                 const int *dp = D.disp + cc * kDictLen;
                 const double *dv = D.val + cc * kDictLen;
+                int start = 0;
+                if (!CLS_VALS) {
+                    int incl = len;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    start = __ldg(a.ia + row0) + incl - len;
+                }
                 const int maxlen = __reduce_max_sync(0xffffffffu, len);
                 sum = 0.0;
 #pragma unroll 1
                 for (int k0 = 0; k0 < maxlen; k0 += 4) {
-                    double xv[4];
+                    double xv[4], av[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) xv[q] = (k0 + q < len) ? xrow[dp[k0 + q]] : 0.0;
+                    for (int q = 0; q < 4; ++q) {
+                        const bool p = k0 + q < len;
+                        xv[q] = p ? xrow[dp[k0 + q]] : 0.0;
+                        av[q] = p ? (CLS_VALS ? dv[k0 + q] : __ldg(a.val + start + k0 + q)) : 0.0;
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        if (k0 + q < len) sum = __fma_rn(dv[k0 + q], xv[q], sum);
+                        if (k0 + q < len) sum = __fma_rn(av[q], xv[q], sum);
                 }
             }
         } else {
-            sum = class_row_general<true>(a.x, a.val, a.ia, active ? cid[j] : 0, row0, row, active, lane, D);
+            sum = class_row_general<CLS_VALS>(a.x, a.val, a.ia, active ? cid[j] : 0, row0, row, active, lane, D);
         }
         if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
         if (active) a.y[row] = sum;
@@ -613,18 +628,21 @@ template <bool HAS_D, int NDOT>
 static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
     const int grid = (a.n + kTile - 1) / kTile;
     if (grid == 0) return CUDAMAT_OK;
-    if (variant == CUDAMAT_SPMV_TILED && s->cls[1].h_tdict && ((uintptr_t)a.x % 16) == 0) {
-        const TiledArgs c{s->cls[1].d_cls, s->cls[1].d_tile_ok, s->cls[1].ncls, s->n + s->nhalo};
-        auto kern = k_spmv_tiled<HAS_D, NDOT>;
-        static bool attr_set = false;
-        if (!attr_set) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = true; }
+    if (variant == CUDAMAT_SPMV_TILED && ((uintptr_t)a.x % 16) == 0 && (s->cls[1].h_tdict || s->cls[0].h_tdict)) {
+        const int m = s->cls[1].h_tdict ? 1 : 0;                   // 1: values from the dictionary, 0: values from CSR
+        const RowClasses &C = s->cls[m];
+        const TiledArgs c{C.d_cls, C.d_tile_ok, C.ncls, s->n + s->nhalo};
+        const void *kern = m ? (const void *)k_spmv_tiled<HAS_D, NDOT, true> : (const void *)k_spmv_tiled<HAS_D, NDOT, false>;
+        static bool attr_set[2] = {false, false};
+        if (!attr_set[m]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[m] = true; }
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCtaThreads); cfg.dynamicSmemBytes = s->cls[1].tiled_smem; cfg.stream = s->stream;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCtaThreads); cfg.dynamicSmemBytes = C.tiled_smem; cfg.stream = s->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-        CM_CUDA(cudaLaunchKernelEx(&cfg, kern, a, c, *s->cls[1].h_tdict));
+        void *args[] = {(void *)&a, (void *)&c, (void *)C.h_tdict};
+        CM_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
         s->launches++;
         CM_CUDA(cudaGetLastError());
         return CUDAMAT_OK;

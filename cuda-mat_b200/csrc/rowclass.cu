@@ -70,8 +70,10 @@ __global__ void k_cls_number(const int *ia, const int *ja, const double *a, int 
                              const unsigned long long *tab, const int *rep, int *slot_id, RowDict *dict, int *ncls_out, int *fail) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int slots[kDictMax], m = 0;
+    for (int sl = 0; sl < kTab; ++sl) slot_id[sl] = -1;
+    *ncls_out = 0;
+    if (*fail) return;                                       // pass 1 already gave up (too many classes / long rows)
     for (int sl = 0; sl < kTab; ++sl) {
-        slot_id[sl] = -1;
         if (tab[sl] != 0ull) {
             if (m >= kDictMax) { *fail = 1; *ncls_out = 0; return; }
             int pos = m++;                                   // insertion sort by representative row
@@ -96,7 +98,7 @@ __global__ void k_cls_number(const int *ia, const int *ja, const double *a, int 
 __global__ void k_cls_assign(int n, const int *ia, const int *ja, const double *a, int with_vals,
                              const unsigned long long *tab, const int *slot_id, const RowDict *dict, unsigned char *cls, int *fail) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n) return;
+    if (row >= n || *fail) return;                           // an earlier pass gave up: the dictionary is not valid
     int len;
     const uint64_t key = row_key(row, ia, ja, a, with_vals != 0, &len);
     const int slot = tab_find(tab, key);
@@ -266,7 +268,8 @@ int rowclass_analyze(cudamat_solver *s) {
     }
     cudaStreamSynchronize(s->stream);
     dev_free(tab); dev_free(rep); dev_free(slot_id); dev_free(flags);
-    if (rc == CUDAMAT_OK && s->cls[1].ncls > 0) rc = tiled_plan(s, s->cls[1]);
+    for (int m = 1; m >= 0 && rc == CUDAMAT_OK; --m)
+        if (s->cls[m].ncls > 0) rc = tiled_plan(s, s->cls[m]);
     return rc;
 }
 

@@ -379,6 +379,26 @@ def test_tiled_spmv_mixed_tiles_periodic_stencil(cm, O, torch_cuda):
             s.close()
 
 
+def test_variable_coefficient_stencil_uses_offset_dictionary(cm, O, torch_cuda):
+    """a stencil with per-entry coefficients: no value dictionary, but the offset dictionary (PATTERN) and its TILED form
+    (x windows in shared memory, values streamed from CSR) apply and stay bit-identical to the CSR kernel / the oracle"""
+    torch = torch_cuda
+    ia, ja, a = O.poisson3d(24)
+    rng = np.random.default_rng(9)
+    a = a * (1.0 + 0.05 * rng.random(len(a)))
+    n = len(ia) - 1
+    x = rng.standard_normal(n)
+    want = O.spmv(ia, ja, a, x)
+    s, st = make_solver(cm, torch, ia, ja, a)
+    assert st["spmv_variant"] == cm.SPMV_TILED, st
+    for v in (1, 3, 4, 5):
+        dx, dy = dev(torch, x), torch.zeros(n, dtype=torch.float64, device="cuda")
+        s.spmv(dx.data_ptr(), dy.data_ptr(), variant=v)
+        torch.cuda.synchronize()
+        assert np.array_equal(dy.cpu().numpy(), want), v
+    s.close()
+
+
 def test_spmv_agrees_with_cusparse_through_torch(cm, torch_cuda):
     """Independent on-box comparator: torch's CSR mat-vec calls modern cuSPARSE (cusparseSpMV). Summation
     orders differ, so the check is a tight tolerance, not bits: |y - y_cusparse| <= 1e-13 * (|A| |x|) row by row."""

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--iters", type=int, default=60)
     ap.add_argument("--configs", default="1:0,2:2,2:3,2:4,2:0")
     ap.add_argument("--mode", type=int, default=0)
+    ap.add_argument("--perturb", action="store_true", help="variable-coefficient stencil (values differ per row)")
     args = ap.parse_args()
     import torch
     cm = ge.load_package()
@@ -29,6 +30,9 @@ def main():
     ja = torch.empty(nnz, dtype=torch.int32, device="cuda")
     a = torch.empty(nnz, **f64)
     cm.gen_poisson3d_device(N, 0, n, ia.data_ptr(), ja.data_ptr(), a.data_ptr())
+    if args.perturb:        # variable coefficients: the offset dictionary still applies, the value dictionary does not
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        a *= 1.0 + 0.01 * torch.rand(nnz, generator=g, **f64)
     xt = torch.empty(n, **f64)
     cm.gen_xtrue_device(1234, 0, n, xt.data_ptr())
     b = torch.empty(n, **f64)
