@@ -74,6 +74,18 @@ struct P2P {
     std::vector<int> src;                      // ranks I receive halo rows from
 };
 
+// Mappings of the neighbours' work arenas are cached for the life of the process (keyed by the IPC handle): a recycled
+// arena keeps its handle, so the next solver handle finds the mapping instead of paying cudaIpcOpenMemHandle again.
+struct PeerMap { cudaIpcMemHandle_t h; void *ptr; };
+static std::vector<PeerMap> g_peer_maps;
+static void *peer_map_open(const cudaIpcMemHandle_t &h) {
+    for (const PeerMap &m : g_peer_maps) if (!memcmp(&m.h, &h, sizeof h)) return m.ptr;
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    g_peer_maps.push_back(PeerMap{h, p});
+    return p;
+}
+
 struct Comm {
     P2P p2p;
     int rank = 0, world = 1;
@@ -210,8 +222,7 @@ static void p2p_release(Comm *c) {
     P2P &P = c->p2p;
     for (size_t r = 0; r < P.peer_arena.size(); ++r)
         if ((int)r != c->rank && P.peer_arena[r]) cudaIpcCloseMemHandle(P.peer_arena[r]);
-    for (size_t r = 0; r < P.peer_work.size(); ++r)
-        if ((int)r != c->rank && P.peer_work[r]) cudaIpcCloseMemHandle(P.peer_work[r]);
+    // peer work-arena mappings stay cached (g_peer_maps)
     if (P.arena) cudaFree(P.arena);
     if (P.d_peers) cudaFree(P.d_peers);
     if (P.d_local_cnt) cudaFree(P.d_local_cnt);
@@ -273,8 +284,8 @@ static int p2p_setup(cudamat_solver *s, const std::vector<int> &W) {
             if (cudaIpcOpenMemHandle(&pa, all[r].arena, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened = 0; break; }
             P.peer_arena[r] = (unsigned char *)pa;
             if (c->send_cnt[r] > 0) {
-                void *pw = nullptr;
-                if (cudaIpcOpenMemHandle(&pw, all[r].work, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened = 0; break; }
+                void *pw = peer_map_open(all[r].work);
+                if (!pw) { opened = 0; break; }
                 P.peer_work[r] = (double *)pw;
             }
         }

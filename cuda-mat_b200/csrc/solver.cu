@@ -121,15 +121,37 @@ static int alloc_reduction(cudamat_solver *s) {
     return CUDAMAT_OK;
 }
 
+// IPC-shared work arenas of sharded handles are recycled process-wide: mapping / unmapping a 0.6 GB arena in the
+// neighbour processes (cudaIpcOpenMemHandle / CloseMemHandle) and cudaFree of it cost ~0.4 s per handle; a recycled arena
+// keeps its IPC handle, so the neighbours' cached mappings (comm.cu) stay valid.
+static std::mutex g_arena_mu;
+static double *g_arena_ptr = nullptr; static size_t g_arena_bytes = 0;
+static cudaError_t shared_arena_get(double **p, size_t bytes, size_t *got) {
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        if (g_arena_ptr && g_arena_bytes >= bytes) { *p = g_arena_ptr; *got = g_arena_bytes; g_arena_ptr = nullptr; g_arena_bytes = 0; return cudaSuccess; }
+        if (g_arena_ptr) { cudaFree(g_arena_ptr); g_arena_ptr = nullptr; g_arena_bytes = 0; }
+    }
+    *got = bytes;
+    return cudaMalloc(p, bytes);
+}
+static void shared_arena_put(double *p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (g_arena_ptr) cudaFree(g_arena_ptr);
+    g_arena_ptr = p; g_arena_bytes = bytes;
+}
+
 int ensure_work(cudamat_solver *s, int nvec) {
     const size_t elems = (size_t)s->n + (size_t)s->nhalo;
     // keep each vector 256-byte aligned
     const size_t stride = ((elems + 31) / 32) * 32;
     if (s->work && s->work_nvec >= nvec && s->work_elems == stride) return CUDAMAT_OK;
-    if (s->work) { cudaStreamSynchronize(s->stream); if (s->work_pooled) dev_free(s->work); else cudaFree(s->work); s->work = nullptr; }
-    s->work_pooled = (s->comm == nullptr);          // sharded handles share the arena over CUDA IPC: plain cudaMalloc
-    if (s->work_pooled) CM_CUDA(dev_alloc((void **)&s->work, sizeof(double) * std::max<size_t>(stride * nvec, 32)));
-    else CM_CUDA(cudaMalloc(&s->work, sizeof(double) * std::max<size_t>(stride * nvec, 32)));
+    if (s->work) { cudaStreamSynchronize(s->stream); if (s->work_pooled) dev_free(s->work); else shared_arena_put(s->work, s->work_bytes); s->work = nullptr; }
+    s->work_pooled = (s->comm == nullptr);          // sharded handles share the arena over CUDA IPC: plain cudaMalloc, recycled
+    const size_t need = sizeof(double) * std::max<size_t>(stride * nvec, 32);
+    if (s->work_pooled) { CM_CUDA(dev_alloc((void **)&s->work, need)); s->work_bytes = need; }
+    else CM_CUDA(shared_arena_get(&s->work, need, &s->work_bytes));
     s->work_elems = stride; s->work_nvec = nvec;
     return CUDAMAT_OK;
 }
@@ -452,7 +474,7 @@ int cudamat_destroy(cudamat_solver *s) {
     dev_free(s->d_sc);
     pinned_scalars_put(s->h_sc);
     dev_free(s->d_hist);
-    if (s->work) { if (s->work_pooled) dev_free(s->work); else cudaFree(s->work); }
+    if (s->work) { if (s->work_pooled) dev_free(s->work); else shared_arena_put(s->work, s->work_bytes); }
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : s->poll_ev) if (e) cudaEventDestroy(e);
     if (tm) fprintf(stderr, "cudamat_destroy: sync+release %.4f s, frees %.4f s\n", t1 - t0, now_s() - t1);

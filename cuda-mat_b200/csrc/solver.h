@@ -132,7 +132,7 @@ struct cudamat_solver {
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     double *d_hist = nullptr; int hist_cap = 0;
     // work vectors (n + nhalo each)
-    double *work = nullptr; size_t work_elems = 0; int work_nvec = 0; bool work_pooled = false;
+    double *work = nullptr; size_t work_elems = 0; int work_nvec = 0; bool work_pooled = false; size_t work_bytes = 0;
     // ILU0
     double *d_M = nullptr; int *d_diag = nullptr;
     // matrix behind the preconditioner: the CSR itself, or (sharded handles) the local diagonal block blk_*
