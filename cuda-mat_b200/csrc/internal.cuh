@@ -284,6 +284,37 @@ __device__ __forceinline__ void p2p_push(const RedCtx &rc, const double *local, 
 // the bandwidth kernels: a gpu-scope fence per CTA invalidates the SM's L1 under the co-resident CTAs' x gathers
 // and the barrier in front of a CTA-level tail parked 27 % of the warp samples (profiles/r1c_*).  Tiles, groups,
 // the final sum and the scalar recurrence are formed by k_reduce_finish, launched right behind.
+// M (= 4 or 8) independent butterflies in 1 + log2(M) .. shuffles instead of 5 M: at each of the first log2(M) steps
+// a lane keeps one value of a pair and hands the other one to its partner, so the number of live values halves while
+// the partner distance halves.  Every addition is `own + partner's` exactly as in warp_butterfly and IEEE addition is
+// commutative, so the result is bit-identical to M separate warp_butterfly calls.  On return the sum of v[idx] is
+// held by all lanes that share `idx` = (lane>>4 & 1) + 2 (lane>>3 & 1) [+ 4 (lane>>2 & 1)].
+// one step for one pair: lanes with bit `s` clear keep a, the others keep b; result = own + partner's (distance s)
+__device__ __forceinline__ double packed_pair(double a, double b, int s, int lane) {
+    const bool up = (lane & s) != 0;
+    const double send = up ? a : b, keep = up ? b : a;
+    return __dadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, s));
+}
+template <int M>
+__device__ __forceinline__ double packed_butterfly(double (&v)[M], int lane, int &idx) {
+    static_assert(M == 4 || M == 8, "packed_butterfly: 4 or 8 values");
+    int s = 16;
+#pragma unroll
+    for (int m = M; m > 1; m >>= 1, s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int k = 0; k < m / 2; ++k) {
+            const double a = v[2 * k], b = v[2 * k + 1];
+            const double send = up ? a : b, keep = up ? b : a;
+            v[k] = __dadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, s));
+        }
+    }
+#pragma unroll
+    for (; s >= 1; s >>= 1) v[0] = __dadd_rn(v[0], __shfl_xor_sync(0xffffffffu, v[0], s));
+    idx = ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + (M == 8 ? 4 * ((lane >> 2) & 1) : 0);
+    return v[0];
+}
+
 __device__ __forceinline__ void slab_deposit(const RedCtx &rc, int q, int slab_local, double prod, int lane) {
     const double s = warp_butterfly(prod);
     if (lane == 0) __stcg(rc.slab_part + (size_t)q * rc.slab_stride + slab_local, s);

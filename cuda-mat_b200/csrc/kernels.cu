@@ -279,17 +279,41 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 // windows (halo columns of a shard, irregular rows) take the gather path of the CLASS kernel inside the same launch.
 // Entry order = storage order: bit-identical to every other variant.
 // ------------------------------------------------------------------------------------------
-template <int LEN, bool CLS_VALS>
-__device__ __forceinline__ double tiled_row_uniform(const double *xrow, const int *disp, const double *dv, const double *vrow) {
-    double xv[LEN], av[CLS_VALS ? 1 : LEN];
-#pragma unroll
-    for (int q = 0; q < LEN; ++q) {
-        xv[q] = xrow[disp[q]];
-        if (!CLS_VALS) av[q] = __ldg(vrow + q);
-    }
+// one row out of the staged windows: the lane's class record (shared memory) gives the byte offset of every entry
+// relative to the row's own position (-1 = no entry) and, for the values dictionary, its value
+// `minlen` = shortest class of the matrix: passes that lie below it need no per-entry predicate
+template <bool CLS_VALS>
+__device__ __forceinline__ double tiled_row(const char *xrow, const TiledSmemClass *rec, const double *vrow, int maxlen, int minlen) {
     double sum = 0.0;
+#pragma unroll 1
+    for (int h = 0; h < maxlen; h += 4) {                           // 4 entries per pass: 3 (1) 16-byte dictionary reads
+        const int4 b = *reinterpret_cast<const int4 *>(rec->boff + h);
+        const int bo[4] = {b.x, b.y, b.z, b.w};
+        double av[4];
+        if (CLS_VALS) {
+            const double2 t0 = *reinterpret_cast<const double2 *>(rec->val + h), t1 = *reinterpret_cast<const double2 *>(rec->val + h + 2);
+            av[0] = t0.x; av[1] = t0.y; av[2] = t1.x; av[3] = t1.y;
+        }
+        if (h + 4 <= minlen) {                                      // kernel-uniform
+            double xv[4];
 #pragma unroll
-    for (int q = 0; q < LEN; ++q) sum = __fma_rn(CLS_VALS ? dv[q] : av[q], xv[q], sum);
+            for (int q = 0; q < 4; ++q) {
+                xv[q] = *reinterpret_cast<const double *>(xrow + bo[q]);
+                if (!CLS_VALS) av[q] = __ldg(vrow + h + q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sum = __fma_rn(av[q], xv[q], sum);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (bo[q] >= 0) {
+                    const double xq = *reinterpret_cast<const double *>(xrow + bo[q]);
+                    const double aq = CLS_VALS ? av[q] : __ldg(vrow + h + q);
+                    sum = __fma_rn(aq, xq, sum);
+                }
+            }
+        }
+    }
     return sum;
 }
 #ifndef CUDAMAT_TILED_MINB
@@ -310,6 +334,7 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
         cid[j] = (row < a.n) ? (int)__ldg(c.cls + row) : 0xff;
     }
     const bool tiled = __ldg(c.tile_ok + tile) != 0;               // CTA-uniform, solve-constant
+    const TiledSmemClass *sdict = reinterpret_cast<const TiledSmemClass *>(xs + D.sdict_base);
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -333,7 +358,9 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
                     }
                 }
             }
-            mbar_expect_tx(&s_bar, total);
+            const uint32_t dict_bytes = (uint32_t)sizeof(TiledSmemClass) * (uint32_t)c.ncls;
+            mbar_expect_tx(&s_bar, total + dict_bytes);
+            tma_bulk_g2s((void *)sdict, c.sdict, dict_bytes, &s_bar);
 #pragma unroll
             for (int g = 0; g < kMaxSeg; ++g) {
                 if (g < D.nseg) {
@@ -350,69 +377,58 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
         }
         __syncthreads();
     }
-    double pp0[kSlabsPerWarp], pp1[kSlabsPerWarp];
+    // SpMV 2 of the loop takes its dot operand from x itself (t.s): it is already in shared memory
+    const bool u_staged = NDOT >= 1 && tiled && a.u == a.x && D.disp0 >= 0;
+    // slab sums of the fused dots: the first butterfly step (distance 16) is taken pairwise as soon as two slabs of the
+    // warp are done (packed_pair), which halves the values carried through the row loop
+    double pp[NDOT > 0 ? NDOT : 1], w[NDOT > 0 ? NDOT * 2 : 1];
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
-        pp0[j] = 0.0; pp1[j] = 0.0;
+        double p0 = 0.0, p1 = 0.0;
         const int row0 = row_base + (j * kCtaWarps + warp) * kSlab;
-        if (row0 >= a.n) continue;                                // warp-uniform
-        const int row = row0 + lane;
-        const bool active = row < a.n;
-        double uval = 0.0;
-        if (NDOT >= 1 && active) uval = __ldg(a.u + row);
-        double sum;
-        if (tiled) {
-            const double *xrow = xs + (row - row_base);
-            const int c0 = __shfl_sync(0xffffffffu, cid[j], 0);
-            const bool uni = __all_sync(0xffffffffu, cid[j] == c0) && c0 != 0xff;
-            const int len0 = uni ? D.len[c0] : 0;
-            const double *vrow = CLS_VALS ? nullptr : a.val + (__ldg(a.ia + row0) + lane * len0);   // uniform length: no scan
-            if (len0 == 7) sum = tiled_row_uniform<7, CLS_VALS>(xrow, D.disp + c0 * kDictLen, D.val + c0 * kDictLen, vrow);
-            else if (len0 == 5) sum = tiled_row_uniform<5, CLS_VALS>(xrow, D.disp + c0 * kDictLen, D.val + c0 * kDictLen, vrow);
-            else {
-                const int cc = active ? cid[j] : 0;
-                const int len = active ? D.len[cc] : 0;
-                const int *dp = D.disp + cc * kDictLen;
-                const double *dv = D.val + cc * kDictLen;
-                int start = 0;
-                if (!CLS_VALS) {
-                    int incl = len;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                    start = __ldg(a.ia + row0) + incl - len;
-                }
-                const int maxlen = __reduce_max_sync(0xffffffffu, len);
-                sum = 0.0;
-#pragma unroll 1
-                for (int k0 = 0; k0 < maxlen; k0 += 4) {
-                    double xv[4], av[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const bool p = k0 + q < len;
-                        xv[q] = p ? xrow[dp[k0 + q]] : 0.0;
-                        av[q] = p ? (CLS_VALS ? dv[k0 + q] : __ldg(a.val + start + k0 + q)) : 0.0;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (k0 + q < len) sum = __fma_rn(av[q], xv[q], sum);
-                }
+        if (row0 < a.n) {                                         // warp-uniform
+            const int row = row0 + lane;
+            const bool active = row < a.n;
+            double uval = 0.0;
+            if (NDOT >= 1 && active && !u_staged) uval = __ldg(a.u + row);
+            double sum;
+            if (tiled) {
+                const double *xrow = xs + (row - row_base);
+                if (NDOT >= 1 && u_staged) uval = xrow[D.disp0];
+                const double *vrow = CLS_VALS ? nullptr : a.val + __ldg(a.ia + (active ? row : row0));
+                sum = tiled_row<CLS_VALS>(reinterpret_cast<const char *>(xrow), sdict + (active ? cid[j] : 0), vrow, active ? D.maxlen : 0, D.minlen);
+            } else {
+                sum = class_row_general<CLS_VALS>(a.x, a.val, a.ia, active ? cid[j] : 0, row0, row, active, lane, D);
             }
-        } else {
-            sum = class_row_general<CLS_VALS>(a.x, a.val, a.ia, active ? cid[j] : 0, row0, row, active, lane, D);
+            if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
+            if (active) a.y[row] = sum;
+            if (NDOT >= 1) p0 = active ? __dmul_rn(sum, uval) : 0.0;
+            if (NDOT >= 2) p1 = active ? __dmul_rn(sum, sum) : 0.0;
         }
-        if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
-        if (active) a.y[row] = sum;
-        if (NDOT >= 1) pp0[j] = active ? __dmul_rn(sum, uval) : 0.0;
-        if (NDOT >= 2) pp1[j] = active ? __dmul_rn(sum, sum) : 0.0;
+        if constexpr (NDOT >= 1) {
+            if (j & 1) {
+                w[j >> 1] = packed_pair(pp[0], p0, 16, lane);
+                if constexpr (NDOT >= 2) w[2 + (j >> 1)] = packed_pair(pp[1], p1, 16, lane);
+            } else {
+                pp[0] = p0;
+                if constexpr (NDOT >= 2) pp[1] = p1;
+            }
+        }
     }
-    if (NDOT >= 1) {
-#pragma unroll
-        for (int j = 0; j < kSlabsPerWarp; ++j) {
-            if (row_base + (j * kCtaWarps + warp) * kSlab < a.n) {
-                slab_deposit(a.rc, 0, tile * kTileSlabs + j * kCtaWarps + warp, pp0[j], lane);
-                if (NDOT >= 2) slab_deposit(a.rc, 1, tile * kTileSlabs + j * kCtaWarps + warp, pp1[j], lane);
-            }
-        }
+    if constexpr (NDOT >= 1) {
+        // remaining steps; the sum of (dot q, slab j) ends in the lanes with (lane>>4 & 1) + 2 (lane>>3 & 1) [+ 4 (lane>>2 & 1)]
+        // == q * 4 + j.  Bit-identical to one warp_butterfly per slab sum (see packed_butterfly).
+        static_assert(kSlabsPerWarp == 4, "packed slab sums assume 4 slabs per warp");
+        double z = packed_pair(w[0], w[1], 8, lane);
+        if constexpr (NDOT >= 2) z = packed_pair(z, packed_pair(w[2], w[3], 8, lane), 4, lane);
+        else z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 4));
+        z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 2));
+        z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 1));
+        const int idx = ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + (NDOT >= 2 ? 4 * ((lane >> 2) & 1) : 0);
+        const int j = idx & 3, q = idx >> 2;
+        const bool writer = (lane & (NDOT >= 2 ? 3 : 7)) == 0;
+        if (writer && row_base + (j * kCtaWarps + warp) * kSlab < a.n)
+            __stcg(a.rc.slab_part + (size_t)q * a.rc.slab_stride + tile * kTileSlabs + j * kCtaWarps + warp, z);
     }
 }
 
@@ -631,10 +647,10 @@ static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
     if (variant == CUDAMAT_SPMV_TILED && ((uintptr_t)a.x % 16) == 0 && (s->cls[1].h_tdict || s->cls[0].h_tdict)) {
         const int m = s->cls[1].h_tdict ? 1 : 0;                   // 1: values from the dictionary, 0: values from CSR
         const RowClasses &C = s->cls[m];
-        const TiledArgs c{C.d_cls, C.d_tile_ok, C.ncls, s->n + s->nhalo};
+        const TiledArgs c{C.d_cls, C.d_tile_ok, C.d_sdict, C.ncls, s->n + s->nhalo};
         const void *kern = m ? (const void *)k_spmv_tiled<HAS_D, NDOT, true> : (const void *)k_spmv_tiled<HAS_D, NDOT, false>;
         static bool attr_set[2] = {false, false};
-        if (!attr_set[m]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[m] = true; }
+        if (!attr_set[m]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024)); attr_set[m] = true; }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCtaThreads); cfg.dynamicSmemBytes = C.tiled_smem; cfg.stream = s->stream;
         cudaLaunchAttribute at[1];

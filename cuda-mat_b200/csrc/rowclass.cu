@@ -13,6 +13,7 @@
 #include "solver.h"
 #include <cstring>
 #include <algorithm>
+#include <memory>
 #include <vector>
 
 namespace cudamat {
@@ -155,8 +156,8 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
     if (offs.empty()) return CUDAMAT_OK;
     std::sort(offs.begin(), offs.end());
     offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
-    TiledDict *T = new TiledDict();
-    memset(T, 0, sizeof(TiledDict));
+    std::unique_ptr<TiledDict> T(new TiledDict());           // released into C.h_tdict on success
+    memset(T.get(), 0, sizeof(TiledDict));
     int nseg = 0, base = 0;
     size_t k = 0;
     bool fits = true;
@@ -173,7 +174,7 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
         ++nseg;
     }
     const size_t smem = sizeof(double) * (size_t)base;
-    if (!fits || smem > 100 * 1024) { delete T; return CUDAMAT_OK; }
+    if (!fits || smem > 100 * 1024) return CUDAMAT_OK;
     T->nseg = nseg;
     unsigned long long ok_mask = 0;
     for (int c = 0; c < C.ncls; ++c) {
@@ -194,14 +195,33 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
         }
         if (ok) ok_mask |= 1ull << c;
     }
+    // shared-memory form of the dictionary (one TMA bulk copy per CTA, behind the windows)
+    T->sdict_base = base;
+    T->maxlen = 0; T->minlen = kDictLen;
+    T->disp0 = -1;
+    for (int g = 0; g < nseg; ++g)
+        if (0 >= T->seg_lo[g] && kTile <= T->seg_lo[g] + T->seg_len[g]) { T->disp0 = T->seg_base[g] - T->seg_lo[g]; break; }
+    std::vector<TiledSmemClass> sd((size_t)C.ncls);
+    for (int c = 0; c < C.ncls; ++c) {
+        memset(&sd[c], 0, sizeof(TiledSmemClass));
+        T->maxlen = std::max(T->maxlen, T->len[c]);
+        T->minlen = std::min(T->minlen, T->len[c]);
+        for (int q = 0; q < kDictLen; ++q) {
+            sd[c].boff[q] = q < T->len[c] ? T->disp[c * kDictLen + q] * 8 : -1;
+            sd[c].val[q] = q < T->len[c] ? T->val[c * kDictLen + q] : 0.0;
+        }
+    }
+    CM_CUDA(dev_alloc((void **)&C.d_sdict, sizeof(TiledSmemClass) * (size_t)C.ncls));
+    CM_CUDA(cudaMemcpyAsync(C.d_sdict, sd.data(), sizeof(TiledSmemClass) * (size_t)C.ncls, cudaMemcpyHostToDevice, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));                       // sd is a local
     const int ntile = (n + kTile - 1) / kTile;
     CM_CUDA(dev_alloc((void **)&C.d_tile_ok, (size_t)std::max(ntile, 1)));
     k_tile_ok<<<ntile, 256, 0, s->stream>>>(n, C.d_cls, ok_mask, C.d_tile_ok);
     CM_CUDA(cudaGetLastError());
     CM_CUDA(cudaStreamSynchronize(s->stream));
     s->launches++;
-    C.h_tdict = T;
-    C.tiled_smem = smem;
+    C.h_tdict = T.release();
+    C.tiled_smem = smem + sizeof(TiledSmemClass) * (size_t)C.ncls;
     return CUDAMAT_OK;
 }
 
@@ -211,6 +231,7 @@ void rowclass_release(cudamat_solver *s) {
         delete s->cls[m].h_dict;
         delete s->cls[m].h_tdict;
         dev_free(s->cls[m].d_tile_ok);
+        dev_free(s->cls[m].d_sdict);
         dev_free(s->cls[m].d_dict);
         s->cls[m] = RowClasses();
     }

@@ -38,9 +38,9 @@ static double now_s() {
 static cudaStream_t g_pool_stream = nullptr;
 static cudaMemPool_t g_pool = nullptr;            // the library's OWN pool: the device's default pool is left untouched
 static bool pool_ready() {
-    static int state = 0;                       // 0 untried, 1 ok, -1 unavailable
-    if (state == 0) {
-        state = -1;
+    static std::once_flag once;
+    static bool ok = false;
+    std::call_once(once, [] {
         const char *off = getenv("CUDAMAT_NO_POOL");
         int dev = 0, supported = 0;
         if (!(off && *off && *off != '0') && cudaGetDevice(&dev) == cudaSuccess &&
@@ -55,12 +55,12 @@ static bool pool_ready() {
                 const char *mb = getenv("CUDAMAT_POOL_KEEP_MB");
                 unsigned long long keep = (mb ? strtoull(mb, nullptr, 10) : 8192ull) << 20;
                 cudaMemPoolSetAttribute(g_pool, cudaMemPoolAttrReleaseThreshold, &keep);
-                state = 1;
+                ok = true;
             }
         }
         cudaGetLastError();
-    }
-    return state == 1;
+    });
+    return ok;
 }
 cudaError_t dev_alloc(void **p, size_t bytes) {
     if (!pool_ready()) return cudaMalloc(p, bytes);
@@ -289,7 +289,10 @@ static int run_iterations(cudamat_solver *s, int maxit, Iter &&one_iteration) {
         if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
         if (!ok) cudaGetLastError();
         while (ok && !stop && it + poll <= maxit) {
-            CM_CUDA(cudaGraphLaunch(exec, s->stream));
+            if (!cuda_ok(cudaGraphLaunch(exec, s->stream), "cudaGraphLaunch", __FILE__, __LINE__)) {
+                cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+                return CUDAMAT_E_CUDA;
+            }
             s->launches += per_batch;
             it += poll;
             if ((rc = poll_step(s, it, maxit, &npoll, &stop))) { cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); return rc; }
@@ -585,7 +588,7 @@ int cudamat_solve_device(cudamat_solver *s, int mode, const double *d_b, const d
     s->ev_used = 0;
     int rc;
     if (mode == CUDAMAT_MODE_ILU0) rc = solve_ilu0(s, d_b, d_x, maxit, tol);
-    else rc = solve_unprec(s, d_b, d_x0, mode == CUDAMAT_MODE_SHIFTED ? d_d : d_d, d_x, maxit, tol);
+    else rc = solve_unprec(s, d_b, d_x0, d_d, d_x, maxit, tol);
     if (rc) return rc;
     CM_CUDA(cudaStreamSynchronize(s->stream));
     const double t1 = now_s();

@@ -64,14 +64,25 @@ struct TiledDict {                     // kernel parameter (16.9 KB)
     int seg_lo[kMaxSeg];               // first column offset of the window (even)
     int seg_len[kMaxSeg];              // window length in elements = kTile + span (even)
     int seg_base[kMaxSeg];             // start of the window in shared memory (elements)
+    int maxlen, minlen;                // longest / shortest class
+    int disp0;                         // shared-memory index of x[row] itself relative to the row's position, -1 = not staged
+    int sdict_base;                    // start of the shared-memory copy of the dictionary (elements, even)
 };
-struct TiledArgs { const unsigned char *cls; const unsigned char *tile_ok; int ncls; int nx; };
+// Shared-memory form of the TILED dictionary, one record per class, copied by the same TMA transaction as the windows:
+// byte offset of every entry relative to the row's own position in the staged windows (-1 = no entry) and its value.
+// Records are read per LANE (16-byte shared loads, broadcast when the lanes of a warp share a class): no indexed
+// constant loads in the row loop and no special case for slabs that mix classes.  208 B = 52 words: neighbouring class
+// ids fall into different banks.
+struct TiledSmemClass { int boff[kDictLen]; double val[kDictLen]; int pad[4]; };
+static_assert(sizeof(TiledSmemClass) == 208, "TiledSmemClass layout");
+struct TiledArgs { const unsigned char *cls; const unsigned char *tile_ok; const TiledSmemClass *sdict; int ncls; int nx; };
 struct RowClasses {
     unsigned char *d_cls = nullptr;    // class id per row
     RowDict *d_dict = nullptr;
     DictParam *h_dict = nullptr;       // host copy handed to the kernel launches
     TiledDict *h_tdict = nullptr;      // TILED plan (only for the offsets+values dictionary), nullptr = unavailable
     unsigned char *d_tile_ok = nullptr;
+    TiledSmemClass *d_sdict = nullptr; // shared-memory form of the dictionary (TILED)
     size_t tiled_smem = 0;
     int ncls = 0;                      // 0 = not available
 };
