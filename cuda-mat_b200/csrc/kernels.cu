@@ -316,6 +316,117 @@ __device__ __forceinline__ double tiled_row(const char *xrow, const TiledSmemCla
     }
     return sum;
 }
+#ifndef CUDAMAT_TILED_REGCACHE
+#define CUDAMAT_TILED_REGCACHE 0
+#endif
+// row out of the staged windows with the lane's class record held in registers (rows of up to 8 entries);
+// the first NP entries exist in every class of the matrix and need no predicate
+template <bool CLS_VALS, int NP>
+__device__ __forceinline__ double tiled_row_regs(const char *xrow, const int (&bo)[8], const double (&av)[8], const double *vrow) {
+    double sum = 0.0;
+    double xv[NP > 0 ? NP : 1], vv[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        xv[q] = *reinterpret_cast<const double *>(xrow + bo[q]);
+        vv[q] = CLS_VALS ? av[q] : __ldg(vrow + q);
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) sum = __fma_rn(vv[q], xv[q], sum);
+#pragma unroll
+    for (int q = NP; q < 8; ++q) {
+        if (bo[q] >= 0) {
+            const double xq = *reinterpret_cast<const double *>(xrow + bo[q]);
+            const double aq = CLS_VALS ? av[q] : __ldg(vrow + q);
+            sum = __fma_rn(aq, xq, sum);
+        }
+    }
+    return sum;
+}
+// The 4 slabs of a warp.  FULL: every row of the tile exists and the tile is staged (no per-row guards).
+// xs == nullptr: the tile is not eligible for the windows, rows take the gather path of the CLASS kernel.
+template <bool HAS_D, int NDOT, bool CLS_VALS, bool FULL>
+__device__ __forceinline__ void tiled_slabs(const SpmvArgs &a, const TiledDict &D, const double *xs, const TiledSmemClass *sdict,
+                                            unsigned cids, bool u_staged, int tile, int warp, int lane) {
+    static_assert(kSlabsPerWarp == 4, "packed slab sums assume 4 slabs per warp");
+    const int row_base = tile * kTile;
+    const bool tiled = FULL || xs != nullptr;
+    // slab sums of the fused dots: the first butterfly step (distance 16) is taken pairwise as soon as two slabs of the
+    // warp are done (packed_pair), which halves the values carried through the row loop
+    double pp[NDOT > 0 ? NDOT : 1], w[NDOT > 0 ? NDOT * 2 : 1];
+#if CUDAMAT_TILED_REGCACHE
+    // The class record of a lane usually repeats over the warp's 4 slabs (their rows are 512 apart: same position in
+    // the grid line): it is kept in registers and re-read from shared memory only when some lane's class changes.
+    const bool regpath = FULL && D.maxlen <= 8;
+    int bo[8]; double av[8]; int have = -1;
+#endif
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        double p0 = 0.0, p1 = 0.0;
+        const int row0 = row_base + (j * kCtaWarps + warp) * kSlab;
+        if (FULL || row0 < a.n) {                                 // warp-uniform
+            const int row = row0 + lane;
+            const bool active = FULL || row < a.n;
+            const int cid = active ? (int)((cids >> (8 * j)) & 0xffu) : 0;
+            double uval = 0.0;
+            if (NDOT >= 1 && active && !u_staged) uval = __ldg(a.u + row);
+            double sum;
+            if (tiled) {
+                const double *xrow = xs + (row - row_base);
+                if (NDOT >= 1 && u_staged) uval = xrow[D.disp0];
+                const double *vrow = CLS_VALS ? nullptr : a.val + __ldg(a.ia + (active ? row : row0));
+#if CUDAMAT_TILED_REGCACHE
+                if (regpath) {
+                    if (__any_sync(0xffffffffu, cid != have)) {
+                        const TiledSmemClass *rec = sdict + cid;
+                        const int4 b0 = *reinterpret_cast<const int4 *>(rec->boff), b1 = *reinterpret_cast<const int4 *>(rec->boff + 4);
+                        bo[0] = b0.x; bo[1] = b0.y; bo[2] = b0.z; bo[3] = b0.w; bo[4] = b1.x; bo[5] = b1.y; bo[6] = b1.z; bo[7] = b1.w;
+                        if (CLS_VALS) {
+#pragma unroll
+                            for (int q = 0; q < 8; q += 2) {
+                                const double2 t = *reinterpret_cast<const double2 *>(rec->val + q);
+                                av[q] = t.x; av[q + 1] = t.y;
+                            }
+                        }
+                        have = cid;
+                    }
+                    sum = D.minlen >= 4 ? tiled_row_regs<CLS_VALS, 4>(reinterpret_cast<const char *>(xrow), bo, av, vrow)
+                                        : tiled_row_regs<CLS_VALS, 0>(reinterpret_cast<const char *>(xrow), bo, av, vrow);
+                } else
+#endif
+                sum = tiled_row<CLS_VALS>(reinterpret_cast<const char *>(xrow), sdict + cid, vrow, active ? D.maxlen : 0, D.minlen);
+            } else {
+                sum = class_row_general<CLS_VALS>(a.x, a.val, a.ia, cid, row0, row, active, lane, D);
+            }
+            if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
+            if (active) a.y[row] = sum;
+            if (NDOT >= 1) p0 = active ? __dmul_rn(sum, uval) : 0.0;
+            if (NDOT >= 2) p1 = active ? __dmul_rn(sum, sum) : 0.0;
+        }
+        if constexpr (NDOT >= 1) {
+            if (j & 1) {
+                w[j >> 1] = packed_pair(pp[0], p0, 16, lane);
+                if constexpr (NDOT >= 2) w[2 + (j >> 1)] = packed_pair(pp[1], p1, 16, lane);
+            } else {
+                pp[0] = p0;
+                if constexpr (NDOT >= 2) pp[1] = p1;
+            }
+        }
+    }
+    if constexpr (NDOT >= 1) {
+        // remaining steps; the sum of (dot q, slab j) ends in the lanes with (lane>>4 & 1) + 2 (lane>>3 & 1) [+ 4 (lane>>2 & 1)]
+        // == q * 4 + j.  Bit-identical to one warp_butterfly per slab sum (see packed_butterfly).
+        double z = packed_pair(w[0], w[1], 8, lane);
+        if constexpr (NDOT >= 2) z = packed_pair(z, packed_pair(w[2], w[3], 8, lane), 4, lane);
+        else z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 4));
+        z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 2));
+        z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 1));
+        const int idx = ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + (NDOT >= 2 ? 4 * ((lane >> 2) & 1) : 0);
+        const int j = idx & 3, q = idx >> 2;
+        const bool writer = (lane & (NDOT >= 2 ? 3 : 7)) == 0;
+        if (writer && (FULL || row_base + (j * kCtaWarps + warp) * kSlab < a.n))
+            __stcg(a.rc.slab_part + (size_t)q * a.rc.slab_stride + tile * kTileSlabs + j * kCtaWarps + warp, z);
+    }
+}
 #ifndef CUDAMAT_TILED_MINB
 #define CUDAMAT_TILED_MINB 3
 #endif
@@ -379,57 +490,9 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
     }
     // SpMV 2 of the loop takes its dot operand from x itself (t.s): it is already in shared memory
     const bool u_staged = NDOT >= 1 && tiled && a.u == a.x && D.disp0 >= 0;
-    // slab sums of the fused dots: the first butterfly step (distance 16) is taken pairwise as soon as two slabs of the
-    // warp are done (packed_pair), which halves the values carried through the row loop
-    double pp[NDOT > 0 ? NDOT : 1], w[NDOT > 0 ? NDOT * 2 : 1];
-#pragma unroll
-    for (int j = 0; j < kSlabsPerWarp; ++j) {
-        double p0 = 0.0, p1 = 0.0;
-        const int row0 = row_base + (j * kCtaWarps + warp) * kSlab;
-        if (row0 < a.n) {                                         // warp-uniform
-            const int row = row0 + lane;
-            const bool active = row < a.n;
-            double uval = 0.0;
-            if (NDOT >= 1 && active && !u_staged) uval = __ldg(a.u + row);
-            double sum;
-            if (tiled) {
-                const double *xrow = xs + (row - row_base);
-                if (NDOT >= 1 && u_staged) uval = xrow[D.disp0];
-                const double *vrow = CLS_VALS ? nullptr : a.val + __ldg(a.ia + (active ? row : row0));
-                sum = tiled_row<CLS_VALS>(reinterpret_cast<const char *>(xrow), sdict + (active ? cid[j] : 0), vrow, active ? D.maxlen : 0, D.minlen);
-            } else {
-                sum = class_row_general<CLS_VALS>(a.x, a.val, a.ia, active ? cid[j] : 0, row0, row, active, lane, D);
-            }
-            if (HAS_D) { if (active) sum = __dadd_rn(sum, __dmul_rn(__ldg(a.d + row), __ldg(a.x + row))); }
-            if (active) a.y[row] = sum;
-            if (NDOT >= 1) p0 = active ? __dmul_rn(sum, uval) : 0.0;
-            if (NDOT >= 2) p1 = active ? __dmul_rn(sum, sum) : 0.0;
-        }
-        if constexpr (NDOT >= 1) {
-            if (j & 1) {
-                w[j >> 1] = packed_pair(pp[0], p0, 16, lane);
-                if constexpr (NDOT >= 2) w[2 + (j >> 1)] = packed_pair(pp[1], p1, 16, lane);
-            } else {
-                pp[0] = p0;
-                if constexpr (NDOT >= 2) pp[1] = p1;
-            }
-        }
-    }
-    if constexpr (NDOT >= 1) {
-        // remaining steps; the sum of (dot q, slab j) ends in the lanes with (lane>>4 & 1) + 2 (lane>>3 & 1) [+ 4 (lane>>2 & 1)]
-        // == q * 4 + j.  Bit-identical to one warp_butterfly per slab sum (see packed_butterfly).
-        static_assert(kSlabsPerWarp == 4, "packed slab sums assume 4 slabs per warp");
-        double z = packed_pair(w[0], w[1], 8, lane);
-        if constexpr (NDOT >= 2) z = packed_pair(z, packed_pair(w[2], w[3], 8, lane), 4, lane);
-        else z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 4));
-        z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 2));
-        z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 1));
-        const int idx = ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + (NDOT >= 2 ? 4 * ((lane >> 2) & 1) : 0);
-        const int j = idx & 3, q = idx >> 2;
-        const bool writer = (lane & (NDOT >= 2 ? 3 : 7)) == 0;
-        if (writer && row_base + (j * kCtaWarps + warp) * kSlab < a.n)
-            __stcg(a.rc.slab_part + (size_t)q * a.rc.slab_stride + tile * kTileSlabs + j * kCtaWarps + warp, z);
-    }
+    const unsigned cids = (unsigned)(cid[0] & 0xff) | ((unsigned)(cid[1] & 0xff) << 8) | ((unsigned)(cid[2] & 0xff) << 16) | ((unsigned)cid[3] << 24);
+    if (tiled && row_base + kTile <= a.n) tiled_slabs<HAS_D, NDOT, CLS_VALS, true>(a, D, xs, sdict, cids, u_staged, tile, warp, lane);
+    else tiled_slabs<HAS_D, NDOT, CLS_VALS, false>(a, D, tiled ? xs : nullptr, sdict, cids, u_staged, tile, warp, lane);
 }
 
 struct StagedArgs {
