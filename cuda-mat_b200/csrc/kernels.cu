@@ -316,31 +316,42 @@ __device__ __forceinline__ double tiled_row(const char *xrow, const TiledSmemCla
     }
     return sum;
 }
-#ifndef CUDAMAT_TILED_REGCACHE
-#define CUDAMAT_TILED_REGCACHE 0
-#endif
-// row out of the staged windows with the lane's class record held in registers (rows of up to 8 entries);
-// the first NP entries exist in every class of the matrix and need no predicate
-template <bool CLS_VALS, int NP>
-__device__ __forceinline__ double tiled_row_regs(const char *xrow, const int (&bo)[8], const double (&av)[8], const double *vrow) {
+// row = superset pattern + presence mask: byte offsets and values are kernel-wide constants at compile-time positions
+// of the parameter block (uniform / constant-bank operands), entries in ascending-offset = storage order.  The x reads
+// are unconditional (every pattern position of every row lies inside the staged windows); only the FMA is predicated.
+template <bool CLS_VALS, int SL>
+__device__ __forceinline__ double tiled_row_sup(const char *xrow, const TiledDict &D, unsigned mask, const double *vrow) {
     double sum = 0.0;
-    double xv[NP > 0 ? NP : 1], vv[NP > 0 ? NP : 1];
+    if constexpr (!CLS_VALS) {                                      // values streamed from CSR: entry by entry (registers)
+        int k = 0;
 #pragma unroll
-    for (int q = 0; q < NP; ++q) {
-        xv[q] = *reinterpret_cast<const double *>(xrow + bo[q]);
-        vv[q] = CLS_VALS ? av[q] : __ldg(vrow + q);
-    }
+        for (int q = 0; q < SL; ++q) {
+            if (mask & (1u << q)) {
+                const double xq = *reinterpret_cast<const double *>(xrow + D.sup_boff[q]);
+                sum = __fma_rn(__ldg(vrow + k), xq, sum);
+                ++k;
+            }
+        }
+    } else {
+        double xv[SL];
 #pragma unroll
-    for (int q = 0; q < NP; ++q) sum = __fma_rn(vv[q], xv[q], sum);
+        for (int q = 0; q < SL; ++q) xv[q] = *reinterpret_cast<const double *>(xrow + D.sup_boff[q]);
+        if (__all_sync(0xffffffffu, mask == (1u << SL) - 1u)) {      // interior slab: every row holds the whole pattern
 #pragma unroll
-    for (int q = NP; q < 8; ++q) {
-        if (bo[q] >= 0) {
-            const double xq = *reinterpret_cast<const double *>(xrow + bo[q]);
-            const double aq = CLS_VALS ? av[q] : __ldg(vrow + q);
-            sum = __fma_rn(aq, xq, sum);
+            for (int q = 0; q < SL; ++q) sum = __fma_rn(D.sup_val[q], xv[q], sum);
+        } else {
+#pragma unroll
+            for (int q = 0; q < SL; ++q)
+                if (mask & (1u << q)) sum = __fma_rn(D.sup_val[q], xv[q], sum);
         }
     }
     return sum;
+}
+template <bool CLS_VALS>
+__device__ __forceinline__ double tiled_row_sup_any(const char *xrow, const TiledDict &D, unsigned mask, const double *vrow) {
+    if (D.sup_len == 7) return tiled_row_sup<CLS_VALS, 7>(xrow, D, mask, vrow);          // kernel-uniform
+    if (D.sup_len == 5) return tiled_row_sup<CLS_VALS, 5>(xrow, D, mask, vrow);
+    return tiled_row_sup<CLS_VALS, 8>(xrow, D, mask, vrow);
 }
 // The 4 slabs of a warp.  FULL: every row of the tile exists and the tile is staged (no per-row guards).
 // xs == nullptr: the tile is not eligible for the windows, rows take the gather path of the CLASS kernel.
@@ -353,12 +364,6 @@ __device__ __forceinline__ void tiled_slabs(const SpmvArgs &a, const TiledDict &
     // slab sums of the fused dots: the first butterfly step (distance 16) is taken pairwise as soon as two slabs of the
     // warp are done (packed_pair), which halves the values carried through the row loop
     double pp[NDOT > 0 ? NDOT : 1], w[NDOT > 0 ? NDOT * 2 : 1];
-#if CUDAMAT_TILED_REGCACHE
-    // The class record of a lane usually repeats over the warp's 4 slabs (their rows are 512 apart: same position in
-    // the grid line): it is kept in registers and re-read from shared memory only when some lane's class changes.
-    const bool regpath = FULL && D.maxlen <= 8;
-    int bo[8]; double av[8]; int have = -1;
-#endif
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         double p0 = 0.0, p1 = 0.0;
@@ -374,25 +379,8 @@ __device__ __forceinline__ void tiled_slabs(const SpmvArgs &a, const TiledDict &
                 const double *xrow = xs + (row - row_base);
                 if (NDOT >= 1 && u_staged) uval = xrow[D.disp0];
                 const double *vrow = CLS_VALS ? nullptr : a.val + __ldg(a.ia + (active ? row : row0));
-#if CUDAMAT_TILED_REGCACHE
-                if (regpath) {
-                    if (__any_sync(0xffffffffu, cid != have)) {
-                        const TiledSmemClass *rec = sdict + cid;
-                        const int4 b0 = *reinterpret_cast<const int4 *>(rec->boff), b1 = *reinterpret_cast<const int4 *>(rec->boff + 4);
-                        bo[0] = b0.x; bo[1] = b0.y; bo[2] = b0.z; bo[3] = b0.w; bo[4] = b1.x; bo[5] = b1.y; bo[6] = b1.z; bo[7] = b1.w;
-                        if (CLS_VALS) {
-#pragma unroll
-                            for (int q = 0; q < 8; q += 2) {
-                                const double2 t = *reinterpret_cast<const double2 *>(rec->val + q);
-                                av[q] = t.x; av[q + 1] = t.y;
-                            }
-                        }
-                        have = cid;
-                    }
-                    sum = D.minlen >= 4 ? tiled_row_regs<CLS_VALS, 4>(reinterpret_cast<const char *>(xrow), bo, av, vrow)
-                                        : tiled_row_regs<CLS_VALS, 0>(reinterpret_cast<const char *>(xrow), bo, av, vrow);
-                } else
-#endif
+                if (D.sup_len > 0) sum = tiled_row_sup_any<CLS_VALS>(reinterpret_cast<const char *>(xrow), D, active ? (unsigned)cid : 0u, vrow);
+                else
                 sum = tiled_row<CLS_VALS>(reinterpret_cast<const char *>(xrow), sdict + cid, vrow, active ? D.maxlen : 0, D.minlen);
             } else {
                 sum = class_row_general<CLS_VALS>(a.x, a.val, a.ia, cid, row0, row, active, lane, D);
@@ -438,13 +426,15 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
     const int row_base = tile * kTile;
+    const bool tiled = __ldg(c.tile_ok + tile) != 0;               // CTA-uniform, solve-constant
+    // per row: the presence mask w.r.t. the superset pattern when the tile is staged and the pattern exists, else the class id
+    const unsigned char *ids = (tiled && D.sup_len > 0) ? c.tmask : c.cls;
     int cid[kSlabsPerWarp];
 #pragma unroll
     for (int j = 0; j < kSlabsPerWarp; ++j) {
         const int row = row_base + (j * kCtaWarps + warp) * kSlab + lane;
-        cid[j] = (row < a.n) ? (int)__ldg(c.cls + row) : 0xff;
+        cid[j] = (row < a.n) ? (int)__ldg(ids + row) : 0xff;
     }
-    const bool tiled = __ldg(c.tile_ok + tile) != 0;               // CTA-uniform, solve-constant
     const TiledSmemClass *sdict = reinterpret_cast<const TiledSmemClass *>(xs + D.sdict_base);
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -469,9 +459,9 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
                     }
                 }
             }
-            const uint32_t dict_bytes = (uint32_t)sizeof(TiledSmemClass) * (uint32_t)c.ncls;
+            const uint32_t dict_bytes = D.sup_len > 0 ? 0u : (uint32_t)sizeof(TiledSmemClass) * (uint32_t)c.ncls;
             mbar_expect_tx(&s_bar, total + dict_bytes);
-            tma_bulk_g2s((void *)sdict, c.sdict, dict_bytes, &s_bar);
+            if (dict_bytes) tma_bulk_g2s((void *)sdict, c.sdict, dict_bytes, &s_bar);
 #pragma unroll
             for (int g = 0; g < kMaxSeg; ++g) {
                 if (g < D.nseg) {
@@ -710,7 +700,7 @@ static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
     if (variant == CUDAMAT_SPMV_TILED && ((uintptr_t)a.x % 16) == 0 && (s->cls[1].h_tdict || s->cls[0].h_tdict)) {
         const int m = s->cls[1].h_tdict ? 1 : 0;                   // 1: values from the dictionary, 0: values from CSR
         const RowClasses &C = s->cls[m];
-        const TiledArgs c{C.d_cls, C.d_tile_ok, C.d_sdict, C.ncls, s->n + s->nhalo};
+        const TiledArgs c{C.d_cls, C.d_tile_ok, C.d_tmask, C.d_sdict, C.ncls, s->n + s->nhalo};
         const void *kern = m ? (const void *)k_spmv_tiled<HAS_D, NDOT, true> : (const void *)k_spmv_tiled<HAS_D, NDOT, false>;
         static bool attr_set[2] = {false, false};
         if (!attr_set[m]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024)); attr_set[m] = true; }

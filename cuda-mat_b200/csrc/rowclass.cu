@@ -133,6 +133,13 @@ __global__ void k_tile_ok(int n, const unsigned char *cls, unsigned long long ok
     if (threadIdx.x == 0) tile_ok[tile] = bad ? 0 : 1;
 }
 
+// presence mask of every row w.r.t. the superset pattern: tmask[r] = cmask[cls[r]]
+struct ClassMasks { unsigned char m[kDictMax]; };
+__global__ void k_cls_to_mask(int n, const unsigned char *cls, const ClassMasks cm, unsigned char *tmask) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) tmask[r] = cm.m[cls[r] & 63];
+}
+
 // TILED plan for the offsets+values dictionary: windows = clusters of the column offsets of the frequent classes
 static int tiled_plan(cudamat_solver *s, RowClasses &C) {
     const int n = s->n;
@@ -214,6 +221,40 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
     CM_CUDA(dev_alloc((void **)&C.d_sdict, sizeof(TiledSmemClass) * (size_t)C.ncls));
     CM_CUDA(cudaMemcpyAsync(C.d_sdict, sd.data(), sizeof(TiledSmemClass) * (size_t)C.ncls, cudaMemcpyHostToDevice, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));                       // sd is a local
+    // superset pattern over the staged classes: sorted union of their offsets (every class ascending, so each is an
+    // order-preserving subset); for the values dictionary the value at an offset must be the same in every class
+    {
+        const bool with_vals = (&C == &s->cls[1]);
+        std::vector<int> so; std::vector<double> sv;
+        bool ok = true;
+        for (int c = 0; c < C.ncls && ok; ++c) {
+            if (!((ok_mask >> c) & 1ull)) continue;
+            for (int q = 0; q < T->len[c] && ok; ++q) {
+                const int o = T->off[c * kDictLen + q];
+                if (q > 0 && o <= T->off[c * kDictLen + q - 1]) ok = false;
+                const double v = T->val[c * kDictLen + q];
+                size_t k = 0;
+                while (k < so.size() && so[k] < o) ++k;
+                if (k < so.size() && so[k] == o) { if (with_vals && memcmp(&sv[k], &v, sizeof v) != 0) ok = false; }
+                else { so.insert(so.begin() + k, o); sv.insert(sv.begin() + k, v); }
+            }
+        }
+        if (ok && !so.empty() && so.size() <= 8) {
+            ClassMasks cm; memset(&cm, 0, sizeof cm);
+            for (int c = 0; c < C.ncls; ++c) {
+                if (!((ok_mask >> c) & 1ull)) continue;
+                for (int q = 0; q < T->len[c]; ++q)
+                    for (size_t k = 0; k < so.size(); ++k)
+                        if (so[k] == T->off[c * kDictLen + q]) { cm.m[c] |= (unsigned char)(1u << k); T->sup_boff[k] = T->disp[c * kDictLen + q] * 8; }
+            }
+            for (size_t k = 0; k < so.size(); ++k) T->sup_val[k] = sv[k];
+            T->sup_len = (int)so.size();
+            CM_CUDA(dev_alloc((void **)&C.d_tmask, (size_t)n + 16));
+            k_cls_to_mask<<<(n + 255) / 256, 256, 0, s->stream>>>(n, C.d_cls, cm, C.d_tmask);
+            CM_CUDA(cudaGetLastError());
+            s->launches++;
+        }
+    }
     const int ntile = (n + kTile - 1) / kTile;
     CM_CUDA(dev_alloc((void **)&C.d_tile_ok, (size_t)std::max(ntile, 1)));
     k_tile_ok<<<ntile, 256, 0, s->stream>>>(n, C.d_cls, ok_mask, C.d_tile_ok);
@@ -232,6 +273,7 @@ void rowclass_release(cudamat_solver *s) {
         delete s->cls[m].h_tdict;
         dev_free(s->cls[m].d_tile_ok);
         dev_free(s->cls[m].d_sdict);
+        dev_free(s->cls[m].d_tmask);
         dev_free(s->cls[m].d_dict);
         s->cls[m] = RowClasses();
     }

@@ -67,6 +67,13 @@ struct TiledDict {                     // kernel parameter (16.9 KB)
     int maxlen, minlen;                // longest / shortest class
     int disp0;                         // shared-memory index of x[row] itself relative to the row's position, -1 = not staged
     int sdict_base;                    // start of the shared-memory copy of the dictionary (elements, even)
+    // Superset pattern (stencils): when every staged class is an order-preserving subset of ONE pattern of <= 8 entries
+    // with identical values at identical offsets, a row is that pattern plus a presence mask (1 byte per row).  Byte
+    // offsets and values are then kernel-wide constants with compile-time positions: constant-bank operands of the
+    // address add and the FMA, no dictionary read at all in the row loop.  sup_len = 0: not available.
+    int sup_len;
+    int sup_boff[8];
+    double sup_val[8];
 };
 // Shared-memory form of the TILED dictionary, one record per class, copied by the same TMA transaction as the windows:
 // byte offset of every entry relative to the row's own position in the staged windows (-1 = no entry) and its value.
@@ -75,7 +82,7 @@ struct TiledDict {                     // kernel parameter (16.9 KB)
 // ids fall into different banks.
 struct TiledSmemClass { int boff[kDictLen]; double val[kDictLen]; int pad[4]; };
 static_assert(sizeof(TiledSmemClass) == 208, "TiledSmemClass layout");
-struct TiledArgs { const unsigned char *cls; const unsigned char *tile_ok; const TiledSmemClass *sdict; int ncls; int nx; };
+struct TiledArgs { const unsigned char *cls; const unsigned char *tile_ok; const unsigned char *tmask; const TiledSmemClass *sdict; int ncls; int nx; };
 struct RowClasses {
     unsigned char *d_cls = nullptr;    // class id per row
     RowDict *d_dict = nullptr;
@@ -83,6 +90,7 @@ struct RowClasses {
     TiledDict *h_tdict = nullptr;      // TILED plan (only for the offsets+values dictionary), nullptr = unavailable
     unsigned char *d_tile_ok = nullptr;
     TiledSmemClass *d_sdict = nullptr; // shared-memory form of the dictionary (TILED)
+    unsigned char *d_tmask = nullptr;  // presence mask per row w.r.t. the superset pattern (TILED, when sup_len > 0)
     size_t tiled_smem = 0;
     int ncls = 0;                      // 0 = not available
 };
