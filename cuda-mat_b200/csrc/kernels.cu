@@ -445,32 +445,27 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     halo_wait(a.hw, tile);
     if (tiled) {
-        if (tid == 0) {
-            uint32_t total = 0;
-#pragma unroll
-            for (int g = 0; g < kMaxSeg; ++g) {
-                if (g < D.nseg) {
-                    const long long gs = (long long)row_base + D.seg_lo[g];
-                    const long long cs = max(gs, 0LL), ce = min(gs + D.seg_len[g], (long long)c.nx);
-                    const long long cnt = ce - cs;
-                    if (cnt > 0) {
-                        total += (uint32_t)(cnt & ~1LL) * 8u;
-                        if (cnt & 1) xs[D.seg_base[g] + (int)(ce - 1 - gs)] = a.x[ce - 1];      // odd tail element
-                    }
+        if (warp == 0) {
+            // lane g clips and issues window g (the windows are independent: no serial loop in one thread)
+            uint32_t bytes = 0;
+            long long gs = 0, cs = 0;
+            if (lane < D.nseg) {
+                gs = (long long)row_base + D.seg_lo[lane];
+                cs = max(gs, 0LL);
+                const long long ce = min(gs + D.seg_len[lane], (long long)c.nx), cnt = ce - cs;
+                if (cnt > 0) {
+                    bytes = (uint32_t)(cnt & ~1LL) * 8u;
+                    if (cnt & 1) xs[D.seg_base[lane] + (int)(ce - 1 - gs)] = a.x[ce - 1];         // odd tail element
                 }
             }
             const uint32_t dict_bytes = D.sup_len > 0 ? 0u : (uint32_t)sizeof(TiledSmemClass) * (uint32_t)c.ncls;
-            mbar_expect_tx(&s_bar, total + dict_bytes);
-            if (dict_bytes) tma_bulk_g2s((void *)sdict, c.sdict, dict_bytes, &s_bar);
-#pragma unroll
-            for (int g = 0; g < kMaxSeg; ++g) {
-                if (g < D.nseg) {
-                    const long long gs = (long long)row_base + D.seg_lo[g];
-                    const long long cs = max(gs, 0LL), ce = min(gs + D.seg_len[g], (long long)c.nx);
-                    const long long cnt = (ce - cs) & ~1LL;
-                    if (cnt > 0) tma_bulk_g2s(xs + D.seg_base[g] + (int)(cs - gs), a.x + cs, (uint32_t)cnt * 8u, &s_bar);
-                }
+            const uint32_t total = __reduce_add_sync(0xffffffffu, bytes) + dict_bytes;
+            if (lane == 0) {
+                mbar_expect_tx(&s_bar, total);
+                if (dict_bytes) tma_bulk_g2s((void *)sdict, c.sdict, dict_bytes, &s_bar);
             }
+            __syncwarp();
+            if (bytes) tma_bulk_g2s(xs + D.seg_base[lane] + (int)(cs - gs), a.x + cs, bytes, &s_bar);
         }
         if (warp == 0) {                                           // one warp probes the barrier, the others sleep at bar.sync
             unsigned spins = 0;
