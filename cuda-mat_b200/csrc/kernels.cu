@@ -357,7 +357,7 @@ __device__ __forceinline__ double tiled_row_sup_any(const char *xrow, const Tile
 // xs == nullptr: the tile is not eligible for the windows, rows take the gather path of the CLASS kernel.
 template <bool HAS_D, int NDOT, bool CLS_VALS, bool FULL>
 __device__ __forceinline__ void tiled_slabs(const SpmvArgs &a, const TiledDict &D, const double *xs, const TiledSmemClass *sdict,
-                                            unsigned cids, bool u_staged, int tile, int warp, int lane) {
+                                            unsigned cids, bool u_staged, const double (&upre)[kSlabsPerWarp], int tile, int warp, int lane) {
     static_assert(kSlabsPerWarp == 4, "packed slab sums assume 4 slabs per warp");
     const int row_base = tile * kTile;
     const bool tiled = FULL || xs != nullptr;
@@ -373,7 +373,7 @@ __device__ __forceinline__ void tiled_slabs(const SpmvArgs &a, const TiledDict &
             const bool active = FULL || row < a.n;
             const int cid = active ? (int)((cids >> (8 * j)) & 0xffu) : 0;
             double uval = 0.0;
-            if (NDOT >= 1 && active && !u_staged) uval = __ldg(a.u + row);
+            if (NDOT >= 1 && !u_staged) uval = CLS_VALS ? upre[j] : (active ? __ldg(a.u + row) : 0.0);
             double sum;
             if (tiled) {
                 const double *xrow = xs + (row - row_base);
@@ -444,6 +444,16 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
     pdl_sync();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     halo_wait(a.hw, tile);
+    // SpMV 2 of the loop takes its dot operand from x itself (t.s): it is already in shared memory.  Any other operand
+    // is fetched here, ahead of the wait for the windows, so that its DRAM latency overlaps the bulk copies (values
+    // dictionary only: the kernel that streams the values from CSR has no registers to spare for it).
+    const bool u_staged = NDOT >= 1 && tiled && a.u == a.x && D.disp0 >= 0;
+    double upre[kSlabsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + (j * kCtaWarps + warp) * kSlab + lane;
+        upre[j] = (CLS_VALS && NDOT >= 1 && !u_staged && row < a.n) ? __ldg(a.u + row) : 0.0;
+    }
     if (tiled) {
         if (warp == 0) {
             // lane g clips and issues window g (the windows are independent: no serial loop in one thread)
@@ -473,11 +483,9 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
         }
         __syncthreads();
     }
-    // SpMV 2 of the loop takes its dot operand from x itself (t.s): it is already in shared memory
-    const bool u_staged = NDOT >= 1 && tiled && a.u == a.x && D.disp0 >= 0;
     const unsigned cids = (unsigned)(cid[0] & 0xff) | ((unsigned)(cid[1] & 0xff) << 8) | ((unsigned)(cid[2] & 0xff) << 16) | ((unsigned)cid[3] << 24);
-    if (tiled && row_base + kTile <= a.n) tiled_slabs<HAS_D, NDOT, CLS_VALS, true>(a, D, xs, sdict, cids, u_staged, tile, warp, lane);
-    else tiled_slabs<HAS_D, NDOT, CLS_VALS, false>(a, D, tiled ? xs : nullptr, sdict, cids, u_staged, tile, warp, lane);
+    if (tiled && row_base + kTile <= a.n) tiled_slabs<HAS_D, NDOT, CLS_VALS, true>(a, D, xs, sdict, cids, u_staged, upre, tile, warp, lane);
+    else tiled_slabs<HAS_D, NDOT, CLS_VALS, false>(a, D, tiled ? xs : nullptr, sdict, cids, u_staged, upre, tile, warp, lane);
 }
 
 struct StagedArgs {

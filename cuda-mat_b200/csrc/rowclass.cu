@@ -136,8 +136,11 @@ __global__ void k_tile_ok(int n, const unsigned char *cls, unsigned long long ok
 // presence mask of every row w.r.t. the superset pattern: tmask[r] = cmask[cls[r]]
 struct ClassMasks { unsigned char m[kDictMax]; };
 __global__ void k_cls_to_mask(int n, const unsigned char *cls, const ClassMasks cm, unsigned char *tmask) {
+    __shared__ unsigned char tab[kDictMax];                        // per-thread indexing of a parameter array is slow
+    if (threadIdx.x < kDictMax) tab[threadIdx.x] = cm.m[threadIdx.x];
+    __syncthreads();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) tmask[r] = cm.m[cls[r] & 63];
+    if (r < n) tmask[r] = tab[cls[r] & 63];
 }
 
 // TILED plan for the offsets+values dictionary: windows = clusters of the column offsets of the frequent classes
