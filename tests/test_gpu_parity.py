@@ -379,6 +379,54 @@ def test_tiled_spmv_mixed_tiles_periodic_stencil(cm, O, torch_cuda):
             s.close()
 
 
+def test_tiled_class_records_when_no_superset_pattern(cm, O, torch_cuda):
+    """TILED without the superset pattern: (a) a 7-point stencil whose diagonal is the row's degree - the classes
+    disagree on the value at offset 0; (b) a 2-D 9-point stencil - 9 distinct offsets (> 8), rows of 4 / 6 / 9 entries, so the
+    per-class records in shared memory are walked in three passes.  Both must stay bit-identical to CSR and the oracle."""
+    torch = torch_cuda
+    import scipy.sparse as sp
+    mats = []
+    ia, ja, a = O.poisson3d(20)
+    a = a.copy()
+    for i in range(len(ia) - 1):
+        lo, hi = ia[i], ia[i + 1]
+        a[lo:hi][ja[lo:hi] == i] = (hi - lo - 1) + 0.5
+    mats.append((ia, ja, a))
+    N = 96
+    n = N * N
+    rows, cols, vals = [], [], []
+    jj, ii = np.meshgrid(np.arange(N), np.arange(N), indexing="ij")
+    for dj in (-1, 0, 1):
+        for di in (-1, 0, 1):
+            ok = (jj + dj >= 0) & (jj + dj < N) & (ii + di >= 0) & (ii + di < N)
+            rows.append((jj * N + ii)[ok]); cols.append(((jj + dj) * N + ii + di)[ok])
+            vals.append(np.full(ok.sum(), 8.5 if (dj == 0 and di == 0) else -1.0 - 0.125 * (dj + 1) - 0.03125 * (di + 1)))
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+    A.sort_indices()
+    mats.append((A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()))
+    for k, (ia, ja, a) in enumerate(mats):
+        n = len(ia) - 1
+        x = np.random.default_rng(40 + k).standard_normal(n)
+        want = O.spmv(ia, ja, a, x)
+        ref = None
+        for v in (1, 4, 5):
+            s, st = make_solver(cm, torch, ia, ja, a, variant=v)
+            if v == 5:
+                assert st["spmv_variant"] == cm.SPMV_TILED, (k, st)
+            dx, dy = dev(torch, x), torch.zeros(n, dtype=torch.float64, device="cuda")
+            s.spmv(dx.data_ptr(), dy.data_ptr(), variant=v)
+            torch.cuda.synchronize()
+            assert np.array_equal(dy.cpu().numpy(), want), (k, v)
+            b = dev(torch, want)
+            xs = torch.zeros(n, dtype=torch.float64, device="cuda")
+            r = s.solve(0, b.data_ptr(), xs.data_ptr(), maxit=300, tol=1e-10)
+            if ref is None:
+                ref = (r["iterations"], xs.clone())
+            else:
+                assert r["iterations"] == ref[0] and torch.equal(xs, ref[1]), (k, v)
+            s.close()
+
+
 def test_variable_coefficient_stencil_uses_offset_dictionary(cm, O, torch_cuda):
     """a stencil with per-entry coefficients: no value dictionary, but the offset dictionary (PATTERN) and its TILED form
     (x windows in shared memory, values streamed from CSR) apply and stay bit-identical to the CSR kernel / the oracle"""
