@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 
 namespace cudamat {
 
@@ -78,7 +79,9 @@ struct P2P {
 // arena keeps its handle, so the next solver handle finds the mapping instead of paying cudaIpcOpenMemHandle again.
 struct PeerMap { cudaIpcMemHandle_t h; void *ptr; };
 static std::vector<PeerMap> g_peer_maps;
+static std::mutex g_peer_maps_mu;
 static void *peer_map_open(const cudaIpcMemHandle_t &h) {
+    std::lock_guard<std::mutex> lk(g_peer_maps_mu);
     for (const PeerMap &m : g_peer_maps) if (!memcmp(&m.h, &h, sizeof h)) return m.ptr;
     void *p = nullptr;
     if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
