@@ -56,7 +56,7 @@ EXPORTS = [
     "cudamat_set_csr_host", "cudamat_set_csr_device", "cudamat_analyze", "cudamat_solve_device",
     "cudamat_get_history", "cudamat_spmv_device", "cudamat_dot_device", "cudamat_get_ilu0_host",
     "cudamat_sptrsv_device", "cudamat_comm_p2p_enabled", "cudamat_write_mm", "cudamat_write_mm_vector", "cudamat_comm_unique_id", "cudamat_comm_init", "cudamat_partition_rows",
-    "cudamat_halo_plan_host",
+    "cudamat_halo_plan_host", "cudamat_tiled_plan_host",
     "cudamat_gen_poisson3d_device", "cudamat_poisson3d_nnz", "cudamat_gen_xtrue_device",
     "cudamat_gen_random_dd_device", "cudamat_load_mm", "cudamat_free",
 ]
@@ -67,6 +67,8 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 lib.cudamat_last_error.restype = C.c_char_p
+lib.cudamat_tiled_plan_host.argtypes = [C.c_int, c_ip, c_ip, c_dp, C.POINTER(C.c_uint), C.c_int, C.c_int, c_ip, c_ip, c_ip, c_ip, c_ip,
+                                        C.POINTER(C.c_ulonglong), c_ip, c_ip, c_dp, C.POINTER(C.c_ubyte), C.POINTER(C.c_longlong)]
 lib.cudamat_bicgstab_host.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_ip, c_dp, c_dp, c_dp, C.c_int,
                                       C.c_double, C.c_int, c_dp, c_dp, C.POINTER(Stats)]
 lib.cudamat_ilu0_host.argtypes = [C.c_int, C.c_int, c_dp, c_ip, c_ip, c_dp, c_ip, c_ip]
@@ -293,6 +295,38 @@ def halo_plan_host(row0, row1, ja_global, row_starts):
     halo = np.ctypeslib.as_array(hp, (max(nh.value, 1),))[:nh.value].copy()
     lib.cudamat_free(C.cast(hp, C.c_void_p))
     return halo, np.array(list(rc), dtype=np.int64)
+
+
+def tiled_plan_host(lens, offs, vals, hist, n, with_vals=True):
+    """Host planner of the TILED SpMV variant (pure host code).  lens[c], offs[c][q] (column offsets in storage order),
+    vals[c][q] or None, hist[c] rows per class, n rows.  Returns None when there is no plan, else a dict with the staged
+    windows, the shared-memory index of every entry, the classes that fit and the superset pattern (sup_len 0: none)."""
+    ncls = len(lens)
+    L = _i32(lens)
+    O = np.zeros((ncls, 16), dtype=np.int32)
+    V = np.zeros((ncls, 16), dtype=np.float64)
+    for c in range(ncls):
+        O[c, :len(offs[c])] = offs[c]
+        if vals is not None:
+            V[c, :len(vals[c])] = vals[c]
+    H = np.ascontiguousarray(hist, dtype=np.uint32)
+    nseg, sup_len = C.c_int(0), C.c_int(0)
+    seg_lo, seg_len, seg_base = (C.c_int * 4)(), (C.c_int * 4)(), (C.c_int * 4)()
+    disp = np.zeros((ncls, 16), dtype=np.int32)
+    ok = C.c_ulonglong(0)
+    sup_boff = (C.c_int * 8)()
+    sup_val = (C.c_double * 8)()
+    cmask = (C.c_ubyte * 64)()
+    smem = C.c_longlong(0)
+    _check(lib.cudamat_tiled_plan_host(ncls, _ip(L), _ip(O), _dp(V) if vals is not None else None,
+                                       H.ctypes.data_as(C.POINTER(C.c_uint)), int(n), 1 if with_vals else 0, C.byref(nseg), seg_lo, seg_len,
+                                       seg_base, _ip(disp), C.byref(ok), C.byref(sup_len), sup_boff, sup_val, cmask, C.byref(smem)))
+    if nseg.value == 0:
+        return None
+    k = nseg.value
+    return {"windows": [(seg_lo[g], seg_len[g], seg_base[g]) for g in range(k)], "disp": disp, "ok_mask": ok.value,
+            "sup_len": sup_len.value, "sup_boff": list(sup_boff)[:sup_len.value], "sup_val": list(sup_val)[:sup_len.value],
+            "class_mask": list(cmask)[:ncls], "smem_bytes": smem.value}
 
 
 class Comm:

@@ -143,31 +143,32 @@ __global__ void k_cls_to_mask(int n, const unsigned char *cls, const ClassMasks 
     if (r < n) tmask[r] = tab[cls[r] & 63];
 }
 
-// TILED plan for the offsets+values dictionary: windows = clusters of the column offsets of the frequent classes
-static int tiled_plan(cudamat_solver *s, RowClasses &C) {
-    const int n = s->n;
-    unsigned *d_hist = nullptr;
-    CM_CUDA(dev_alloc((void **)&d_hist, sizeof(unsigned) * kDictMax));
-    CM_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * kDictMax, s->stream));
-    k_cls_hist<<<296, 256, 0, s->stream>>>(n, C.d_cls, d_hist);
-    unsigned hist[kDictMax];
-    CM_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, s->stream));
-    CM_CUDA(cudaStreamSynchronize(s->stream));
-    dev_free(d_hist);
-    s->launches++;
-    const DictParam &D = *C.h_dict;
+// ---- TILED plan, host part (pure host code, also reachable through cudamat_tiled_plan_host for the CPU tests) -------
+// From the class dictionary and the class histogram: the windows (clusters of the column offsets of the frequent classes),
+// the shared-memory position of every entry, which classes fit the windows, the shared-memory records and — when it
+// exists — the superset pattern with the presence mask of every class.
+struct TiledPlanHost {
+    std::unique_ptr<TiledDict> T;
+    std::vector<TiledSmemClass> sd;
+    ClassMasks cm;
+    unsigned long long ok_mask = 0;
+    size_t smem_windows = 0;
+};
+static bool tiled_plan_host(const DictParam &D, int ncls, const unsigned *hist, int n, bool with_vals, TiledPlanHost &P) {
+    if (ncls <= 0 || ncls > kDictMax) return false;
     // offsets of the frequent classes (>= 1/64 of the rows, or the most frequent one)
     int top = 0;
-    for (int c = 1; c < C.ncls; ++c) if (hist[c] > hist[top]) top = c;
+    for (int c = 1; c < ncls; ++c) if (hist[c] > hist[top]) top = c;
     std::vector<int> offs;
-    for (int c = 0; c < C.ncls; ++c)
+    for (int c = 0; c < ncls; ++c)
         if (c == top || hist[c] >= (unsigned)std::max(1, n / 64))
             for (int k = 0; k < D.len[c]; ++k) offs.push_back(D.off[c * kDictLen + k]);
-    if (offs.empty()) return CUDAMAT_OK;
+    if (offs.empty()) return false;
     std::sort(offs.begin(), offs.end());
     offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
-    std::unique_ptr<TiledDict> T(new TiledDict());           // released into C.h_tdict on success
-    memset(T.get(), 0, sizeof(TiledDict));
+    P.T.reset(new TiledDict());
+    TiledDict *T = P.T.get();
+    memset(T, 0, sizeof(TiledDict));
     int nseg = 0, base = 0;
     size_t k = 0;
     bool fits = true;
@@ -183,11 +184,11 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
         base += len;
         ++nseg;
     }
-    const size_t smem = sizeof(double) * (size_t)base;
-    if (!fits || smem > 100 * 1024) return CUDAMAT_OK;
+    P.smem_windows = sizeof(double) * (size_t)base;
+    if (!fits || P.smem_windows > 100 * 1024) { P.T.reset(); return false; }
     T->nseg = nseg;
-    unsigned long long ok_mask = 0;
-    for (int c = 0; c < C.ncls; ++c) {
+    P.ok_mask = 0;
+    for (int c = 0; c < ncls; ++c) {
         T->len[c] = D.len[c];
         bool ok = true;
         for (int q = 0; q < kDictLen; ++q) {
@@ -203,7 +204,7 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
             }
             T->disp[c * kDictLen + q] = disp;
         }
-        if (ok) ok_mask |= 1ull << c;
+        if (ok) P.ok_mask |= 1ull << c;
     }
     // shared-memory form of the dictionary (one TMA bulk copy per CTA, behind the windows)
     T->sdict_base = base;
@@ -211,61 +212,77 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
     T->disp0 = -1;
     for (int g = 0; g < nseg; ++g)
         if (0 >= T->seg_lo[g] && kTile <= T->seg_lo[g] + T->seg_len[g]) { T->disp0 = T->seg_base[g] - T->seg_lo[g]; break; }
-    std::vector<TiledSmemClass> sd((size_t)C.ncls);
-    for (int c = 0; c < C.ncls; ++c) {
-        memset(&sd[c], 0, sizeof(TiledSmemClass));
+    P.sd.assign((size_t)ncls, TiledSmemClass());
+    for (int c = 0; c < ncls; ++c) {
+        memset(&P.sd[c], 0, sizeof(TiledSmemClass));
         T->maxlen = std::max(T->maxlen, T->len[c]);
         T->minlen = std::min(T->minlen, T->len[c]);
         for (int q = 0; q < kDictLen; ++q) {
-            sd[c].boff[q] = q < T->len[c] ? T->disp[c * kDictLen + q] * 8 : -1;
-            sd[c].val[q] = q < T->len[c] ? T->val[c * kDictLen + q] : 0.0;
+            P.sd[c].boff[q] = q < T->len[c] ? T->disp[c * kDictLen + q] * 8 : -1;
+            P.sd[c].val[q] = q < T->len[c] ? T->val[c * kDictLen + q] : 0.0;
         }
     }
-    CM_CUDA(dev_alloc((void **)&C.d_sdict, sizeof(TiledSmemClass) * (size_t)C.ncls));
-    CM_CUDA(cudaMemcpyAsync(C.d_sdict, sd.data(), sizeof(TiledSmemClass) * (size_t)C.ncls, cudaMemcpyHostToDevice, s->stream));
-    CM_CUDA(cudaStreamSynchronize(s->stream));                       // sd is a local
     // superset pattern over the staged classes: sorted union of their offsets (every class ascending, so each is an
     // order-preserving subset); for the values dictionary the value at an offset must be the same in every class
-    {
-        const bool with_vals = (&C == &s->cls[1]);
-        std::vector<int> so; std::vector<double> sv;
-        bool ok = true;
-        for (int c = 0; c < C.ncls && ok; ++c) {
-            if (!((ok_mask >> c) & 1ull)) continue;
-            for (int q = 0; q < T->len[c] && ok; ++q) {
-                const int o = T->off[c * kDictLen + q];
-                if (q > 0 && o <= T->off[c * kDictLen + q - 1]) ok = false;
-                const double v = T->val[c * kDictLen + q];
-                size_t k = 0;
-                while (k < so.size() && so[k] < o) ++k;
-                if (k < so.size() && so[k] == o) { if (with_vals && memcmp(&sv[k], &v, sizeof v) != 0) ok = false; }
-                else { so.insert(so.begin() + k, o); sv.insert(sv.begin() + k, v); }
-            }
+    memset(&P.cm, 0, sizeof P.cm);
+    std::vector<int> so; std::vector<double> sv;
+    bool ok = true;
+    for (int c = 0; c < ncls && ok; ++c) {
+        if (!((P.ok_mask >> c) & 1ull)) continue;
+        for (int q = 0; q < T->len[c] && ok; ++q) {
+            const int o = T->off[c * kDictLen + q];
+            if (q > 0 && o <= T->off[c * kDictLen + q - 1]) ok = false;
+            const double v = T->val[c * kDictLen + q];
+            size_t j = 0;
+            while (j < so.size() && so[j] < o) ++j;
+            if (j < so.size() && so[j] == o) { if (with_vals && memcmp(&sv[j], &v, sizeof v) != 0) ok = false; }
+            else { so.insert(so.begin() + j, o); sv.insert(sv.begin() + j, v); }
         }
-        if (ok && !so.empty() && so.size() <= 8) {
-            ClassMasks cm; memset(&cm, 0, sizeof cm);
-            for (int c = 0; c < C.ncls; ++c) {
-                if (!((ok_mask >> c) & 1ull)) continue;
-                for (int q = 0; q < T->len[c]; ++q)
-                    for (size_t k = 0; k < so.size(); ++k)
-                        if (so[k] == T->off[c * kDictLen + q]) { cm.m[c] |= (unsigned char)(1u << k); T->sup_boff[k] = T->disp[c * kDictLen + q] * 8; }
-            }
-            for (size_t k = 0; k < so.size(); ++k) T->sup_val[k] = sv[k];
-            T->sup_len = (int)so.size();
-            CM_CUDA(dev_alloc((void **)&C.d_tmask, (size_t)n + 16));
-            k_cls_to_mask<<<(n + 255) / 256, 256, 0, s->stream>>>(n, C.d_cls, cm, C.d_tmask);
-            CM_CUDA(cudaGetLastError());
-            s->launches++;
+    }
+    if (ok && !so.empty() && so.size() <= 8) {
+        for (int c = 0; c < ncls; ++c) {
+            if (!((P.ok_mask >> c) & 1ull)) continue;
+            for (int q = 0; q < T->len[c]; ++q)
+                for (size_t j = 0; j < so.size(); ++j)
+                    if (so[j] == T->off[c * kDictLen + q]) { P.cm.m[c] |= (unsigned char)(1u << j); T->sup_boff[j] = T->disp[c * kDictLen + q] * 8; }
         }
+        for (size_t j = 0; j < so.size(); ++j) T->sup_val[j] = sv[j];
+        T->sup_len = (int)so.size();
+    }
+    return true;
+}
+
+// TILED plan: class histogram on the device, the host plan above, then the device-side tables (shared-memory records,
+// presence mask per row, eligibility byte per tile)
+static int tiled_plan(cudamat_solver *s, RowClasses &C) {
+    const int n = s->n;
+    unsigned *d_hist = nullptr;
+    CM_CUDA(dev_alloc((void **)&d_hist, sizeof(unsigned) * kDictMax));
+    CM_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * kDictMax, s->stream));
+    k_cls_hist<<<296, 256, 0, s->stream>>>(n, C.d_cls, d_hist);
+    unsigned hist[kDictMax];
+    CM_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));
+    dev_free(d_hist);
+    s->launches++;
+    TiledPlanHost P;
+    if (!tiled_plan_host(*C.h_dict, C.ncls, hist, n, &C == &s->cls[1], P)) return CUDAMAT_OK;
+    CM_CUDA(dev_alloc((void **)&C.d_sdict, sizeof(TiledSmemClass) * (size_t)C.ncls));
+    CM_CUDA(cudaMemcpyAsync(C.d_sdict, P.sd.data(), sizeof(TiledSmemClass) * (size_t)C.ncls, cudaMemcpyHostToDevice, s->stream));
+    if (P.T->sup_len > 0) {
+        CM_CUDA(dev_alloc((void **)&C.d_tmask, (size_t)n + 16));
+        k_cls_to_mask<<<(n + 255) / 256, 256, 0, s->stream>>>(n, C.d_cls, P.cm, C.d_tmask);
+        CM_CUDA(cudaGetLastError());
+        s->launches++;
     }
     const int ntile = (n + kTile - 1) / kTile;
     CM_CUDA(dev_alloc((void **)&C.d_tile_ok, (size_t)std::max(ntile, 1)));
-    k_tile_ok<<<ntile, 256, 0, s->stream>>>(n, C.d_cls, ok_mask, C.d_tile_ok);
+    k_tile_ok<<<ntile, 256, 0, s->stream>>>(n, C.d_cls, P.ok_mask, C.d_tile_ok);
     CM_CUDA(cudaGetLastError());
-    CM_CUDA(cudaStreamSynchronize(s->stream));
+    CM_CUDA(cudaStreamSynchronize(s->stream));                       // P.sd is a local
     s->launches++;
-    C.h_tdict = T.release();
-    C.tiled_smem = smem + sizeof(TiledSmemClass) * (size_t)C.ncls;
+    C.h_tdict = P.T.release();
+    C.tiled_smem = P.smem_windows + sizeof(TiledSmemClass) * (size_t)C.ncls;
     return CUDAMAT_OK;
 }
 
@@ -340,3 +357,36 @@ int rowclass_analyze(cudamat_solver *s) {
 }
 
 }  // namespace cudamat
+
+// host planner of the TILED SpMV variant, exported for the CPU tests (no device needed)
+extern "C" int cudamat_tiled_plan_host(int ncls, const int *len, const int *off, const double *val, const unsigned *hist, int n,
+                                       int with_vals, int *nseg, int *seg_lo, int *seg_len, int *seg_base, int *disp,
+                                       unsigned long long *ok_mask, int *sup_len, int *sup_boff, double *sup_val,
+                                       unsigned char *class_mask, long long *smem_bytes) {
+    using namespace cudamat;
+    if (ncls <= 0 || ncls > kDictMax || !len || !off || !hist || n <= 0) { set_error("tiled_plan_host: invalid argument"); return CUDAMAT_E_INVALID; }
+    std::unique_ptr<DictParam> D(new DictParam());
+    memset(D.get(), 0, sizeof(DictParam));
+    for (int c = 0; c < ncls; ++c) {
+        if (len[c] < 0 || len[c] > kDictLen) { set_error("tiled_plan_host: class length %d out of range", len[c]); return CUDAMAT_E_INVALID; }
+        D->len[c] = len[c];
+        for (int q = 0; q < kDictLen; ++q) { D->off[c * kDictLen + q] = off[c * kDictLen + q]; D->val[c * kDictLen + q] = val ? val[c * kDictLen + q] : 0.0; }
+    }
+    TiledPlanHost P;
+    const bool have = tiled_plan_host(*D, ncls, hist, n, with_vals != 0, P);
+    if (nseg) *nseg = have ? P.T->nseg : 0;
+    if (!have) return CUDAMAT_OK;
+    for (int g = 0; g < kMaxSeg; ++g) {
+        if (seg_lo) seg_lo[g] = P.T->seg_lo[g];
+        if (seg_len) seg_len[g] = P.T->seg_len[g];
+        if (seg_base) seg_base[g] = P.T->seg_base[g];
+    }
+    if (disp) for (int k = 0; k < ncls * kDictLen; ++k) disp[k] = P.T->disp[k];
+    if (ok_mask) *ok_mask = P.ok_mask;
+    if (sup_len) *sup_len = P.T->sup_len;
+    for (int q = 0; q < 8; ++q) { if (sup_boff) sup_boff[q] = P.T->sup_boff[q]; if (sup_val) sup_val[q] = P.T->sup_val[q]; }
+    if (class_mask) for (int c = 0; c < kDictMax; ++c) class_mask[c] = P.cm.m[c];
+    if (smem_bytes) *smem_bytes = (long long)(P.smem_windows + sizeof(TiledSmemClass) * (size_t)ncls);
+    return CUDAMAT_OK;
+}
+

@@ -158,6 +158,18 @@ int cudamat_sptrsv_device(cudamat_solver *s, int upper, const double *d_rhs, dou
 int cudamat_partition_rows(int64_t n_global, int world, int rank, int64_t *row0, int64_t *row1);
 int cudamat_halo_plan_host(int64_t row0, int64_t row1, int64_t nnz, const int *ja_global, int world,
                            const int64_t *row_starts, int *nhalo, int **halo_cols, int *recv_cnt);
+/* Host planner of the TILED SpMV variant (pure host code, no device needed; used by cudamat_analyze and exported for
+ * the CPU tests).  Input: the row-class dictionary — ncls <= 64 classes of len[c] <= 16 entries, column offsets
+ * off[c*16+q] = ja - row in storage order, values val[c*16+q] (may be NULL), rows per class hist[c] — and the row count.
+ * Output (arrays sized 4, 4, 4, ncls*16, -, -, 8, 8, 64): the x windows staged per 2048-row tile (first offset, length
+ * and shared-memory base in elements), the shared-memory index of every entry relative to its row, the bit mask of the
+ * classes that fit the windows, and the superset pattern (sup_len = 0: none): byte offset and value per pattern entry
+ * and the presence mask of every class.  *nseg = 0: no plan (too many / too wide windows).  No reference counterpart:
+ * the reference hands CSR to cusparseDcsrmv (pbicgstab.cu:67,104,132). */
+int cudamat_tiled_plan_host(int ncls, const int *len, const int *off, const double *val, const unsigned *hist, int n,
+                            int with_vals, int *nseg, int *seg_lo, int *seg_len, int *seg_base, int *disp,
+                            unsigned long long *ok_mask, int *sup_len, int *sup_boff, double *sup_val,
+                            unsigned char *class_mask, long long *smem_bytes);
 #define CUDAMAT_UNIQUE_ID_BYTES 128
 int cudamat_comm_unique_id(void *id128);
 int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world);
