@@ -252,7 +252,9 @@ static int p2p_setup(cudamat_solver *s, const std::vector<int> &W) {
     if (s->work && s->work_pooled) {                  // an arena from the memory pool cannot be shared over IPC
         cudaStreamSynchronize(s->stream); dev_free(s->work); s->work = nullptr; s->work_nvec = 0;
     }
-    if (ok && ensure_work(s, 9) != CUDAMAT_OK) ok = 0;
+    // the arena is sized ONCE for the largest solve (its IPC handle goes to the neighbours: it must never be reallocated
+    // while the peer-memory path is on, see ensure_work)
+    if (ok && ensure_work(s, kWorkVecsShared) != CUDAMAT_OK) ok = 0;
     if (ok && cudaMalloc(&P.arena, abytes) != cudaSuccess) { ok = 0; P.arena = nullptr; }
     if (ok) {
         cudaMemsetAsync(P.arena, 0, abytes, s->stream);
@@ -405,6 +407,7 @@ int cudamat_comm_unique_id(void *id128) {
 int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world) {
     if (!s || !id128 || world < 1 || rank < 0 || rank >= world) { set_error("comm_init: invalid argument"); return CUDAMAT_E_INVALID; }
     if (!s->d_ia) { set_error("comm_init: set the CSR shard first"); return CUDAMAT_E_STATE; }
+    DeviceGuard dg(s->device);
     int rc = load_nccl();
     if (rc) return rc;
     comm_release(s);

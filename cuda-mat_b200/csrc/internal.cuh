@@ -24,7 +24,8 @@ constexpr int kSlabsPerWarp = kTileSlabs / kCtaWarps;   // 4
 constexpr int kMaxQ        = 2;       // reduced quantities per kernel
 
 // solver status (device side)
-enum : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BRK_OMEGA = 2, ST_BRK_NAN = 3, ST_MAXIT = 4 };
+enum : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BRK_OMEGA = 2, ST_BRK_NAN = 3, ST_MAXIT = 4,
+              ST_COMM_TIMEOUT = 5 /* a peer's halo rows / partial sums never arrived: the host returns CUDAMAT_E_COMM */ };
 
 // phases of the scalar recurrences executed by the last CTA of a reducing kernel
 enum : int {
@@ -160,12 +161,16 @@ __device__ __forceinline__ void halo_signal(const HaloPush &hp, int row_base, in
         }
     }
 }
-__device__ __forceinline__ void halo_wait(const HaloWait &hw, int tile) {
+// A peer that never delivers must neither hang the GPU nor kill the CUDA context: after the spin limit the waiting
+// thread records ST_COMM_TIMEOUT in the solver status (every later kernel of the solve returns at entry, the host poll
+// turns it into CUDAMAT_E_COMM) and the kernel carries on with whatever the halo holds.
+constexpr unsigned kPeerSpinLimit = 1u << 26;
+__device__ __forceinline__ void halo_wait(const HaloWait &hw, int tile, int *status) {
     if (hw.nsrc == 0 || !hw.tile_wait[tile]) return;
     if ((int)threadIdx.x < hw.nsrc) {
         unsigned spins = 0;
         while (ld_acquire_sys_u64(hw.flag[threadIdx.x]) < hw.epoch)
-            if (++spins > (1u << 26)) __trap();         // a lost neighbour must not hang the GPU
+            if (++spins > kPeerSpinLimit) { if (status) atomicExch(status, ST_COMM_TIMEOUT); break; }
     }
     __syncthreads();
 }
@@ -195,6 +200,7 @@ __device__ __forceinline__ void hist_push(DevScalars *sc, double *hist, double v
 
 // scalar recurrences; executed by one thread. Forms follow pbicgstab.cu (cited per phase).
 __device__ __forceinline__ void apply_phase(DevScalars *sc, double *hist, int phase, const double *red) {
+    if (sc->status == ST_COMM_TIMEOUT) return;          // sticky: the sums below were formed from missing peer data
     switch (phase) {
     case PH_STORE:
         sc->red[0] = red[0]; sc->red[1] = red[1];

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_ROWLANE_MINB) k_spmv_rowl
     }
     pdl_sync();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
-    halo_wait(a.hw, blockIdx.x);
+    halo_wait(a.hw, blockIdx.x, a.sc ? &a.sc->status : nullptr);
     // fused-dot products of the previous slab: their butterflies are issued right after the next slab's
     // row-pointer loads, so the shuffle latency hides under that memory round trip
     double pp0 = 0.0, pp1 = 0.0;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_CLASS_MINB) k_spmv_class(
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     for (int tile = blockIdx.x * c.tiles_per_cta; tile < tile_end; ++tile) {
         const int row_base = tile * kTile;
-        halo_wait(a.hw, tile);
+        halo_wait(a.hw, tile, a.sc ? &a.sc->status : nullptr);
         load_ids(tile + 1, nid);
 #pragma unroll
         for (int j = 0; j < kSlabsPerWarp; ++j) {
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kCtaThreads, CUDAMAT_TILED_MINB) k_spmv_tiled(
     __syncthreads();
     pdl_sync();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
-    halo_wait(a.hw, tile);
+    halo_wait(a.hw, tile, a.sc ? &a.sc->status : nullptr);
     // SpMV 2 of the loop takes its dot operand from x itself (t.s): it is already in shared memory.  Any other operand
     // is fetched here, ahead of the wait for the windows, so that its DRAM latency overlaps the bulk copies (values
     // dictionary only: the kernel that streams the values from CSR has no registers to spare for it).
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_spmv_staged(const StagedArgs
     const SpmvArgs &a = g.a;
     pdl_prologue();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
-    halo_wait(a.hw, blockIdx.x);
+    halo_wait(a.hw, blockIdx.x, a.sc ? &a.sc->status : nullptr);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_bar[kCtaWarps][8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -705,8 +705,10 @@ static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
         const RowClasses &C = s->cls[m];
         const TiledArgs c{C.d_cls, C.d_tile_ok, C.d_tmask, C.d_sdict, C.ncls, s->n + s->nhalo};
         const void *kern = m ? (const void *)k_spmv_tiled<HAS_D, NDOT, true> : (const void *)k_spmv_tiled<HAS_D, NDOT, false>;
-        static bool attr_set[2] = {false, false};
-        if (!attr_set[m]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024)); attr_set[m] = true; }
+        // function attributes are per device and per template instance: one flag per (device, instance)
+        static bool attr_set[64][2] = {};
+        const int dv = s->device & 63;
+        if (!attr_set[dv][m]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024)); attr_set[dv][m] = true; }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCtaThreads); cfg.dynamicSmemBytes = C.tiled_smem; cfg.stream = s->stream;
         cudaLaunchAttribute at[1];
@@ -1003,7 +1005,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_reduce_finish(const RedCtx rc, 
         if ((int)threadIdx.x < rc.p2p.world) {                 // every rank's partial sums must have arrived
             unsigned spins = 0;
             while (ld_acquire_sys_u64(flags + threadIdx.x) < rc.p2p.epoch)
-                if (++spins > (1u << 26)) __trap();            // a lost rank must not hang the GPU
+                if (++spins > kPeerSpinLimit) { atomicExch(&sc->status, ST_COMM_TIMEOUT); break; }   // a lost rank must not hang the GPU
         }
         __syncthreads();
         src = rc.p2p.peers[rc.p2p.me].gather[rc.p2p.epoch & 1ull];
@@ -1171,7 +1173,9 @@ int launch_normalize_base(cudaStream_t st, int *ia, int64_t n1, int *ja, int64_t
     return CUDAMAT_OK;
 }
 
-// first offending row (row pointers not monotone) / entry (column outside [0, ncols)), or INT_MAX
+// first offending row (row pointers not monotone) / entry (column outside [0, ncols)) / entry whose column is not
+// strictly larger than its predecessor's in the same row (unsorted or duplicate: the reference loader guarantees
+// strictly ascending rows through verify_pattern, mmio_wrapper.h:123-126, and the ILU0 path relies on it), or INT_MAX
 __global__ void k_validate_csr(const int *ia, int n, const int *ja, int64_t nnz, int64_t ncols, int *bad) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1179,21 +1183,25 @@ __global__ void k_validate_csr(const int *ia, int n, const int *ja, int64_t nnz,
         const int c = ja[k];
         if (c < 0 || c >= ncols) atomicMin(bad + 1, (int)k);
     }
-    for (int64_t r = i; r < n; r += stride)
-        if (ia[r + 1] < ia[r]) atomicMin(bad + 0, (int)r);
+    for (int64_t r = i; r < n; r += stride) {
+        const int s = ia[r], e = ia[r + 1];
+        if (e < s) { atomicMin(bad + 0, (int)r); continue; }
+        if (s < 0 || e > nnz) continue;                       // reported through the row-pointer end check of the caller
+        for (int k = s + 1; k < e; ++k)
+            if (ja[k] <= ja[k - 1]) { atomicMin(bad + 2, k); break; }
+    }
 }
 int launch_validate_csr(cudaStream_t st, const int *ia, int n, const int *ja, int64_t nnz, int64_t ncols, int *h_bad) {
     int *d_bad = nullptr;
-    CM_CUDA(dev_alloc((void **)&d_bad, 2 * sizeof(int)));
-    CM_CUDA(cudaMemsetAsync(d_bad, 0x7f, 2 * sizeof(int), st));
+    CM_CUDA(dev_alloc((void **)&d_bad, 3 * sizeof(int)));
+    CM_CUDA(cudaMemsetAsync(d_bad, 0x7f, 3 * sizeof(int), st));
     k_validate_csr<<<1184, 256, 0, st>>>(ia, n, ja, nnz, ncols, d_bad);
     CM_CUDA(cudaGetLastError());
-    int h[2];
+    int h[3];
     CM_CUDA(cudaMemcpyAsync(h, d_bad, sizeof h, cudaMemcpyDeviceToHost, st));
     CM_CUDA(cudaStreamSynchronize(st));
     dev_free(d_bad);
-    h_bad[0] = h[0] == 0x7f7f7f7f ? -1 : h[0];
-    h_bad[1] = h[1] == 0x7f7f7f7f ? -1 : h[1];
+    for (int q = 0; q < 3; ++q) h_bad[q] = h[q] == 0x7f7f7f7f ? -1 : h[q];
     return CUDAMAT_OK;
 }
 

@@ -35,43 +35,55 @@ static double now_s() {
 // Large buffers of the one-shot host entry points come from a stream-ordered memory pool that keeps freed memory
 // mapped: cudaFree of the 2.5 GB a 256^3 solve holds costs ~0.4 s of page unmapping, more than the solve itself.
 // (IPC-shared buffers of the multi-GPU path cannot live in the default pool and stay with cudaMalloc.)
-static cudaStream_t g_pool_stream = nullptr;
-static cudaMemPool_t g_pool = nullptr;            // the library's OWN pool: the device's default pool is left untouched
-static bool pool_ready() {
-    static std::once_flag once;
-    static bool ok = false;
-    std::call_once(once, [] {
+// One pool (+ its allocation stream) PER DEVICE, created on first use from that device; an allocation remembers nothing:
+// cudaFreeAsync returns memory to the pool it came from whatever device is current.
+constexpr int kMaxDev = 64;
+struct DevPool { std::once_flag once; bool ok = false; cudaMemPool_t pool = nullptr; cudaStream_t stream = nullptr; };
+static DevPool g_pools[kMaxDev];
+static DevPool *pool_for_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { cudaGetLastError(); return nullptr; }
+    DevPool &P = g_pools[dev];
+    std::call_once(P.once, [&P, dev] {
         const char *off = getenv("CUDAMAT_NO_POOL");
-        int dev = 0, supported = 0;
-        if (!(off && *off && *off != '0') && cudaGetDevice(&dev) == cudaSuccess &&
+        int supported = 0;
+        if (!(off && *off && *off != '0') &&
             cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && supported) {
             cudaMemPoolProps props{};
             props.allocType = cudaMemAllocationTypePinned;
             props.handleTypes = cudaMemHandleTypeNone;
             props.location.type = cudaMemLocationTypeDevice;
             props.location.id = dev;
-            if (cudaMemPoolCreate(&g_pool, &props) == cudaSuccess &&
-                cudaStreamCreateWithFlags(&g_pool_stream, cudaStreamNonBlocking) == cudaSuccess) {
+            if (cudaMemPoolCreate(&P.pool, &props) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking) == cudaSuccess) {
                 const char *mb = getenv("CUDAMAT_POOL_KEEP_MB");
                 unsigned long long keep = (mb ? strtoull(mb, nullptr, 10) : 8192ull) << 20;
-                cudaMemPoolSetAttribute(g_pool, cudaMemPoolAttrReleaseThreshold, &keep);
-                ok = true;
+                cudaMemPoolSetAttribute(P.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                P.ok = true;
             }
         }
         cudaGetLastError();
     });
-    return ok;
+    return P.ok ? &P : nullptr;
 }
 cudaError_t dev_alloc(void **p, size_t bytes) {
-    if (!pool_ready()) return cudaMalloc(p, bytes);
-    cudaError_t e = cudaMallocFromPoolAsync(p, bytes, g_pool, g_pool_stream);
+    DevPool *P = pool_for_current_device();
+    if (!P) return cudaMalloc(p, bytes);
+    cudaError_t e = cudaMallocFromPoolAsync(p, bytes, P->pool, P->stream);
     if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(g_pool_stream);    // usable from any stream on return
+    return cudaStreamSynchronize(P->stream);        // usable from any stream on return
 }
 void dev_free(void *p) {                            // no work may still use p (callers synchronise their stream first)
     if (!p) return;
-    if (!pool_ready()) { cudaFree(p); return; }
-    cudaFreeAsync(p, g_pool_stream);
+    // the pointer's own device decides (the caller may have switched devices since the allocation)
+    cudaPointerAttributes at{};
+    int cur = -1;
+    cudaGetDevice(&cur);
+    const bool known = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    if (!known) cudaGetLastError();
+    const int dev = known ? at.device : cur;
+    if (dev >= 0 && dev < kMaxDev && g_pools[dev].ok) { cudaFreeAsync(p, g_pools[dev].stream); return; }
+    cudaFree(p);
 }
 
 // pinned status mirrors are recycled process-wide: cudaMallocHost / cudaFreeHost cost up to 0.1-0.4 s when other
@@ -147,6 +159,12 @@ int ensure_work(cudamat_solver *s, int nvec) {
     // keep each vector 256-byte aligned
     const size_t stride = ((elems + 31) / 32) * 32;
     if (s->work && s->work_nvec >= nvec && s->work_elems == stride) return CUDAMAT_OK;
+    if (s->work && comm_p2p(s)) {
+        // the neighbours hold IPC mappings of this arena and push halo rows into it: reallocating it would leave them
+        // writing into freed memory.  p2p_setup sizes it for kWorkVecsShared vectors, which covers every solve mode.
+        set_error("work arena of a peer-memory handle cannot grow (%d > %d vectors)", nvec, s->work_nvec);
+        return CUDAMAT_E_STATE;
+    }
     if (s->work) { cudaStreamSynchronize(s->stream); if (s->work_pooled) dev_free(s->work); else shared_arena_put(s->work, s->work_bytes); s->work = nullptr; }
     s->work_pooled = (s->comm == nullptr);          // sharded handles share the arena over CUDA IPC: plain cudaMalloc, recycled
     const size_t need = sizeof(double) * std::max<size_t>(stride * nvec, 32);
@@ -157,6 +175,7 @@ int ensure_work(cudamat_solver *s, int nvec) {
 }
 static inline double *wv(cudamat_solver *s, int k) { return s->work + (size_t)k * s->work_elems; }
 
+constexpr int64_t kHistCapMax = 1 << 20;      // residual norms kept per solve (8 MB)
 static int ensure_hist(cudamat_solver *s, int cap) {
     if (s->d_hist && s->hist_cap >= cap) return CUDAMAT_OK;
     if (s->d_hist) { cudaStreamSynchronize(s->stream); dev_free(s->d_hist); }
@@ -315,10 +334,12 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
                         double *d_x, int maxit, double tol) {
     int rc;
     if ((rc = ensure_work(s, 7))) return rc;
-    if ((rc = ensure_hist(s, maxit + 2))) return rc;
+    // residual history: capped (a caller may pass a huge maxit as "no limit"); hist_push tolerates the overflow
+    const int hcap = (int)std::min<int64_t>((int64_t)maxit + 2, kHistCapMax);
+    if ((rc = ensure_hist(s, hcap))) return rc;
     double *r0 = wv(s, 0), *r = wv(s, 1), *v = wv(s, 2), *p = wv(s, 3), *sv = wv(s, 4), *t = wv(s, 5), *xk = wv(s, 6);
     const int var = s->spmv_variant;
-    if ((rc = start_scalars(s, maxit, tol, maxit + 2))) return rc;
+    if ((rc = start_scalars(s, maxit, tol, hcap))) return rc;
     const size_t nb = sizeof(double) * (size_t)s->n;
     if (d_x0) CM_CUDA(cudaMemcpyAsync(xk, d_x0, nb, cudaMemcpyDeviceToDevice, s->stream));
     else if ((rc = launch_fill(s, xk, 1.0, s->n))) return rc;
@@ -342,6 +363,7 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
     });
     if (rc) return rc;
     if ((rc = poll_status(s))) return rc;
+    if (s->h_sc->status == ST_COMM_TIMEOUT) { set_error("a peer rank's halo rows or partial sums did not arrive (spin limit reached)"); return CUDAMAT_E_COMM; }
     CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
     return CUDAMAT_OK;
 }
@@ -350,7 +372,8 @@ static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0
 static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int maxit, double tol) {
     int rc;
     if ((rc = ensure_work(s, s->d_perm ? 10 : 9))) return rc;
-    if ((rc = ensure_hist(s, 2 * maxit + 2))) return rc;
+    const int hcap = (int)std::min<int64_t>(2 * (int64_t)maxit + 2, kHistCapMax);
+    if ((rc = ensure_hist(s, hcap))) return rc;
     double *r = wv(s, 0), *rw = wv(s, 1), *p = wv(s, 2), *pw = wv(s, 3), *sv = wv(s, 4), *t = wv(s, 5), *v = wv(s, 6), *xk = wv(s, 7);
     double *tl = wv(s, 8);          // private output of the L sweeps (carries the sync-free ready sentinel)
     double *tp = s->d_perm ? wv(s, 9) : nullptr;      // multicolour ordering: permuted right-hand side / permuted solution
@@ -373,7 +396,7 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
         return launch_permute(s, true, tp, out);
     };
     const int var = s->spmv_variant;
-    if ((rc = start_scalars(s, maxit, tol, 2 * maxit + 2))) return rc;
+    if ((rc = start_scalars(s, maxit, tol, hcap))) return rc;
     const size_t nb = sizeof(double) * (size_t)s->n;
     if ((rc = launch_fill(s, xk, 1.0, s->n))) return rc;                                            // :306-308
     CM_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * s->work_elems, s->stream));
@@ -392,6 +415,7 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
     });
     if (rc) return rc;
     if ((rc = poll_status(s))) return rc;
+    if (s->h_sc->status == ST_COMM_TIMEOUT) { set_error("a peer rank's halo rows or partial sums did not arrive (spin limit reached)"); return CUDAMAT_E_COMM; }
     CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
     return CUDAMAT_OK;
 }
@@ -464,6 +488,7 @@ int cudamat_create(cudamat_solver **out, int64_t n_global, int64_t row0, int64_t
 
 int cudamat_destroy(cudamat_solver *s) {
     if (!s) return CUDAMAT_OK;
+    DeviceGuard dg(s->device);
     const bool tm = getenv("CUDAMAT_TIMING") != nullptr;
     const double t0 = now_s();
     cudaStreamSynchronize(s->stream);
@@ -505,6 +530,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
 
 int cudamat_set_csr_host(cudamat_solver *s, int nnz, const double *A, const int *iA, const int *jA) {
     if (!s || !iA || (nnz > 0 && (!A || !jA)) || nnz < 0) { set_error("set_csr_host: null argument"); return CUDAMAT_E_INVALID; }
+    DeviceGuard dg(s->device);
     const int n = s->n;
     const int base = iA[0];
     if (base != 0 && base != 1) { set_error("set_csr_host: index base %d is neither 0 nor 1 (pbicgstab.cu:201)", base); return CUDAMAT_E_INVALID; }
@@ -523,10 +549,11 @@ int cudamat_set_csr_host(cudamat_solver *s, int nnz, const double *A, const int 
     if (rc) return rc;
     // structure checks run on the device over the uploaded arrays (a host pass over nnz entries would cost as much
     // as the upload itself): monotone row pointers, column indices inside [0, n_global)
-    int bad[2] = {-1, -1};
+    int bad[3] = {-1, -1, -1};
     if ((rc = launch_validate_csr(s->stream, s->own_ia, n, s->own_ja, nnz, s->n_global, bad))) return rc;
     if (bad[0] >= 0) { set_error("set_csr_host: row pointers not monotone at row %d", bad[0]); return CUDAMAT_E_INVALID; }
     if (bad[1] >= 0) { set_error("set_csr_host: column index out of range at entry %d", bad[1]); return CUDAMAT_E_INVALID; }
+    if (bad[2] >= 0) { set_error("set_csr_host: column indices must be strictly ascending within a row (entry %d; mmio_wrapper.h:123-126)", bad[2]); return CUDAMAT_E_INVALID; }
     s->d_ia = s->own_ia; s->d_ja = s->own_ja; s->d_a = s->own_a; s->d_ja_global = s->own_ja;
     s->nnz = nnz; s->analyzed = false;
     return CUDAMAT_OK;
@@ -534,18 +561,26 @@ int cudamat_set_csr_host(cudamat_solver *s, int nnz, const double *A, const int 
 
 int cudamat_set_csr_device(cudamat_solver *s, int64_t nnz, const double *dA, const int *dIA, const int *dJA) {
     if (!s || !dIA || (nnz > 0 && (!dA || !dJA)) || nnz < 0 || nnz > 0x7fffffffLL) { set_error("set_csr_device: invalid argument"); return CUDAMAT_E_INVALID; }
+    DeviceGuard dg(s->device);
     int ends[2] = {0, 0};
     CM_CUDA(cudaMemcpyAsync(&ends[0], dIA, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaMemcpyAsync(&ends[1], dIA + s->n, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));
     if (ends[0] != 0 || ends[1] != nnz) { set_error("set_csr_device: expects base-0 row pointers with ia[n]==nnz (got ia[0]=%d ia[n]=%d nnz=%lld)", ends[0], ends[1], (long long)nnz); return CUDAMAT_E_INVALID; }
-    s->d_ia = dIA; s->d_ja = dJA; s->d_a = dA; s->d_ja_global = dJA; s->nnz = nnz; s->analyzed = false;
+    s->d_ia = dIA; s->d_ja = dJA; s->d_a = dA; s->d_ja_global = dJA; s->nnz = nnz; s->analyzed = false; s->csr_checked = false;
     return CUDAMAT_OK;
 }
 
 int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
     if (!s || !s->d_ia) { set_error("analyze: no matrix set"); return CUDAMAT_E_STATE; }
     if (mode < 0 || mode > 2) { set_error("analyze: bad mode %d", mode); return CUDAMAT_E_INVALID; }
+    DeviceGuard dg(s->device);
+    if (!s->comm && (s->row0 != 0 || s->row1 != s->n_global)) {
+        // the CSR of a true shard still holds GLOBAL column ids until cudamat_comm_init renumbers them [local | halo]
+        set_error("analyze: handle owns the shard [%lld,%lld) of %lld rows but cudamat_comm_init was not called",
+                  (long long)s->row0, (long long)s->row1, (long long)s->n_global);
+        return CUDAMAT_E_STATE;
+    }
     const double t0 = now_s();
     int hs[3] = {0, 0, 0};
     int rc = launch_row_stats(s, hs, &s->mean_row_len);
@@ -571,6 +606,16 @@ int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
     s->spmv_variant = variant;
     if (st) st->t_analysis += now_s() - t0;
     if (mode == CUDAMAT_MODE_ILU0) {
+        // borrowed device CSR was never validated: the ILU0 path (diagonal search, L/U split, level analysis, sync-free
+        // sweeps) needs strictly ascending columns within a row, as the reference loader guarantees (mmio_wrapper.h:123-126)
+        if (!s->comm && s->d_ia != s->own_ia && !s->csr_checked) {
+            int bad[3] = {-1, -1, -1};
+            if ((rc = launch_validate_csr(s->stream, s->d_ia, s->n, s->d_ja, s->nnz, s->n_global, bad))) return rc;
+            if (bad[0] >= 0) { set_error("analyze: row pointers not monotone at row %d", bad[0]); return CUDAMAT_E_INVALID; }
+            if (bad[1] >= 0) { set_error("analyze: column index out of range at entry %d", bad[1]); return CUDAMAT_E_INVALID; }
+            if (bad[2] >= 0) { set_error("analyze: ILU0 needs strictly ascending column indices within a row (entry %d)", bad[2]); return CUDAMAT_E_INVALID; }
+            s->csr_checked = true;
+        }
         if ((rc = ilu0_analyze_and_factor(s, st))) return rc;
     }
     s->analyzed = true; s->analyzed_mode = mode;
@@ -584,6 +629,7 @@ int cudamat_solve_device(cudamat_solver *s, int mode, const double *d_b, const d
     if (!s->analyzed || (mode == CUDAMAT_MODE_ILU0 && !s->d_M)) { set_error("solve_device: call cudamat_analyze(mode) first"); return CUDAMAT_E_STATE; }
     if (mode == CUDAMAT_MODE_SHIFTED && (!d_d || !d_x0)) { set_error("solve_device: shifted mode needs d and x0 (pbicgstab.h:116)"); return CUDAMAT_E_INVALID; }
     if (maxit < 0) maxit = 0;
+    DeviceGuard dg(s->device);
     const double t0 = now_s();
     s->ev_used = 0;
     int rc;
@@ -622,6 +668,7 @@ int cudamat_get_history(cudamat_solver *s, double *hist, int cap) {
 int cudamat_spmv_device(cudamat_solver *s, const double *d_x, const double *d_d, double *d_y, int variant) {
     if (!s || !d_x || !d_y) { set_error("spmv_device: null argument"); return CUDAMAT_E_INVALID; }
     if (!s->analyzed) { set_error("spmv_device: call cudamat_analyze first"); return CUDAMAT_E_STATE; }
+    DeviceGuard dg(s->device);
     if (s->comm) {
         // sharded handle: stage x next to its halo, exchange, multiply (collective over all ranks)
         int rc = ensure_work(s, 8);
@@ -637,6 +684,7 @@ int cudamat_spmv_device(cudamat_solver *s, const double *d_x, const double *d_d,
 int cudamat_dot_device(cudamat_solver *s, const double *d_a, const double *d_b, double *result) {
     if (!s || !d_a || !d_b || !result) { set_error("dot_device: null argument"); return CUDAMAT_E_INVALID; }
     if (s->n == 0) { *result = 0.0; return CUDAMAT_OK; }
+    DeviceGuard dg(s->device);
     int rc = launch_dot(s, d_a, d_b);
     if (rc) return rc;
     if ((rc = poll_status(s))) return rc;
@@ -647,6 +695,7 @@ int cudamat_dot_device(cudamat_solver *s, const double *d_a, const double *d_b, 
 int cudamat_get_ilu0_host(cudamat_solver *s, double *M_out) {
     if (!s || !M_out) return CUDAMAT_E_INVALID;
     if (!s->d_M) { set_error("get_ilu0_host: no factor (analyze with CUDAMAT_MODE_ILU0)"); return CUDAMAT_E_STATE; }
+    DeviceGuard dg(s->device);
     if (s->d_perm) { set_error("get_ilu0_host: the factor belongs to the multicolour-permuted matrix (option ilu0_reorder)"); return CUDAMAT_E_STATE; }
     if (s->pre_nnz != s->nnz) { set_error("get_ilu0_host: sharded handles hold a block-Jacobi factor of the local block (%lld entries), not A's pattern", (long long)s->pre_nnz); return CUDAMAT_E_STATE; }
     CM_CUDA(cudaMemcpyAsync(M_out, s->d_M, sizeof(double) * (size_t)s->nnz, cudaMemcpyDeviceToHost, s->stream));
@@ -656,6 +705,7 @@ int cudamat_get_ilu0_host(cudamat_solver *s, double *M_out) {
 
 int cudamat_sptrsv_device(cudamat_solver *s, int upper, const double *d_rhs, double *d_out) {
     if (!s || !d_rhs || !d_out) return CUDAMAT_E_INVALID;
+    DeviceGuard dg(s->device);
     // kernel-level calls must not be gated by a finished solve
     int st = ST_RUNNING;
     CM_CUDA(cudaMemcpyAsync(&s->d_sc->status, &st, sizeof(int), cudaMemcpyHostToDevice, s->stream));
@@ -681,7 +731,10 @@ int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *
     if (rc) return rc;
     // one private non-blocking stream per thread for the one-shot entry points (CUDA graphs cannot be captured on the
     // legacy default stream); every operation of the call is enqueued on it or is synchronous
-    static thread_local cudaStream_t host_stream = nullptr;
+    static thread_local cudaStream_t host_streams[kMaxDev] = {};          // per thread AND per device
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= kMaxDev) { cudaGetLastError(); cur_dev = 0; }
+    cudaStream_t &host_stream = host_streams[cur_dev];
     if (!host_stream && cudaStreamCreateWithFlags(&host_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); host_stream = nullptr; }
     rc = cudamat_create(&s, n, 0, n, host_stream);
     if (rc) return rc;
@@ -700,15 +753,18 @@ int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *
     const size_t nb = sizeof(double) * (size_t)std::max(n, 1);
     HOST_CUDA(dev_alloc((void **)&d_b, nb));
     HOST_CUDA(dev_alloc((void **)&d_x, nb));
-    HOST_CUDA(cudaMemcpy(d_b, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    // uploads are ordered on the call's own stream (a legacy-stream cudaMemcpy from pageable memory is not ordered against
+    // a cudaStreamNonBlocking stream); the host arrays stay untouched until the stream is synchronised by analyze / solve
+    HOST_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
     if (mode == CUDAMAT_MODE_SHIFTED || (mode == CUDAMAT_MODE_PLAIN && x0)) {
         HOST_CUDA(dev_alloc((void **)&d_x0, nb));
-        HOST_CUDA(cudaMemcpy(d_x0, x0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+        HOST_CUDA(cudaMemcpyAsync(d_x0, x0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
     }
     if (mode != CUDAMAT_MODE_ILU0 && d) {
         HOST_CUDA(dev_alloc((void **)&d_d, nb));
-        HOST_CUDA(cudaMemcpy(d_d, d, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+        HOST_CUDA(cudaMemcpyAsync(d_d, d, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
     }
+    HOST_CUDA(cudaStreamSynchronize(s->stream));
     st.t_h2d = now_s() - t0;
     const double tt1 = now_s();
     HOST_TRY(cudamat_analyze(s, mode, &st));
@@ -719,7 +775,8 @@ int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *
     }
     HOST_TRY(cudamat_solve_device(s, mode, d_b, d_x0, d_d, d_x, maxit, tol, &st));
     t0 = now_s();
-    HOST_CUDA(cudaMemcpy(x, d_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    HOST_CUDA(cudaMemcpyAsync(x, d_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    HOST_CUDA(cudaStreamSynchronize(s->stream));
     st.t_d2h = now_s() - t0;
     st.kernel_launches = s->launches;
     if (dtAlg) *dtAlg = st.t_loop;

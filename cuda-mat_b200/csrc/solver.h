@@ -97,6 +97,7 @@ struct RowClasses {
 struct ClassArgs { const unsigned char *cls; int ncls; int tiles_per_cta; };
 
 struct Comm;   // comm.cu
+constexpr int kWorkVecsShared = 12;    // work vectors of a sharded handle's IPC-shared arena (largest solve mode + spare)
 
 struct LevelSchedule {
     int nlevels = 0;
@@ -123,6 +124,7 @@ struct cudamat_solver {
     int nhalo = 0;
     // plan
     bool analyzed = false; int analyzed_mode = -1;
+    bool csr_checked = false;              // borrowed device CSR went through k_validate_csr (ILU0 needs sorted rows)
     int max_row_len = 0; double mean_row_len = 0; int n_long_rows = 0; int max_slab_nnz = 0;
     int spmv_variant = CUDAMAT_SPMV_ROWLANE;
     int opt_spmv_variant = CUDAMAT_SPMV_AUTO;
@@ -175,6 +177,19 @@ struct cudamat_solver {
 
 namespace cudamat {
 
+// Every handle entry point runs on the handle's own device and restores the caller's current device on return
+// (the reference is single-device, callers choose the device beforehand, example.cpp:237).
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev && cudaSetDevice(dev) == cudaSuccess) switched = true;
+    }
+    ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 // kernels.cu
 int launch_spmv(cudamat_solver *s, const SpmvArgs &a, int variant);
 int launch_init_resid(cudamat_solver *s, const double *b, const double *y, double *r, double *c1, double *c2, int phase);
@@ -187,7 +202,7 @@ int launch_dot(cudamat_solver *s, const double *a, const double *b);
 int launch_fill(cudamat_solver *s, double *p, double v, int64_t cnt);
 int launch_row_stats(cudamat_solver *s, int *h_out /*[max_len, n_long, max_slab_nnz]*/, double *mean);
 int launch_normalize_base(cudaStream_t st, int *ia, int64_t n1, int *ja, int64_t nnz, int base);
-int launch_validate_csr(cudaStream_t st, const int *ia, int n, const int *ja, int64_t nnz, int64_t ncols, int *h_bad /*[row, entry] or -1*/);
+int launch_validate_csr(cudaStream_t st, const int *ia, int n, const int *ja, int64_t nnz, int64_t ncols, int *h_bad /*[row, entry out of range, entry out of order] or -1*/);
 int plan_staged(cudamat_solver *s);
 bool pdl_enabled();
 

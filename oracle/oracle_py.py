@@ -212,7 +212,8 @@ def to_dense_vector(n, A, IA):
 
 # ---- reference pieces compiled into oracle/_ref (present only if built in this container) ----
 def ref_available(which):
-    return os.path.exists(os.path.join(_HERE, "_ref", {"mmio": "libref_mmio.so", "bicg": "libref_bicg.so"}[which]))
+    return os.path.exists(os.path.join(_HERE, "_ref", {"mmio": "libref_mmio.so", "bicg": "libref_bicg.so",
+                                                       "pbicgstab": "libref_pbicgstab.so"}[which]))
 
 
 def ref_load_mm(path):
@@ -255,3 +256,87 @@ def ref_bicg(ia0, ja0, a, b, maxit=2000):
 def ref_omp_threads():
     ref_bicg(np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([1.0]), np.array([1.0]), 1)
     return _REF_BICG.ref_omp_threads()
+
+
+# ---- the reference's own GPU solver: /root/reference/pbicgstab.cu compiled unmodified (oracle/Makefile) ----
+_REF_GPU = None
+
+
+def _ref_gpu():
+    global _REF_GPU
+    if _REF_GPU is None:
+        L = C.CDLL(os.path.join(_HERE, "_ref", "libref_pbicgstab.so"))
+        L.ref_bicgstab_lu_precond.argtypes = [C.c_int, C.c_int, c_dp, c_ip, c_ip, c_dp, C.c_int, C.c_double, c_dp, c_dp, C.c_char_p]
+        L.ref_bicgstab_plain.argtypes = L.ref_bicgstab_lu_precond.argtypes
+        L.ref_bicgstab_shifted.argtypes = [C.c_int, C.c_int, c_dp, c_ip, c_ip, c_dp, c_dp, c_dp, C.c_int, C.c_double, c_dp, c_dp, C.c_char_p]
+        _REF_GPU = L
+    return _REF_GPU
+
+
+def _parse_ref_trace(path, mode):
+    """The reference's debug lines (pbicgstab.cu:76,113,144 / :484,550) -> dict(nrm_r0, hist, iterations).
+    `iterations` follows the loop counter i at exit: ILU0 loop: number of 'residual norm = ' lines (i is incremented
+    after the second check only, :147-151); unpreconditioned loop: number of 'k = ' lines."""
+    import re
+    txt = open(path, errors="replace").read()
+    out = {"trace": txt}
+    if mode == "ilu0":
+        m = re.search(r"init residual:norm\s+([-+0-9.eEinfa]+)", txt)
+        out["nrm_r0"] = float(m.group(1)) if m else float("nan")
+        half = [float(v) for v in re.findall(r"residual norm \(before precond\) = ([-+0-9.eEinfa]+)", txt)]
+        full = [float(v) for v in re.findall(r"i = \d+, residual norm = ([-+0-9.eEinfa]+)", txt)]
+        out["hist_half"], out["hist"], out["iterations"] = half, full, len(full)
+    else:
+        m = re.search(r"initial norm = ([-+0-9.eEinfa]+)", txt)
+        out["nrm_r0"] = float(m.group(1)) if m else float("nan")
+        full = [float(v) for v in re.findall(r"k = \d+, norm = ([-+0-9.eEinfa]+)", txt)]
+        out["hist"], out["iterations"] = full, len(full)
+    return out
+
+
+def ref_gpu_bicgstab_lu_precond(ia, ja, a, b, maxit=2000, tol=1e-6, trace=True):
+    """bicgstab_lu_precond of the reference (pbicgstab.cu:157), host arrays in the caller's index base.
+    Returns (x, dtAlg, info); info carries the parsed debug trace when trace=True."""
+    import tempfile
+    ia, ja, a, b = _i32(ia).copy(), _i32(ja).copy(), _f64(a).copy(), _f64(b).copy()
+    n = len(ia) - 1
+    x = np.zeros(n)
+    dt = C.c_double(0.0)
+    with tempfile.NamedTemporaryFile(suffix=".trace") as tf:
+        ok = _ref_gpu().ref_bicgstab_lu_precond(n, len(a), _dp(a), _ip(ia), _ip(ja), _dp(b), maxit, tol, _dp(x), C.byref(dt),
+                                                tf.name.encode() if trace else None)
+        info = _parse_ref_trace(tf.name, "ilu0") if trace else {}
+    info["returned"] = bool(ok)
+    return x, dt.value, info
+
+
+def ref_gpu_bicgstab_shifted(ia, ja, a0, d, x0, b, maxit=2000, tol=1e-6, trace=True):
+    """bicgstab(A0, d, x0, b) of the reference (pbicgstab.cu:926).  Valid for n <= 524288 only: mult_spec is launched
+    with grid and block swapped (pbicgstab.cu:645,675,703)."""
+    import tempfile
+    ia, ja, a0, b = _i32(ia).copy(), _i32(ja).copy(), _f64(a0).copy(), _f64(b).copy()
+    d, x0 = _f64(d).copy(), _f64(x0).copy()
+    n = len(ia) - 1
+    x = np.zeros(n)
+    dt = C.c_double(0.0)
+    with tempfile.NamedTemporaryFile(suffix=".trace") as tf:
+        ok = _ref_gpu().ref_bicgstab_shifted(n, len(a0), _dp(a0), _ip(ia), _ip(ja), _dp(d), _dp(x0), _dp(b), maxit, tol, _dp(x),
+                                             C.byref(dt), tf.name.encode() if trace else None)
+        info = _parse_ref_trace(tf.name, "unprec") if trace else {}
+    info["returned"] = bool(ok)
+    return x, dt.value, info
+
+
+def ref_gpu_bicgstab_plain(ia, ja, a, b, maxit=2000, tol=1e-6, trace=True):
+    """bicgstab(A, b) of the reference (pbicgstab.cu:756): its initial residual is broken (pbicgstab.cu:469-478)."""
+    import tempfile
+    ia, ja, a, b = _i32(ia).copy(), _i32(ja).copy(), _f64(a).copy(), _f64(b).copy()
+    n = len(ia) - 1
+    x = np.zeros(n)
+    dt = C.c_double(0.0)
+    with tempfile.NamedTemporaryFile(suffix=".trace") as tf:
+        ok = _ref_gpu().ref_bicgstab_plain(n, len(a), _dp(a), _ip(ia), _ip(ja), _dp(b), maxit, tol, _dp(x), C.byref(dt),
+                                           tf.name.encode() if trace else None)
+        info = _parse_ref_trace(tf.name, "unprec") if trace else {}
+    info["returned"] = bool(ok)
+    return x, dt.value, info
