@@ -102,6 +102,13 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's own CPU implementation (bicstab_omp BiCG) on host cores
 # ---------------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_run(N, budget_s=25.0, iters=None):
     """Times the reference's bicstab_omp BiCG() (oracle/_ref, compiled from the reference sources) on the
     Poisson N^3 system, x0 = ones. BiCG() transposes the matrix inside the call, so the rate is taken from
@@ -112,7 +119,7 @@ def cpu_reference_run(N, budget_s=25.0, iters=None):
     xt = O.xtrue(1234, 0, n)
     b = O.spmv(ia, ja, a, xt)
     if O.ref_available("bicg"):
-        cores = O.ref_omp_threads()
+        cores = O.ref_omp_threads(host_cores())
         O.ref_bicg(ia, ja, a, b, maxit=1)                      # untimed: library load, OpenMP pool, first-touch pages
         t1 = None
         for _ in range(2):                                     # T(maxit=1) = set-up + transpose + 1 iteration (best of 2)
@@ -139,12 +146,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its children: the reference arm must use the box's host cores whatever the
+    # launcher (set before libgomp is loaded by the shim; also forced through omp_set_num_threads below)
+    os.environ["OMP_NUM_THREADS"] = str(host_cores())
     cb, its, secs = cpu_reference_run(args.grid, budget_s=60.0, iters=None if args.steps <= 0 else min(args.steps, 200))
     n = args.grid ** 3
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "poisson3d_%d" % args.grid, "n": n, "mode": "reference CPU path (bicstab_omp BiCG)",
+            "config": {"workload": "poisson3d_%d" % args.grid, "n": n,
+                       "mode": "reference CPU path: bicstab_omp BiCG (NOT BiCGSTAB: 2 SpMV per iteration incl. A^T, bicstab.cpp:93-196), OpenMP threads = %d" % cb["cores"],
                        "timed_iterations": its},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -154,7 +165,33 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+VNAME = {1: "k_spmv_rowlane (CSR)", 2: "k_spmv_staged (CSR, TMA ring)", 3: "k_spmv_class<values from CSR>",
+         4: "k_spmv_class<values from dictionary>", 5: "k_spmv_tiled<class dictionary, x windows staged by TMA>",
+         6: "k_spmv_march<plane-marching ring, class dictionary>"}
+
+
+def kernel_bytes(variant, fused, nloc, nnz_loc):
+    """bytes each timed kernel of ONE iteration must move in the storage format it really reads (per rank), by timing slot
+    (cudamat_stats.t_kernel): 0 = SpMV 1 (+ folded p update), 1 = SpMV 2 (+ folded s update), 2 = x/r update + 2 dots,
+    3 = separate p and s updates (average of the two launches).  Dictionary formats read 1 B per row instead of 12 B per entry."""
+    if variant in (4, 5, 6):
+        mat = nloc                                  # class id / presence mask, 1 B per row
+    elif variant == 3:
+        mat = 8 * nnz_loc + nloc + 4 * (nloc // 32 + 1)
+    else:
+        mat = 12 * nnz_loc + 4 * (nloc + 1)
+    if fused:
+        return {0: ("MAKE_P: p'=r+beta(p-omega v); v'=A p'; rhat.v'", mat + 8 * nloc * 6),      # r, p, v, rhat in; p', v' out
+                1: ("MAKE_S: s=r-alpha v; t=A s; t.s, t.t", mat + 8 * nloc * 4),                # r, v in; s, t out
+                2: ("k_update_xr: x, r update + rhat.r, r.r", 56 * nloc)}
+    return {0: ("SpMV 1 + rhat.v", mat + 8 * nloc * 3),                                         # x, rhat in; y out
+            1: ("SpMV 2 + t.s, t.t", mat + 8 * nloc * 2),
+            2: ("k_update_xr: x, r update + rhat.r, r.r", 56 * nloc),
+            3: ("k_update_p / k_update_s (average)", 28 * nloc)}
+
+
 def run_ours(args):
+    import hashlib
     import torch
     import torch.distributed as dist
     cm = ge.load_package()
@@ -178,17 +215,23 @@ def run_ours(args):
     ja = torch.empty(nnz_loc, dtype=torch.int32, device="cuda")
     a = torch.empty(nnz_loc, **f64)
     cm.gen_poisson3d_device(N, row0, row1, ia.data_ptr(), ja.data_ptr(), a.data_ptr(), stream)
-    s = cm.Solver(n, row0, row1, stream=stream)
-    s.set_csr_device(nnz_loc, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
-    if world > 1:
-        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idbuf = torch.tensor(list(cm.Comm.unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idbuf, 0)
-        cm.Comm.init(s, bytes(idbuf.cpu().tolist()), rank, world)
-    if args.variant:
-        s.set_option("spmv_variant", args.variant)
-    sa = s.analyze(cm.MODE_PLAIN)
+
+    def new_solver(variant=0):
+        sol = cm.Solver(n, row0, row1, stream=stream)
+        sol.set_csr_device(nnz_loc, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
+        if world > 1:
+            idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idbuf = torch.tensor(list(cm.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(idbuf, 0)
+            cm.Comm.init(sol, bytes(idbuf.cpu().tolist()), rank, world)
+        if variant:
+            sol.set_option("spmv_variant", variant)
+        if args.no_fuse:
+            sol.set_option("fuse", 0)
+        return sol, sol.analyze(cm.MODE_PLAIN)
+
+    s, sa = new_solver(args.variant)
     xt = torch.empty(nloc, **f64)
     cm.gen_xtrue_device(1234, row0, nloc, xt.data_ptr(), stream)
     b = torch.empty(nloc, **f64)
@@ -202,6 +245,8 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    clk = ClockSampler(local_rank, period=0.004)
+    clk.__enter__()                               # samples from here to the end of the timed region (the GPU is under load throughout)
     # ---- full solve to 1e-10: the convergence claim of the metric (also part of the warm-up) ----
     barrier()
     t0 = time.time()
@@ -215,108 +260,153 @@ def run_ours(args):
     converge = {"tol": 1e-10, "iterations": stc["iterations"], "converged": bool(stc["converged"]),
                 "relres": stc["nrm_r"] / stc["nrm_r0"], "rel_err_vs_xtrue": relerr, "seconds": t_conv,
                 "iters_per_s": stc["iterations"] / stc["t_loop"]}
+    # bit-identity evidence: sha256 of the full solution (gathered in rank order) against the committed digest of the CPU
+    # oracle's own run (tests/golden/poisson<N>_oracle_digest.json) - the same digest whatever the number of GPUs
+    if not args.no_converge:
+        try:
+            if world > 1:
+                cnt = torch.tensor([nloc], dtype=torch.int64, device="cuda")
+                cnts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+                dist.all_gather(cnts, cnt)
+                mx = int(max(int(c[0]) for c in cnts))
+                pad = torch.zeros(mx, **f64); pad[:nloc] = x
+                parts = [torch.empty(mx, **f64) for _ in range(world)] if rank == 0 else None
+                dist.gather(pad, parts, dst=0)
+                xfull = torch.cat([parts[r][:int(cnts[r][0])] for r in range(world)]).cpu().numpy() if rank == 0 else None
+            else:
+                xfull = x.cpu().numpy()
+            if rank == 0:
+                converge["x_sha256"] = hashlib.sha256(np.ascontiguousarray(xfull).tobytes()).hexdigest()
+                dp = os.path.join(ROOT, "tests", "golden", "poisson%d_oracle_digest.json" % N)
+                if os.path.exists(dp):
+                    dg = json.load(open(dp))
+                    converge["oracle_digest"] = {"file": "tests/golden/poisson%d_oracle_digest.json" % N, "iterations": dg["iterations"],
+                                                 "x_sha256": dg["x_sha256"]}
+                    converge["bit_identical_to_cpu_oracle"] = bool(dg["x_sha256"] == converge["x_sha256"] and dg["iterations"] == stc["iterations"])
+                del xfull
+        except Exception as e:      # noqa: BLE001
+            converge["x_sha256_error"] = str(e)
 
-    # ---- warm-up: W iterations ----
-    chunk = max(1, min(args.chunk, converge["iterations"] // 2 if converge["converged"] else args.chunk))
+    chunk = max(8, min(args.chunk, converge["iterations"] // 2 if converge["converged"] else args.chunk))
     peak, peak_src = peaks()
-    b_spmv = bytes_spmv(n, nnz)           # whole-problem algorithmic bytes of one CSR SpMV (SURVEY.md §8d)
+    b_spmv = bytes_spmv(n, nnz)           # whole-problem algorithmic bytes of one CSR SpMV (SURVEY.md 8d)
     b_it = bytes_iter(n, nnz)
-    b_spmv_loc = 12 * nnz_loc + 4 * (nloc + 1) + 16 * nloc      # this rank's share of one SpMV launch
-    VNAME = {1: "k_spmv_rowlane", 2: "k_spmv_staged", 3: "k_spmv_class<values from CSR>", 4: "k_spmv_class<values from dictionary>",
-             5: "k_spmv_tiled<class dictionary, x windows staged by TMA>"}
-
-    def moved_bytes(variant):
-        """bytes one SpMV launch of this rank has to move in the variant's own storage format (x read once, y written
-        once, + the dot operand for the fused epilogue is not counted, as in B_spmv)"""
-        if variant in (4, 5):
-            return 17 * nloc
-        if variant == 3:
-            return 8 * nnz_loc + 17 * nloc + 4 * (nloc // 32 + 1)
-        return b_spmv_loc
 
     def timed_region(sol, K, W):
-        """exactly K iterations, CUDA events on the launching stream, max over ranks"""
-        sol.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=max(W, 3), tol=0.0)
-        sol.set_option("time_spmv", 32)          # the SpMVs of every 32nd iteration are event-timed
-        plan = [chunk] * (K // chunk) + ([K % chunk] if K % chunk else [])
+        """EXACTLY K iterations between the two events (CUDA events on the launching stream, max over ranks).  The warm-up
+        solve (residual set-up + W iterations) runs before the first event; the timed window CONTINUES that solve (option
+        "resume") so no set-up work sits inside a short window, and restarts from x0 = ones every `chunk` iterations
+        (tol = 0: nothing stops early; a restart's 1-SpMV residual set-up is inside the window, 1 per `chunk` iterations)."""
+        W = max(W, 3)
+        first = max(1, min(K, chunk - min(W, chunk - 1)))
+        plan = [first] + [chunk] * ((K - first) // chunk) + ([(K - first) % chunk] if (K - first) % chunk else [])
+        sol.set_option("resume", 0)
+        sol.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=W, tol=0.0)
+        sol.set_option("time_spmv", 2 if K < 64 else 8)      # the main kernels of every 2nd (8th) iteration are event-timed
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_spmv, n_spmv, done, launches = 0.0, 0, 0, 0
+        tk, nk, done, launches, prev = [0.0] * 4, [0] * 4, 0, 0, W
         barrier()
-        with ClockSampler(local_rank) as clk:
-            e0.record()
-            for m in plan:
-                st = sol.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=m, tol=0.0)
-                done += st["iterations"]
-                t_spmv += st["t_spmv"]; n_spmv += st["n_spmv"]
-                launches = st["kernel_launches"]
-            e1.record()
-            barrier()
+        e0.record()
+        for i, m in enumerate(plan):
+            sol.set_option("resume", 1 if i == 0 else 0)
+            st = sol.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=m, tol=0.0)
+            done += st["iterations"] - (prev if i == 0 else 0)
+            for q in range(4):
+                tk[q] += st["t_kernel"][q]; nk[q] += st["n_kernel"][q]
+            launches = st["kernel_launches"]
+            fused = bool(st["fused"])
+        e1.record()
+        barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         if done != K:
             raise SystemExit("timed region ran %d iterations instead of %d (break-down?)" % (done, K))
         sol.set_option("time_spmv", 0)
-        return float(ms[0]), (t_spmv * 1e3 / n_spmv) if n_spmv else None, n_spmv, launches, clk.summary()
+        sol.set_option("resume", 0)
+        kms = [(tk[q] * 1e3 / nk[q]) if nk[q] else None for q in range(4)]
+        return float(ms[0]), kms, nk, launches, fused
 
-    def roofline(variant, ms, K, spmv_ms, n_spmv):
-        if not spmv_ms:
+    def roofline(variant, fused, ms, K, kms, nk):
+        """`frac` = bytes the dominant timed kernel must move in its own storage format / its average launch duration / peak."""
+        kb = kernel_bytes(variant, fused, nloc, nnz_loc)
+        per = ms / K
+        rows = []
+        for q, (nm, by) in kb.items():
+            if kms[q]:
+                launches_per_it = 2 if q == 3 else 1
+                rows.append({"slot": q, "kernel": nm, "bytes_per_launch": by, "avg_launch_ms": kms[q], "launches_timed": nk[q],
+                             "GBps": by / (kms[q] * 1e-3) / 1e9, "frac": by / (kms[q] * 1e-3) / 1e9 / peak,
+                             "share_of_step": launches_per_it * kms[q] / per})
+        if not rows:
             return None
+        dom = max(rows, key=lambda r: r["share_of_step"])
         its = K / (ms * 1e-3)
-        ach = b_spmv_loc / (spmv_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-        if os.path.exists(tp):
+        it_bytes = sum(r["bytes_per_launch"] * (2 if r["slot"] == 3 else 1) for r in rows) + 3 * 16 * (nloc // 32)
+        out = {"bound": "hbm", "kernel": dom["kernel"] + " [" + VNAME.get(variant, "?") + "]",
+               "achieved": dom["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"],
+               "frac_of_8TBps_datasheet": dom["GBps"] / 8000.0, "traffic": None,
+               "bytes_per_launch": dom["bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"], "launches_timed": dom["launches_timed"],
+               "bytes_definition": "bytes the kernel must move in the storage format it reads (dictionary variants: 1 B/row instead of "
+                                   "12 B/entry), every vector read / written once; SURVEY.md 8d CSR-algorithmic figures are under iteration.csr_*",
+               "kernels": rows,
+               "iteration": {"format_bytes": it_bytes, "format_GBps": it_bytes * its / 1e9, "format_frac": it_bytes * its / 1e9 / peak,
+                             "format_frac_of_8TBps": it_bytes * its / 1e9 / 8000.0,
+                             "csr_algorithmic_bytes": b_it // world, "csr_equivalent_GBps": b_it / world * its / 1e9,
+                             "csr_equivalent_frac": b_it / world * its / 1e9 / peak}}
+        tp = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+        if os.path.exists(tp) and N == 256 and world == 1:
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch_256_variant%d" % variant)
+                tr = json.load(open(tp))
+                key = "fused" if fused else ("variant%d" % variant)
+                ent = tr.get(key)
+                if ent:
+                    out["traffic"] = ent.get("dominant_kernel_dram_bytes_per_launch")
+                    if ent.get("iteration_dram_bytes"):
+                        out["iteration"]["dram_bytes_ncu"] = ent["iteration_dram_bytes"]
+                        out["iteration"]["dram_GBps"] = ent["iteration_dram_bytes"] * its / 1e9
+                        out["iteration"]["dram_frac"] = ent["iteration_dram_bytes"] * its / 1e9 / peak
+                        out["iteration"]["dram_frac_of_8TBps"] = ent["iteration_dram_bytes"] * its / 1e9 / 8000.0
+                        out["iteration"]["dram_source"] = ent.get("source")
             except Exception:       # noqa: BLE001
-                traffic = None
-        mv = moved_bytes(variant)
-        return {"bound": "hbm", "kernel": "%s (fused dot epilogue)" % VNAME.get(variant, "?"),
-                "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
-                "frac_of_8TBps_datasheet": ach / 8000.0, "traffic": traffic if (N == 256 and world == 1) else None,
-                "algorithmic_bytes_per_launch": b_spmv_loc, "avg_launch_ms": spmv_ms, "launches_timed": n_spmv,
-                "format_bytes_per_launch": mv, "format_GBps": mv / (spmv_ms * 1e-3) / 1e9, "format_frac": mv / (spmv_ms * 1e-3) / 1e9 / peak,
-                "note": "achieved/frac use the CSR algorithmic bytes of SURVEY.md 8d (12 nnz + 4(n+1) + 16 n); the dictionary variants "
-                        "(3, 4, 5) replace index / value streams by 1 B per row, so frac can exceed 1 - format_* is what the kernel really has to move",
-                "iteration": {"algorithmic_bytes": b_it, "achieved_GBps": b_it / world * its / 1e9,
-                              "frac": b_it / world * its / 1e9 / peak, "spmv_share_of_step": 2 * spmv_ms / (ms / K)}}
+                pass
+        return out
 
     # ---- timed region: the planned (AUTO) SpMV variant ----
     K = args.steps
-    ms, spmv_ms, n_spmv, last_launches, clocks = timed_region(s, K, args.warmup)
+    ms, kms, nk, last_launches, fused = timed_region(s, K, args.warmup)
+    clk.__exit__()
+    clocks = clk.summary()
     its_per_s = K / (ms * 1e-3)
-    roof = roofline(sa["spmv_variant"], ms, K, spmv_ms, n_spmv)
+    roof = roofline(sa["spmv_variant"], fused, ms, K, kms, nk)
 
     line = {"metric": METRIC, "value": its_per_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "poisson3d_%d" % N, "n": n, "nnz": nnz, "mode": "unpreconditioned BiCGSTAB (pbicgstab.h:113)",
                        "x0": "ones", "b": "A*x_true, x_true=hash(1234,i) in (-1,1)", "chunk": chunk,
+                       "timed_window": "continues the warm-up solve (no set-up inside), restart every `chunk` iterations",
                        "l2": "inputs (%.1f GB CSR + vectors) larger than the 126 MB L2, no flush" % ((12 * nnz + 4 * n) / 1e9),
                        "spmv_variant": sa["spmv_variant"], "spmv_format": VNAME.get(sa["spmv_variant"]),
+                       "fused_updates": fused,
                        "sharding": "row slabs, %d rank(s)" % world,
                        "comm": ("none" if world == 1 else ("peer memory over NVLink (CUDA IPC): fused halo pushes + in-kernel gather of the partial sums, no NCCL call per iteration"
                                                             if cm.Comm.p2p_enabled(s) else "NCCL send/recv halo + allreduce of the partial sums"))},
             "gpu_launches": int(last_launches),
             "converge": converge, "roofline": roof, "clocks": clocks}
 
-    # ---- the same K steps with the plain CSR kernel (variant ROWLANE): the apples-to-apples roofline of SURVEY.md 8d ----
-    if sa["spmv_variant"] != 1 and not args.no_csr:
-        s1 = cm.Solver(n, row0, row1, stream=stream)
-        s1.set_csr_device(nnz_loc, a.data_ptr(), ia.data_ptr(), ja.data_ptr(), keep=(ia, ja, a))
-        if world > 1:
-            idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                idbuf = torch.tensor(list(cm.Comm.unique_id()), dtype=torch.uint8, device="cuda")
-            dist.broadcast(idbuf, 0)
-            cm.Comm.init(s1, bytes(idbuf.cpu().tolist()), rank, world)
-        s1.set_option("spmv_variant", 1)
-        s1.analyze(cm.MODE_PLAIN)
-        K1 = min(K, 1000)
-        ms1, spmv_ms1, n_spmv1, _, _ = timed_region(s1, K1, args.warmup)
-        line["csr_format"] = {"value": K1 / (ms1 * 1e-3), "unit": UNIT, "steps": K1, "ms_per_step": ms1 / K1,
-                              "roofline": roofline(1, ms1, K1, spmv_ms1, n_spmv1)}
+    # ---- the same steps with the plain CSR kernel (variant ROWLANE): the apples-to-apples roofline of SURVEY.md 8d ----
+    if sa["spmv_variant"] != 1 and not args.no_csr and roof is not None:
+        s1, _ = new_solver(1)
+        K1 = min(K, 400)
+        ms1, kms1, nk1, _, _ = timed_region(s1, K1, args.warmup)
+        r1 = roofline(1, False, ms1, K1, kms1, nk1)
+        roof["csr_kernel"] = {"value": K1 / (ms1 * 1e-3), "unit": UNIT, "steps": K1, "ms_per_step": ms1 / K1,
+                              "note": "same timed window with the plain CSR kernel (12 B/entry streamed): SURVEY.md 8d's B_spmv / B_iter apply literally",
+                              "spmv": [k for k in (r1["kernels"] if r1 else []) if k["slot"] in (0, 1)],
+                              "iteration_GBps": r1["iteration"]["csr_equivalent_GBps"] if r1 else None,
+                              "iteration_frac": r1["iteration"]["csr_equivalent_frac"] if r1 else None,
+                              "iteration_frac_of_8TBps": (r1["iteration"]["csr_equivalent_GBps"] / 8000.0) if r1 else None}
         s1.close()
 
     if rank == 0 and world == 1 and not args.no_extras:
@@ -329,9 +419,11 @@ def run_ours(args):
     torch.cuda.empty_cache()
     if not args.no_512 and N != 512:
         try:
-            line["poisson512"] = big_grid_run(cm, torch, dist, 512, world, rank, stream, barrier, steps=200)
+            big = big_grid_run(cm, torch, dist, 512, world, rank, stream, barrier, steps=100)
         except Exception as e:      # noqa: BLE001
-            line["poisson512"] = {"error": str(e)}
+            big = {"error": str(e)}
+        # inside `config` so that it survives into the driver's parsed record (SCALE: one line per N from the same code)
+        line["config"]["poisson512"] = big
 
     if rank == 0:
         print(json.dumps(line))
@@ -367,12 +459,14 @@ def big_grid_run(cm, torch, dist, N, world, rank, stream, barrier, steps=200):
     s.spmv(xt.data_ptr(), b.data_ptr())
     x = torch.zeros(nloc, **f64)
     s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=5, tol=0.0)
+    s.set_option("resume", 1)                      # the timed window continues the warm-up solve: no set-up inside
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     st = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=steps, tol=0.0)
     e1.record()
     barrier()
+    st["iterations"] -= 5
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -383,8 +477,10 @@ def big_grid_run(cm, torch, dist, N, world, rank, stream, barrier, steps=200):
     torch.cuda.empty_cache()
     return {"workload": "poisson3d_%d" % N, "n": n, "nnz": nnz, "steps": st["iterations"], "ms_per_step": ms / max(st["iterations"], 1),
             "iters_per_s": st["iterations"] / (ms * 1e-3), "spmv_variant": sa["spmv_variant"],
+            "fused_updates": bool(st.get("fused", 0)), "n_gpus": world,
             "iteration_csr_GBps_per_gpu": bytes_iter(n, nnz) / world * st["iterations"] / (ms * 1e-3) / 1e9,
-            "note": "strong scaling of the SAME 512^3 system over the ranks of this run; includes the 1 SpMV residual set-up of the restart"}
+            "note": "strong scaling of the SAME 512^3 system over the ranks of this run (BASELINE config 5): parallel efficiency = "
+                    "iters_per_s(N) / (N * iters_per_s(1)) across the driver's N = 1, 2, 4, 8 lines"}
 
 
 def random_dd_run(cm, torch, n):
@@ -473,37 +569,68 @@ def multi_gpu_e2e(cm, torch, dist, N, n, row0, row1, nnz_loc, ia, ja, a, b, rank
 
 def single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, converge):
     out = {}
-    # ---- e2e: the reference-facing host-pointer C-ABI call (cudamat_bicgstab_host), pinned HOST buffers,
-    #      H2D of CSR + b and D2H of x inside the timed region; full solve to 1e-10 ----
+    # ---- e2e: the reference-facing host-pointer C-ABI call (cudamat_bicgstab_host), HOST buffers, H2D of CSR + b and
+    #      D2H of x inside the timed region; full solve to 1e-10.  Measured with pinned host arrays (the contract's e2e) and
+    #      with pageable ones (what the reference's callers hand over: malloc'ed arrays, example.cpp:96-104,252), each as
+    #      first call of the process (grows the library's device memory pool) and steady state ----
     try:
-        h_ia = torch.empty(n + 1, dtype=torch.int32, pin_memory=True); h_ia.copy_(ia)
-        h_ja = torch.empty(nnz, dtype=torch.int32, pin_memory=True); h_ja.copy_(ja)
-        h_a = torch.empty(nnz, dtype=torch.float64, pin_memory=True); h_a.copy_(a)
-        h_b = torch.empty(n, dtype=torch.float64, pin_memory=True); h_b.copy_(b)
-        h_x = torch.empty(n, dtype=torch.float64, pin_memory=True)
-        torch.cuda.synchronize()
         import ctypes as C
-        walls = []
-        for _ in range(2):          # first call grows the library's memory pool (cold), second is the steady state
+
+        def host_solve(h_a, h_ia, h_ja, h_b, h_x):
             st = cm.Stats(); dt = C.c_double(0.0)
             t0 = time.time()
             rc = cm.lib.cudamat_bicgstab_host(cm.MODE_PLAIN, n, nnz, C.cast(h_a.data_ptr(), cm.c_dp), C.cast(h_ia.data_ptr(), cm.c_ip),
                                               C.cast(h_ja.data_ptr(), cm.c_ip), None, None, C.cast(h_b.data_ptr(), cm.c_dp),
                                               5000, 1e-10, 0, C.cast(h_x.data_ptr(), cm.c_dp), C.byref(dt), C.byref(st))
-            walls.append(time.time() - t0)
+            wall = time.time() - t0
             cm._check(rc)
-        wall = walls[-1]
+            return wall, st
+
+        res = {}
+        for kind in ("pageable", "pinned"):
+            pin = kind == "pinned"
+            h_ia = torch.empty(n + 1, dtype=torch.int32, pin_memory=pin); h_ia.copy_(ia)
+            h_ja = torch.empty(nnz, dtype=torch.int32, pin_memory=pin); h_ja.copy_(ja)
+            h_a = torch.empty(nnz, dtype=torch.float64, pin_memory=pin); h_a.copy_(a)
+            h_b = torch.empty(n, dtype=torch.float64, pin_memory=pin); h_b.copy_(b)
+            h_x = torch.empty(n, dtype=torch.float64, pin_memory=pin)
+            torch.cuda.synchronize()
+            walls = []
+            for _ in range(2):
+                wall, st = host_solve(h_a, h_ia, h_ja, h_b, h_x)
+                walls.append(wall)
+            res[kind] = {"value": st.iterations / walls[-1], "wall_s": walls[-1], "value_first_call": st.iterations / walls[0],
+                         "wall_s_first_call": walls[0], "t_h2d_s": st.t_h2d, "t_analysis_s": st.t_analysis, "t_loop_s": st.t_loop,
+                         "t_d2h_s": st.t_d2h, "iterations": st.iterations, "converged": bool(st.converged)}
+            del h_ia, h_ja, h_a, h_b, h_x
         h2d = 12 * nnz + 4 * (n + 1) + 8 * n
-        out["e2e"] = {"value": st.iterations / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(st.iterations, 1),
-                      "d2h_bytes_per_step": 8 * n / max(st.iterations, 1), "iterations": st.iterations, "wall_s": wall,
-                      "wall_s_first_call": walls[0], "value_first_call": st.iterations / walls[0],
-                      "t_h2d_s": st.t_h2d, "t_analysis_s": st.t_analysis, "t_loop_s": st.t_loop, "t_d2h_s": st.t_d2h,
-                      "converged": bool(st.converged),
-                      "call": "cudamat_bicgstab_host(MODE_PLAIN, tol=1e-10) on pinned host CSR/b/x; second of two identical calls "
-                              "(the first also pays the one-time growth of the library's device memory pool)"}
-        del h_ia, h_ja, h_a, h_b, h_x
+        its = res["pinned"]["iterations"]
+        out["e2e"] = {"value": res["pinned"]["value"], "unit": UNIT, "h2d_bytes_per_step": h2d / max(its, 1),
+                      "d2h_bytes_per_step": 8 * n / max(its, 1), "iterations": its, "wall_s": res["pinned"]["wall_s"],
+                      "pinned": res["pinned"], "pageable": res["pageable"],
+                      "call": "cudamat_bicgstab_host(MODE_PLAIN, tol=1e-10) on host CSR/b/x: H2D 1.54 GB + analysis + %d iterations + D2H; "
+                              "`value` = pinned host arrays, steady state (second call); `pageable` = malloc'ed arrays as the reference's "
+                              "callers pass them; `*_first_call` = first call of the process (the very first one also grows the device memory pool)" % its}
     except Exception as e:      # noqa: BLE001
         out["e2e"] = {"value": None, "error": str(e)}
+
+    # ---- same-box GPU bar: the REFERENCE's own GPU code (pbicgstab.cu compiled unmodified against the test-only legacy-cuSPARSE
+    #      shim, oracle/_ref) on the same 256^3 system in its only live mode (bicgstab_lu_precond, example.cpp:352), next to ours ----
+    if not args.no_ilu0 and not args.no_refgpu:
+        try:
+            O = ge.load_oracle()
+            if O.ref_available("pbicgstab"):
+                h = [t.cpu().numpy() for t in (ia, ja, a, b)]
+                t0 = time.time()
+                xr, dtr, info = O.ref_gpu_bicgstab_lu_precond(h[0], h[1], h[2], h[3], maxit=2000, tol=1e-10)
+                wall = time.time() - t0
+                relerr = float(np.linalg.norm(xr - xt.cpu().numpy()) / np.linalg.norm(xt.cpu().numpy()))
+                out["reference_gpu_ilu0"] = {"iterations": info["iterations"], "t_loop_s": dtr, "iters_per_s": info["iterations"] / max(dtr, 1e-9),
+                                             "wall_s": wall, "rel_err_vs_xtrue": relerr,
+                                             "what": "reference bicgstab_lu_precond (cuSPARSE SpMV/SpSV/csrilu02 + cuBLAS L1) on this GPU, tol 1e-10"}
+                del xr, h
+        except Exception as e:      # noqa: BLE001
+            out["reference_gpu_ilu0"] = {"error": str(e)}
 
     # ---- same-box bar: modern cuSPARSE SpMV (cusparseSpMV through torch's CSR mat-vec) on the same matrix; library
     #      comparator only, never on the product path ----
@@ -607,9 +734,11 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="force an SpMV variant (1 rowlane, 2 staged)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-ilu0", action="store_true", help="skip the ILU0 extra")
+    ap.add_argument("--no-refgpu", action="store_true", help="skip the run of the reference's own GPU code (oracle/_ref/libref_pbicgstab.so)")
     ap.add_argument("--no-random", action="store_true", help="skip the 50 M-row random matrix extra (BASELINE config 4)")
     ap.add_argument("--random-rows", type=int, default=50_000_000)
     ap.add_argument("--no-512", action="store_true", help="skip the 512^3 extra (BASELINE config 5)")
+    ap.add_argument("--no-fuse", action="store_true", help="keep the p / s updates as separate kernels (A/B against the fused MARCH loop)")
     ap.add_argument("--no-csr", action="store_true", help="skip the second timed region with the plain CSR SpMV kernel")
     ap.add_argument("--no-converge", action="store_true", help="skip the full solve to 1e-10 (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / ilu0 / mat10000 / cpu extras (profiling runs)")

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CUDAMAT_LIB") or os.path.join(_HERE, "libcudamat_b200
 ROOT = os.path.dirname(_HERE)
 
 MODE_PLAIN, MODE_SHIFTED, MODE_ILU0 = 0, 1, 2
-SPMV_AUTO, SPMV_ROWLANE, SPMV_STAGED, SPMV_PATTERN, SPMV_CLASS, SPMV_TILED = 0, 1, 2, 3, 4, 5
+SPMV_AUTO, SPMV_ROWLANE, SPMV_STAGED, SPMV_PATTERN, SPMV_CLASS, SPMV_TILED, SPMV_MARCH = 0, 1, 2, 3, 4, 5, 6
 E_NO_DEVICE = -2
 
 c_dp = C.POINTER(C.c_double)
@@ -33,10 +33,10 @@ class Stats(C.Structure):
                 ("t_loop", C.c_double), ("t_d2h", C.c_double), ("levels_l", C.c_int),
                 ("levels_u", C.c_int), ("spmv_variant", C.c_int), ("zero_pivot", C.c_int),
                 ("kernel_launches", C.c_int64), ("t_spmv", C.c_double), ("n_spmv", C.c_int),
-                ("graph_replay", C.c_int)]
+                ("graph_replay", C.c_int), ("t_kernel", C.c_double * 4), ("n_kernel", C.c_int * 4), ("fused", C.c_int)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k in ("t_kernel", "n_kernel") else getattr(self, k)) for k, _ in self._fields_}
 
 
 class CudamatError(RuntimeError):
@@ -56,7 +56,7 @@ EXPORTS = [
     "cudamat_set_csr_host", "cudamat_set_csr_device", "cudamat_analyze", "cudamat_solve_device",
     "cudamat_get_history", "cudamat_spmv_device", "cudamat_dot_device", "cudamat_get_ilu0_host",
     "cudamat_sptrsv_device", "cudamat_comm_p2p_enabled", "cudamat_write_mm", "cudamat_write_mm_vector", "cudamat_comm_unique_id", "cudamat_comm_init", "cudamat_partition_rows",
-    "cudamat_halo_plan_host", "cudamat_tiled_plan_host",
+    "cudamat_halo_plan_host", "cudamat_tiled_plan_host", "cudamat_march_plan_host",
     "cudamat_gen_poisson3d_device", "cudamat_poisson3d_nnz", "cudamat_gen_xtrue_device",
     "cudamat_gen_random_dd_device", "cudamat_load_mm", "cudamat_free",
 ]
@@ -295,6 +295,19 @@ def halo_plan_host(row0, row1, ja_global, row_starts):
     halo = np.ctypeslib.as_array(hp, (max(nh.value, 1),))[:nh.value].copy()
     lib.cudamat_free(C.cast(hp, C.c_void_p))
     return halo, np.array(list(rc), dtype=np.int64)
+
+
+def march_plan_host(sup_off, sup_val, n):
+    """Host planner of the MARCH SpMV variant: None, or dict(D, H, S, P, dz, loff) for the superset pattern sup_off."""
+    so = _i32(sup_off)
+    sv = _f64(sup_val if sup_val is not None else np.ones(len(so)))
+    ok, D, H, S, P = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    dz, lo = (C.c_int * 8)(), (C.c_int * 8)()
+    lib.cudamat_march_plan_host.argtypes = [C.c_int, c_ip, c_dp, C.c_longlong, c_ip, c_ip, c_ip, c_ip, c_ip, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _check(lib.cudamat_march_plan_host(len(so), _ip(so), _dp(sv), int(n), C.byref(ok), C.byref(D), C.byref(H), C.byref(S), C.byref(P), dz, lo))
+    if not ok.value:
+        return None
+    return {"D": D.value, "H": H.value, "S": S.value, "P": P.value, "dz": list(dz)[:len(so)], "loff": list(lo)[:len(so)]}
 
 
 def tiled_plan_host(lens, offs, vals, hist, n, with_vals=True):

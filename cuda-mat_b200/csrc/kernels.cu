@@ -751,14 +751,24 @@ static int launch_spmv_t(cudamat_solver *s, const SpmvArgs &a, int variant) {
     return CUDAMAT_OK;
 }
 
-int launch_spmv(cudamat_solver *s, const SpmvArgs &a, int variant) {
+static int launch_spmv_any(cudamat_solver *s, const SpmvArgs &a, int variant) {
     if (variant == CUDAMAT_SPMV_AUTO) variant = s->spmv_variant;
+    if (variant == CUDAMAT_SPMV_MARCH) {
+        if (march_spmv_usable(s, a)) return launch_march_spmv(s, a);
+        variant = CUDAMAT_SPMV_TILED;
+    }
     const bool hd = a.d != nullptr;
     switch (a.ndot) {
     case 0: return hd ? launch_spmv_t<true, 0>(s, a, variant) : launch_spmv_t<false, 0>(s, a, variant);
     case 1: return hd ? launch_spmv_t<true, 1>(s, a, variant) : launch_spmv_t<false, 1>(s, a, variant);
     default: return hd ? launch_spmv_t<true, 2>(s, a, variant) : launch_spmv_t<false, 2>(s, a, variant);
     }
+}
+int launch_spmv(cudamat_solver *s, const SpmvArgs &a, int variant) {       // exactly one kernel: event-bracketed when sampled
+    int rc = ev_mark(s, true);
+    if (rc) return rc;
+    if ((rc = launch_spmv_any(s, a, variant))) return rc;
+    return ev_mark(s, false);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1069,9 +1079,11 @@ static inline int tiles_of(int n) { return (n + kTile - 1) / kTile; }
     do {                                                                       \
         const int grid_ = tiles_of((a).n);                                     \
         if (grid_ > 0) {                                                       \
+            { const int e_ = ev_mark(s, true); if (e_) return e_; }            \
             CM_CUDA(launch_pdl(kern, grid_, kCtaThreads, 0, s->stream, (a)));  \
             s->launches++;                                                     \
             CM_CUDA(cudaGetLastError());                                       \
+            { const int e_ = ev_mark(s, false); if (e_) return e_; }           \
         }                                                                      \
     } while (0)
 

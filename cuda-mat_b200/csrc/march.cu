@@ -44,144 +44,199 @@ struct MarchArgs {
     RedCtx rc; DevScalars *sc; int check_status;
 };
 
-template <int EPT>
-struct MarchStage { double a[EPT], b[EPT], c[EPT]; };
+// Work split: items (z-chunk, column) in z-chunk-major order, item = blockIdx.x (+ k * gridDim.x).  Neighbouring CTAs walk
+// neighbouring columns through the SAME planes at about the same time, so the +-H halo lines a tile shares with the
+// tiles next to it are still in L2 when the second reader arrives.
+//
+// Thread mapping.  Staging: a thread moves PAIRS of consecutive elements (16-byte loads / stores); pair tid + 512 j.
+// Multiply: lane l of warp w owns rows 64 g + 2 l and 64 g + 2 l + 1 of the row groups g = w and g = w + 16: an aligned
+// pair of x feeds two rows with one 16-byte shared-memory load, and every row's FMA chain still runs in storage order.
+// Slab sums: rows 32 s .. 32 s + 31 sit in one half-warp, two rows per lane; the spec's butterfly (partner row ^ 16, 8,
+// 4, 2, 1 — internal.cuh) becomes lane ^ 8, 4, 2, 1 on each of the two row parities followed by the in-thread sum of the
+// two: the same tree, `own + partner` at every node, hence the same bits.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds64(uint32_t ad) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ad)); return v; }
+__device__ __forceinline__ double2 lds128(uint32_t ad) {
+    double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ad)); return v;
+}
+__device__ __forceinline__ void sts128(uint32_t ad, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ad), "d"(v.x), "d"(v.y) : "memory"); }
 
-// Work split: linear order q = column * P + plane over the S * P tiles; CTA b owns q in [T b / G, T (b+1) / G).
-template <int MODE, int NDOT, bool HAS_D, int SL, int EPT>
+// SHAPE 1: the 7-entry pattern (-D, -a, -1, 0, +1, +a, +D) with a even — every 7-point grid stencil with an even line
+//          length: planes and the 16-byte alignment of every tap are compile-time facts (5 aligned pair loads, 2 x 2
+//          single loads per two rows).
+// SHAPE 0: any other pattern of <= 8 entries: planes / offsets are kernel parameters, every tap is two 8-byte loads.
+template <int MODE, int NDOT, bool HAS_D, bool U_RING, int SHAPE, int HB>
 __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a, const __grid_constant__ MarchPlan M) {
-    extern __shared__ __align__(16) double ring[];
+    constexpr int SL = SHAPE == 1 ? 7 : 8;
+    constexpr int H = HB * 256;
+    constexpr int BUF = kTile + 2 * H;                             // elements per ring slot
+    constexpr int PAIRS = BUF / 2;
+    constexpr int PPT = (PAIRS + kCtaThreads - 1) / kCtaThreads;   // pairs per thread: 3 (H = 256: the last one half populated)
+    constexpr int NV = MODE == MARCH_MAKE_P ? 3 : MODE == MARCH_MAKE_S ? 2 : 1;
+    extern __shared__ __align__(16) double ring[];                 // 4 slots
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int BUF = M.buf_elems, H = M.H, S = M.S, P = M.P;
-    const long long T = (long long)S * P;
-    long long q = T * blockIdx.x / gridDim.x;
-    const long long q_end = T * (blockIdx.x + 1) / gridDim.x;
+    const int S = M.S, P = M.P, Zc = M.Zc, n = a.n;
     pdl_sync();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     double c1 = 0.0, c2 = 0.0;                                     // MAKE_P: beta, -omega; MAKE_S: -alpha
     if (MODE == MARCH_MAKE_P) { c1 = a.sc->beta; c2 = -a.sc->omega; }
     if (MODE == MARCH_MAKE_S) { c2 = -a.sc->alpha; }
-
-    // global loads of tile (col, pl) with its halo -> registers
-    auto issue = [&](int col, int pl, double (&ra)[EPT], double (&rb)[EPT], double (&rcv)[EPT]) {
-        const long long g0 = ((long long)pl * S + col) * kTile - H;
+    const double *const in[3] = {a.in0, a.in1, a.in2};
+    const uint32_t ring_s = smem_addr(ring);
+    // byte offset of this thread's first row (of its first row group) inside a ring slot, as seen through every tap
+    uint32_t toff[SL];
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            const int e = tid + j * kCtaThreads;
-            const long long g = g0 + e;
-            const bool ok = e < BUF && g >= 0 && g < a.n;
-            ra[j] = ok ? __ldg(a.in0 + g) : 0.0;
-            if (MODE != MARCH_LOAD_X) rb[j] = ok ? __ldg(a.in1 + g) : 0.0;
-            if (MODE == MARCH_MAKE_P) rcv[j] = ok ? __ldg(a.in2 + g) : 0.0;
+    for (int t = 0; t < SL; ++t) toff[t] = (uint32_t)(H + M.loff[t] + warp * 64 + 2 * lane) * 8u;
+    const uint32_t coff = (uint32_t)(H + warp * 64 + 2 * lane) * 8u;
+
+    // global loads of the tile whose buffer starts at element g0 = tile base - H -> registers
+    auto issue = [&](int g0, double2 (&st)[NV][PPT]) {
+        if (g0 >= 0 && g0 + BUF <= n) {                            // CTA-uniform: everything but the two ends of the vector
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const double2 *src = reinterpret_cast<const double2 *>(in[v] + g0) + tid;
+#pragma unroll
+                for (int j = 0; j < PPT; ++j)
+                    if ((j + 1) * kCtaThreads <= PAIRS || tid + j * kCtaThreads < PAIRS) st[v][j] = __ldg(src + j * kCtaThreads);
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) {
+                    const int g = g0 + 2 * (tid + j * kCtaThreads);
+                    const bool inb = tid + j * kCtaThreads < PAIRS;
+                    st[v][j].x = (inb && g >= 0 && g < n) ? __ldg(in[v] + g) : 0.0;
+                    st[v][j].y = (inb && g + 1 >= 0 && g + 1 < n) ? __ldg(in[v] + g + 1) : 0.0;
+                }
         }
     };
-    // registers -> operand values -> ring slot pl & 3; centre rows of an owned tile also go to global memory
-    auto convert = [&](int col, int pl, bool owned, const double (&ra)[EPT], const double (&rb)[EPT], const double (&rcv)[EPT]) {
-        const long long g0 = ((long long)pl * S + col) * kTile - H;
-        double *slot = ring + (pl & 3) * BUF;
+    auto make = [&](double r, double p, double v) -> double {
+        if (MODE == MARCH_LOAD_X) return r;
+        if (MODE == MARCH_MAKE_P) {                                // pbicgstab.cu:668-672: scal, axpy, scal, axpy
+            double q = __dmul_rn(c2, v);
+            q = __dadd_rn(p, q);
+            q = __dmul_rn(c1, q);
+            return __dadd_rn(r, q);
+        }
+        return __dadd_rn(r, __dmul_rn(c2, p));                     // pbicgstab.cu:698-700 (p = v here)
+    };
+    // registers -> operand values -> ring slot; centre pairs of an owned tile also go to global memory (written once)
+    auto convert = [&](int g0, int slot, bool owned, const double2 (&st)[NV][PPT]) {
+        const uint32_t dst = ring_s + (uint32_t)(slot * BUF + 2 * tid) * 8u;
+        double2 *gout = reinterpret_cast<double2 *>(a.xout + g0) + tid;
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            const int e = tid + j * kCtaThreads;
-            if (e < BUF) {
-                double v;
-                if (MODE == MARCH_LOAD_X) v = ra[j];
-                else if (MODE == MARCH_MAKE_P) {                   // pbicgstab.cu:668-672
-                    v = __dmul_rn(c2, rcv[j]);
-                    v = __dadd_rn(rb[j], v);
-                    v = __dmul_rn(c1, v);
-                    v = __dadd_rn(ra[j], v);
-                } else {                                           // pbicgstab.cu:698-700
-                    v = __dadd_rn(ra[j], __dmul_rn(c2, rb[j]));
-                }
-                slot[e] = v;
-                if (MODE != MARCH_LOAD_X && owned && e >= H && e < H + kTile) a.xout[g0 + e] = v;
+        for (int j = 0; j < PPT; ++j) {
+            const int pi = tid + j * kCtaThreads;
+            if ((j + 1) * kCtaThreads <= PAIRS || pi < PAIRS) {
+                double2 o;
+                o.x = make(st[0][j].x, st[NV > 1 ? 1 : 0][j].x, st[NV > 2 ? 2 : 0][j].x);
+                o.y = make(st[0][j].y, st[NV > 1 ? 1 : 0][j].y, st[NV > 2 ? 2 : 0][j].y);
+                sts128(dst + j * kCtaThreads * 16, o);
+                if (MODE != MARCH_LOAD_X && owned && 2 * pi >= H && 2 * pi < H + kTile) gout[j * kCtaThreads] = o;
             }
         }
     };
 
-    while (q < q_end) {
-        const int col = (int)(q / P), k0 = (int)(q % P);
-        const int k1 = (int)min((long long)P - 1, k0 + (q_end - q) - 1);
-        q += k1 - k0 + 1;
-        __syncthreads();                                           // previous segment's last reads of the ring are done
+    const int items = Zc * S;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int zc = item / S, col = item - zc * S;
+        const int k0 = (int)((long long)P * zc / Zc), k1 = (int)((long long)P * (zc + 1) / Zc) - 1;
+        if (k1 < k0) continue;
+        __syncthreads();                                           // the previous item's last reads of the ring are done
         {   // fill the ring: planes k0-1, k0, k0+1
-            double ra[EPT], rb[EPT], rcv[EPT];
+            double2 st[NV][PPT];
 #pragma unroll 1
             for (int pl = k0 - 1; pl <= k0 + 1; ++pl) {
                 if (pl < 0 || pl >= P) continue;
-                issue(col, pl, ra, rb, rcv);
-                convert(col, pl, pl >= k0 && pl <= k1, ra, rb, rcv);
+                const int g0 = (pl * S + col) * kTile - H;
+                issue(g0, st);
+                convert(g0, pl & 3, pl >= k0 && pl <= k1, st);
             }
         }
 #pragma unroll 1
         for (int k = k0; k <= k1; ++k) {
             const int tile = k * S + col;
-            const int row_base = tile * kTile;
-            // ---- issue: plane k+2 (consumed after the multiply), masks / dot operand / shift of plane k ----
-            double ra[EPT], rb[EPT], rcv[EPT];
+            const int row0 = tile * kTile + warp * 64 + 2 * lane;  // this thread's first row (first row group)
+            // ---- issue: plane k+2 (consumed after the multiply); masks / dot operand / shift of plane k ----
+            double2 st[NV][PPT];
             const bool pre = k + 2 <= min(k1 + 1, P - 1);
-            if (pre) issue(col, k + 2, ra, rb, rcv);
-            unsigned mk[kSlabsPerWarp];
-            double uu[kSlabsPerWarp], dd[kSlabsPerWarp];
+            const int g2 = ((k + 2) * S + col) * kTile - H;
+            if (pre) issue(g2, st);
+            unsigned mk[2];
+            double2 uu[2], dd[2];
 #pragma unroll
-            for (int j = 0; j < kSlabsPerWarp; ++j) {
-                const int row = row_base + (j * kCtaWarps + warp) * kSlab + lane;
-                mk[j] = __ldg(a.tmask + row);
-                if (NDOT >= 1 && a.u) uu[j] = __ldg(a.u + row);
-                if (HAS_D) dd[j] = __ldg(a.d + row);
+            for (int gi = 0; gi < 2; ++gi) {
+                const int r0 = row0 + gi * kCtaWarps * 64;
+                mk[gi] = __ldg(reinterpret_cast<const unsigned short *>(a.tmask + r0));
+                if (NDOT >= 1 && !U_RING) uu[gi] = __ldg(reinterpret_cast<const double2 *>(a.u + r0));
+                if (HAS_D) dd[gi] = __ldg(reinterpret_cast<const double2 *>(a.d + r0));
             }
             __syncthreads();                                       // ring stores of the previous step are visible
             // ---- multiply plane k out of the ring ----
-            int eoff[SL];
+            uint32_t sb[3];                                        // slots of planes k-1, k, k+1 (shared-memory byte addresses)
 #pragma unroll
-            for (int t = 0; t < SL; ++t) eoff[t] = ((k + M.dz[t]) & 3) * BUF + H + M.loff[t];
-            const double *cen = ring + (k & 3) * BUF + H;
-            double pp[NDOT > 0 ? NDOT : 1], w[NDOT > 0 ? NDOT * 2 : 1];
+            for (int d = 0; d < 3; ++d) sb[d] = ring_s + (uint32_t)(((k + d - 1) & 3) * BUF) * 8u;
+            constexpr unsigned FULL2 = ((1u << SL) - 1u) * 0x101u;
+            double2 *yp = reinterpret_cast<double2 *>(a.y + row0);
 #pragma unroll
-            for (int j = 0; j < kSlabsPerWarp; ++j) {
-                const int i = (j * kCtaWarps + warp) * kSlab + lane;
-                const unsigned mask = mk[j];
-                double xv[SL];
+            for (int gi = 0; gi < 2; ++gi) {
+                constexpr int GB = kCtaWarps * 64 * 8;             // byte distance of the warp's second row group
+                double s0 = 0.0, s1 = 0.0;
+                const unsigned m0 = mk[gi] & 0xffu, m1 = mk[gi] >> 8;
+                auto tap = [&](int t, double &x0, double &x1) {    // the two rows' operand through tap t
+                    uint32_t ad;
+                    bool odd;
+                    if (SHAPE == 1) { ad = sb[t == 0 ? 0 : t == 6 ? 2 : 1] + toff[t] + gi * GB; odd = (t == 2 || t == 4); }
+                    else { ad = sb[M.dz[t] + 1] + toff[t] + gi * GB; odd = true; }
+                    if (odd) { x0 = lds64(ad); x1 = lds64(ad + 8); }
+                    else { const double2 xx = lds128(ad); x0 = xx.x; x1 = xx.y; }
+                };
+                if (__all_sync(0xffffffffu, mk[gi] == FULL2)) {    // interior rows: the whole pattern, no predicates
+                    double x0[SL], x1[SL];
 #pragma unroll
-                for (int t = 0; t < SL; ++t) xv[t] = ring[eoff[t] + i];
-                double sum = 0.0;
-                if (__all_sync(0xffffffffu, mask == (1u << SL) - 1u)) {
+                    for (int t = 0; t < SL; ++t) tap(t, x0[t], x1[t]);
 #pragma unroll
-                    for (int t = 0; t < SL; ++t) sum = __fma_rn(M.val[t], xv[t], sum);
+                    for (int t = 0; t < SL; ++t) { s0 = __fma_rn(M.val[t], x0[t], s0); s1 = __fma_rn(M.val[t], x1[t], s1); }
                 } else {
 #pragma unroll
-                    for (int t = 0; t < SL; ++t)
-                        if (mask & (1u << t)) sum = __fma_rn(M.val[t], xv[t], sum);
-                }
-                const double xc = (HAS_D || (NDOT >= 1)) ? cen[i] : 0.0;
-                if (HAS_D) sum = __dadd_rn(sum, __dmul_rn(dd[j], xc));
-                a.y[row_base + i] = sum;
-                double p0 = 0.0, p1 = 0.0;
-                if (NDOT >= 1) p0 = __dmul_rn(sum, a.u ? uu[j] : xc);
-                if (NDOT >= 2) p1 = __dmul_rn(sum, sum);
-                if constexpr (NDOT >= 1) {
-                    if (j & 1) {
-                        w[j >> 1] = packed_pair(pp[0], p0, 16, lane);
-                        if constexpr (NDOT >= 2) w[2 + (j >> 1)] = packed_pair(pp[1], p1, 16, lane);
-                    } else {
-                        pp[0] = p0;
-                        if constexpr (NDOT >= 2) pp[1] = p1;
+                    for (int t = 0; t < SL; ++t) {
+                        double x0, x1;
+                        tap(t, x0, x1);
+                        if (m0 & (1u << t)) s0 = __fma_rn(M.val[t], x0, s0);
+                        if (m1 & (1u << t)) s1 = __fma_rn(M.val[t], x1, s1);
                     }
                 }
-            }
-            if constexpr (NDOT >= 1) {                             // same packed butterfly as k_spmv_tiled (bit-identical slab sums)
-                double z = packed_pair(w[0], w[1], 8, lane);
-                if constexpr (NDOT >= 2) z = packed_pair(z, packed_pair(w[2], w[3], 8, lane), 4, lane);
-                else z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 4));
-                z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 2));
-                z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, 1));
-                const int idx = ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + (NDOT >= 2 ? 4 * ((lane >> 2) & 1) : 0);
-                const int j = idx & 3, qq = idx >> 2;
-                if ((lane & (NDOT >= 2 ? 3 : 7)) == 0)
-                    __stcg(a.rc.slab_part + (size_t)qq * a.rc.slab_stride + (size_t)tile * kTileSlabs + j * kCtaWarps + warp, z);
+                double2 xc = make_double2(0.0, 0.0);
+                if (HAS_D || (NDOT >= 1 && U_RING)) xc = lds128(sb[1] + coff + gi * GB);
+                if (HAS_D) { s0 = __dadd_rn(s0, __dmul_rn(dd[gi].x, xc.x)); s1 = __dadd_rn(s1, __dmul_rn(dd[gi].y, xc.y)); }
+                yp[gi * kCtaWarps * 32] = make_double2(s0, s1);
+                if constexpr (NDOT >= 1) {
+                    const double2 uv = U_RING ? xc : uu[gi];
+                    // slab sums of (y.u [, y.y]): lane ^ 8, 4, 2, 1 on both row parities, then parity 0 + parity 1
+                    double e0 = __dmul_rn(s0, uv.x), e1 = __dmul_rn(s1, uv.y);
+                    if constexpr (NDOT >= 2) {
+                        // two dots: lanes with bit 3 clear carry dot 0, the others dot 1 (packed first step)
+                        e0 = packed_pair(e0, __dmul_rn(s0, s0), 8, lane);
+                        e1 = packed_pair(e1, __dmul_rn(s1, s1), 8, lane);
+                    } else {
+                        e0 = __dadd_rn(e0, __shfl_xor_sync(0xffffffffu, e0, 8));
+                        e1 = __dadd_rn(e1, __shfl_xor_sync(0xffffffffu, e1, 8));
+                    }
+#pragma unroll
+                    for (int sh = 4; sh >= 1; sh >>= 1) {
+                        e0 = __dadd_rn(e0, __shfl_xor_sync(0xffffffffu, e0, sh));
+                        e1 = __dadd_rn(e1, __shfl_xor_sync(0xffffffffu, e1, sh));
+                    }
+                    const double z = __dadd_rn(e0, e1);
+                    const int slab = tile * kTileSlabs + ((gi * kCtaWarps + warp) << 1) + (lane >> 4);
+                    if ((lane & 15) == 0) __stcg(a.rc.slab_part + slab, z);
+                    if (NDOT >= 2 && (lane & 15) == 8) __stcg(a.rc.slab_part + (size_t)a.rc.slab_stride + slab, z);
+                }
             }
             // ---- convert + store plane k+2 into the slot plane k-2 left ----
-            if (pre) convert(col, k + 2, k + 2 <= k1, ra, rb, rcv);
+            if (pre) convert(g2, (k + 2) & 3, k + 2 <= k1, st);
         }
     }
 }
@@ -213,55 +268,69 @@ bool march_plan_host(const TiledDict &T, long long n, MarchPlan &M) {
         M.dz[q] = dz; M.loff[q] = (int)lo; M.val[q] = T.sup_val[q];
         H = std::max(H, (int)(lo < 0 ? -lo : lo));
     }
-    H = (H + 31) / 32 * 32;
+    H = std::max(256, (H + 255) / 256 * 256);                      // 256 or 512: ring slots of 5 or 6 x 512 elements
     M.D = (int)D; M.H = H; M.S = (int)(D / kTile); M.P = (int)(n / D);
     M.buf_elems = kTile + 2 * H; M.len = T.sup_len;
+    M.Zc = 1;
+    // SHAPE 1: (-D, -a, -1, 0, +1, +a, +D), a even (the kernel then knows planes and alignment at compile time)
+    M.shape = (M.len == 7 && M.dz[0] == -1 && M.dz[6] == 1 && M.loff[0] == 0 && M.loff[6] == 0 && M.dz[1] == 0 && M.dz[2] == 0 &&
+               M.dz[3] == 0 && M.dz[4] == 0 && M.dz[5] == 0 && M.loff[2] == -1 && M.loff[3] == 0 && M.loff[4] == 1 &&
+               (M.loff[1] & 1) == 0 && (M.loff[5] & 1) == 0) ? 1 : 0;
     return true;
 }
 
-template <int MODE, int NDOT, bool HAS_D, int SL, int EPT>
+template <int MODE, int NDOT, bool HAS_D, bool U_RING, int SHAPE, int HB>
 static int launch_march_t(cudamat_solver *s, const MarchArgs &a) {
-    const MarchPlan &M = *s->march;
-    const void *kern = (const void *)k_spmv_march<MODE, NDOT, HAS_D, SL, EPT>;
-    const size_t smem = sizeof(double) * 4 * (size_t)M.buf_elems;
+    MarchPlan M = *s->march;
+    const void *kern = (const void *)k_spmv_march<MODE, NDOT, HAS_D, U_RING, SHAPE, HB>;
+    const size_t smem = sizeof(double) * 4 * (size_t)(kTile + 2 * HB * 256);
     static bool attr_set[64] = {};
     const int dv = s->device & 63;
-    if (!attr_set[dv]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); attr_set[dv] = true; }
-    const long long T = (long long)M.S * M.P;
-    const int grid = (int)std::min<long long>(T, (long long)s->march_grid);
+    if (!attr_set[dv]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[dv] = true; }
+    // z-chunks: as many as the CTA budget allows, but runs of at least 8 planes (each run re-reads 2 extra planes)
+    const int G = std::max(1, s->march_grid);
+    M.Zc = std::max(1, std::min(G / std::max(1, M.S), std::max(1, M.P / 8)));
+    const int grid = (int)std::min<long long>((long long)M.Zc * M.S, (long long)G);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCtaThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    void *args[] = {(void *)&a, (void *)s->march};
+    void *args[] = {(void *)&a, (void *)&M};
     CM_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
     s->launches++;
     CM_CUDA(cudaGetLastError());
     return CUDAMAT_OK;
 }
-template <int MODE, int NDOT, bool HAS_D>
+template <int MODE, int NDOT, bool HAS_D, bool U_RING>
 static int launch_march_m(cudamat_solver *s, const MarchArgs &a) {
     const MarchPlan &M = *s->march;
-    const bool seven = M.len == 7;
-    if (M.H <= 256) return seven ? launch_march_t<MODE, NDOT, HAS_D, 7, 5>(s, a) : launch_march_t<MODE, NDOT, HAS_D, 8, 5>(s, a);
-    return seven ? launch_march_t<MODE, NDOT, HAS_D, 7, 6>(s, a) : launch_march_t<MODE, NDOT, HAS_D, 8, 6>(s, a);
+    if (M.H <= 256) return M.shape == 1 ? launch_march_t<MODE, NDOT, HAS_D, U_RING, 1, 1>(s, a) : launch_march_t<MODE, NDOT, HAS_D, U_RING, 0, 1>(s, a);
+    return M.shape == 1 ? launch_march_t<MODE, NDOT, HAS_D, U_RING, 1, 2>(s, a) : launch_march_t<MODE, NDOT, HAS_D, U_RING, 0, 2>(s, a);
 }
+static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 bool march_available(const cudamat_solver *s) { return s->march != nullptr && s->comm == nullptr; }
 
-// y = A x (+ d.x) with ndot fused dots against u (nullptr: against x itself)
+// y = A x (+ d.x) with ndot fused dots (red0 = y.u, red1 = y.y); u == x: the operand comes out of the ring.
+// Staging and stores move 16-byte pairs: operands that are not 16-byte aligned are left to the TILED kernel (returns 1).
+bool march_spmv_usable(const cudamat_solver *s, const SpmvArgs &sa) {
+    return march_available(s) && sa.n > 0 && sa.x != sa.y && al16(sa.x) && al16(sa.y) && (sa.ndot == 0 || al16(sa.u)) && al16(sa.d);
+}
 int launch_march_spmv(cudamat_solver *s, const SpmvArgs &sa) {
     MarchArgs a{};
-    a.n = sa.n; a.in0 = sa.x; a.y = sa.y; a.u = (sa.u == sa.x) ? nullptr : sa.u; a.d = sa.d;
+    const bool ring = sa.ndot >= 1 && sa.u == sa.x;
+    a.n = sa.n; a.in0 = sa.x; a.y = sa.y; a.u = ring ? nullptr : sa.u; a.d = sa.d;
     a.tmask = s->cls[1].d_tmask; a.rc = sa.rc; a.sc = sa.sc; a.check_status = sa.check_status;
     const bool hd = sa.d != nullptr;
-    switch (sa.ndot) {
-    case 0: return hd ? launch_march_m<MARCH_LOAD_X, 0, true>(s, a) : launch_march_m<MARCH_LOAD_X, 0, false>(s, a);
-    case 1: return hd ? launch_march_m<MARCH_LOAD_X, 1, true>(s, a) : launch_march_m<MARCH_LOAD_X, 1, false>(s, a);
-    default: return hd ? launch_march_m<MARCH_LOAD_X, 2, true>(s, a) : launch_march_m<MARCH_LOAD_X, 2, false>(s, a);
+    if (sa.ndot == 0) return hd ? launch_march_m<MARCH_LOAD_X, 0, true, false>(s, a) : launch_march_m<MARCH_LOAD_X, 0, false, false>(s, a);
+    if (sa.ndot == 1) {
+        if (ring) return hd ? launch_march_m<MARCH_LOAD_X, 1, true, true>(s, a) : launch_march_m<MARCH_LOAD_X, 1, false, true>(s, a);
+        return hd ? launch_march_m<MARCH_LOAD_X, 1, true, false>(s, a) : launch_march_m<MARCH_LOAD_X, 1, false, false>(s, a);
     }
+    if (ring) return hd ? launch_march_m<MARCH_LOAD_X, 2, true, true>(s, a) : launch_march_m<MARCH_LOAD_X, 2, false, true>(s, a);
+    return hd ? launch_march_m<MARCH_LOAD_X, 2, true, false>(s, a) : launch_march_m<MARCH_LOAD_X, 2, false, false>(s, a);
 }
 // p' = r + beta (p - omega v) [unprec form]; v' = (A + diag d) p'; red0 = rhat . v'        (pbicgstab.cu:668-689)
 int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old, const double *v_old, double *p_new, double *v_new,
@@ -269,14 +338,39 @@ int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old,
     MarchArgs a{};
     a.n = s->n; a.in0 = r; a.in1 = p_old; a.in2 = v_old; a.xout = p_new; a.y = v_new; a.u = rhat; a.d = d;
     a.tmask = s->cls[1].d_tmask; a.rc = rc; a.sc = s->d_sc; a.check_status = 1;
-    return d ? launch_march_m<MARCH_MAKE_P, 1, true>(s, a) : launch_march_m<MARCH_MAKE_P, 1, false>(s, a);
+    int e = ev_mark(s, true);
+    if (e) return e;
+    if ((e = d ? launch_march_m<MARCH_MAKE_P, 1, true, false>(s, a) : launch_march_m<MARCH_MAKE_P, 1, false, false>(s, a))) return e;
+    return ev_mark(s, false);
 }
 // s = r - alpha v; t = (A + diag d) s; red0 = t . s, red1 = t . t                            (pbicgstab.cu:698-709)
 int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc) {
     MarchArgs a{};
     a.n = s->n; a.in0 = r; a.in1 = v; a.xout = sv; a.y = t; a.u = nullptr; a.d = d;
     a.tmask = s->cls[1].d_tmask; a.rc = rc; a.sc = s->d_sc; a.check_status = 1;
-    return d ? launch_march_m<MARCH_MAKE_S, 2, true>(s, a) : launch_march_m<MARCH_MAKE_S, 2, false>(s, a);
+    int e = ev_mark(s, true);
+    if (e) return e;
+    if ((e = d ? launch_march_m<MARCH_MAKE_S, 2, true, true>(s, a) : launch_march_m<MARCH_MAKE_S, 2, false, true>(s, a))) return e;
+    return ev_mark(s, false);
 }
 
 }  // namespace cudamat
+
+// host planner of the MARCH variant, exported for the CPU tests (no device needed)
+extern "C" int cudamat_march_plan_host(int sup_len, const int *sup_off, const double *sup_val, long long n, int *ok, int *D, int *H,
+                                       int *S, int *P, int *dz, int *loff) {
+    using namespace cudamat;
+    if (sup_len < 0 || sup_len > 8 || !sup_off || !ok) { set_error("march_plan_host: invalid argument"); return CUDAMAT_E_INVALID; }
+    TiledDict *T = new TiledDict();
+    memset(T, 0, sizeof(TiledDict));
+    T->sup_len = sup_len;
+    for (int q = 0; q < sup_len; ++q) { T->sup_off[q] = sup_off[q]; T->sup_val[q] = sup_val ? sup_val[q] : 1.0; }
+    MarchPlan M;
+    *ok = march_plan_host(*T, n, M) ? 1 : 0;
+    delete T;
+    if (*ok) {
+        if (D) *D = M.D; if (H) *H = M.H; if (S) *S = M.S; if (P) *P = M.P;
+        for (int q = 0; q < 8; ++q) { if (dz) dz[q] = M.dz[q]; if (loff) loff[q] = M.loff[q]; }
+    }
+    return CUDAMAT_OK;
+}

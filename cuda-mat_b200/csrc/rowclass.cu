@@ -246,7 +246,7 @@ static bool tiled_plan_host(const DictParam &D, int ncls, const unsigned *hist, 
                 for (size_t j = 0; j < so.size(); ++j)
                     if (so[j] == T->off[c * kDictLen + q]) { P.cm.m[c] |= (unsigned char)(1u << j); T->sup_boff[j] = T->disp[c * kDictLen + q] * 8; }
         }
-        for (size_t j = 0; j < so.size(); ++j) T->sup_val[j] = sv[j];
+        for (size_t j = 0; j < so.size(); ++j) { T->sup_val[j] = sv[j]; T->sup_off[j] = so[j]; }
         T->sup_len = (int)so.size();
     }
     return true;
@@ -287,6 +287,7 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
 }
 
 void rowclass_release(cudamat_solver *s) {
+    delete s->march; s->march = nullptr;
     for (int m = 0; m < 2; ++m) {
         dev_free(s->cls[m].d_cls);
         delete s->cls[m].h_dict;
@@ -353,6 +354,23 @@ int rowclass_analyze(cudamat_solver *s) {
     dev_free(tab); dev_free(rep); dev_free(slot_id); dev_free(flags);
     for (int m = 1; m >= 0 && rc == CUDAMAT_OK; --m)
         if (s->cls[m].ncls > 0) rc = tiled_plan(s, s->cls[m]);
+    // MARCH: needs the values dictionary with a superset pattern and EVERY tile inside the windows
+    if (rc == CUDAMAT_OK && s->cls[1].h_tdict && s->cls[1].h_tdict->sup_len > 0 && s->cls[1].d_tmask && !s->comm) {
+        const int ntile = (n + kTile - 1) / kTile;
+        std::vector<unsigned char> ok((size_t)ntile);
+        cudaError_t e = cudaMemcpyAsync(ok.data(), s->cls[1].d_tile_ok, (size_t)ntile, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) { cuda_ok(e, "tile_ok download", __FILE__, __LINE__); return CUDAMAT_E_CUDA; }
+        bool all_ok = true;
+        for (unsigned char b : ok) if (!b) { all_ok = false; break; }
+        MarchPlan M;
+        if (all_ok && march_plan_host(*s->cls[1].h_tdict, n, M)) {
+            s->march = new MarchPlan(M);
+            int dev = 0, sms = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            s->march_grid = 2 * sms;
+        }
+    }
     return rc;
 }
 

@@ -193,33 +193,47 @@ static SpmvArgs spmv_args(cudamat_solver *s, const double *x, const double *d, d
     return a;
 }
 
-// SpMV launch bracketed by CUDA events on the launching stream when "time_spmv" is set
-// ("time_spmv" = k times the SpMVs of every k-th iteration only: event records between two kernels suspend
-// the programmatic-dependent-launch overlap at that boundary, so sparse sampling keeps the loop undisturbed)
-static int timed_spmv(cudamat_solver *s, const SpmvArgs &a, int var) {
-    const bool timed = s->opt_time_spmv > 0 && (s->loop_it % s->opt_time_spmv) == 0 && s->ev_used + 2 <= 8192;
-    if (timed) {
+// Event timing of single kernels ("time_spmv" = k: the main kernels of every k-th iteration are bracketed by CUDA events on
+// the launching stream; an event record between two kernels suspends the programmatic-dependent-launch overlap at that
+// boundary, so sparse sampling keeps the loop undisturbed).  The loop sets s->time_slot around a launch wrapper; the
+// wrappers call ev_mark() right before and after the ONE kernel they launch.
+//   slot 0: SpMV 1 (MARCH fused loop: incl. the folded p update)   slot 1: SpMV 2 (incl. the folded s update)
+//   slot 2: x / r update with its two dots                          slot 3: separate p / s updates (unfused loop)
+int ev_mark(cudamat_solver *s, bool begin) {
+    if (s->time_slot < 0) return CUDAMAT_OK;
+    if (begin) {
+        s->ev_open = false;
+        if (s->ev_used + 2 > 16384) return CUDAMAT_OK;
         while ((int)s->ev_pool.size() < s->ev_used + 2) {
             cudaEvent_t e; CM_CUDA(cudaEventCreate(&e)); s->ev_pool.push_back(e);
         }
         CM_CUDA(cudaEventRecord(s->ev_pool[s->ev_used], s->stream));
+        s->ev_open = true;
+    } else if (s->ev_open) {
+        CM_CUDA(cudaEventRecord(s->ev_pool[s->ev_used + 1], s->stream));
+        s->ev_slot.push_back(s->time_slot);
+        s->ev_used += 2;
+        s->ev_open = false;
     }
-    int rc = launch_spmv(s, a, var);
-    if (rc) return rc;
-    if (timed) { CM_CUDA(cudaEventRecord(s->ev_pool[s->ev_used + 1], s->stream)); s->ev_used += 2; }
-    if (a.ndot > 0) return finish_reduction(s, a.rc, a.phase, a.ndot);
     return CUDAMAT_OK;
 }
+static inline bool timed_iteration(const cudamat_solver *s) { return s->opt_time_spmv > 0 && (s->loop_it % s->opt_time_spmv) == 0; }
+
 // SpMV step of the loop: halo exchange of the operand (multi-GPU), the kernel, then the cross-rank
 // part of its fused reductions
 // (pushed_slot >= 0: the kernel that produced x has already stored its halo rows into the neighbours' copies over
 // NVLink — the SpMV's boundary CTAs wait for the neighbours' flags instead of an NCCL exchange)
 static int spmv_step(cudamat_solver *s, double *x, const double *d, double *y, const double *u, int ndot, int phase, int check,
-                     int pushed_slot = -1) {
+                     int pushed_slot, int tslot) {
     SpmvArgs a = spmv_args(s, x, d, y, u, ndot, phase, check);
     if (pushed_slot >= 0 && comm_p2p(s)) comm_halo_wait(s, pushed_slot, &a.hw);
     else { int rc = comm_halo_exchange(s, x); if (rc) return rc; }
-    return timed_spmv(s, a, s->spmv_variant);
+    s->time_slot = timed_iteration(s) ? tslot : -1;
+    int rc = launch_spmv(s, a, s->spmv_variant);
+    s->time_slot = -1;
+    if (rc) return rc;
+    if (a.ndot > 0) return finish_reduction(s, a.rc, a.phase, a.ndot);
+    return CUDAMAT_OK;
 }
 
 static int poll_status(cudamat_solver *s) {
@@ -286,14 +300,15 @@ static int start_scalars(cudamat_solver *s, int maxit, double tol, int hist_cap)
 // not change between iterations — every scalar lives on the device) and replayed; the programmatic-dependent-launch
 // edges are kept by the capture.  Large systems and sharded handles (per-launch epochs) launch directly.
 template <typename Iter>
-static int run_iterations(cudamat_solver *s, int maxit, Iter &&one_iteration) {
+static int run_iterations(cudamat_solver *s, int maxit, Iter &&one_iteration, bool even_batches = false) {
     int rc, npoll = 0, it = 0;
     bool stop = false;
     const int poll = std::max(1, s->opt_poll_every);
     static const bool no_graph = [] { const char *e = getenv("CUDAMAT_NO_GRAPH"); return e && *e && *e != '0'; }();
     const bool use_graph = !no_graph && s->opt_graph != 0 && !s->comm && s->opt_time_spmv == 0 && s->stream != nullptr &&
                            s->stream != cudaStreamLegacy && s->stream != cudaStreamPerThread &&
-                           (s->opt_graph > 0 || s->n <= (1 << 22)) && maxit >= 2 * poll;
+                           (s->opt_graph > 0 || s->n <= (1 << 22)) && maxit >= 2 * poll &&
+                           (!even_batches || poll % 2 == 0);       // ping-pong buffers: a replayed batch must restore the parity
     if (use_graph) {
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         const int64_t l0 = s->launches;
@@ -330,41 +345,93 @@ static int run_iterations(cudamat_solver *s, int maxit, Iter &&one_iteration) {
 }
 
 // ---- unpreconditioned loop (gpu_pbicgstab2 shifted overload, pbicgstab.cu:581-754) --------------
-static int solve_unprec(cudamat_solver *s, const double *d_b, const double *d_x0, const double *d_d,
+// Two schedules, same arithmetic (bit-identical results):
+//   * unfused (any SpMV variant, sharded handles): p update | SpMV 1 + dot | s update | SpMV 2 + 2 dots | x, r update + 2 dots
+//   * fused (MARCH variant, single GPU): the p and s updates are formed inside the SpMV kernels while the operand is staged
+//     (march.cu): 3 bandwidth kernels per iteration; p' and v' go to a second buffer each (ping-pong by iteration parity).
+// Option "resume" = 1: continue the previous solve of this handle for `maxit` more iterations without re-initialising
+// (bench.py uses it to keep the residual set-up outside a short timed window).
+static int solve_unprec(cudamat_solver *s, int mode, const double *d_b, const double *d_x0, const double *d_d,
                         double *d_x, int maxit, double tol) {
     int rc;
-    if ((rc = ensure_work(s, 7))) return rc;
+    const bool fused = s->spmv_variant == CUDAMAT_SPMV_MARCH && march_available(s) && s->opt_fuse != 0 &&
+                       (reinterpret_cast<uintptr_t>(d_d) & 15u) == 0;     // 16-byte pairs (work vectors are 256-byte aligned)
+    const bool resume = s->opt_resume != 0 && s->last_mode == mode && s->last_fused == (fused ? 1 : 0) && s->work != nullptr;
+    if ((rc = ensure_work(s, fused ? 9 : 7))) return rc;
     // residual history: capped (a caller may pass a huge maxit as "no limit"); hist_push tolerates the overflow
     const int hcap = (int)std::min<int64_t>((int64_t)maxit + 2, kHistCapMax);
-    if ((rc = ensure_hist(s, hcap))) return rc;
+    if (!resume && (rc = ensure_hist(s, hcap))) return rc;
     double *r0 = wv(s, 0), *r = wv(s, 1), *v = wv(s, 2), *p = wv(s, 3), *sv = wv(s, 4), *t = wv(s, 5), *xk = wv(s, 6);
+    double *pb[2] = {p, fused ? wv(s, 8) : p}, *vb[2] = {v, fused ? wv(s, 7) : v};
     const int var = s->spmv_variant;
-    if ((rc = start_scalars(s, maxit, tol, hcap))) return rc;
     const size_t nb = sizeof(double) * (size_t)s->n;
-    if (d_x0) CM_CUDA(cudaMemcpyAsync(xk, d_x0, nb, cudaMemcpyDeviceToDevice, s->stream));
-    else if ((rc = launch_fill(s, xk, 1.0, s->n))) return rc;
-    CM_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * s->work_elems, s->stream));     // v = p = 0 (:611)
-    CM_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * s->work_elems, s->stream));
-    // r = b - (A0 + diag d) x0 ; r0 = r ; ||r0|| (:645-655)
-    if ((rc = comm_halo_exchange(s, xk))) return rc;
-    if ((rc = launch_spmv(s, spmv_args(s, xk, d_d, t, nullptr, 0, PH_NONE, 0), var))) return rc;
-    if ((rc = launch_init_resid(s, d_b, t, r, r0, nullptr, PH_U_INIT))) return rc;
-    if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
-    rc = run_iterations(s, maxit, [&]() -> int {
-        int r2;
-        HaloPush hp;
-        int slot = comm_halo_push(s, p, 0, &hp) ? 0 : -1;
-        if ((r2 = launch_update_p(s, false, r, v, p, &hp))) return r2;                              // :668-672
-        if ((r2 = spmv_step(s, p, d_d, v, r0, 1, PH_U_A, 1, slot))) return r2;           // :675-689
-        slot = comm_halo_push(s, sv, 1, &hp) ? 1 : -1;
-        if ((r2 = launch_update_s(s, r, v, sv, &hp))) return r2;                                    // :698-700
-        if ((r2 = spmv_step(s, sv, d_d, t, sv, 2, PH_U_B, 1, slot))) return r2;         // :703-710
-        return launch_update_xr(s, false, p, sv, t, r0, xk, r);                                     // :694-696,714-747
-    });
+    if (resume) {
+        DevScalars h = *s->h_sc;                                   // final state of the previous solve (poll_status)
+        h.maxit = h.iter + maxit; h.tol = tol; h.status = maxit > 0 ? ST_RUNNING : ST_MAXIT;
+        *s->h_sc = h;
+        CM_CUDA(cudaMemcpyAsync(s->d_sc, s->h_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+    } else {
+        s->last_mode = -1;
+        if ((rc = start_scalars(s, maxit, tol, hcap))) return rc;
+        if (d_x0) CM_CUDA(cudaMemcpyAsync(xk, d_x0, nb, cudaMemcpyDeviceToDevice, s->stream));
+        else if ((rc = launch_fill(s, xk, 1.0, s->n))) return rc;
+        s->pp = 0;
+        CM_CUDA(cudaMemsetAsync(pb[0], 0, sizeof(double) * s->work_elems, s->stream));     // v = p = 0 (:611)
+        CM_CUDA(cudaMemsetAsync(vb[0], 0, sizeof(double) * s->work_elems, s->stream));
+        // r = b - (A0 + diag d) x0 ; r0 = r ; ||r0|| (:645-655)
+        if ((rc = comm_halo_exchange(s, xk))) return rc;
+        if ((rc = launch_spmv(s, spmv_args(s, xk, d_d, t, nullptr, 0, PH_NONE, 0), var))) return rc;
+        if ((rc = launch_init_resid(s, d_b, t, r, r0, nullptr, PH_U_INIT))) return rc;
+        if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
+    }
+    if (fused) {
+        rc = run_iterations(s, maxit, [&]() -> int {
+            int r2;
+            const bool tm = timed_iteration(s);
+            double *p_old = pb[s->pp], *p_new = pb[s->pp ^ 1], *v_old = vb[s->pp], *v_new = vb[s->pp ^ 1];
+            s->time_slot = tm ? 0 : -1;
+            r2 = launch_march_make_p(s, r, p_old, v_old, p_new, v_new, r0, d_d, s->rc);            // :668-689
+            s->time_slot = -1;
+            if (r2 || (r2 = finish_reduction(s, s->rc, PH_U_A, 1))) return r2;
+            s->time_slot = tm ? 1 : -1;
+            r2 = launch_march_make_s(s, r, v_new, sv, t, d_d, s->rc);                               // :698-710
+            s->time_slot = -1;
+            if (r2 || (r2 = finish_reduction(s, s->rc, PH_U_B, 2))) return r2;
+            s->time_slot = tm ? 2 : -1;
+            r2 = launch_update_xr(s, false, p_new, sv, t, r0, xk, r);                               // :694-696,714-747
+            s->time_slot = -1;
+            s->pp ^= 1;
+            return r2;
+        }, /*even_batches=*/true);
+    } else {
+        rc = run_iterations(s, maxit, [&]() -> int {
+            int r2;
+            const bool tm = timed_iteration(s);
+            HaloPush hp;
+            int slot = comm_halo_push(s, p, 0, &hp) ? 0 : -1;
+            s->time_slot = tm ? 3 : -1;
+            r2 = launch_update_p(s, false, r, v, p, &hp);                                           // :668-672
+            s->time_slot = -1;
+            if (r2) return r2;
+            if ((r2 = spmv_step(s, p, d_d, v, r0, 1, PH_U_A, 1, slot, 0))) return r2;               // :675-689
+            slot = comm_halo_push(s, sv, 1, &hp) ? 1 : -1;
+            s->time_slot = tm ? 3 : -1;
+            r2 = launch_update_s(s, r, v, sv, &hp);                                                 // :698-700
+            s->time_slot = -1;
+            if (r2) return r2;
+            if ((r2 = spmv_step(s, sv, d_d, t, sv, 2, PH_U_B, 1, slot, 1))) return r2;              // :703-710
+            s->time_slot = tm ? 2 : -1;
+            r2 = launch_update_xr(s, false, p, sv, t, r0, xk, r);                                   // :694-696,714-747
+            s->time_slot = -1;
+            return r2;
+        }, false);
+    }
     if (rc) return rc;
     if ((rc = poll_status(s))) return rc;
     if (s->h_sc->status == ST_COMM_TIMEOUT) { set_error("a peer rank's halo rows or partial sums did not arrive (spin limit reached)"); return CUDAMAT_E_COMM; }
     CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
+    s->last_mode = mode; s->last_fused = fused ? 1 : 0;
     return CUDAMAT_OK;
 }
 
@@ -407,10 +474,10 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
         int rc;
         if ((rc = launch_update_p(s, true, r, v, p))) return rc;                                    // :83-89 (skips i == 0)
         if ((rc = precond(p, pw))) return rc;                                                      // :92-98
-        if ((rc = spmv_step(s, pw, nullptr, v, rw, 1, PH_I_A, 1))) return rc;        // :104-107
+        if ((rc = spmv_step(s, pw, nullptr, v, rw, 1, PH_I_A, 1, -1, 0))) return rc;        // :104-107
         if ((rc = launch_update_rx_ilu(s, v, pw, r, xk))) return rc;                                // :109-118
         if ((rc = precond(r, sv))) return rc;                                                      // :121-127
-        if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1))) return rc;         // :132-137
+        if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1, -1, 1))) return rc;         // :132-137
         return launch_update_xr(s, true, nullptr, sv, t, rw, xk, r);                                // :139-151, :81
     });
     if (rc) return rc;
@@ -524,6 +591,9 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "sptrsv_no_smem")) s->opt_sptrsv_no_smem = (int)value;
     else if (!strcmp(key, "class_tiles_per_cta")) s->opt_class_tiles_per_cta = (int)value;
     else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
+    else if (!strcmp(key, "fuse")) s->opt_fuse = (int)value;
+    else if (!strcmp(key, "resume")) s->opt_resume = (int)value;
+    else if (!strcmp(key, "march_grid")) s->march_grid = std::max(1, (int)value);
     else { set_error("unknown option '%s'", key); return CUDAMAT_E_INVALID; }
     return CUDAMAT_OK;
 }
@@ -597,8 +667,10 @@ int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
     if ((rc = rowclass_analyze(s))) return rc;
     int variant = s->opt_spmv_variant;
     if (variant == CUDAMAT_SPMV_AUTO)
-        variant = (s->cls[1].h_tdict || s->cls[0].h_tdict) ? CUDAMAT_SPMV_TILED : s->cls[1].ncls > 0 ? CUDAMAT_SPMV_CLASS
+        variant = march_available(s) ? CUDAMAT_SPMV_MARCH
+                : (s->cls[1].h_tdict || s->cls[0].h_tdict) ? CUDAMAT_SPMV_TILED : s->cls[1].ncls > 0 ? CUDAMAT_SPMV_CLASS
                 : CUDAMAT_SPMV_ROWLANE;      // PATTERN without the staged windows measured slower than CSR (0.36 vs 0.32 ms): explicit only
+    if (variant == CUDAMAT_SPMV_MARCH && !march_available(s)) variant = CUDAMAT_SPMV_TILED;
     if (variant == CUDAMAT_SPMV_TILED && !s->cls[1].h_tdict && !s->cls[0].h_tdict) variant = CUDAMAT_SPMV_CLASS;
     if (variant == CUDAMAT_SPMV_CLASS && s->cls[1].ncls == 0) variant = CUDAMAT_SPMV_PATTERN;
     if (variant == CUDAMAT_SPMV_PATTERN && s->cls[0].ncls == 0) variant = CUDAMAT_SPMV_ROWLANE;
@@ -618,7 +690,7 @@ int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
         }
         if ((rc = ilu0_analyze_and_factor(s, st))) return rc;
     }
-    s->analyzed = true; s->analyzed_mode = mode;
+    s->analyzed = true; s->analyzed_mode = mode; s->last_mode = -1;
     if (st) { st->spmv_variant = s->spmv_variant; st->kernel_launches = s->launches; }
     return CUDAMAT_OK;
 }
@@ -631,10 +703,10 @@ int cudamat_solve_device(cudamat_solver *s, int mode, const double *d_b, const d
     if (maxit < 0) maxit = 0;
     DeviceGuard dg(s->device);
     const double t0 = now_s();
-    s->ev_used = 0;
+    s->ev_used = 0; s->ev_slot.clear(); s->time_slot = -1;
     int rc;
     if (mode == CUDAMAT_MODE_ILU0) rc = solve_ilu0(s, d_b, d_x, maxit, tol);
-    else rc = solve_unprec(s, d_b, d_x0, d_d, d_x, maxit, tol);
+    else rc = solve_unprec(s, mode, d_b, d_x0, d_d, d_x, maxit, tol);
     if (rc) return rc;
     CM_CUDA(cudaStreamSynchronize(s->stream));
     const double t1 = now_s();
@@ -647,13 +719,20 @@ int cudamat_solve_device(cudamat_solver *s, int mode, const double *d_b, const d
     }
     if (s->opt_debug) print_debug_trace(s, mode);
     if (st) { fill_stats(s, st); st->t_loop = t1 - t0; }
+    if (st) {
+        for (int q = 0; q < 4; ++q) { st->t_kernel[q] = 0.0; st->n_kernel[q] = 0; }
+        st->t_spmv = 0.0; st->n_spmv = 0;
+        st->fused = (mode != CUDAMAT_MODE_ILU0 && s->last_fused) ? 1 : 0;
+    }
     if (st && s->ev_used > 0) {
-        double ms_total = 0.0;
         for (int k = 0; k + 1 < s->ev_used; k += 2) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, s->ev_pool[k], s->ev_pool[k + 1]) == cudaSuccess) ms_total += ms;
+            const int slot = s->ev_slot[(size_t)k / 2];
+            if (slot >= 0 && slot < 4 && cudaEventElapsedTime(&ms, s->ev_pool[k], s->ev_pool[k + 1]) == cudaSuccess) {
+                st->t_kernel[slot] += ms * 1e-3; st->n_kernel[slot] += 1;
+            }
         }
-        st->t_spmv = ms_total * 1e-3; st->n_spmv = s->ev_used / 2;
+        st->t_spmv = st->t_kernel[0] + st->t_kernel[1]; st->n_spmv = st->n_kernel[0] + st->n_kernel[1];
     }
     return CUDAMAT_OK;
 }

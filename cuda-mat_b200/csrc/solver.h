@@ -74,6 +74,22 @@ struct TiledDict {                     // kernel parameter (16.9 KB)
     int sup_len;
     int sup_boff[8];
     double sup_val[8];
+    int sup_off[8];                    // column offsets of the superset pattern (ascending)
+};
+// MARCH variant (march.cu): the superset pattern's offsets split into planes -D / 0 / +D with D a multiple of the tile;
+// a persistent CTA walks a column of tiles plane by plane and keeps three planes of the operand in a shared-memory ring.
+struct MarchPlan {                     // kernel parameter
+    int D;                             // plane stride in rows
+    int H;                             // halo elements on each side of a tile buffer (256 or 512)
+    int S;                             // tiles per plane = D / kTile
+    int P;                             // planes = n / D
+    int buf_elems;                     // kTile + 2 H
+    int len;                           // entries of the superset pattern
+    int shape;                         // 1: (-D, -a, -1, 0, +1, +a, +D) with a even (compile-time planes / alignment), 0: generic
+    int Zc;                            // z-chunks: the grid is Zc x S work items (z-chunk-major), set at launch from the CTA budget
+    int dz[8];                         // -1 / 0 / +1: plane the entry reads
+    int loff[8];                       // offset inside that plane's buffer relative to the row's own position
+    double val[8];
 };
 // Shared-memory form of the TILED dictionary, one record per class, copied by the same TMA transaction as the windows:
 // byte offset of every entry relative to the row's own position in the staged windows (-1 = no entry) and its value.
@@ -143,8 +159,16 @@ struct cudamat_solver {
     bool sptrsv_smem_ready = false;
     int sptrsv_grid = 0;
     std::vector<cudaEvent_t> ev_pool; int ev_used = 0;
+    std::vector<int> ev_slot; int time_slot = -1; bool ev_open = false;   // event-timed kernels (solver.cu ev_mark)
+    int last_fused = 0;
     cudamat::StagedPlan staged;
     cudamat::RowClasses cls[2];            // [0] offsets only (PATTERN), [1] offsets + values (CLASS)
+    cudamat::MarchPlan *march = nullptr;   // MARCH plan (host copy handed to the launches), nullptr = unavailable
+    int march_grid = 296;                  // persistent CTAs of the MARCH kernels (2 per SM)
+    int opt_fuse = 1;                      // 1: fold the p / s updates into the MARCH SpMVs (unpreconditioned loop)
+    int pp = 0;                            // ping-pong parity of the p / v buffers of the fused loop
+    int opt_resume = 0;                    // 1: the next solve continues the previous one (no re-initialisation)
+    int last_mode = -1;                    // mode of the last finished solve (resume)
     // reduction context + scalars
     cudamat::RedCtx rc{};
     double *slots_own = nullptr;           // the allocation behind rc.slots (rc.slots may be redirected by comm)
@@ -190,6 +214,8 @@ struct DeviceGuard {
     DeviceGuard &operator=(const DeviceGuard &) = delete;
 };
 
+int ev_mark(cudamat_solver *s, bool begin);      // solver.cu: event brackets of sampled kernels
+
 // kernels.cu
 int launch_spmv(cudamat_solver *s, const SpmvArgs &a, int variant);
 int launch_init_resid(cudamat_solver *s, const double *b, const double *y, double *r, double *c1, double *c2, int phase);
@@ -205,6 +231,15 @@ int launch_normalize_base(cudaStream_t st, int *ia, int64_t n1, int *ja, int64_t
 int launch_validate_csr(cudaStream_t st, const int *ia, int n, const int *ja, int64_t nnz, int64_t ncols, int *h_bad /*[row, entry out of range, entry out of order] or -1*/);
 int plan_staged(cudamat_solver *s);
 bool pdl_enabled();
+
+// march.cu
+bool march_plan_host(const TiledDict &T, long long n, MarchPlan &M);
+bool march_available(const cudamat_solver *s);
+bool march_spmv_usable(const cudamat_solver *s, const SpmvArgs &a);     // incl. the 16-byte alignment of the operands
+int launch_march_spmv(cudamat_solver *s, const SpmvArgs &a);
+int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old, const double *v_old, double *p_new, double *v_new,
+                        const double *rhat, const double *d, const RedCtx &rc);
+int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc);
 
 // rowclass.cu
 int rowclass_analyze(cudamat_solver *s);

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CUDAMAT_ABI_VERSION 1
+#define CUDAMAT_ABI_VERSION 2
 
 /* status codes */
 #define CUDAMAT_OK              0
@@ -55,6 +55,8 @@ extern "C" {
 #define CUDAMAT_SPMV_PATTERN   3    /* column offsets from a per-row class dictionary (1 B/row), values from CSR */
 #define CUDAMAT_SPMV_CLASS     4    /* offsets AND values from the class dictionary: CSR arrays are not read   */
 #define CUDAMAT_SPMV_TILED     5    /* CLASS + the x windows of a 2048-row tile staged in shared memory by TMA  */
+#define CUDAMAT_SPMV_MARCH     6    /* plane-marching stencil kernel: 3 planes of x in a shared-memory ring, one new tile per step;
+                                       in the unpreconditioned loop the p / s vector updates are folded into it (option "fuse") */
 
 typedef struct cudamat_stats {
     int    iterations;      /* the reference's loop counter i at exit                          */
@@ -78,6 +80,11 @@ typedef struct cudamat_stats {
                                k-th iteration are timed), else 0 */
     int    n_spmv;          /* SpMV launches covered by t_spmv                                  */
     int    graph_replay;    /* 1 iff the iteration loop ran as CUDA-graph replays of poll_every-iteration batches */
+    /* ABI 2: per-kernel event timings of the sampled iterations ("time_spmv"): [0] SpMV 1 (MARCH fused loop: with the
+     * folded p update), [1] SpMV 2 (with the folded s update), [2] x / r update + dots, [3] separate p / s updates */
+    double t_kernel[4];
+    int    n_kernel[4];
+    int    fused;           /* 1 iff the p / s updates ran folded into the SpMV kernels (MARCH)                  */
 } cudamat_stats;
 
 typedef struct cudamat_solver cudamat_solver;   /* opaque per-matrix handle */
@@ -120,7 +127,8 @@ int cudamat_destroy(cudamat_solver *s);
  * launch per level), "sptrsv_no_smem" (1: never use the single-CTA shared-memory sweep), "sptrsv_ctas_per_sm",
  * "ilu0_reorder" (1: multicolour ordering of the preconditioner matrix — few sweep levels, a different ILU(0), opt-in),
  * "host_analysis" (1: ILU0 level analysis on the host, cross-check), "graph" (-1 auto, 0 off, 1 force CUDA-graph replay),
- * "debug", "time_spmv" (k: event-time the SpMVs of every k-th iteration) */
+ * "debug", "time_spmv" (k: event-time the main kernels of every k-th iteration), "fuse" (0: never fold the p / s updates into the
+ * MARCH SpMVs), "resume" (1: the next solve continues the previous one for maxit more iterations), "march_grid" (CTAs) */
 int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value);
 
 /* CSR rows of this shard with GLOBAL column indices (cusparseDcsrmv operand pbicgstab.cu:67).
@@ -170,6 +178,12 @@ int cudamat_tiled_plan_host(int ncls, const int *len, const int *off, const doub
                             int with_vals, int *nseg, int *seg_lo, int *seg_len, int *seg_base, int *disp,
                             unsigned long long *ok_mask, int *sup_len, int *sup_boff, double *sup_val,
                             unsigned char *class_mask, long long *smem_bytes);
+/* Host planner of the MARCH SpMV variant (pure host code; used by cudamat_analyze and exported for the CPU tests).  Input: the
+ * superset pattern of the TILED plan (ascending column offsets, values) and the row count.  *ok = 1 when the offsets split into
+ * planes -D / 0 / +D (D a multiple of the 2048-row tile, n a multiple of D, in-plane offsets within H <= 512): then D, H, tiles
+ * per plane S, planes P and per entry the plane (dz[8] in {-1,0,1}) and in-plane offset (loff[8]).  No reference counterpart. */
+int cudamat_march_plan_host(int sup_len, const int *sup_off, const double *sup_val, long long n, int *ok, int *D, int *H,
+                            int *S, int *P, int *dz, int *loff);
 #define CUDAMAT_UNIQUE_ID_BYTES 128
 int cudamat_comm_unique_id(void *id128);
 int cudamat_comm_init(cudamat_solver *s, const void *id128, int rank, int world);

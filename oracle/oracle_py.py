@@ -253,8 +253,12 @@ def ref_bicg(ia0, ja0, a, b, maxit=2000):
     return x, it.value
 
 
-def ref_omp_threads():
+def ref_omp_threads(set_to=None):
+    """OpenMP threads the reference's BiCG() will use; set_to = n forces omp_set_num_threads(n) first (torchrun exports
+    OMP_NUM_THREADS=1 to its children, which would silently serialise the CPU baseline)."""
     ref_bicg(np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([1.0]), np.array([1.0]), 1)
+    if set_to:
+        _REF_BICG.ref_omp_set_threads(int(set_to))
     return _REF_BICG.ref_omp_threads()
 
 

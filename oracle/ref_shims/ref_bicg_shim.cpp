@@ -18,3 +18,4 @@ extern "C" int ref_bicg(int n, int nz, double *val, int *col, int *rowindex,
     return rc;
 }
 extern "C" int ref_omp_threads(void) { return omp_get_max_threads(); }
+extern "C" void ref_omp_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }

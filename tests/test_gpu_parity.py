@@ -15,7 +15,7 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 2, 3, 4, 5]   # ROWLANE, STAGED, PATTERN, CLASS, TILED (the dictionary variants fall back to ROWLANE when a matrix has no small row-class dictionary)
+VARIANTS = [1, 2, 3, 4, 5, 6]   # ROWLANE, STAGED, PATTERN, CLASS, TILED, MARCH (the dictionary variants fall back when a matrix has no small row-class dictionary / no plane structure)
 
 
 def dev(torch, a, dtype=None):
@@ -98,9 +98,9 @@ def test_spmv_linearity_and_variants_agree_large(cm, torch_cuda):
     cm.gen_xtrue_device(99, 0, n, y.data_ptr())
     ax1, ax2, ay = (torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3))
     st = s.analyze(0)
-    assert st["spmv_variant"] == cm.SPMV_TILED          # a constant-coefficient stencil: class dictionary + staged x windows
+    assert st["spmv_variant"] == cm.SPMV_MARCH          # a constant-coefficient 3-D stencil: class dictionary + plane-marching ring
     s.spmv(x.data_ptr(), ax1.data_ptr(), variant=1)
-    for v in (2, 3, 4, 5):
+    for v in (2, 3, 4, 5, 6):
         s.spmv(x.data_ptr(), ax2.data_ptr(), variant=v)
         torch.cuda.synchronize()
         assert torch.equal(ax1, ax2), v

@@ -127,7 +127,7 @@ def test_abi_exports_every_declared_symbol(cm):
     for name in declared:
         assert hasattr(lib, name), "missing export " + name
     assert sorted(cm.EXPORTS) == declared
-    assert lib.cudamat_abi_version() == 1
+    assert lib.cudamat_abi_version() == 2
 
 
 def test_poisson_nnz_closed_form(cm, O):
