@@ -180,14 +180,15 @@ def kernel_bytes(variant, fused, nloc, nnz_loc):
         mat = 8 * nnz_loc + nloc + 4 * (nloc // 32 + 1)
     else:
         mat = 12 * nnz_loc + 4 * (nloc + 1)
-    if fused:
-        return {0: ("MAKE_P: p'=r+beta(p-omega v); v'=A p'; rhat.v'", mat + 8 * nloc * 6),      # r, p, v, rhat in; p', v' out
-                1: ("MAKE_S: s=r-alpha v; t=A s; t.s, t.t", mat + 8 * nloc * 4),                # r, v in; s, t out
-                2: ("k_update_xr: x, r update + rhat.r, r.r", 56 * nloc)}
-    return {0: ("SpMV 1 + rhat.v", mat + 8 * nloc * 3),                                         # x, rhat in; y out
-            1: ("SpMV 2 + t.s, t.t", mat + 8 * nloc * 2),
-            2: ("k_update_xr: x, r update + rhat.r, r.r", 56 * nloc),
-            3: ("k_update_p / k_update_s (average)", 28 * nloc)}
+    out = {2: ("k_update_xr: x, r update + rhat.r, r.r", 56 * nloc)}
+    out[0] = (("MAKE_P: p'=r+beta(p-omega v); v'=A p'; rhat.v'", mat + 8 * nloc * 6) if fused & 1          # r, p, v, rhat in; p', v' out
+              else ("SpMV 1 + rhat.v", mat + 8 * nloc * 3))                                                 # x, rhat in; y out
+    out[1] = (("MAKE_S: s=r-alpha v; t=A s; t.s, t.t", mat + 8 * nloc * 4) if fused & 2                     # r, v in; s, t out
+              else ("SpMV 2 + t.s, t.t", mat + 8 * nloc * 2))
+    if fused != 3:
+        sep = [b for b, f in ((32 * nloc, 1), (24 * nloc, 2)) if not fused & f]
+        out[3] = ("k_update_p / k_update_s (separate launches: %d per iteration)" % len(sep), sum(sep) // len(sep))
+    return out
 
 
 def run_ours(args):
@@ -227,8 +228,8 @@ def run_ours(args):
             cm.Comm.init(sol, bytes(idbuf.cpu().tolist()), rank, world)
         if variant:
             sol.set_option("spmv_variant", variant)
-        if args.no_fuse:
-            sol.set_option("fuse", 0)
+        if args.fuse >= 0:
+            sol.set_option("fuse", args.fuse)
         return sol, sol.analyze(cm.MODE_PLAIN)
 
     s, sa = new_solver(args.variant)
@@ -314,7 +315,7 @@ def run_ours(args):
             for q in range(4):
                 tk[q] += st["t_kernel"][q]; nk[q] += st["n_kernel"][q]
             launches = st["kernel_launches"]
-            fused = bool(st["fused"])
+            fused = int(st["fused"])
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -334,7 +335,7 @@ def run_ours(args):
         rows = []
         for q, (nm, by) in kb.items():
             if kms[q]:
-                launches_per_it = 2 if q == 3 else 1
+                launches_per_it = (2 - bin(fused & 3).count("1")) if q == 3 else 1
                 rows.append({"slot": q, "kernel": nm, "bytes_per_launch": by, "avg_launch_ms": kms[q], "launches_timed": nk[q],
                              "GBps": by / (kms[q] * 1e-3) / 1e9, "frac": by / (kms[q] * 1e-3) / 1e9 / peak,
                              "share_of_step": launches_per_it * kms[q] / per})
@@ -342,7 +343,7 @@ def run_ours(args):
             return None
         dom = max(rows, key=lambda r: r["share_of_step"])
         its = K / (ms * 1e-3)
-        it_bytes = sum(r["bytes_per_launch"] * (2 if r["slot"] == 3 else 1) for r in rows) + 3 * 16 * (nloc // 32)
+        it_bytes = sum(r["bytes_per_launch"] * ((2 - bin(fused & 3).count("1")) if r["slot"] == 3 else 1) for r in rows) + 3 * 16 * (nloc // 32)
         out = {"bound": "hbm", "kernel": dom["kernel"] + " [" + VNAME.get(variant, "?") + "]",
                "achieved": dom["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"],
                "frac_of_8TBps_datasheet": dom["GBps"] / 8000.0, "traffic": None,
@@ -358,7 +359,7 @@ def run_ours(args):
         if os.path.exists(tp) and N == 256 and world == 1:
             try:
                 tr = json.load(open(tp))
-                key = "fused" if fused else ("variant%d" % variant)
+                key = ("fuse%d" % fused) if fused else ("variant%d" % variant)
                 ent = tr.get(key)
                 if ent:
                     out["traffic"] = ent.get("dominant_kernel_dram_bytes_per_launch")
@@ -400,7 +401,7 @@ def run_ours(args):
         s1, _ = new_solver(1)
         K1 = min(K, 400)
         ms1, kms1, nk1, _, _ = timed_region(s1, K1, args.warmup)
-        r1 = roofline(1, False, ms1, K1, kms1, nk1)
+        r1 = roofline(1, 0, ms1, K1, kms1, nk1)
         roof["csr_kernel"] = {"value": K1 / (ms1 * 1e-3), "unit": UNIT, "steps": K1, "ms_per_step": ms1 / K1,
                               "note": "same timed window with the plain CSR kernel (12 B/entry streamed): SURVEY.md 8d's B_spmv / B_iter apply literally",
                               "spmv": [k for k in (r1["kernels"] if r1 else []) if k["slot"] in (0, 1)],
@@ -477,7 +478,7 @@ def big_grid_run(cm, torch, dist, N, world, rank, stream, barrier, steps=200):
     torch.cuda.empty_cache()
     return {"workload": "poisson3d_%d" % N, "n": n, "nnz": nnz, "steps": st["iterations"], "ms_per_step": ms / max(st["iterations"], 1),
             "iters_per_s": st["iterations"] / (ms * 1e-3), "spmv_variant": sa["spmv_variant"],
-            "fused_updates": bool(st.get("fused", 0)), "n_gpus": world,
+            "fused_updates": int(st.get("fused", 0)), "n_gpus": world,
             "iteration_csr_GBps_per_gpu": bytes_iter(n, nnz) / world * st["iterations"] / (ms * 1e-3) / 1e9,
             "note": "strong scaling of the SAME 512^3 system over the ranks of this run (BASELINE config 5): parallel efficiency = "
                     "iters_per_s(N) / (N * iters_per_s(1)) across the driver's N = 1, 2, 4, 8 lines"}
@@ -738,7 +739,7 @@ def main():
     ap.add_argument("--no-random", action="store_true", help="skip the 50 M-row random matrix extra (BASELINE config 4)")
     ap.add_argument("--random-rows", type=int, default=50_000_000)
     ap.add_argument("--no-512", action="store_true", help="skip the 512^3 extra (BASELINE config 5)")
-    ap.add_argument("--no-fuse", action="store_true", help="keep the p / s updates as separate kernels (A/B against the fused MARCH loop)")
+    ap.add_argument("--fuse", type=int, default=-1, help="MARCH loop: bit 0 folds the p update into SpMV 1, bit 1 the s update into SpMV 2 (-1: library default)")
     ap.add_argument("--no-csr", action="store_true", help="skip the second timed region with the plain CSR SpMV kernel")
     ap.add_argument("--no-converge", action="store_true", help="skip the full solve to 1e-10 (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / ilu0 / mat10000 / cpu extras (profiling runs)")

@@ -59,6 +59,12 @@ __device__ __forceinline__ double lds64(uint32_t ad) { double v; asm volatile("l
 __device__ __forceinline__ double2 lds128(uint32_t ad) {
     double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ad)); return v;
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS): a register-free prefetch into a slot only this thread reads
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t ad, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ad), "d"(v.x), "d"(v.y) : "memory"); }
 
 // SHAPE 1: the 7-entry pattern (-D, -a, -1, 0, +1, +a, +D) with a even — every 7-point grid stencil with an even line
@@ -73,6 +79,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
     constexpr int PAIRS = BUF / 2;
     constexpr int PPT = (PAIRS + kCtaThreads - 1) / kCtaThreads;   // pairs per thread: 3 (H = 256: the last one half populated)
     constexpr int NV = MODE == MARCH_MAKE_P ? 3 : MODE == MARCH_MAKE_S ? 2 : 1;
+    constexpr int DEPTH = 1;                                       // planes in flight ahead of the multiply (2 measured slower: spills)
     extern __shared__ __align__(16) double ring[];                 // 4 slots
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = M.S, P = M.P, Zc = M.Zc, n = a.n;
@@ -83,6 +90,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
     if (MODE == MARCH_MAKE_S) { c2 = -a.sc->alpha; }
     const double *const in[3] = {a.in0, a.in1, a.in2};
     const uint32_t ring_s = smem_addr(ring);
+    const uint32_t side_s = ring_s + 4u * BUF * 8u;                // [u: 2 x 512 x 16 B][d: 2 x 512 x 16 B] thread-private slots
     // byte offset of this thread's first row (of its first row group) inside a ring slot, as seen through every tap
     uint32_t toff[SL];
 #pragma unroll
@@ -155,69 +163,90 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
                 convert(g0, pl & 3, pl >= k0 && pl <= k1, st);
             }
         }
-#pragma unroll 1
-        for (int k = k0; k <= k1; ++k) {
-            const int tile = k * S + col;
-            const int row0 = tile * kTile + warp * 64 + 2 * lane;  // this thread's first row (first row group)
-            // ---- issue: plane k+2 (consumed after the multiply); masks / dot operand / shift of plane k ----
-            double2 st[NV][PPT];
-            const bool pre = k + 2 <= min(k1 + 1, P - 1);
-            const int g2 = ((k + 2) * S + col) * kTile - H;
-            if (pre) issue(g2, st);
-            unsigned mk[2];
-            double2 uu[2], dd[2];
+        // Per-row side inputs of a plane — presence masks, dot operand u, shift d — are fetched one step AHEAD, right after
+        // the previous plane's products are formed: the masks into two registers, u and d with 16-byte asynchronous copies
+        // (cp.async) into shared-memory slots that only the issuing thread reads back, so they cost no registers while
+        // in flight and need no barrier.
+        unsigned mk[2];
+        auto fetch_side = [&](int k) {
+            const int row0 = (k * S + col) * kTile + warp * 64 + 2 * lane;
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
                 const int r0 = row0 + gi * kCtaWarps * 64;
                 mk[gi] = __ldg(reinterpret_cast<const unsigned short *>(a.tmask + r0));
-                if (NDOT >= 1 && !U_RING) uu[gi] = __ldg(reinterpret_cast<const double2 *>(a.u + r0));
-                if (HAS_D) dd[gi] = __ldg(reinterpret_cast<const double2 *>(a.d + r0));
+                if (NDOT >= 1 && !U_RING) cp_async16(side_s + (uint32_t)(gi * kCtaThreads + tid) * 16u, a.u + r0);
+                if (HAS_D) cp_async16(side_s + (uint32_t)((2 + gi) * kCtaThreads + tid) * 16u, a.d + r0);
             }
+            if ((NDOT >= 1 && !U_RING) || HAS_D) cp_async_commit();
+        };
+        fetch_side(k0);
+        // Software pipeline: DEPTH planes ahead of the multiply are in flight in registers (LOAD_X: 2 x 1 vector, MAKE_*: 1 x
+        // 2-3 vectors).  One step = barrier, multiply plane k out of the ring, convert + store plane k+2 into the slot plane
+        // k-2 left, issue the loads of plane k+2+DEPTH into the registers that just became free.
+        const int lim = min(k1 + 1, P - 1);
+        auto step = [&](int k, double2 (&st)[NV][PPT]) {
+            const int tile = k * S + col;
+            const int row0 = tile * kTile + warp * 64 + 2 * lane;  // this thread's first row (first row group)
             __syncthreads();                                       // ring stores of the previous step are visible
             // ---- multiply plane k out of the ring ----
             uint32_t sb[3];                                        // slots of planes k-1, k, k+1 (shared-memory byte addresses)
 #pragma unroll
             for (int d = 0; d < 3; ++d) sb[d] = ring_s + (uint32_t)(((k + d - 1) & 3) * BUF) * 8u;
             constexpr unsigned FULL2 = ((1u << SL) - 1u) * 0x101u;
+            constexpr int GB = kCtaWarps * 64 * 8;                 // byte distance of the warp's second row group
             double2 *yp = reinterpret_cast<double2 *>(a.y + row0);
+            if ((NDOT >= 1 && !U_RING) || HAS_D) cp_async_wait_all();   // this thread's u / d of plane k (issued a step ago)
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
-                constexpr int GB = kCtaWarps * 64 * 8;             // byte distance of the warp's second row group
                 double s0 = 0.0, s1 = 0.0;
-                const unsigned m0 = mk[gi] & 0xffu, m1 = mk[gi] >> 8;
-                auto tap = [&](int t, double &x0, double &x1) {    // the two rows' operand through tap t
-                    uint32_t ad;
-                    bool odd;
-                    if (SHAPE == 1) { ad = sb[t == 0 ? 0 : t == 6 ? 2 : 1] + toff[t] + gi * GB; odd = (t == 2 || t == 4); }
-                    else { ad = sb[M.dz[t] + 1] + toff[t] + gi * GB; odd = true; }
-                    if (odd) { x0 = lds64(ad); x1 = lds64(ad + 8); }
-                    else { const double2 xx = lds128(ad); x0 = xx.x; x1 = xx.y; }
-                };
-                if (__all_sync(0xffffffffu, mk[gi] == FULL2)) {    // interior rows: the whole pattern, no predicates
-                    double x0[SL], x1[SL];
+                double x0[SL], x1[SL];                             // the two rows' operand through every tap
+                double2 xc = make_double2(0.0, 0.0);               // the operand at the rows themselves
+                if (SHAPE == 1) {
+                    // taps (-D, -a, -1, 0, +1, +a, +D): five aligned pairs; the +-1 taps come from the neighbouring lanes
+                    // (the two edge lanes of the warp read theirs)
 #pragma unroll
-                    for (int t = 0; t < SL; ++t) tap(t, x0[t], x1[t]);
-#pragma unroll
-                    for (int t = 0; t < SL; ++t) { s0 = __fma_rn(M.val[t], x0[t], s0); s1 = __fma_rn(M.val[t], x1[t], s1); }
+                    for (int t = 0; t < SL; ++t) {
+                        if (t == 2 || t == 4) continue;
+                        const double2 xx = lds128(sb[t == 0 ? 0 : t == 6 ? 2 : 1] + toff[t] + gi * GB);
+                        x0[t] = xx.x; x1[t] = xx.y;
+                    }
+                    xc = make_double2(x0[3], x1[3]);
+                    double lft = __shfl_up_sync(0xffffffffu, xc.y, 1), rgt = __shfl_down_sync(0xffffffffu, xc.x, 1);
+                    if (lane == 0) lft = lds64(sb[1] + coff + gi * GB - 8);
+                    if (lane == 31) rgt = lds64(sb[1] + coff + gi * GB + 16);
+                    x0[2] = lft; x1[2] = xc.x;
+                    x0[4] = xc.y; x1[4] = rgt;
                 } else {
 #pragma unroll
                     for (int t = 0; t < SL; ++t) {
-                        double x0, x1;
-                        tap(t, x0, x1);
-                        if (m0 & (1u << t)) s0 = __fma_rn(M.val[t], x0, s0);
-                        if (m1 & (1u << t)) s1 = __fma_rn(M.val[t], x1, s1);
+                        const uint32_t ad = sb[M.dz[t] + 1] + toff[t] + gi * GB;
+                        x0[t] = lds64(ad); x1[t] = lds64(ad + 8);
+                    }
+                    if (HAS_D || (NDOT >= 1 && U_RING)) xc = lds128(sb[1] + coff + gi * GB);
+                }
+                if (__all_sync(0xffffffffu, mk[gi] == FULL2)) {    // interior rows: the whole pattern, no predicates
+#pragma unroll
+                    for (int t = 0; t < SL; ++t) { s0 = __fma_rn(M.val[t], x0[t], s0); s1 = __fma_rn(M.val[t], x1[t], s1); }
+                } else {
+                    const unsigned m0 = mk[gi] & 0xffu, m1 = mk[gi] >> 8;
+#pragma unroll
+                    for (int t = 0; t < SL; ++t) {
+                        if (m0 & (1u << t)) s0 = __fma_rn(M.val[t], x0[t], s0);
+                        if (m1 & (1u << t)) s1 = __fma_rn(M.val[t], x1[t], s1);
                     }
                 }
-                double2 xc = make_double2(0.0, 0.0);
-                if (HAS_D || (NDOT >= 1 && U_RING)) xc = lds128(sb[1] + coff + gi * GB);
-                if (HAS_D) { s0 = __dadd_rn(s0, __dmul_rn(dd[gi].x, xc.x)); s1 = __dadd_rn(s1, __dmul_rn(dd[gi].y, xc.y)); }
+                if (HAS_D) {
+                    const double2 dv = lds128(side_s + (uint32_t)((2 + gi) * kCtaThreads + tid) * 16u);
+                    s0 = __dadd_rn(s0, __dmul_rn(dv.x, xc.x)); s1 = __dadd_rn(s1, __dmul_rn(dv.y, xc.y));
+                }
                 yp[gi * kCtaWarps * 32] = make_double2(s0, s1);
                 if constexpr (NDOT >= 1) {
-                    const double2 uv = U_RING ? xc : uu[gi];
-                    // slab sums of (y.u [, y.y]): lane ^ 8, 4, 2, 1 on both row parities, then parity 0 + parity 1
+                    // slab sums of y.u [and y.y] of this row group's two slabs.  Spec tree of a slab (internal.cuh): partner row
+                    // ^ 16, 8, 4, 2, 1 = lane ^ 8, 4, 2, 1 on each row parity, then parity 0 + parity 1.  With two dots the
+                    // first level is PACKED (packed_pair): lanes with bit 3 clear carry y.u, the others y.y.
+                    const double2 uv = U_RING ? xc : lds128(side_s + (uint32_t)(gi * kCtaThreads + tid) * 16u);
                     double e0 = __dmul_rn(s0, uv.x), e1 = __dmul_rn(s1, uv.y);
                     if constexpr (NDOT >= 2) {
-                        // two dots: lanes with bit 3 clear carry dot 0, the others dot 1 (packed first step)
                         e0 = packed_pair(e0, __dmul_rn(s0, s0), 8, lane);
                         e1 = packed_pair(e1, __dmul_rn(s1, s1), 8, lane);
                     } else {
@@ -231,12 +260,21 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
                     }
                     const double z = __dadd_rn(e0, e1);
                     const int slab = tile * kTileSlabs + ((gi * kCtaWarps + warp) << 1) + (lane >> 4);
-                    if ((lane & 15) == 0) __stcg(a.rc.slab_part + slab, z);
-                    if (NDOT >= 2 && (lane & 15) == 8) __stcg(a.rc.slab_part + (size_t)a.rc.slab_stride + slab, z);
+                    if ((lane & 7) == 0 && (NDOT >= 2 || (lane & 8) == 0))
+                        __stcg(a.rc.slab_part + (size_t)(NDOT >= 2 ? ((lane >> 3) & 1) : 0) * a.rc.slab_stride + slab, z);
                 }
+                if (gi == 1 && k < k1) fetch_side(k + 1);
             }
-            // ---- convert + store plane k+2 into the slot plane k-2 left ----
-            if (pre) convert(g2, (k + 2) & 3, k + 2 <= k1, st);
+            if (k + 2 <= lim) convert(((k + 2) * S + col) * kTile - H, (k + 2) & 3, k + 2 <= k1, st);
+            if (k + 2 + DEPTH <= lim) issue(((k + 2 + DEPTH) * S + col) * kTile - H, st);
+        };
+        double2 stA[NV][PPT], stB[DEPTH > 1 ? NV : 1][DEPTH > 1 ? PPT : 1];
+        if (k0 + 2 <= lim) issue(((k0 + 2) * S + col) * kTile - H, stA);
+        if constexpr (DEPTH > 1) { if (k0 + 3 <= lim) issue(((k0 + 3) * S + col) * kTile - H, stB); }
+#pragma unroll 1
+        for (int k = k0; k <= k1; k += DEPTH) {
+            step(k, stA);
+            if constexpr (DEPTH > 1) { if (k + 1 <= k1) step(k + 1, stB); }
         }
     }
 }
@@ -283,10 +321,11 @@ template <int MODE, int NDOT, bool HAS_D, bool U_RING, int SHAPE, int HB>
 static int launch_march_t(cudamat_solver *s, const MarchArgs &a) {
     MarchPlan M = *s->march;
     const void *kern = (const void *)k_spmv_march<MODE, NDOT, HAS_D, U_RING, SHAPE, HB>;
-    const size_t smem = sizeof(double) * 4 * (size_t)(kTile + 2 * HB * 256);
+    const size_t smem = sizeof(double) * 4 * (size_t)(kTile + 2 * HB * 256) +
+                        ((NDOT >= 1 && !U_RING) || HAS_D ? (HAS_D ? 4 : 2) * kCtaThreads * 16 : 0);
     static bool attr_set[64] = {};
     const int dv = s->device & 63;
-    if (!attr_set[dv]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[dv] = true; }
+    if (!attr_set[dv]) { CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set[dv] = true; }
     // z-chunks: as many as the CTA budget allows, but runs of at least 8 planes (each run re-reads 2 extra planes)
     const int G = std::max(1, s->march_grid);
     M.Zc = std::max(1, std::min(G / std::max(1, M.S), std::max(1, M.P / 8)));

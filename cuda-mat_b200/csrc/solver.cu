@@ -354,15 +354,17 @@ static int run_iterations(cudamat_solver *s, int maxit, Iter &&one_iteration, bo
 static int solve_unprec(cudamat_solver *s, int mode, const double *d_b, const double *d_x0, const double *d_d,
                         double *d_x, int maxit, double tol) {
     int rc;
-    const bool fused = s->spmv_variant == CUDAMAT_SPMV_MARCH && march_available(s) && s->opt_fuse != 0 &&
-                       (reinterpret_cast<uintptr_t>(d_d) & 15u) == 0;     // 16-byte pairs (work vectors are 256-byte aligned)
-    const bool resume = s->opt_resume != 0 && s->last_mode == mode && s->last_fused == (fused ? 1 : 0) && s->work != nullptr;
-    if ((rc = ensure_work(s, fused ? 9 : 7))) return rc;
+    // option "fuse": bit 0 folds the p update into SpMV 1 (MAKE_P), bit 1 the s update into SpMV 2 (MAKE_S)
+    const int fuse = (s->spmv_variant == CUDAMAT_SPMV_MARCH && march_available(s) &&
+                      (reinterpret_cast<uintptr_t>(d_d) & 15u) == 0) ? (s->opt_fuse & 3) : 0;   // 16-byte pairs (work vectors are 256-byte aligned)
+    const bool fold_p = (fuse & 1) != 0, fold_s = (fuse & 2) != 0;
+    const bool resume = s->opt_resume != 0 && s->last_mode == mode && s->last_fused == fuse && s->work != nullptr;
+    if ((rc = ensure_work(s, fold_p ? 9 : 7))) return rc;
     // residual history: capped (a caller may pass a huge maxit as "no limit"); hist_push tolerates the overflow
     const int hcap = (int)std::min<int64_t>((int64_t)maxit + 2, kHistCapMax);
     if (!resume && (rc = ensure_hist(s, hcap))) return rc;
     double *r0 = wv(s, 0), *r = wv(s, 1), *v = wv(s, 2), *p = wv(s, 3), *sv = wv(s, 4), *t = wv(s, 5), *xk = wv(s, 6);
-    double *pb[2] = {p, fused ? wv(s, 8) : p}, *vb[2] = {v, fused ? wv(s, 7) : v};
+    double *pb[2] = {p, fold_p ? wv(s, 8) : p}, *vb[2] = {v, fold_p ? wv(s, 7) : v};
     const int var = s->spmv_variant;
     const size_t nb = sizeof(double) * (size_t)s->n;
     if (resume) {
@@ -385,53 +387,48 @@ static int solve_unprec(cudamat_solver *s, int mode, const double *d_b, const do
         if ((rc = launch_init_resid(s, d_b, t, r, r0, nullptr, PH_U_INIT))) return rc;
         if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
     }
-    if (fused) {
-        rc = run_iterations(s, maxit, [&]() -> int {
-            int r2;
-            const bool tm = timed_iteration(s);
-            double *p_old = pb[s->pp], *p_new = pb[s->pp ^ 1], *v_old = vb[s->pp], *v_new = vb[s->pp ^ 1];
+    rc = run_iterations(s, maxit, [&]() -> int {
+        int r2;
+        const bool tm = timed_iteration(s);
+        HaloPush hp;
+        double *p_old = pb[s->pp], *p_new = pb[s->pp ^ (fold_p ? 1 : 0)], *v_old = vb[s->pp], *v_new = vb[s->pp ^ (fold_p ? 1 : 0)];
+        if (fold_p) {
             s->time_slot = tm ? 0 : -1;
             r2 = launch_march_make_p(s, r, p_old, v_old, p_new, v_new, r0, d_d, s->rc);            // :668-689
             s->time_slot = -1;
             if (r2 || (r2 = finish_reduction(s, s->rc, PH_U_A, 1))) return r2;
+        } else {
+            int slot = comm_halo_push(s, p_new, 0, &hp) ? 0 : -1;
+            s->time_slot = tm ? 3 : -1;
+            r2 = launch_update_p(s, false, r, v_old, p_new, &hp);                                   // :668-672 (in place)
+            s->time_slot = -1;
+            if (r2) return r2;
+            if ((r2 = spmv_step(s, p_new, d_d, v_new, r0, 1, PH_U_A, 1, slot, 0))) return r2;       // :675-689
+        }
+        if (fold_s) {
             s->time_slot = tm ? 1 : -1;
             r2 = launch_march_make_s(s, r, v_new, sv, t, d_d, s->rc);                               // :698-710
             s->time_slot = -1;
             if (r2 || (r2 = finish_reduction(s, s->rc, PH_U_B, 2))) return r2;
-            s->time_slot = tm ? 2 : -1;
-            r2 = launch_update_xr(s, false, p_new, sv, t, r0, xk, r);                               // :694-696,714-747
-            s->time_slot = -1;
-            s->pp ^= 1;
-            return r2;
-        }, /*even_batches=*/true);
-    } else {
-        rc = run_iterations(s, maxit, [&]() -> int {
-            int r2;
-            const bool tm = timed_iteration(s);
-            HaloPush hp;
-            int slot = comm_halo_push(s, p, 0, &hp) ? 0 : -1;
+        } else {
+            int slot = comm_halo_push(s, sv, 1, &hp) ? 1 : -1;
             s->time_slot = tm ? 3 : -1;
-            r2 = launch_update_p(s, false, r, v, p, &hp);                                           // :668-672
-            s->time_slot = -1;
-            if (r2) return r2;
-            if ((r2 = spmv_step(s, p, d_d, v, r0, 1, PH_U_A, 1, slot, 0))) return r2;               // :675-689
-            slot = comm_halo_push(s, sv, 1, &hp) ? 1 : -1;
-            s->time_slot = tm ? 3 : -1;
-            r2 = launch_update_s(s, r, v, sv, &hp);                                                 // :698-700
+            r2 = launch_update_s(s, r, v_new, sv, &hp);                                             // :698-700
             s->time_slot = -1;
             if (r2) return r2;
             if ((r2 = spmv_step(s, sv, d_d, t, sv, 2, PH_U_B, 1, slot, 1))) return r2;              // :703-710
-            s->time_slot = tm ? 2 : -1;
-            r2 = launch_update_xr(s, false, p, sv, t, r0, xk, r);                                   // :694-696,714-747
-            s->time_slot = -1;
-            return r2;
-        }, false);
-    }
+        }
+        s->time_slot = tm ? 2 : -1;
+        r2 = launch_update_xr(s, false, p_new, sv, t, r0, xk, r);                                   // :694-696,714-747
+        s->time_slot = -1;
+        if (fold_p) s->pp ^= 1;
+        return r2;
+    }, /*even_batches=*/fold_p);
     if (rc) return rc;
     if ((rc = poll_status(s))) return rc;
     if (s->h_sc->status == ST_COMM_TIMEOUT) { set_error("a peer rank's halo rows or partial sums did not arrive (spin limit reached)"); return CUDAMAT_E_COMM; }
     CM_CUDA(cudaMemcpyAsync(d_x, xk, nb, cudaMemcpyDeviceToDevice, s->stream));
-    s->last_mode = mode; s->last_fused = fused ? 1 : 0;
+    s->last_mode = mode; s->last_fused = fuse;
     return CUDAMAT_OK;
 }
 
@@ -722,7 +719,7 @@ int cudamat_solve_device(cudamat_solver *s, int mode, const double *d_b, const d
     if (st) {
         for (int q = 0; q < 4; ++q) { st->t_kernel[q] = 0.0; st->n_kernel[q] = 0; }
         st->t_spmv = 0.0; st->n_spmv = 0;
-        st->fused = (mode != CUDAMAT_MODE_ILU0 && s->last_fused) ? 1 : 0;
+        st->fused = mode != CUDAMAT_MODE_ILU0 ? s->last_fused : 0;
     }
     if (st && s->ev_used > 0) {
         for (int k = 0; k + 1 < s->ev_used; k += 2) {

@@ -165,7 +165,7 @@ struct cudamat_solver {
     cudamat::RowClasses cls[2];            // [0] offsets only (PATTERN), [1] offsets + values (CLASS)
     cudamat::MarchPlan *march = nullptr;   // MARCH plan (host copy handed to the launches), nullptr = unavailable
     int march_grid = 296;                  // persistent CTAs of the MARCH kernels (2 per SM)
-    int opt_fuse = 1;                      // 1: fold the p / s updates into the MARCH SpMVs (unpreconditioned loop)
+    int opt_fuse = 2;                      // bit 0: fold the p update into MARCH SpMV 1, bit 1: the s update into SpMV 2
     int pp = 0;                            // ping-pong parity of the p / v buffers of the fused loop
     int opt_resume = 0;                    // 1: the next solve continues the previous one (no re-initialisation)
     int last_mode = -1;                    // mode of the last finished solve (resume)

@@ -84,7 +84,7 @@ typedef struct cudamat_stats {
      * folded p update), [1] SpMV 2 (with the folded s update), [2] x / r update + dots, [3] separate p / s updates */
     double t_kernel[4];
     int    n_kernel[4];
-    int    fused;           /* 1 iff the p / s updates ran folded into the SpMV kernels (MARCH)                  */
+    int    fused;           /* bit 0: the p update ran folded into SpMV 1, bit 1: the s update into SpMV 2 (MARCH) */
 } cudamat_stats;
 
 typedef struct cudamat_solver cudamat_solver;   /* opaque per-matrix handle */
@@ -127,8 +127,8 @@ int cudamat_destroy(cudamat_solver *s);
  * launch per level), "sptrsv_no_smem" (1: never use the single-CTA shared-memory sweep), "sptrsv_ctas_per_sm",
  * "ilu0_reorder" (1: multicolour ordering of the preconditioner matrix — few sweep levels, a different ILU(0), opt-in),
  * "host_analysis" (1: ILU0 level analysis on the host, cross-check), "graph" (-1 auto, 0 off, 1 force CUDA-graph replay),
- * "debug", "time_spmv" (k: event-time the main kernels of every k-th iteration), "fuse" (0: never fold the p / s updates into the
- * MARCH SpMVs), "resume" (1: the next solve continues the previous one for maxit more iterations), "march_grid" (CTAs) */
+ * "debug", "time_spmv" (k: event-time the main kernels of every k-th iteration), "fuse" (bit 0: fold the p update into MARCH SpMV 1,
+ * bit 1: the s update into SpMV 2; 0: never), "resume" (1: the next solve continues the previous one for maxit more iterations), "march_grid" (CTAs) */
 int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value);
 
 /* CSR rows of this shard with GLOBAL column indices (cusparseDcsrmv operand pbicgstab.cu:67).

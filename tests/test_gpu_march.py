@@ -51,7 +51,7 @@ def test_march_is_planned_and_spmv_bit_exact(cm, O, torch_cuda, p64):
     s.close()
 
 
-@pytest.mark.parametrize("variant,fuse", [(6, 1), (6, 0), (5, 1), (1, 1)])
+@pytest.mark.parametrize("variant,fuse", [(6, 3), (6, 2), (6, 1), (6, 0), (5, 3), (1, 3)])
 def test_fused_loop_bit_identical_to_oracle(cm, O, torch_cuda, p64, variant, fuse):
     torch = torch_cuda
     ia, ja, a, xt, b = p64
@@ -68,7 +68,7 @@ def test_fused_loop_bit_identical_to_oracle(cm, O, torch_cuda, p64, variant, fus
         st = s.solve(cm.MODE_PLAIN, db.data_ptr(), dx.data_ptr(), maxit=5000, tol=1e-10)
         torch.cuda.synchronize()
         assert st["converged"] and st["iterations"] == so["iterations"]
-        assert st["fused"] == (1 if (variant == 6 and fuse) else 0)
+        assert st["fused"] == (fuse if variant == 6 else 0)
         assert np.array_equal(dx.cpu().numpy(), xo)
         assert np.array_equal(s.history(), so["hist"])
     s.close()
@@ -83,8 +83,19 @@ def test_fused_shifted_loop_bit_identical_to_oracle(cm, O, torch_cuda, p64):
     x0 = rng.standard_normal(n)
     xo, so = O.bicgstab_unprec(ia, ja, a, b, d=d, x0=x0, maxit=5000, tol=1e-10)
     x, dt, st = cm.bicgstab_shifted(a, ia, ja, d, x0, b, maxit=5000, tol=1e-10)
-    assert st["converged"] and st["fused"] == 1 and st["iterations"] == so["iterations"]
+    assert st["converged"] and st["iterations"] == so["iterations"]
     assert np.array_equal(x, xo)
+    # every folding of the updates, with the diagonal shift
+    s = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
+    s.set_csr_host(a, ia, ja)
+    s.analyze(cm.MODE_SHIFTED)
+    db, dd, dx0, dx = _dev(torch, b), _dev(torch, d), _dev(torch, x0), torch.zeros(n, dtype=torch.float64, device="cuda")
+    for fuse in (3, 2, 1, 0):
+        s.set_option("fuse", fuse)
+        st = s.solve(cm.MODE_SHIFTED, db.data_ptr(), dx.data_ptr(), d_x0=dx0.data_ptr(), d_d=dd.data_ptr(), maxit=5000, tol=1e-10)
+        torch.cuda.synchronize()
+        assert st["fused"] == fuse and st["iterations"] == so["iterations"] and np.array_equal(dx.cpu().numpy(), xo), fuse
+    s.close()
 
 
 def test_resume_continues_the_same_iteration_sequence(cm, torch_cuda, p64):
@@ -92,7 +103,7 @@ def test_resume_continues_the_same_iteration_sequence(cm, torch_cuda, p64):
     ia, ja, a, xt, b = p64
     n = len(ia) - 1
     out = []
-    for fuse in (1, 0):
+    for fuse in (3, 0):
         s = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
         s.set_option("fuse", fuse)
         s.set_csr_host(a, ia, ja)
