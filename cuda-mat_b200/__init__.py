@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CUDAMAT_LIB") or os.path.join(_HERE, "libcudamat_b200
 ROOT = os.path.dirname(_HERE)
 
 MODE_PLAIN, MODE_SHIFTED, MODE_ILU0 = 0, 1, 2
-SPMV_AUTO, SPMV_ROWLANE, SPMV_STAGED, SPMV_PATTERN, SPMV_CLASS, SPMV_TILED, SPMV_MARCH = 0, 1, 2, 3, 4, 5, 6
+SPMV_AUTO, SPMV_ROWLANE, SPMV_STAGED, SPMV_PATTERN, SPMV_CLASS, SPMV_TILED, SPMV_MARCH, SPMV_STREAM = 0, 1, 2, 3, 4, 5, 6, 7
 E_NO_DEVICE = -2
 
 c_dp = C.POINTER(C.c_double)

@@ -757,6 +757,7 @@ static int launch_spmv_any(cudamat_solver *s, const SpmvArgs &a, int variant) {
         if (march_spmv_usable(s, a)) return launch_march_spmv(s, a);
         variant = CUDAMAT_SPMV_TILED;
     }
+    if (variant == CUDAMAT_SPMV_STREAM) return launch_stream_spmv(s, a);
     const bool hd = a.d != nullptr;
     switch (a.ndot) {
     case 0: return hd ? launch_spmv_t<true, 0>(s, a, variant) : launch_spmv_t<false, 0>(s, a, variant);

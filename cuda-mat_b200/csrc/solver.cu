@@ -559,6 +559,7 @@ int cudamat_destroy(cudamat_solver *s) {
     comm_release(s);
     ilu0_release(s);
     rowclass_release(s);
+    stream_release(s);
     const double t1 = now_s();
     dev_free(s->own_ia); dev_free(s->own_ja); dev_free(s->own_a);
     dev_free(s->rc.tile_part); dev_free(s->rc.slab_part); dev_free(s->rc.done_cnt);
@@ -588,6 +589,12 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "sptrsv_no_smem")) s->opt_sptrsv_no_smem = (int)value;
     else if (!strcmp(key, "class_tiles_per_cta")) s->opt_class_tiles_per_cta = (int)value;
     else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
+    else if (!strcmp(key, "l2_fetch")) {
+        // device-wide hint: bytes the L2 fetches from DRAM per miss (32 / 64 / 128); random gathers want 32 (see analyze)
+        DeviceGuard dg(s->device);
+        CM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+    }
+    else if (!strcmp(key, "stream_blocks")) { s->opt_stream_blocks = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "fuse")) s->opt_fuse = (int)value;
     else if (!strcmp(key, "resume")) s->opt_resume = (int)value;
     else if (!strcmp(key, "march_grid")) s->march_grid = std::max(1, (int)value);
@@ -667,12 +674,19 @@ int cudamat_analyze(cudamat_solver *s, int mode, cudamat_stats *st) {
         variant = march_available(s) ? CUDAMAT_SPMV_MARCH
                 : (s->cls[1].h_tdict || s->cls[0].h_tdict) ? CUDAMAT_SPMV_TILED : s->cls[1].ncls > 0 ? CUDAMAT_SPMV_CLASS
                 : CUDAMAT_SPMV_ROWLANE;      // PATTERN without the staged windows measured slower than CSR (0.36 vs 0.32 ms): explicit only
+    // Row-length statistics (k_row_stats): the row-per-lane kernel walks every lane of a warp through the longest row of its
+    // 32; when the fullest slab holds much more than 32 x the mean row length, or rows > 32 entries exist (the warp serialises
+    // on them), the entry-parallel STREAM kernel takes over.
+    if (variant == CUDAMAT_SPMV_ROWLANE && s->opt_spmv_variant == CUDAMAT_SPMV_AUTO && s->n > 0 &&
+        (s->n_long_rows > 0 || s->max_row_len > 2.0 * s->mean_row_len + 4.0))
+        variant = CUDAMAT_SPMV_STREAM;
     if (variant == CUDAMAT_SPMV_MARCH && !march_available(s)) variant = CUDAMAT_SPMV_TILED;
     if (variant == CUDAMAT_SPMV_TILED && !s->cls[1].h_tdict && !s->cls[0].h_tdict) variant = CUDAMAT_SPMV_CLASS;
     if (variant == CUDAMAT_SPMV_CLASS && s->cls[1].ncls == 0) variant = CUDAMAT_SPMV_PATTERN;
     if (variant == CUDAMAT_SPMV_PATTERN && s->cls[0].ncls == 0) variant = CUDAMAT_SPMV_ROWLANE;
     if (variant == CUDAMAT_SPMV_STAGED && s->staged.cap_nnz == 0) variant = CUDAMAT_SPMV_ROWLANE;
     s->spmv_variant = variant;
+    if (variant == CUDAMAT_SPMV_STREAM) { if ((rc = stream_plan(s))) return rc; } else stream_release(s);
     if (st) st->t_analysis += now_s() - t0;
     if (mode == CUDAMAT_MODE_ILU0) {
         // borrowed device CSR was never validated: the ILU0 path (diagonal search, L/U split, level analysis, sync-free

@@ -113,6 +113,7 @@ struct RowClasses {
 struct ClassArgs { const unsigned char *cls; int ncls; int tiles_per_cta; };
 
 struct Comm;   // comm.cu
+struct StreamBlocks;   // stream.cu
 constexpr int kWorkVecsShared = 12;    // work vectors of a sharded handle's IPC-shared arena (largest solve mode + spare)
 
 struct LevelSchedule {
@@ -163,6 +164,8 @@ struct cudamat_solver {
     int last_fused = 0;
     cudamat::StagedPlan staged;
     cudamat::RowClasses cls[2];            // [0] offsets only (PATTERN), [1] offsets + values (CLASS)
+    cudamat::StreamBlocks *sblk = nullptr;  // STREAM variant: column-blocked copy (x larger than the L2), nullptr = one pass
+    int opt_stream_blocks = 0;             // 0: automatic (x bytes / 64 MB), 1: never block, K: K column blocks
     cudamat::MarchPlan *march = nullptr;   // MARCH plan (host copy handed to the launches), nullptr = unavailable
     int march_grid = 296;                  // persistent CTAs of the MARCH kernels (2 per SM)
     int opt_fuse = 2;                      // bit 0: fold the p update into MARCH SpMV 1, bit 1: the s update into SpMV 2
@@ -240,6 +243,11 @@ int launch_march_spmv(cudamat_solver *s, const SpmvArgs &a);
 int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old, const double *v_old, double *p_new, double *v_new,
                         const double *rhat, const double *d, const RedCtx &rc);
 int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc);
+
+// stream.cu
+int launch_stream_spmv(cudamat_solver *s, const SpmvArgs &a);
+int stream_plan(cudamat_solver *s);         // column-blocked copy of an irregular matrix whose x does not fit the L2
+void stream_release(cudamat_solver *s);
 
 // rowclass.cu
 int rowclass_analyze(cudamat_solver *s);

@@ -57,6 +57,8 @@ extern "C" {
 #define CUDAMAT_SPMV_TILED     5    /* CLASS + the x windows of a 2048-row tile staged in shared memory by TMA  */
 #define CUDAMAT_SPMV_MARCH     6    /* plane-marching stencil kernel: 3 planes of x in a shared-memory ring, one new tile per step;
                                        in the unpreconditioned loop the p / s vector updates are folded into it (option "fuse") */
+#define CUDAMAT_SPMV_STREAM    7    /* irregular rows: (col, val) streamed and x gathered entry-parallel per warp chunk, row
+                                       chains out of shared memory (chosen from the row-length statistics)                   */
 
 typedef struct cudamat_stats {
     int    iterations;      /* the reference's loop counter i at exit                          */

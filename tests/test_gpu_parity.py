@@ -15,7 +15,7 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 2, 3, 4, 5, 6]   # ROWLANE, STAGED, PATTERN, CLASS, TILED, MARCH (the dictionary variants fall back when a matrix has no small row-class dictionary / no plane structure)
+VARIANTS = [1, 2, 3, 4, 5, 6, 7]   # ROWLANE, STAGED, PATTERN, CLASS, TILED, MARCH, STREAM (the dictionary variants fall back when a matrix has no small row-class dictionary / no plane structure)
 
 
 def dev(torch, a, dtype=None):
@@ -100,7 +100,7 @@ def test_spmv_linearity_and_variants_agree_large(cm, torch_cuda):
     st = s.analyze(0)
     assert st["spmv_variant"] == cm.SPMV_MARCH          # a constant-coefficient 3-D stencil: class dictionary + plane-marching ring
     s.spmv(x.data_ptr(), ax1.data_ptr(), variant=1)
-    for v in (2, 3, 4, 5, 6):
+    for v in (2, 3, 4, 5, 6, 7):
         s.spmv(x.data_ptr(), ax2.data_ptr(), variant=v)
         torch.cuda.synchronize()
         assert torch.equal(ax1, ax2), v
@@ -532,4 +532,55 @@ def test_full_size_properties_poisson128(cm, torch_cuda):
     st = s.solve(2, b.data_ptr(), x.data_ptr(), maxit=5000, tol=1e-10)
     assert st["converged"] and st["iterations"] < results[0][0]
     assert float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt)) <= 1e-5
+    s.close()
+
+
+def test_row_statistics_pick_the_stream_kernel_for_irregular_rows(cm, O, torch_cuda):
+    """north_star: SpMV variants chosen by row-length statistics.  generator.cpp-style random rows (90 / 9 / 1 % mixture, rows of
+    > 32 and > 64 entries) -> STREAM; a regular non-stencil matrix (every row 6 random columns) -> ROWLANE.  Both bit-identical to
+    the oracle, and the full solve on the irregular matrix equals the oracle's bit for bit."""
+    torch = torch_cuda
+    ia, ja, a = O.random_dd(20000, 20240)
+    n = len(ia) - 1
+    s, st = make_solver(cm, torch, ia, ja, a)
+    assert st["spmv_variant"] == cm.SPMV_STREAM, st
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(n)
+    dx, dy = dev(torch, x), torch.zeros(n, dtype=torch.float64, device="cuda")
+    s.spmv(dx.data_ptr(), dy.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(dy.cpu().numpy(), O.spmv(ia, ja, a, x))
+    xt = O.xtrue(7, 0, n)
+    b = O.spmv(ia, ja, a, xt)
+    xo, so = O.bicgstab_unprec(ia, ja, a, b, maxit=2000, tol=1e-10)
+    db, dxs = dev(torch, b), torch.zeros(n, dtype=torch.float64, device="cuda")
+    r = s.solve(0, db.data_ptr(), dxs.data_ptr(), maxit=2000, tol=1e-10)
+    torch.cuda.synchronize()
+    assert r["converged"] and r["iterations"] == so["iterations"] and np.array_equal(dxs.cpu().numpy(), xo)
+    s.close()
+    # column-blocked form of the same kernel (what a matrix whose x does not fit the L2 gets): K launches, the row chains carried
+    # through y, rows of > 32 entries by the warp-per-row kernel - still the oracle's bits, with and without the diagonal shift
+    for K in (2, 5):
+        s = cm.Solver(n)
+        s.set_option("stream_blocks", K)
+        s.set_csr_host(a, ia, ja)
+        assert s.analyze(0)["spmv_variant"] == cm.SPMV_STREAM
+        for use_d in (False, True):
+            d = rng.standard_normal(n) if use_d else None
+            dd = dev(torch, d) if use_d else None
+            dy.zero_()
+            s.spmv(dx.data_ptr(), dy.data_ptr(), dd.data_ptr() if use_d else None)
+            torch.cuda.synchronize()
+            assert np.array_equal(dy.cpu().numpy(), O.spmv(ia, ja, a, x, d=d)), (K, use_d)
+        r = s.solve(0, db.data_ptr(), dxs.data_ptr(), maxit=2000, tol=1e-10)
+        torch.cuda.synchronize()
+        assert r["converged"] and r["iterations"] == so["iterations"] and np.array_equal(dxs.cpu().numpy(), xo), K
+        s.close()
+    # regular rows, irregular columns
+    import scipy.sparse as sp
+    m = 4096
+    cols = np.sort(np.stack([rng.choice(m, 6, replace=False) for _ in range(m)]), axis=1)
+    R = sp.csr_matrix((rng.standard_normal(6 * m), cols.ravel(), np.arange(0, 6 * m + 1, 6)), shape=(m, m))
+    s, st = make_solver(cm, torch, R.indptr.astype(np.int32), R.indices.astype(np.int32), R.data)
+    assert st["spmv_variant"] == cm.SPMV_ROWLANE, st
     s.close()
