@@ -230,6 +230,8 @@ def run_ours(args):
             sol.set_option("spmv_variant", variant)
         if args.fuse >= 0:
             sol.set_option("fuse", args.fuse)
+        if args.persist >= -1:
+            sol.set_option("persist", args.persist)
         return sol, sol.analyze(cm.MODE_PLAIN)
 
     s, sa = new_solver(args.variant)
@@ -340,7 +342,11 @@ def run_ours(args):
                              "GBps": by / (kms[q] * 1e-3) / 1e9, "frac": by / (kms[q] * 1e-3) / 1e9 / peak,
                              "share_of_step": launches_per_it * kms[q] / per})
         if not rows:
-            return None
+            # persistent cooperative iteration kernel (small shards): the whole iteration is ONE kernel, timed as ms / K
+            by = sum(v[1] * (2 if q == 3 else 1) for q, v in kernel_bytes(variant, 0, nloc, nnz_loc).items())
+            rows = [{"slot": -1, "kernel": "k_bicgstab_persist: whole iteration (p, SpMV 1, s, SpMV 2, x/r update, 3 reductions) in one cooperative kernel",
+                     "bytes_per_launch": by, "avg_launch_ms": per, "launches_timed": K, "GBps": by / (per * 1e-3) / 1e9,
+                     "frac": by / (per * 1e-3) / 1e9 / peak, "share_of_step": 1.0}]
         dom = max(rows, key=lambda r: r["share_of_step"])
         its = K / (ms * 1e-3)
         it_bytes = sum(r["bytes_per_launch"] * ((2 - bin(fused & 3).count("1")) if r["slot"] == 3 else 1) for r in rows) + 3 * 16 * (nloc // 32)
@@ -739,6 +745,7 @@ def main():
     ap.add_argument("--no-random", action="store_true", help="skip the 50 M-row random matrix extra (BASELINE config 4)")
     ap.add_argument("--random-rows", type=int, default=50_000_000)
     ap.add_argument("--no-512", action="store_true", help="skip the 512^3 extra (BASELINE config 5)")
+    ap.add_argument("--persist", type=int, default=-2, help="persistent cooperative iteration kernel: -1 auto, 0 off, 1 force (-2: library default)")
     ap.add_argument("--fuse", type=int, default=-1, help="MARCH loop: bit 0 folds the p update into SpMV 1, bit 1 the s update into SpMV 2 (-1: library default)")
     ap.add_argument("--no-csr", action="store_true", help="skip the second timed region with the plain CSR SpMV kernel")
     ap.add_argument("--no-converge", action="store_true", help="skip the full solve to 1e-10 (profiling runs)")

@@ -333,6 +333,19 @@ static int p2p_setup(cudamat_solver *s, const std::vector<int> &W) {
     return CUDAMAT_OK;
 }
 
+void comm_epochs_get(const cudamat_solver *s, unsigned long long e[3]) {
+    e[0] = e[1] = e[2] = 0;
+    if (!comm_p2p(s)) return;
+    const P2P &P = s->comm->p2p;
+    e[0] = P.halo_epoch[0]; e[1] = P.halo_epoch[1]; e[2] = P.red_epoch;
+}
+void comm_epochs_set(cudamat_solver *s, const unsigned long long e[3]) {
+    if (!comm_p2p(s)) return;
+    P2P &P = s->comm->p2p;
+    P.halo_epoch[0] = e[0]; P.halo_epoch[1] = e[1]; P.red_epoch = e[2];
+}
+const unsigned long long *comm_red_flags(const cudamat_solver *s) { return comm_p2p(s) ? s->comm->p2p.flags : nullptr; }
+
 void comm_release(cudamat_solver *s) {
     Comm *c = s->comm;
     if (!c) return;

@@ -355,7 +355,8 @@ static int solve_unprec(cudamat_solver *s, int mode, const double *d_b, const do
                         double *d_x, int maxit, double tol) {
     int rc;
     // option "fuse": bit 0 folds the p update into SpMV 1 (MAKE_P), bit 1 the s update into SpMV 2 (MAKE_S)
-    const int fuse = (s->spmv_variant == CUDAMAT_SPMV_MARCH && march_available(s) &&
+    const bool persist = persist_eligible(s);                      // one cooperative kernel per batch of iterations (persist.cu)
+    const int fuse = persist ? 4 : (s->spmv_variant == CUDAMAT_SPMV_MARCH && march_available(s) &&
                       (reinterpret_cast<uintptr_t>(d_d) & 15u) == 0) ? (s->opt_fuse & 3) : 0;   // 16-byte pairs (work vectors are 256-byte aligned)
     const bool fold_p = (fuse & 1) != 0, fold_s = (fuse & 2) != 0;
     const bool resume = s->opt_resume != 0 && s->last_mode == mode && s->last_fused == fuse && s->work != nullptr;
@@ -387,6 +388,40 @@ static int solve_unprec(cudamat_solver *s, int mode, const double *d_b, const do
         if ((rc = launch_init_resid(s, d_b, t, r, r0, nullptr, PH_U_INIT))) return rc;
         if (maxit <= 0) CM_CUDA(cudaMemsetAsync(xk, 0, nb, s->stream));                 // x stays zero-filled (:1003)
     }
+    if (persist) {
+        unsigned long long e0[3];
+        comm_epochs_get(s, e0);
+        const int iter0 = resume ? s->h_sc->iter : 0;
+        const int batch = std::max(1, s->opt_poll_every);
+        int it = 0, npoll = 0;
+        bool stop = false;
+        s->graph_used = false;
+        while (!stop && it < maxit) {
+            const int m = std::min(batch, maxit - it);
+            PersistLaunch L{};
+            L.r0 = r0; L.r = r; L.v = v; L.p = p; L.sv = sv; L.t = t; L.x = xk; L.d = d_d; L.iters = m;
+            L.rc = s->rc;
+            if (comm_p2p(s)) {
+                unsigned long long e[3];
+                comm_halo_push(s, p, 0, &L.hp_p);  comm_halo_wait(s, 0, &L.hw_p);      // epochs of the batch's first iteration
+                comm_halo_push(s, sv, 1, &L.hp_s); comm_halo_wait(s, 1, &L.hw_s);
+                comm_begin_reduction(s, L.rc);
+                comm_epochs_get(s, e);
+                e[0] += (unsigned long long)(m - 1); e[1] += (unsigned long long)(m - 1); e[2] += 3ull * m - 1ull;
+                comm_epochs_set(s, e);
+                L.red_flags = comm_red_flags(s);
+            }
+            if ((rc = launch_persist(s, L))) return rc;
+            it += m;
+            if ((rc = poll_step(s, it, maxit, &npoll, &stop))) return rc;
+        }
+        if ((rc = poll_status(s))) return rc;
+        // a batch that stopped early (converged / break-down) consumed fewer epochs than the host assumed
+        const unsigned long long done = (unsigned long long)std::max(0, s->h_sc->iter - iter0);
+        const unsigned long long e1[3] = {e0[0] + done, e0[1] + done, e0[2] + 3ull * done};
+        comm_epochs_set(s, e1);
+        rc = CUDAMAT_OK;
+    } else
     rc = run_iterations(s, maxit, [&]() -> int {
         int r2;
         const bool tm = timed_iteration(s);
@@ -594,6 +629,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
         DeviceGuard dg(s->device);
         CM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
     }
+    else if (!strcmp(key, "persist")) s->opt_persist = (int)value;
     else if (!strcmp(key, "stream_blocks")) { s->opt_stream_blocks = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "fuse")) s->opt_fuse = (int)value;
     else if (!strcmp(key, "resume")) s->opt_resume = (int)value;

@@ -165,6 +165,8 @@ struct cudamat_solver {
     cudamat::StagedPlan staged;
     cudamat::RowClasses cls[2];            // [0] offsets only (PATTERN), [1] offsets + values (CLASS)
     cudamat::StreamBlocks *sblk = nullptr;  // STREAM variant: column-blocked copy (x larger than the L2), nullptr = one pass
+    int opt_persist = -1;                  // persistent cooperative iteration kernel: -1 auto (small systems / shards), 0 off, 1 force
+    int persist_grid = 0;
     int opt_stream_blocks = 0;             // 0: automatic (x bytes / 64 MB), 1: never block, K: K column blocks
     cudamat::MarchPlan *march = nullptr;   // MARCH plan (host copy handed to the launches), nullptr = unavailable
     int march_grid = 296;                  // persistent CTAs of the MARCH kernels (2 per SM)
@@ -244,6 +246,14 @@ int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old,
                         const double *rhat, const double *d, const RedCtx &rc);
 int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc);
 
+// persist.cu: the unpreconditioned iteration as one persistent cooperative kernel per batch of iterations
+struct PersistLaunch {
+    double *r0, *r, *v, *p, *sv, *t, *x; const double *d;
+    RedCtx rc; HaloPush hp_p, hp_s; HaloWait hw_p, hw_s; const unsigned long long *red_flags; int iters;
+};
+bool persist_eligible(const cudamat_solver *s);
+int launch_persist(cudamat_solver *s, const PersistLaunch &L);
+
 // stream.cu
 int launch_stream_spmv(cudamat_solver *s, const SpmvArgs &a);
 int stream_plan(cudamat_solver *s);         // column-blocked copy of an irregular matrix whose x does not fit the L2
@@ -271,6 +281,11 @@ bool comm_halo_push(cudamat_solver *s, double *vec, int slot, HaloPush *hp);   /
 void comm_halo_wait(cudamat_solver *s, int slot, HaloWait *hw);    // fills hw for the SpMV that reads the pushed vector
 int ensure_work(cudamat_solver *s, int nvec);
 void comm_release(cudamat_solver *s);
+// epochs of the peer-memory path {halo slot 0, halo slot 1, reduction}: the persistent kernel consumes one halo epoch per
+// slot and three reduction epochs per iteration on the device; the host keeps its counters in step
+void comm_epochs_get(const cudamat_solver *s, unsigned long long e[3]);
+void comm_epochs_set(cudamat_solver *s, const unsigned long long e[3]);
+const unsigned long long *comm_red_flags(const cudamat_solver *s);
 
 // generators (kernels.cu)
 int gen_poisson3d(int N, int64_t row0, int64_t row1, int *d_ia, int *d_ja, double *d_a, cudaStream_t st);

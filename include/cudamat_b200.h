@@ -86,7 +86,8 @@ typedef struct cudamat_stats {
      * folded p update), [1] SpMV 2 (with the folded s update), [2] x / r update + dots, [3] separate p / s updates */
     double t_kernel[4];
     int    n_kernel[4];
-    int    fused;           /* bit 0: the p update ran folded into SpMV 1, bit 1: the s update into SpMV 2 (MARCH) */
+    int    fused;           /* bit 0: the p update ran folded into SpMV 1, bit 1: the s update into SpMV 2 (MARCH);
+                               4: the whole iteration ran inside the persistent cooperative kernel           */
 } cudamat_stats;
 
 typedef struct cudamat_solver cudamat_solver;   /* opaque per-matrix handle */
@@ -130,7 +131,9 @@ int cudamat_destroy(cudamat_solver *s);
  * "ilu0_reorder" (1: multicolour ordering of the preconditioner matrix — few sweep levels, a different ILU(0), opt-in),
  * "host_analysis" (1: ILU0 level analysis on the host, cross-check), "graph" (-1 auto, 0 off, 1 force CUDA-graph replay),
  * "debug", "time_spmv" (k: event-time the main kernels of every k-th iteration), "fuse" (bit 0: fold the p update into MARCH SpMV 1,
- * bit 1: the s update into SpMV 2; 0: never), "resume" (1: the next solve continues the previous one for maxit more iterations), "march_grid" (CTAs) */
+ * bit 1: the s update into SpMV 2; 0: never), "resume" (1: the next solve continues the previous one for maxit more iterations), "march_grid" (CTAs), "stream_blocks" (column
+ * blocks of the STREAM variant: 0 auto, 1 never), "persist" (unpreconditioned loop as one persistent cooperative kernel per batch of
+ * poll_every iterations: -1 auto = small systems / shards, 0 off, 1 force) */
 int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value);
 
 /* CSR rows of this shard with GLOBAL column indices (cusparseDcsrmv operand pbicgstab.cu:67).

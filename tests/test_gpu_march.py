@@ -60,6 +60,7 @@ def test_fused_loop_bit_identical_to_oracle(cm, O, torch_cuda, p64, variant, fus
     s = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
     s.set_option("spmv_variant", variant)
     s.set_option("fuse", fuse)
+    s.set_option("persist", 0)                                 # the per-kernel loop (a 64^3 system would take the persistent kernel)
     s.set_csr_host(a, ia, ja)
     s.analyze(cm.MODE_PLAIN)
     db, dx = _dev(torch, b), torch.zeros(n, dtype=torch.float64, device="cuda")
@@ -87,6 +88,7 @@ def test_fused_shifted_loop_bit_identical_to_oracle(cm, O, torch_cuda, p64):
     assert np.array_equal(x, xo)
     # every folding of the updates, with the diagonal shift
     s = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
+    s.set_option("persist", 0)
     s.set_csr_host(a, ia, ja)
     s.analyze(cm.MODE_SHIFTED)
     db, dd, dx0, dx = _dev(torch, b), _dev(torch, d), _dev(torch, x0), torch.zeros(n, dtype=torch.float64, device="cuda")
@@ -106,6 +108,7 @@ def test_resume_continues_the_same_iteration_sequence(cm, torch_cuda, p64):
     for fuse in (3, 0):
         s = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
         s.set_option("fuse", fuse)
+        s.set_option("persist", 0)
         s.set_csr_host(a, ia, ja)
         s.analyze(cm.MODE_PLAIN)
         db, dx = _dev(torch, b), torch.zeros(n, dtype=torch.float64, device="cuda")
