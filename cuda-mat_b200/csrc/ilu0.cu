@@ -280,6 +280,7 @@ static int sweep_mode(const cudamat_solver *s) {
 }
 int sptrsv_arm(cudamat_solver *s, double *vec) {
     if (s->n <= 0) return CUDAMAT_OK;
+    if (sweepblk_active(s)) return CUDAMAT_OK;                 // block-wavefront sweeps signal through per-block flags
     if (sweep_mode(s) != 2) return CUDAMAT_OK;                 // only the sync-free sweep needs the sentinel
     int grid = (s->n + 1023) / 1024;
     if (grid > 148 * 16) grid = 148 * 16;
@@ -511,6 +512,7 @@ static int build_schedule(cudamat_solver *s, const std::vector<int> &level, int 
 }
 
 void ilu0_release(cudamat_solver *s) {
+    sweepblk_release(s);
     if (s->d_M) cudaFree(s->d_M);
     if (s->d_diag) cudaFree(s->d_diag);
     for (LevelSchedule *P : {&s->lvl_l, &s->lvl_u}) {
@@ -793,6 +795,8 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     }
     CM_CUDA(cudaGetLastError());
     CM_CUDA(cudaStreamSynchronize(s->stream));
+    // 7-point grid stencils (structure found by the MARCH analysis): block-wavefront sweeps
+    if ((rc = sweepblk_plan(s))) return rc;
     if (st) { st->t_ilu0 += now_s() - t0; st->zero_pivot = s->zero_pivot; }
     return CUDAMAT_OK;
 }
@@ -800,6 +804,7 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
 // With the sync-free schedule `out` must be armed (all sentinel) on entry.
 int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out) {
     if (!s->d_M) { set_error("sptrsv: ILU0 factor not available (call cudamat_analyze with CUDAMAT_MODE_ILU0)"); return CUDAMAT_E_STATE; }
+    if (sweepblk_active(s) && rhs != out) return launch_sptrsv_blocked(s, upper, rhs, out);
     const LevelSchedule &L = upper ? s->lvl_u : s->lvl_l;
     const int *status = s->d_sc ? &s->d_sc->status : nullptr;
     const size_t smem_y = sizeof(double) * (size_t)s->n;

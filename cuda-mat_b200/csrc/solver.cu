@@ -630,6 +630,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
         CM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
     }
     else if (!strcmp(key, "persist")) s->opt_persist = (int)value;
+    else if (!strcmp(key, "sptrsv_blocked")) { s->opt_sptrsv_blocked = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "stream_blocks")) { s->opt_stream_blocks = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "fuse")) s->opt_fuse = (int)value;
     else if (!strcmp(key, "resume")) s->opt_resume = (int)value;

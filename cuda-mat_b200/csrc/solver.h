@@ -114,6 +114,7 @@ struct ClassArgs { const unsigned char *cls; int ncls; int tiles_per_cta; };
 
 struct Comm;   // comm.cu
 struct StreamBlocks;   // stream.cu
+struct BlockSweep;     // sweepblk.cu
 constexpr int kWorkVecsShared = 12;    // work vectors of a sharded handle's IPC-shared arena (largest solve mode + spare)
 
 struct LevelSchedule {
@@ -164,6 +165,8 @@ struct cudamat_solver {
     int last_fused = 0;
     cudamat::StagedPlan staged;
     cudamat::RowClasses cls[2];            // [0] offsets only (PATTERN), [1] offsets + values (CLASS)
+    cudamat::BlockSweep *bsweep = nullptr;  // block-wavefront ILU0 sweeps (7-point grids), nullptr = generic sweeps
+    int opt_sptrsv_blocked = 1;
     cudamat::StreamBlocks *sblk = nullptr;  // STREAM variant: column-blocked copy (x larger than the L2), nullptr = one pass
     int opt_persist = -1;                  // persistent cooperative iteration kernel: -1 auto (small systems / shards), 0 off, 1 force
     int persist_grid = 0;
@@ -245,6 +248,12 @@ int launch_march_spmv(cudamat_solver *s, const SpmvArgs &a);
 int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old, const double *v_old, double *p_new, double *v_new,
                         const double *rhat, const double *d, const RedCtx &rc);
 int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc);
+
+// sweepblk.cu: block-wavefront triangular sweeps for ILU0 factors of 7-point grid stencils
+int sweepblk_plan(cudamat_solver *s);
+void sweepblk_release(cudamat_solver *s);
+bool sweepblk_active(const cudamat_solver *s);
+int launch_sptrsv_blocked(cudamat_solver *s, bool upper, const double *rhs, double *out);
 
 // persist.cu: the unpreconditioned iteration as one persistent cooperative kernel per batch of iterations
 struct PersistLaunch {

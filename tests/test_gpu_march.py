@@ -164,3 +164,35 @@ def test_oracle_digest_at_metric_sizes(cm, torch_cuda, N, mode):
     assert _sha(s.history()) == dg["hist_sha256"]
     assert _sha(x.cpu().numpy()) == dg["x_sha256"]
     s.close()
+
+
+def test_block_wavefront_sweeps_bit_identical(cm, O, torch_cuda, p64):
+    """ILU0 sweeps of a 7-point grid factor: the block-wavefront kernel (csrc/sweepblk.cu: 16^3 blocks, levels inside a block in
+    shared memory) against the oracle's sweeps and against the generic sync-free kernel, L and U; then the whole ILU0 solve."""
+    torch = torch_cuda
+    ia, ja, a, xt, b = p64
+    n = len(ia) - 1
+    Mo, _ = O.ilu0(ia, ja, a)
+    rng = np.random.default_rng(21)
+    rhs = rng.standard_normal(n)
+    want = {0: O.sptrsv_lower_unit(ia, ja, Mo, rhs), 1: O.sptrsv_upper(ia, ja, Mo, rhs)}
+    xo, so = O.bicgstab_ilu0(ia, ja, a, b, maxit=2000, tol=1e-10)
+    for blocked in (1, 0):
+        s = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
+        s.set_option("sptrsv_blocked", blocked)
+        s.set_csr_host(a, ia, ja)
+        s.analyze(cm.MODE_ILU0)
+        assert np.array_equal(s.ilu0_values(len(a)), Mo)
+        drhs = _dev(torch, rhs)
+        for upper in (0, 1):
+            out = torch.zeros(n, dtype=torch.float64, device="cuda")
+            s.sptrsv(upper, drhs.data_ptr(), out.data_ptr())
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), want[upper]), (blocked, upper)
+        db, dx = _dev(torch, b), torch.zeros(n, dtype=torch.float64, device="cuda")
+        st = s.solve(cm.MODE_ILU0, db.data_ptr(), dx.data_ptr(), maxit=2000, tol=1e-10)
+        torch.cuda.synchronize()
+        assert st["converged"] and st["iterations"] == so["iterations"] and np.array_equal(dx.cpu().numpy(), xo), blocked
+        assert np.array_equal(s.history(), so["hist"])
+        print("ILU0 64^3 blocked=%d: %d iterations, loop %.2f ms" % (blocked, st["iterations"], st["t_loop"] * 1e3))
+        s.close()

@@ -11,6 +11,7 @@ def main():
     ap.add_argument("--grids", default="64,128,256")
     ap.add_argument("--ctas", default="0")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--blocked", default="1,0", help="block-wavefront sweeps (csrc/sweepblk.cu) on / off")
     ap.add_argument("--levels", action="store_true", help="also time the level-per-launch schedule")
     args = ap.parse_args()
     import torch
@@ -26,9 +27,11 @@ def main():
         rhs = torch.empty(n, **f64)
         cm.gen_xtrue_device(7, 0, n, rhs.data_ptr())
         out = torch.zeros(n, **f64)
-        for ctas in [int(v) for v in args.ctas.split(",")]:
+        for blocked in [int(v) for v in args.blocked.split(",")]:
+          for ctas in [int(v) for v in args.ctas.split(",")]:
             for syncfree in ([1, 0] if args.levels else [1]):
                 s = cm.Solver(n)
+                s.set_option("sptrsv_blocked", blocked)
                 s.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr())
                 sa = s.analyze(cm.MODE_ILU0)
                 s.set_option("sptrsv_syncfree", syncfree)
@@ -57,7 +60,7 @@ def main():
                     torch.cuda.synchronize()
                     tl_ += e0.elapsed_time(e1); tu_ += e1.elapsed_time(e2)
                 res["chainL"], res["chainU"] = tl_ / args.reps, tu_ / args.reps
-                print(json.dumps({"grid": N, "chain_L_ms": round(res["chainL"], 4), "chain_U_ms": round(res["chainU"], 4), "levels": sa["levels_l"], "syncfree": syncfree, "ctas_per_sm": ctas,
+                print(json.dumps({"grid": N, "blocked": blocked, "chain_L_ms": round(res["chainL"], 4), "chain_U_ms": round(res["chainU"], 4), "levels": sa["levels_l"], "syncfree": syncfree, "ctas_per_sm": ctas,
                                   "L_ms": round(res["L"], 4), "U_ms": round(res["U"], 4),
                                   "us_per_level": round(res["L"] * 1e3 / sa["levels_l"], 3),
                                   "ns_per_row": round(res["L"] * 1e6 / n, 3), "t_analysis_s": round(sa["t_analysis"], 3)}))
