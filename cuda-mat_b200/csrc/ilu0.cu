@@ -8,7 +8,9 @@
 // U sweep the same over ascending upper columns, then one IEEE division by the diagonal.
 // The parallel schedule (levels / sync-free flags) never changes the per-row operation order.
 #include "solver.h"
+#include "rowfuncs.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace cudamat {
@@ -265,19 +267,244 @@ __global__ void __launch_bounds__(kSmemSweepThreads) k_sptrsv_smem(const int *or
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Small systems, variant RING: the level-to-level chain of k_sptrsv_smem is ~490 cycles per level — a 32-warp barrier and,
+// every 8 levels, a stall on the operand prefetch (the loads' consumers sit in the same in-order warps as the chain).  Here
+// the CTA is split by role: ONE group of 128 threads walks the levels with a 4-warp named barrier, seven loader groups stream
+// the plan (columns, factor values, diagonal and the reciprocal half of its division, rhs[order[t]]) into a ring of
+// shared-memory slots of 128 rows, two mbarriers per slot (full / empty).  The walker's chain per level: full-wait -> slot row
+// from shared memory -> y[c] from shared memory -> <= 4 dependent DFMA (-> division) -> y[i] -> barrier.  Levels wider than 128
+// rows are consecutive slots with the barrier only after the last.  Same per-row operation order as every other sweep.
+// ------------------------------------------------------------------------------------------
+#ifndef CUDAMAT_RING_LOADERS
+#define CUDAMAT_RING_LOADERS 7
+#endif
+constexpr int kRingSlots = 8, kRingBatch = 4, kRingRows = 128, kRingLoaders = CUDAMAT_RING_LOADERS;
+static_assert(kRingSlots == 2 * kRingBatch, "two batches");
+constexpr int kRingThreads = kRingRows * (1 + kRingLoaders);
+struct RingSlot {
+    double m[kPlanW][kRingRows];
+    double dg[kRingRows], rcp[kRingRows], rhs[kRingRows];
+    int c[kPlanW][kRingRows];
+    int i[kRingRows], cnt[kRingRows];
+    int rows, last, beg, pad;
+};
+constexpr size_t kRingBytes = sizeof(RingSlot) * kRingSlots;
+
+template <bool BACKOFF>
+__device__ __forceinline__ void ring_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok) {
+            if (++spins > (1u << 22)) __trap();                    // never hang on a broken ring
+            if (BACKOFF) __nanosleep(256);                         // loaders: 28 polling warps would starve the walker's LDS / barrier traffic
+        }
+    }
+}
+__device__ __forceinline__ void ring_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// explicit 32-bit shared-memory addressing for the walker: with generic pointers the compiler rebuilt the shared window base
+// (S2R SR_CgaCtaId + LEA) in front of every predicated access — 128 dependent instructions per level, 610 cycles (ncu source
+// view, round 2)
+__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+template <bool UPPER>
+__global__ void __launch_bounds__(kRingThreads, 1) k_sptrsv_ring(const int *order, const int *chunk_beg, const int *chunk_info, int nchunks,
+                                                                  int len, int n, const int *p_cnt, const int *p_ptr, const int *p_col,
+                                                                  const double *p_val, const double *p_dg, const int *ja, const double *M,
+                                                                  const double *rhs, double *out, const int *status) {
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    RingSlot *ring = reinterpret_cast<RingSlot *>(ring_raw);
+    double *y = reinterpret_cast<double *>(ring_raw + kRingBytes);  // n solved values + one cell that stays +0.0
+    // the ring is handed over in BATCHES of kRingBatch slots (two batches): one full / one empty barrier per batch, so the walker
+    // touches an mbarrier once per kRingBatch levels instead of twice per level
+    __shared__ unsigned long long full[2], empty[2];
+    pdl_prologue();
+    if (status && *status != ST_RUNNING) return;
+    const int tid = threadIdx.x, g = tid >> 7, lt = tid & (kRingRows - 1);
+    if (tid == 0) {
+        for (int q = 0; q < 2; ++q) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(full + q)), "r"(kRingBatch * kRingRows));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(empty + q)), "r"(kRingRows));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        y[n] = 0.0;
+    }
+    __syncthreads();
+    if (g > 0) {
+        // ---- loaders: group g - 1 fills the slots of chunks g - 1, g - 1 + 7, ...  A chunk's loads are issued one turn before
+        //      they are stored (two register sets, no copies), its row indices order[t] two turns before: no load waits for
+        //      the address of another one, and the only wait of a turn is the ring's empty barrier.  Entries a row does not
+        //      have get the coefficient +0.0 and point at the zero cell y[n]: fma(-0.0, +0.0, acc) = acc for every acc, so the
+        //      walker runs kPlanW unpredicated FMAs. ----
+        struct Ld { int i, cnt, c[kPlanW], rows, info, beg; double m[kPlanW], dg, r; };
+        auto chunk_of = [&](int k) { return g - 1 + k * kRingLoaders; };
+        auto load_index = [&](int j) -> int {
+            if (j >= nchunks) return -1;
+            const int beg = chunk_beg[j], rows = chunk_info[j] & 0xffff;
+            return lt < rows ? order[beg + lt] : -1;
+        };
+        auto load_rows = [&](int j, int i, Ld &d) {
+            d.i = i; d.cnt = 0; d.dg = 1.0; d.r = 0.0; d.rows = 0; d.info = 0; d.beg = 0;
+#pragma unroll
+            for (int q = 0; q < kPlanW; ++q) { d.c[q] = n; d.m[q] = 0.0; }
+            if (j >= nchunks) return;
+            d.beg = chunk_beg[j]; d.info = chunk_info[j]; d.rows = d.info & 0xffff;
+            if (lt < d.rows) {
+                const int t = d.beg + lt;
+                d.cnt = p_cnt[t];
+#pragma unroll
+                for (int q = 0; q < kPlanW; ++q) { d.c[q] = p_col[(size_t)q * len + t]; d.m[q] = p_val[(size_t)q * len + t]; }
+                if (UPPER) d.dg = p_dg[t];
+                if (i >= 0) d.r = rhs[i];
+            }
+        };
+        auto store_rows = [&](int j, const Ld &d) {
+            const int slot = j & (kRingSlots - 1);
+            const int bb = (j >> 2) & 1;                           // batch barrier of the chunk (kRingBatch = 4)
+            if (j >= kRingSlots) ring_wait<true>(empty + bb, (unsigned)(((j >> 3) - 1) & 1));        // the walker is done with the batch of chunk j - 8
+            RingSlot &S = ring[slot];
+#pragma unroll
+            for (int q = 0; q < kPlanW; ++q) {
+                const bool has = q < d.cnt && d.i >= 0;
+                S.c[q][lt] = 8 * (has ? d.c[q] : n);               // byte offset into y
+                S.m[q][lt] = has ? d.m[q] : 0.0;
+            }
+            S.i[lt] = d.i; S.cnt[lt] = d.cnt; S.rhs[lt] = d.r;
+            if (UPPER) { S.dg[lt] = d.dg; S.rcp[lt] = div_prepare(d.dg); }
+            if (lt == 0) { S.rows = d.rows; S.last = d.info >> 16; S.beg = d.beg; }
+            ring_arrive(full + bb);
+        };
+        Ld da, db;
+        int ia = load_index(chunk_of(0)), ib = load_index(chunk_of(1));
+        load_rows(chunk_of(0), ia, da);
+        for (int k = 0; chunk_of(k) < nchunks; k += 2) {
+            load_rows(chunk_of(k + 1), ib, db);
+            ia = load_index(chunk_of(k + 2));
+            store_rows(chunk_of(k), da);
+            if (chunk_of(k + 1) >= nchunks) break;
+            load_rows(chunk_of(k + 2), ia, da);
+            ib = load_index(chunk_of(k + 3));
+            store_rows(chunk_of(k + 1), db);
+        }
+    } else {
+        // ---- the walker: the row of the NEXT chunk is read from its slot before the barrier of the current level whenever the
+        //      loaders are ahead (one non-blocking test of the slot's full barrier), so the level-to-level chain is only
+        //      barrier -> y[c] -> kPlanW DFMAs (-> division) -> y[i] -> barrier ----
+        struct Row { int i, cnt, last, beg; unsigned ya[kPlanW]; double m[kPlanW], dg, rcp, rhs; };
+        // (laundered through asm: otherwise the compiler re-derives the window base, S2R + LEA, at every use)
+        auto opaque_addr = [](const void *p) { unsigned a = (unsigned)__cvta_generic_to_shared(p), b; asm volatile("mov.u32 %0, %1;" : "=r"(b) : "r"(a)); return b; };
+        const unsigned y_a = opaque_addr(y), ring_a = opaque_addr(ring), full_a = opaque_addr(full), empty_a = opaque_addr(empty);
+        constexpr unsigned kOffM = offsetof(RingSlot, m), kOffDg = offsetof(RingSlot, dg), kOffRcp = offsetof(RingSlot, rcp),
+                           kOffRhs = offsetof(RingSlot, rhs), kOffC = offsetof(RingSlot, c), kOffI = offsetof(RingSlot, i),
+                           kOffCnt = offsetof(RingSlot, cnt), kOffLast = offsetof(RingSlot, last), kOffBeg = offsetof(RingSlot, beg);
+        auto read_slot = [&](int j, Row &r) {
+            const unsigned sb = ring_a + (unsigned)(j & (kRingSlots - 1)) * (unsigned)sizeof(RingSlot);
+            const unsigned l4 = sb + 4u * lt, l8 = sb + 8u * lt;
+            r.last = lds_s32(sb + kOffLast); r.beg = lds_s32(sb + kOffBeg);
+            r.i = lds_s32(l4 + kOffI); r.cnt = lds_s32(l4 + kOffCnt);
+#pragma unroll
+            for (int q = 0; q < kPlanW; ++q) r.ya[q] = y_a + (unsigned)lds_s32(l4 + kOffC + q * 4 * kRingRows);
+#pragma unroll
+            for (int q = 0; q < kPlanW; ++q) r.m[q] = lds_f64(l8 + kOffM + q * 8 * kRingRows);
+            r.rhs = lds_f64(l8 + kOffRhs);
+            if (UPPER) { r.dg = lds_f64(l8 + kOffDg); r.rcp = lds_f64(l8 + kOffRcp); } else { r.dg = 1.0; r.rcp = 1.0; }
+            if ((j & (kRingBatch - 1)) == kRingBatch - 1)          // last slot of its batch: hand the batch back
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + 8u * (unsigned)((j >> 2) & 1)) : "memory");
+        };
+        auto batch_full = [&](int j, bool block) -> bool {         // is the batch of chunk j loaded?
+            unsigned ok = 0, spins = 0;
+            const unsigned bar = full_a + 8u * (unsigned)((j >> 2) & 1), par = (unsigned)((j >> 3) & 1);
+            do {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok) : "r"(bar), "r"(par) : "memory");
+                if (!ok && block && ++spins > (1u << 22)) __trap();             // never hang on a broken ring
+            } while (!ok && block);
+            return ok != 0;
+        };
+        auto turn = [&](int j, Row &cur, Row &nxt, bool &have) {
+            if (!have) { batch_full(j, true); read_slot(j, cur); }
+            // the chain: y loads first, the next row's slot reads in their shadow, then the FMAs
+            double yv[kPlanW];
+#pragma unroll
+            for (int q = 0; q < kPlanW; ++q) yv[q] = lds_f64(cur.ya[q]);
+            have = false;
+            if (j + 1 < nchunks) {
+                if (((j + 1) & (kRingBatch - 1)) != 0 || batch_full(j + 1, false)) { read_slot(j + 1, nxt); have = true; }
+            }
+            double acc = cur.rhs;
+#pragma unroll
+            for (int q = 0; q < kPlanW; ++q) acc = __fma_rn(-cur.m[q], yv[q], acc);
+            if (cur.i >= 0) {
+                if (cur.cnt > kPlanW) {                            // rare: the rest of a long row straight from CSR
+                    const int p0 = p_ptr[cur.beg + lt];
+                    for (int pp = p0 + kPlanW; pp < p0 + cur.cnt; ++pp) acc = __fma_rn(-M[pp], y[ja[pp]], acc);
+                }
+                if (UPPER) acc = div_finish(acc, cur.dg, cur.rcp);
+                sts_f64(y_a + 8u * (unsigned)cur.i, acc);          // (a global store here would sit on the chain)
+            }
+            if (cur.last) asm volatile("bar.sync 1, %0;" ::"n"(kRingRows) : "memory");
+        };
+        Row ra, rb;
+        bool have = false;
+        for (int j = 0; j < nchunks; j += 2) {                     // nchunks is a multiple of kRingBatch
+            turn(j, ra, rb, have);
+            turn(j + 1, rb, ra, have);
+        }
+    }
+    // ---- the solved vector leaves shared memory once, coalesced, by all 1024 threads ----
+    __syncthreads();
+    for (int i = tid; i < n; i += kRingThreads) out[i] = y[i];
+}
+
 __global__ void k_fill_bits(unsigned long long *p, unsigned long long v, int64_t cnt) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < cnt; i += stride) p[i] = v;
 }
 // which sweep kernel a handle uses: 0 one launch per level (also: few levels, e.g. the multicolour ordering — every level
-// is a full-occupancy bandwidth-bound launch), 1 single-CTA shared-memory sweep (small systems), 2 sync-free persistent sweep
+// is a full-occupancy bandwidth-bound launch), 1 single-CTA shared-memory sweep (small systems), 2 sync-free persistent sweep,
+// 3 role-split ring sweep (small systems, default)
 static int sweep_mode(const cudamat_solver *s) {
     if (!s->opt_sptrsv_syncfree) return 0;
+    if (sizeof(double) * ((size_t)s->n + 1) + kRingBytes <= 226 * 1024 && !s->opt_sptrsv_no_smem && s->opt_sptrsv_ring) return 3;
     if (sizeof(double) * (size_t)s->n <= 200 * 1024 && !s->opt_sptrsv_no_smem) return 1;
     if (std::max(s->lvl_l.nlevels, s->lvl_u.nlevels) <= 32) return 0;
     return 2;
 }
+// chunk table of the ring sweep: <= 128 plan positions per chunk, `last` marks the end of a level (built at analysis time:
+// nothing may allocate or synchronise inside a captured iteration)
+static int ring_prepare(cudamat_solver *s) {
+    if (sweep_mode(s) != 3) return CUDAMAT_OK;
+    for (LevelSchedule *P : {&s->lvl_l, &s->lvl_u}) {
+        LevelSchedule &LS = *P;
+        if (LS.d_chunk_beg || LS.order_len <= 0) continue;
+        std::vector<int> cb, ci;
+        for (int l = 0; l < LS.nlevels; ++l)
+            for (int off = LS.level_ptr[l]; off < LS.level_ptr[l + 1]; off += kRingRows) {
+                const int rows = std::min(kRingRows, LS.level_ptr[l + 1] - off);
+                cb.push_back(off); ci.push_back(rows | ((off + kRingRows >= LS.level_ptr[l + 1]) ? 1 << 16 : 0));
+            }
+        while (cb.size() % kRingBatch) { cb.push_back(0); ci.push_back(0); }       // empty chunks: the ring is handed over in whole batches
+        LS.nchunks = (int)cb.size();
+        CM_CUDA(cudaMalloc(&LS.d_chunk_beg, sizeof(int) * std::max<size_t>(cb.size(), 1)));
+        CM_CUDA(cudaMalloc(&LS.d_chunk_info, sizeof(int) * std::max<size_t>(ci.size(), 1)));
+        CM_CUDA(cudaMemcpyAsync(LS.d_chunk_beg, cb.data(), sizeof(int) * cb.size(), cudaMemcpyHostToDevice, s->stream));
+        CM_CUDA(cudaMemcpyAsync(LS.d_chunk_info, ci.data(), sizeof(int) * ci.size(), cudaMemcpyHostToDevice, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));             // the host vectors die here
+    }
+    CM_CUDA(cudaFuncSetAttribute(k_sptrsv_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    CM_CUDA(cudaFuncSetAttribute(k_sptrsv_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    return CUDAMAT_OK;
+}
+
 int sptrsv_arm(cudamat_solver *s, double *vec) {
     if (s->n <= 0) return CUDAMAT_OK;
     if (sweepblk_active(s)) return CUDAMAT_OK;                 // block-wavefront sweeps signal through per-block flags
@@ -518,6 +745,9 @@ void ilu0_release(cudamat_solver *s) {
     for (LevelSchedule *P : {&s->lvl_l, &s->lvl_u}) {
         if (P->d_order) cudaFree(P->d_order);
         if (P->d_level_ptr) cudaFree(P->d_level_ptr);
+        if (P->d_chunk_beg) cudaFree(P->d_chunk_beg);
+        if (P->d_chunk_info) cudaFree(P->d_chunk_info);
+        P->d_chunk_beg = P->d_chunk_info = nullptr; P->nchunks = 0;
         if (P->d_cnt) cudaFree(P->d_cnt);
         if (P->d_ptr) cudaFree(P->d_ptr);
         if (P->d_col) cudaFree(P->d_col);
@@ -797,6 +1027,7 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     CM_CUDA(cudaStreamSynchronize(s->stream));
     // 7-point grid stencils (structure found by the MARCH analysis): block-wavefront sweeps
     if ((rc = sweepblk_plan(s))) return rc;
+    if ((rc = ring_prepare(s))) return rc;
     if (st) { st->t_ilu0 += now_s() - t0; st->zero_pivot = s->zero_pivot; }
     return CUDAMAT_OK;
 }
@@ -809,7 +1040,24 @@ int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out)
     const int *status = s->d_sc ? &s->d_sc->status : nullptr;
     const size_t smem_y = sizeof(double) * (size_t)s->n;
     const int mode = sweep_mode(s);
-    if (mode == 1 && L.order_len > 0) {
+    if (mode == 3 && L.order_len > 0) {
+        // small system, role-split CTA: one walker group + seven loader groups around a shared-memory ring
+        const LevelSchedule &LS = L;
+        if (!LS.d_chunk_beg) { set_error("sptrsv: ring plan missing"); return CUDAMAT_E_STATE; }
+        const void *kern = upper ? (const void *)k_sptrsv_ring<true> : (const void *)k_sptrsv_ring<false>;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(kRingThreads); cfg.stream = s->stream; cfg.dynamicSmemBytes = kRingBytes + smem_y + sizeof(double);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        const int *a_order = L.d_order, *a_cb = LS.d_chunk_beg, *a_ci = LS.d_chunk_info, *a_cnt = L.d_cnt, *a_ptr = L.d_ptr, *a_col = L.d_col, *a_ja = s->pre_ja;
+        int a_nc = LS.nchunks, a_len = L.order_len, a_n = s->n;
+        const double *a_val = L.d_val, *a_dg = L.d_dg, *a_M = s->d_M, *a_rhs = rhs;
+        void *args[] = {&a_order, &a_cb, &a_ci, &a_nc, &a_len, &a_n, &a_cnt, &a_ptr, &a_col, &a_val, &a_dg, &a_ja, &a_M, &a_rhs, &out, &status};
+        CM_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+        s->launches++;
+    } else if (mode == 1 && L.order_len > 0) {
         // small system: one CTA, solved values in shared memory, a CTA barrier per level
         const void *kern = upper ? (const void *)k_sptrsv_smem<true> : (const void *)k_sptrsv_smem<false>;
         if (!s->sptrsv_smem_ready) {

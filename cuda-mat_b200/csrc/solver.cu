@@ -300,14 +300,14 @@ static int start_scalars(cudamat_solver *s, int maxit, double tol, int hist_cap)
 // not change between iterations — every scalar lives on the device) and replayed; the programmatic-dependent-launch
 // edges are kept by the capture.  Large systems and sharded handles (per-launch epochs) launch directly.
 template <typename Iter>
-static int run_iterations(cudamat_solver *s, int maxit, Iter &&one_iteration, bool even_batches = false) {
+static int run_iterations(cudamat_solver *s, int maxit, Iter &&one_iteration, bool even_batches = false, bool auto_graph = true) {
     int rc, npoll = 0, it = 0;
     bool stop = false;
     const int poll = std::max(1, s->opt_poll_every);
     static const bool no_graph = [] { const char *e = getenv("CUDAMAT_NO_GRAPH"); return e && *e && *e != '0'; }();
     const bool use_graph = !no_graph && s->opt_graph != 0 && !s->comm && s->opt_time_spmv == 0 && s->stream != nullptr &&
                            s->stream != cudaStreamLegacy && s->stream != cudaStreamPerThread &&
-                           (s->opt_graph > 0 || s->n <= (1 << 22)) && maxit >= 2 * poll &&
+                           (s->opt_graph > 0 || (auto_graph && s->n <= (1 << 22))) && maxit >= 2 * poll &&
                            (!even_batches || poll % 2 == 0);       // ping-pong buffers: a replayed batch must restore the parity
     if (use_graph) {
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
@@ -511,7 +511,7 @@ static int solve_ilu0(cudamat_solver *s, const double *d_b, double *d_x, int max
         if ((rc = precond(r, sv))) return rc;                                                      // :121-127
         if ((rc = spmv_step(s, sv, nullptr, t, r, 2, PH_I_B, 1, -1, 1))) return rc;         // :132-137
         return launch_update_xr(s, true, nullptr, sv, t, rw, xk, r);                                // :139-151, :81
-    });
+    }, /*even_batches=*/false, /*auto_graph=*/false);             // sweeps of 20-600 us hide the launches behind PDL: replay + instantiate measured slower
     if (rc) return rc;
     if ((rc = poll_status(s))) return rc;
     if (s->h_sc->status == ST_COMM_TIMEOUT) { set_error("a peer rank's halo rows or partial sums did not arrive (spin limit reached)"); return CUDAMAT_E_COMM; }
@@ -622,6 +622,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "host_analysis")) { s->opt_host_analysis = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "graph")) s->opt_graph = (int)value;          // -1 auto (small systems), 0 off, 1 force
     else if (!strcmp(key, "sptrsv_no_smem")) s->opt_sptrsv_no_smem = (int)value;
+    else if (!strcmp(key, "sptrsv_ring")) s->opt_sptrsv_ring = (int)value;
     else if (!strcmp(key, "class_tiles_per_cta")) s->opt_class_tiles_per_cta = (int)value;
     else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "l2_fetch")) {

@@ -124,6 +124,7 @@ struct LevelSchedule {
     // level-ordered sweep plan (ilu0.cu k_build_plan)
     int *d_cnt = nullptr, *d_ptr = nullptr, *d_col = nullptr; double *d_val = nullptr, *d_dg = nullptr;
     int order_len = 0;
+    int *d_chunk_beg = nullptr, *d_chunk_info = nullptr; int nchunks = 0;    // ring sweep (small systems): <= 128 positions per chunk
     std::vector<int> level_ptr;    // host: offsets into d_order per level (padded)
 };
 
@@ -158,6 +159,7 @@ struct cudamat_solver {
     int opt_graph = -1;                    // CUDA-graph replay of iteration batches: -1 auto, 0 off, 1 force
     bool graph_used = false;
     int opt_sptrsv_no_smem = 0;            // 1: never use the single-CTA shared-memory sweep
+    int opt_sptrsv_ring = 1;               // small systems: role-split ring sweep (0: the barrier-per-level kernel of round 1)
     bool sptrsv_smem_ready = false;
     int sptrsv_grid = 0;
     std::vector<cudaEvent_t> ev_pool; int ev_used = 0;
