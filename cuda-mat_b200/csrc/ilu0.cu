@@ -270,14 +270,14 @@ __global__ void __launch_bounds__(kSmemSweepThreads) k_sptrsv_smem(const int *or
 // ------------------------------------------------------------------------------------------
 // Small systems, variant RING: the level-to-level chain of k_sptrsv_smem is ~490 cycles per level — a 32-warp barrier and,
 // every 8 levels, a stall on the operand prefetch (the loads' consumers sit in the same in-order warps as the chain).  Here
-// the CTA is split by role: ONE group of 128 threads walks the levels with a 4-warp named barrier, seven loader groups stream
+// the CTA is split by role: ONE group of 128 threads walks the levels with a 4-warp named barrier, three loader groups stream
 // the plan (columns, factor values, diagonal and the reciprocal half of its division, rhs[order[t]]) into a ring of
 // shared-memory slots of 128 rows, two mbarriers per slot (full / empty).  The walker's chain per level: full-wait -> slot row
 // from shared memory -> y[c] from shared memory -> <= 4 dependent DFMA (-> division) -> y[i] -> barrier.  Levels wider than 128
 // rows are consecutive slots with the barrier only after the last.  Same per-row operation order as every other sweep.
 // ------------------------------------------------------------------------------------------
 #ifndef CUDAMAT_RING_LOADERS
-#define CUDAMAT_RING_LOADERS 7
+#define CUDAMAT_RING_LOADERS 3                                   // 2-4 measured equal (mat10000 268-275 us / iteration), 7: 296, 1: 379
 #endif
 constexpr int kRingSlots = 8, kRingBatch = 4, kRingRows = 128, kRingLoaders = CUDAMAT_RING_LOADERS;
 static_assert(kRingSlots == 2 * kRingBatch, "two batches");
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_sptrsv_ring(const int *orde
     }
     __syncthreads();
     if (g > 0) {
-        // ---- loaders: group g - 1 fills the slots of chunks g - 1, g - 1 + 7, ...  A chunk's loads are issued one turn before
+        // ---- loaders: group g - 1 fills the slots of chunks g - 1, g - 1 + kRingLoaders, ...  A chunk's loads are issued one turn before
         //      they are stored (two register sets, no copies), its row indices order[t] two turns before: no load waits for
         //      the address of another one, and the only wait of a turn is the ring's empty barrier.  Entries a row does not
         //      have get the coefficient +0.0 and point at the zero cell y[n]: fma(-0.0, +0.0, acc) = acc for every acc, so the
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_sptrsv_ring(const int *orde
             turn(j + 1, rb, ra, have);
         }
     }
-    // ---- the solved vector leaves shared memory once, coalesced, by all 1024 threads ----
+    // ---- the solved vector leaves shared memory once, coalesced, by all threads ----
     __syncthreads();
     for (int i = tid; i < n; i += kRingThreads) out[i] = y[i];
 }
@@ -1041,7 +1041,7 @@ int launch_sptrsv(cudamat_solver *s, bool upper, const double *rhs, double *out)
     const size_t smem_y = sizeof(double) * (size_t)s->n;
     const int mode = sweep_mode(s);
     if (mode == 3 && L.order_len > 0) {
-        // small system, role-split CTA: one walker group + seven loader groups around a shared-memory ring
+        // small system, role-split CTA: one walker group + loader groups around a shared-memory ring
         const LevelSchedule &LS = L;
         if (!LS.d_chunk_beg) { set_error("sptrsv: ring plan missing"); return CUDAMAT_E_STATE; }
         const void *kern = upper ? (const void *)k_sptrsv_ring<true> : (const void *)k_sptrsv_ring<false>;

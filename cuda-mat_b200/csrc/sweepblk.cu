@@ -35,6 +35,7 @@ constexpr int kSBH = kSB + 1;                                      // edge of th
 // warp on average, 1.0 is ideal).
 constexpr int kSBPY = 18, kSBPZ = 319;
 constexpr int kSBThreads = 256;                                    // >= the widest wavefront (192 cells)
+constexpr int kSBWalkers = 192;                                    // threads that walk the wavefronts (named barrier 1)
 
 struct SweepTable {                                                // cells of a block in wavefront order (kernel parameter, 8.4 KB)
     unsigned short cell[kSBRows];                                  // lx | ly << 4 | lz << 8
@@ -235,16 +236,19 @@ __global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int 
             acc = __fma_rn(-cur.b.x, y2, acc);
             if (UPPER && mine) acc = div_finish(acc, cur.b.y, cur.rcp);
             if (mine) *reinterpret_cast<double *>(const_cast<unsigned char *>(Yb) + cur.li) = acc;
-            __syncthreads();
+            asm volatile("bar.sync 1, %0;" ::"n"(kSBWalkers) : "memory");
             p0 = p1; p1 = p2; p2 = p3;
         };
-        Ops oa, ob;
-        load_ops(min(tid, kSBRows - 1), oa);
+        if (tid < kSBWalkers) {                                    // the widest wavefront has 192 cells: warps 6-7 only copy
+            Ops oa, ob;
+            load_ops(min(tid, kSBRows - 1), oa);
 #pragma unroll 1
-        for (int l = 0; l < kSBLevels; l += 2) {                   // 46 wavefronts: an even number
-            step(oa, ob, l);
-            step(ob, oa, l + 1);
+            for (int l = 0; l < kSBLevels; l += 2) {               // 46 wavefronts: an even number
+                step(oa, ob, l);
+                step(ob, oa, l + 1);
+            }
         }
+        __syncthreads();
         if (dbg && tid == 0) ts[4] = clock64();
         // ---- publish.  Successors need only the three outgoing faces: those first, then the done-flag, then the rest ----
         {
