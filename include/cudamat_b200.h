@@ -127,7 +127,8 @@ int cudamat_ilu0_host(int n, int nnz, const double *A, const int *iA, const int 
 int cudamat_create(cudamat_solver **out, int64_t n_global, int64_t row0, int64_t row1, void *stream);
 int cudamat_destroy(cudamat_solver *s);
 /* option keys: "spmv_variant" (CUDAMAT_SPMV_*), "poll_every" (iterations between status polls), "sptrsv_syncfree" (0: one
- * launch per level), "sptrsv_no_smem" (1: never use the single-CTA shared-memory sweep), "sptrsv_ctas_per_sm",
+ * launch per level), "sptrsv_no_smem" (1: never use the single-CTA shared-memory sweeps), "sptrsv_ring" (0: small systems use the round-1
+ * barrier-per-level kernel instead of the ring kernel), "sptrsv_blocked" (0: no block-wavefront sweeps on grid stencils), "sptrsv_ctas_per_sm",
  * "ilu0_reorder" (1: multicolour ordering of the preconditioner matrix — few sweep levels, a different ILU(0), opt-in),
  * "host_analysis" (1: ILU0 level analysis on the host, cross-check), "graph" (-1 auto, 0 off, 1 force CUDA-graph replay),
  * "debug", "time_spmv" (k: event-time the main kernels of every k-th iteration), "fuse" (bit 0: fold the p update into MARCH SpMV 1,
