@@ -139,6 +139,25 @@ __global__ void k_pack(const double *vec, const int *idx, double *out, int cnt) 
     if (k < cnt) out[k] = vec[idx[k]];
 }
 
+// MARCH on a slab shard reads the neighbours' boundary planes straight out of the operand's halo region: that needs the
+// halo to be exactly one whole plane (D entries) of rank - 1 and / or of rank + 1 — nothing else.  The halo columns are
+// sorted by global id, so D distinct ids below row0 within reach D are the plane [row0 - D, row0) in natural order.
+bool comm_halo_planes(const cudamat_solver *s, int D, int *lo_base, int *hi_base) {
+    const Comm *c = s->comm;
+    *lo_base = *hi_base = -1;
+    if (!c || c->world < 2 || (int)c->recv_cnt.size() != c->world) return false;
+    for (int p = 0; p < c->world; ++p) {
+        if (c->recv_cnt[p] == 0) continue;
+        if (c->recv_cnt[p] != D) return false;
+        if (p == c->rank - 1) *lo_base = s->n + c->recv_off[p];
+        else if (p == c->rank + 1) *hi_base = s->n + c->recv_off[p];
+        else return false;
+    }
+    if (c->rank > 0 && *lo_base < 0 && s->row0 > 0) return false;
+    if (c->rank + 1 < c->world && *hi_base < 0 && s->row1 < s->n_global) return false;
+    return true;
+}
+
 // ---- hooks used by solver.cu ---------------------------------------------------------------------
 int comm_halo_exchange(cudamat_solver *s, double *vec) {
     Comm *c = s->comm;

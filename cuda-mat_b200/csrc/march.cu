@@ -42,6 +42,7 @@ struct MarchArgs {
     const double *d;        // optional diagonal shift
     const unsigned char *tmask;
     RedCtx rc; DevScalars *sc; int check_status;
+    HaloWait hw;            // sharded handles (LOAD_X only): flags of the neighbours' boundary planes
 };
 
 // Work split: items (z-chunk, column) in z-chunk-major order, item = blockIdx.x (+ k * gridDim.x).  Neighbouring CTAs walk
@@ -83,6 +84,8 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
     extern __shared__ __align__(16) double ring[];                 // 4 slots
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = M.S, P = M.P, Zc = M.Zc, n = a.n;
+    const int nlim = MODE == MARCH_LOAD_X ? M.n_tot : n;          // LOAD_X reads the operand incl. its halo region (sharded handles)
+    const int lo_base = MODE == MARCH_LOAD_X ? M.lo_base : -1, hi_base = MODE == MARCH_LOAD_X ? M.hi_base : -1;
     pdl_sync();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     double c1 = 0.0, c2 = 0.0;                                     // MAKE_P: beta, -omega; MAKE_S: -alpha
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
 
     // global loads of the tile whose buffer starts at element g0 = tile base - H -> registers
     auto issue = [&](int g0, double2 (&st)[NV][PPT]) {
-        if (g0 >= 0 && g0 + BUF <= n) {                            // CTA-uniform: everything but the two ends of the vector
+        if (g0 >= 0 && g0 + BUF <= nlim) {                         // CTA-uniform: everything but the two ends of the vector
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const double2 *src = reinterpret_cast<const double2 *>(in[v] + g0) + tid;
@@ -114,8 +117,8 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
                 for (int j = 0; j < PPT; ++j) {
                     const int g = g0 + 2 * (tid + j * kCtaThreads);
                     const bool inb = tid + j * kCtaThreads < PAIRS;
-                    st[v][j].x = (inb && g >= 0 && g < n) ? __ldg(in[v] + g) : 0.0;
-                    st[v][j].y = (inb && g + 1 >= 0 && g + 1 < n) ? __ldg(in[v] + g + 1) : 0.0;
+                    st[v][j].x = (inb && g >= 0 && g < nlim) ? __ldg(in[v] + g) : 0.0;
+                    st[v][j].y = (inb && g + 1 >= 0 && g + 1 < nlim) ? __ldg(in[v] + g + 1) : 0.0;
                 }
         }
     };
@@ -153,12 +156,20 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
         const int k0 = (int)((long long)P * zc / Zc), k1 = (int)((long long)P * (zc + 1) / Zc) - 1;
         if (k1 < k0) continue;
         __syncthreads();                                           // the previous item's last reads of the ring are done
+        // first element of plane pl's buffer: planes -1 / P of a shard are the neighbours' planes in the halo region
+        auto gofs = [&](int pl) -> int {
+            return (pl < 0 ? lo_base : pl >= P ? hi_base : pl * S * kTile) + col * kTile - H;
+        };
+        if (MODE == MARCH_LOAD_X && a.hw.nsrc > 0) {               // the neighbours' rows of this exchange have arrived?
+            if (k0 == 0 && lo_base >= 0) halo_wait(a.hw, col, a.sc ? &a.sc->status : nullptr);
+            if (k1 == P - 1 && hi_base >= 0) halo_wait(a.hw, (P - 1) * S + col, a.sc ? &a.sc->status : nullptr);
+        }
         {   // fill the ring: planes k0-1, k0, k0+1
             double2 st[NV][PPT];
 #pragma unroll 1
             for (int pl = k0 - 1; pl <= k0 + 1; ++pl) {
-                if (pl < 0 || pl >= P) continue;
-                const int g0 = (pl * S + col) * kTile - H;
+                if ((pl < 0 && lo_base < 0) || (pl >= P && hi_base < 0) || pl > P) continue;
+                const int g0 = gofs(pl);
                 issue(g0, st);
                 convert(g0, pl & 3, pl >= k0 && pl <= k1, st);
             }
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
         // Software pipeline: DEPTH planes ahead of the multiply are in flight in registers (LOAD_X: 2 x 1 vector, MAKE_*: 1 x
         // 2-3 vectors).  One step = barrier, multiply plane k out of the ring, convert + store plane k+2 into the slot plane
         // k-2 left, issue the loads of plane k+2+DEPTH into the registers that just became free.
-        const int lim = min(k1 + 1, P - 1);
+        const int lim = hi_base >= 0 ? k1 + 1 : min(k1 + 1, P - 1);
         auto step = [&](int k, double2 (&st)[NV][PPT]) {
             const int tile = k * S + col;
             const int row0 = tile * kTile + warp * 64 + 2 * lane;  // this thread's first row (first row group)
@@ -266,11 +277,11 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
                 if (gi == 1 && k < k1) fetch_side(k + 1);
             }
             if (k + 2 <= lim) convert(((k + 2) * S + col) * kTile - H, (k + 2) & 3, k + 2 <= k1, st);
-            if (k + 2 + DEPTH <= lim) issue(((k + 2 + DEPTH) * S + col) * kTile - H, st);
+            if (k + 2 + DEPTH <= lim) issue(gofs(k + 2 + DEPTH), st);
         };
         double2 stA[NV][PPT], stB[DEPTH > 1 ? NV : 1][DEPTH > 1 ? PPT : 1];
-        if (k0 + 2 <= lim) issue(((k0 + 2) * S + col) * kTile - H, stA);
-        if constexpr (DEPTH > 1) { if (k0 + 3 <= lim) issue(((k0 + 3) * S + col) * kTile - H, stB); }
+        if (k0 + 2 <= lim) issue(gofs(k0 + 2), stA);
+        if constexpr (DEPTH > 1) { if (k0 + 3 <= lim) issue(gofs(k0 + 3), stB); }
 #pragma unroll 1
         for (int k = k0; k <= k1; k += DEPTH) {
             step(k, stA);
@@ -354,7 +365,7 @@ static int launch_march_m(cudamat_solver *s, const MarchArgs &a) {
 }
 static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-bool march_available(const cudamat_solver *s) { return s->march != nullptr && s->comm == nullptr; }
+bool march_available(const cudamat_solver *s) { return s->march != nullptr; }     // sharded handles: LOAD_X only (solver.cu keeps fuse = 0)
 
 // y = A x (+ d.x) with ndot fused dots (red0 = y.u, red1 = y.y); u == x: the operand comes out of the ring.
 // Staging and stores move 16-byte pairs: operands that are not 16-byte aligned are left to the TILED kernel (returns 1).
@@ -365,7 +376,7 @@ int launch_march_spmv(cudamat_solver *s, const SpmvArgs &sa) {
     MarchArgs a{};
     const bool ring = sa.ndot >= 1 && sa.u == sa.x;
     a.n = sa.n; a.in0 = sa.x; a.y = sa.y; a.u = ring ? nullptr : sa.u; a.d = sa.d;
-    a.tmask = s->cls[1].d_tmask; a.rc = sa.rc; a.sc = sa.sc; a.check_status = sa.check_status;
+    a.tmask = s->march_tmask; a.rc = sa.rc; a.sc = sa.sc; a.check_status = sa.check_status; a.hw = sa.hw;
     const bool hd = sa.d != nullptr;
     if (sa.ndot == 0) return hd ? launch_march_m<MARCH_LOAD_X, 0, true, false>(s, a) : launch_march_m<MARCH_LOAD_X, 0, false, false>(s, a);
     if (sa.ndot == 1) {
@@ -380,7 +391,7 @@ int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old,
                         const double *rhat, const double *d, const RedCtx &rc) {
     MarchArgs a{};
     a.n = s->n; a.in0 = r; a.in1 = p_old; a.in2 = v_old; a.xout = p_new; a.y = v_new; a.u = rhat; a.d = d;
-    a.tmask = s->cls[1].d_tmask; a.rc = rc; a.sc = s->d_sc; a.check_status = 1;
+    a.tmask = s->march_tmask; a.rc = rc; a.sc = s->d_sc; a.check_status = 1;
     int e = ev_mark(s, true);
     if (e) return e;
     if ((e = d ? launch_march_m<MARCH_MAKE_P, 1, true, false>(s, a) : launch_march_m<MARCH_MAKE_P, 1, false, false>(s, a))) return e;
@@ -390,7 +401,7 @@ int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old,
 int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc) {
     MarchArgs a{};
     a.n = s->n; a.in0 = r; a.in1 = v; a.xout = sv; a.y = t; a.u = nullptr; a.d = d;
-    a.tmask = s->cls[1].d_tmask; a.rc = rc; a.sc = s->d_sc; a.check_status = 1;
+    a.tmask = s->march_tmask; a.rc = rc; a.sc = s->d_sc; a.check_status = 1;
     int e = ev_mark(s, true);
     if (e) return e;
     if ((e = d ? launch_march_m<MARCH_MAKE_S, 2, true, true>(s, a) : launch_march_m<MARCH_MAKE_S, 2, false, true>(s, a))) return e;

@@ -11,6 +11,7 @@
 // row's storage order, so the row sums are bit-identical to the CSR kernels.
 // This is what cusparseDcsrmv (pbicgstab.cu:67,104,132,646,676,704) cannot do: it must stream 12 B per entry.
 #include "solver.h"
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <memory>
@@ -111,6 +112,12 @@ __global__ void k_cls_assign(int n, const int *ia, const int *ja, const double *
         if (with_vals && __double_as_longlong(dict->val[id * kDictLen + k]) != __double_as_longlong(a[s + k])) { *fail = 1; return; }
     }
     cls[row] = (unsigned char)id;
+}
+
+__global__ void k_shift_cols(int64_t nnz, const int *ja_global, int row0, int *out) {     // global column id -> offset-preserving local frame
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < nnz; k += stride) out[k] = ja_global[k] - row0;
 }
 
 __global__ void k_cls_hist(int n, const unsigned char *cls, unsigned *hist) {
@@ -254,7 +261,7 @@ static bool tiled_plan_host(const DictParam &D, int ncls, const unsigned *hist, 
 
 // TILED plan: class histogram on the device, the host plan above, then the device-side tables (shared-memory records,
 // presence mask per row, eligibility byte per tile)
-static int tiled_plan(cudamat_solver *s, RowClasses &C) {
+static int tiled_plan(cudamat_solver *s, RowClasses &C, bool with_vals) {
     const int n = s->n;
     unsigned *d_hist = nullptr;
     CM_CUDA(dev_alloc((void **)&d_hist, sizeof(unsigned) * kDictMax));
@@ -266,7 +273,7 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
     dev_free(d_hist);
     s->launches++;
     TiledPlanHost P;
-    if (!tiled_plan_host(*C.h_dict, C.ncls, hist, n, &C == &s->cls[1], P)) return CUDAMAT_OK;
+    if (!tiled_plan_host(*C.h_dict, C.ncls, hist, n, with_vals, P)) return CUDAMAT_OK;
     CM_CUDA(dev_alloc((void **)&C.d_sdict, sizeof(TiledSmemClass) * (size_t)C.ncls));
     CM_CUDA(cudaMemcpyAsync(C.d_sdict, P.sd.data(), sizeof(TiledSmemClass) * (size_t)C.ncls, cudaMemcpyHostToDevice, s->stream));
     if (P.T->sup_len > 0) {
@@ -287,7 +294,11 @@ static int tiled_plan(cudamat_solver *s, RowClasses &C) {
 }
 
 void rowclass_release(cudamat_solver *s) {
-    delete s->march; s->march = nullptr;
+    delete s->march; s->march = nullptr; s->march_tmask = nullptr;
+    for (RowClasses *C : {&s->cls_g}) {
+        dev_free(C->d_cls); delete C->h_dict; delete C->h_tdict; dev_free(C->d_tile_ok); dev_free(C->d_sdict); dev_free(C->d_tmask); dev_free(C->d_dict);
+        *C = RowClasses();
+    }
     for (int m = 0; m < 2; ++m) {
         dev_free(s->cls[m].d_cls);
         delete s->cls[m].h_dict;
@@ -298,6 +309,48 @@ void rowclass_release(cudamat_solver *s) {
         dev_free(s->cls[m].d_dict);
         s->cls[m] = RowClasses();
     }
+}
+
+// one classification pass (m = 1: offsets + values, m = 0: offsets only) over the column ids `ja` into C
+static int classify_rows(cudamat_solver *s, const int *ja, int m, RowClasses &C, unsigned long long *tab, int *rep, int *slot_id, int *flags) {
+    const int n = s->n;
+    cudaError_t e;
+    if ((e = dev_alloc((void **)&C.d_cls, (size_t)n + 16)) != cudaSuccess || (e = dev_alloc((void **)&C.d_dict, sizeof(RowDict))) != cudaSuccess) {
+        cuda_ok(e, "cudaMalloc(row classes)", __FILE__, __LINE__); return CUDAMAT_E_CUDA;
+    }
+    cudaMemsetAsync(tab, 0, sizeof(unsigned long long) * kTab, s->stream);
+    cudaMemsetAsync(rep, 0x7f, sizeof(int) * kTab, s->stream);
+    cudaMemsetAsync(flags, 0, sizeof(int) * 2, s->stream);
+    const int grid = (n + 255) / 256;
+    k_cls_insert<<<grid, 256, 0, s->stream>>>(n, s->d_ia, ja, s->d_a, m, tab, rep, flags);
+    k_cls_number<<<1, 32, 0, s->stream>>>(s->d_ia, ja, s->d_a, m, tab, rep, slot_id, C.d_dict, flags + 1, flags);
+    k_cls_assign<<<grid, 256, 0, s->stream>>>(n, s->d_ia, ja, s->d_a, m, tab, slot_id, C.d_dict, C.d_cls, flags);
+    s->launches += 3;
+    int h[2] = {1, 0};
+    if ((e = cudaMemcpyAsync(h, flags, sizeof h, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
+        cuda_ok(e, "row class analysis", __FILE__, __LINE__); return CUDAMAT_E_CUDA;
+    }
+    if (h[0] == 0 && h[1] > 0) {
+        RowDict hd;
+        if ((e = cudaMemcpy(&hd, C.d_dict, sizeof hd, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+            cuda_ok(e, "row class dictionary download", __FILE__, __LINE__); return CUDAMAT_E_CUDA;
+        }
+        C.ncls = h[1];
+        C.h_dict = new DictParam();
+        memset(C.h_dict, 0, sizeof(DictParam));
+        for (int id = 0; id < C.ncls; ++id) {
+            C.h_dict->len[id] = hd.len[id];
+            C.h_dict->run[id] = -1;
+            for (int k = 0; k < kDictLen; ++k) {
+                C.h_dict->off[id * kDictLen + k] = hd.off[id * kDictLen + k];
+                C.h_dict->val[id * kDictLen + k] = hd.val[id * kDictLen + k];
+            }
+            for (int k = 0; k + 2 < hd.len[id]; ++k)
+                if (hd.off[id * kDictLen + k] == -1 && hd.off[id * kDictLen + k + 1] == 0 && hd.off[id * kDictLen + k + 2] == 1) { C.h_dict->run[id] = k; break; }
+        }
+    } else { dev_free(C.d_cls); dev_free(C.d_dict); C = RowClasses(); }
+    return CUDAMAT_OK;
 }
 
 // builds s->cls[0] (offsets only) and s->cls[1] (offsets + values) when the matrix allows it
@@ -311,64 +364,62 @@ int rowclass_analyze(cudamat_solver *s) {
     CM_CUDA(dev_alloc((void **)&slot_id, sizeof(int) * kTab));
     CM_CUDA(dev_alloc((void **)&flags, sizeof(int) * 2));
     int rc = CUDAMAT_OK;
-    for (int m = 1; m >= 0 && rc == CUDAMAT_OK; --m) {          // m = 1: with values, m = 0: offsets only
-        RowClasses &C = s->cls[m];
-        cudaError_t e;
-        if ((e = dev_alloc((void **)&C.d_cls, (size_t)n + 16)) != cudaSuccess || (e = dev_alloc((void **)&C.d_dict, sizeof(RowDict))) != cudaSuccess) {
-            cuda_ok(e, "cudaMalloc(row classes)", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
-        }
-        cudaMemsetAsync(tab, 0, sizeof(unsigned long long) * kTab, s->stream);
-        cudaMemsetAsync(rep, 0x7f, sizeof(int) * kTab, s->stream);
-        cudaMemsetAsync(flags, 0, sizeof(int) * 2, s->stream);
-        const int grid = (n + 255) / 256;
-        k_cls_insert<<<grid, 256, 0, s->stream>>>(n, s->d_ia, s->d_ja, s->d_a, m, tab, rep, flags);
-        k_cls_number<<<1, 32, 0, s->stream>>>(s->d_ia, s->d_ja, s->d_a, m, tab, rep, slot_id, C.d_dict, flags + 1, flags);
-        k_cls_assign<<<grid, 256, 0, s->stream>>>(n, s->d_ia, s->d_ja, s->d_a, m, tab, slot_id, C.d_dict, C.d_cls, flags);
-        s->launches += 3;
-        int h[2] = {1, 0};
-        if ((e = cudaMemcpyAsync(h, flags, sizeof h, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
-            (e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
-            cuda_ok(e, "row class analysis", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
-        }
-        if (h[0] == 0 && h[1] > 0) {
-            RowDict hd;
-            if ((e = cudaMemcpy(&hd, C.d_dict, sizeof hd, cudaMemcpyDeviceToHost)) != cudaSuccess) {
-                cuda_ok(e, "row class dictionary download", __FILE__, __LINE__); rc = CUDAMAT_E_CUDA; break;
-            }
-            C.ncls = h[1];
-            C.h_dict = new DictParam();
-            memset(C.h_dict, 0, sizeof(DictParam));
-            for (int id = 0; id < C.ncls; ++id) {
-                C.h_dict->len[id] = hd.len[id];
-                C.h_dict->run[id] = -1;
-                for (int k = 0; k < kDictLen; ++k) {
-                    C.h_dict->off[id * kDictLen + k] = hd.off[id * kDictLen + k];
-                    C.h_dict->val[id * kDictLen + k] = hd.val[id * kDictLen + k];
-                }
-                for (int k = 0; k + 2 < hd.len[id]; ++k)
-                    if (hd.off[id * kDictLen + k] == -1 && hd.off[id * kDictLen + k + 1] == 0 && hd.off[id * kDictLen + k + 2] == 1) { C.h_dict->run[id] = k; break; }
-            }
-        } else { dev_free(C.d_cls); dev_free(C.d_dict); C = RowClasses(); }
-    }
+    for (int m = 1; m >= 0 && rc == CUDAMAT_OK; --m) rc = classify_rows(s, s->d_ja, m, s->cls[m], tab, rep, slot_id, flags);   // m = 1: with values, m = 0: offsets only
     cudaStreamSynchronize(s->stream);
     dev_free(tab); dev_free(rep); dev_free(slot_id); dev_free(flags);
     for (int m = 1; m >= 0 && rc == CUDAMAT_OK; --m)
-        if (s->cls[m].ncls > 0) rc = tiled_plan(s, s->cls[m]);
-    // MARCH: needs the values dictionary with a superset pattern and EVERY tile inside the windows
-    if (rc == CUDAMAT_OK && s->cls[1].h_tdict && s->cls[1].h_tdict->sup_len > 0 && s->cls[1].d_tmask && !s->comm) {
+        if (s->cls[m].ncls > 0) rc = tiled_plan(s, s->cls[m], m == 1);
+    // MARCH: needs the values dictionary with a superset pattern and EVERY tile inside the windows.  On a sharded handle the
+    // local column ids of the boundary planes point into the halo region, which breaks the translation invariance the
+    // classes rest on: there the classes are formed a second time over GLOBAL offsets (ja_global - row0), and the kernel
+    // fetches the planes -1 / P from the halo region instead — if that region is exactly the two neighbours' planes.
+    RowClasses *MC = &s->cls[1];
+    if (rc == CUDAMAT_OK && s->comm && s->d_ja_global && s->cls[1].ncls > 0) {
+        int *ja_g = nullptr;
+        CM_CUDA(dev_alloc((void **)&ja_g, sizeof(int) * (size_t)std::max<int64_t>(s->nnz, 1)));
+        k_shift_cols<<<1184, 256, 0, s->stream>>>(s->nnz, s->d_ja_global, (int)s->row0, ja_g);
+        s->launches++;
+        CM_CUDA(dev_alloc((void **)&tab, sizeof(unsigned long long) * kTab));
+        CM_CUDA(dev_alloc((void **)&rep, sizeof(int) * kTab));
+        CM_CUDA(dev_alloc((void **)&slot_id, sizeof(int) * kTab));
+        CM_CUDA(dev_alloc((void **)&flags, sizeof(int) * 2));
+        rc = classify_rows(s, ja_g, 1, s->cls_g, tab, rep, slot_id, flags);
+        cudaStreamSynchronize(s->stream);
+        dev_free(tab); dev_free(rep); dev_free(slot_id); dev_free(flags); dev_free(ja_g);
+        if (rc == CUDAMAT_OK && s->cls_g.ncls > 0) rc = tiled_plan(s, s->cls_g, true);
+        MC = &s->cls_g;
+    }
+    if (rc == CUDAMAT_OK && MC->h_tdict && MC->h_tdict->sup_len > 0 && MC->d_tmask) {
         const int ntile = (n + kTile - 1) / kTile;
         std::vector<unsigned char> ok((size_t)ntile);
-        cudaError_t e = cudaMemcpyAsync(ok.data(), s->cls[1].d_tile_ok, (size_t)ntile, cudaMemcpyDeviceToHost, s->stream);
+        cudaError_t e = cudaMemcpyAsync(ok.data(), MC->d_tile_ok, (size_t)ntile, cudaMemcpyDeviceToHost, s->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e != cudaSuccess) { cuda_ok(e, "tile_ok download", __FILE__, __LINE__); return CUDAMAT_E_CUDA; }
         bool all_ok = true;
         for (unsigned char b : ok) if (!b) { all_ok = false; break; }
         MarchPlan M;
-        if (all_ok && march_plan_host(*s->cls[1].h_tdict, n, M)) {
-            s->march = new MarchPlan(M);
-            int dev = 0, sms = 148;
-            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            s->march_grid = 2 * sms;
+        if (all_ok && march_plan_host(*MC->h_tdict, n, M)) {
+            M.lo_base = M.hi_base = -1; M.n_tot = n;
+            bool usable = true;
+            if (s->comm) {
+                static const bool env_off = [] { const char *e = getenv("CUDAMAT_MARCH_SHARDS"); return e && *e == '0'; }();
+                usable = comm_halo_planes(s, M.D, &M.lo_base, &M.hi_base) && s->opt_march_shards != 0 && !env_off;
+                M.n_tot = n + s->nhalo;
+                // LOAD_X only (the folded updates would need the neighbours' r and v): MARCH beats TILED on a shard when its
+                // work items fill the CTA slots — 256^3 on 2 GPUs: 288 items for 296 slots, 3415 vs 3300 it/s; 512^3 on 2 GPUs:
+                // 256 items, 511 vs 520 it/s (same box, A/B)
+                int dev = 0, sms = 148;
+                if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                const int G = 2 * sms, Zc = std::max(1, std::min(G / std::max(1, M.S), std::max(1, M.P / 8)));
+                if ((long long)Zc * M.S * 20 < (long long)G * 19 && s->opt_march_shards < 2) usable = false;
+            }
+            if (usable) {
+                s->march = new MarchPlan(M);
+                s->march_tmask = MC->d_tmask;
+                int dev = 0, sms = 148;
+                if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                s->march_grid = 2 * sms;
+            }
         }
     }
     return rc;

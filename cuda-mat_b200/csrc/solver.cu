@@ -356,7 +356,7 @@ static int solve_unprec(cudamat_solver *s, int mode, const double *d_b, const do
     int rc;
     // option "fuse": bit 0 folds the p update into SpMV 1 (MAKE_P), bit 1 the s update into SpMV 2 (MAKE_S)
     const bool persist = persist_eligible(s);                      // one cooperative kernel per batch of iterations (persist.cu)
-    const int fuse = persist ? 4 : (s->spmv_variant == CUDAMAT_SPMV_MARCH && march_available(s) &&
+    const int fuse = persist ? 4 : (s->spmv_variant == CUDAMAT_SPMV_MARCH && march_available(s) && !s->comm &&
                       (reinterpret_cast<uintptr_t>(d_d) & 15u) == 0) ? (s->opt_fuse & 3) : 0;   // 16-byte pairs (work vectors are 256-byte aligned)
     const bool fold_p = (fuse & 1) != 0, fold_s = (fuse & 2) != 0;
     const bool resume = s->opt_resume != 0 && s->last_mode == mode && s->last_fused == fuse && s->work != nullptr;
@@ -623,6 +623,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "graph")) s->opt_graph = (int)value;          // -1 auto (small systems), 0 off, 1 force
     else if (!strcmp(key, "sptrsv_no_smem")) s->opt_sptrsv_no_smem = (int)value;
     else if (!strcmp(key, "sptrsv_ring")) s->opt_sptrsv_ring = (int)value;
+    else if (!strcmp(key, "march_shards")) s->opt_march_shards = (int)value;
     else if (!strcmp(key, "class_tiles_per_cta")) s->opt_class_tiles_per_cta = (int)value;
     else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "l2_fetch")) {

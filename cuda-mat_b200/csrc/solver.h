@@ -87,6 +87,8 @@ struct MarchPlan {                     // kernel parameter
     int len;                           // entries of the superset pattern
     int shape;                         // 1: (-D, -a, -1, 0, +1, +a, +D) with a even (compile-time planes / alignment), 0: generic
     int Zc;                            // z-chunks: the grid is Zc x S work items (z-chunk-major), set at launch from the CTA budget
+    int lo_base, hi_base;              // sharded handles: element offset of the lower / upper neighbour's plane in the operand's halo region (-1: none)
+    int n_tot;                         // elements of an operand vector (local rows + halo)
     int dz[8];                         // -1 / 0 / +1: plane the entry reads
     int loff[8];                       // offset inside that plane's buffer relative to the row's own position
     double val[8];
@@ -159,6 +161,7 @@ struct cudamat_solver {
     int opt_graph = -1;                    // CUDA-graph replay of iteration batches: -1 auto, 0 off, 1 force
     bool graph_used = false;
     int opt_sptrsv_no_smem = 0;            // 1: never use the single-CTA shared-memory sweep
+    int opt_march_shards = 1;              // sharded handles: MARCH with the neighbours' planes read from the halo region (0: TILED, 2: even when the grid underfills)
     int opt_sptrsv_ring = 1;               // small systems: role-split ring sweep (0: the barrier-per-level kernel of round 1)
     bool sptrsv_smem_ready = false;
     int sptrsv_grid = 0;
@@ -174,6 +177,8 @@ struct cudamat_solver {
     int persist_grid = 0;
     int opt_stream_blocks = 0;             // 0: automatic (x bytes / 64 MB), 1: never block, K: K column blocks
     cudamat::MarchPlan *march = nullptr;   // MARCH plan (host copy handed to the launches), nullptr = unavailable
+    cudamat::RowClasses cls_g;             // sharded handles: classes over GLOBAL column offsets (MARCH's presence masks)
+    const unsigned char *march_tmask = nullptr;   // presence mask per row MARCH reads (cls[1] or cls_g)
     int march_grid = 296;                  // persistent CTAs of the MARCH kernels (2 per SM)
     int opt_fuse = 2;                      // bit 0: fold the p update into MARCH SpMV 1, bit 1: the s update into SpMV 2
     int pp = 0;                            // ping-pong parity of the p / v buffers of the fused loop
@@ -283,6 +288,7 @@ void ilu0_release(cudamat_solver *s);
 
 // comm.cu
 int comm_halo_exchange(cudamat_solver *s, double *vec);
+bool comm_halo_planes(const cudamat_solver *s, int D, int *lo_base, int *hi_base);   // halo = whole planes of the two slab neighbours?
 int finish_reduction(cudamat_solver *s, const RedCtx &rc, int phase, int nq);   // groups + cross-rank exchange + final + scalar recurrence
 int launch_reduce_finish(cudamat_solver *s, const RedCtx &rc, int nq, int phase, int stage, const double *glob,
                          const unsigned long long *flags);               // kernels.cu

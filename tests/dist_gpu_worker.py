@@ -82,8 +82,8 @@ def main():
             torch.cuda.synchronize()
             ok = (torch.equal(bg, b1) and torch.equal(xg, x1) and st["iterations"] == st1["iterations"]
                   and bool(st["converged"]) and dt == d1 and ilu_ok)
-            print("DIST N=%d world=%d p2p=%d iters=%d/%d b_equal=%s x_equal=%s dot_equal=%s loop_ms=%.2f/%.2f block_ilu0_iters=%d err=%.1e %s"
-                  % (N, world, int(p2p), st["iterations"], st1["iterations"], torch.equal(bg, b1), torch.equal(xg, x1), dt == d1,
+            print("DIST N=%d world=%d p2p=%d variant=%d iters=%d/%d b_equal=%s x_equal=%s dot_equal=%s loop_ms=%.2f/%.2f block_ilu0_iters=%d err=%.1e %s"
+                  % (N, world, int(p2p), st["spmv_variant"], st["iterations"], st1["iterations"], torch.equal(bg, b1), torch.equal(xg, x1), dt == d1,
                      st["t_loop"] * 1e3, st1["t_loop"] * 1e3, sti["iterations"], ilu_err, "OK" if ok else "MISMATCH"), flush=True)
             s1.close()
         dist.barrier()
