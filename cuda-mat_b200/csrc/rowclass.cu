@@ -406,12 +406,10 @@ int rowclass_analyze(cudamat_solver *s) {
                 usable = comm_halo_planes(s, M.D, &M.lo_base, &M.hi_base) && s->opt_march_shards != 0 && !env_off;
                 M.n_tot = n + s->nhalo;
                 // LOAD_X only (the folded updates would need the neighbours' r and v): MARCH beats TILED on a shard when its
-                // work items fill the CTA slots — 256^3 on 2 GPUs: 288 items for 296 slots, 3415 vs 3300 it/s; 512^3 on 2 GPUs:
-                // 256 items, 511 vs 520 it/s (same box, A/B)
+                // work items fill the CTA slots — 256^3 on 2 GPUs: 288 items for 296 slots, 3415 vs 3300 it/s (same box, A/B)
                 int dev = 0, sms = 148;
                 if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                const int G = 2 * sms, Zc = std::max(1, std::min(G / std::max(1, M.S), std::max(1, M.P / 8)));
-                if ((long long)Zc * M.S * 20 < (long long)G * 19 && s->opt_march_shards < 2) usable = false;
+                if (march_fill(M.S, M.P, 2 * sms) < 0.85 && s->opt_march_shards < 2) usable = false;
             }
             if (usable) {
                 s->march = new MarchPlan(M);
