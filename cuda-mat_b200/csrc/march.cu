@@ -333,12 +333,6 @@ bool march_plan_host(const TiledDict &T, long long n, MarchPlan &M) {
 // items, 86 % of the slots).  Several rounds per CTA were tried for 512^3 (Zc = 9: 1152 items = 3.9 rounds, on paper 94 %
 // instead of 86 %): 245 instead of 275 it/s — CTAs drift apart and the neighbouring columns' shared halo lines leave the L2.
 int march_choose_zc(int S, int P, int G) { return std::max(1, std::min(G / std::max(1, S), std::max(1, P / 8))); }
-double march_fill(int S, int P, int G) {                           // share of the CTA slots the work items fill, net of the re-read planes
-    const int zc = march_choose_zc(S, P, G);
-    const double len = (double)P / zc;
-    return std::min(1.0, (double)zc * S / G) * (len / (len + 2.0));
-}
-
 template <int MODE, int NDOT, bool HAS_D, bool U_RING, int SHAPE, int HB>
 static int launch_march_t(cudamat_solver *s, const MarchArgs &a) {
     MarchPlan M = *s->march;
