@@ -989,7 +989,8 @@ int launch_reduce_finish(cudamat_solver *s, const RedCtx &rc, int nq, int phase,
     cudaLaunchConfig_t cfg{};
     // one warp per (quantity, tile); a few hundred CTAs at most, so the ticket / fence cost stays negligible
     int grid = 1;
-    if (stage != 2) grid = std::max(1, std::min((nq * rc.ntile + kCtaWarps - 1) / kCtaWarps, 592));    // 4 CTAs per SM resident: one (quantity, tile) per warp up to 256^3
+    static const int cap = [] { const char *e = getenv("CUDAMAT_RF_GRID"); return e && *e ? atoi(e) : 592; }();
+    if (stage != 2) grid = std::max(1, std::min((nq * rc.ntile + kCtaWarps - 1) / kCtaWarps, cap));    // 4 CTAs per SM resident: one (quantity, tile) per warp up to 256^3
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCtaThreads); cfg.stream = s->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -179,16 +179,23 @@ def test_ilu0_factor_and_sweeps(cm, O, pin, torch_cuda, nm):
     rhs = np.random.default_rng(17).standard_normal(n)
     yl = O.sptrsv_lower_unit(ia, ja, M_o, rhs)
     yu = O.sptrsv_upper(ia, ja, M_o, rhs)
-    for syncfree in (0, 1):
+    # syncfree 0: one launch per level; 1 + ring 1: the role-split ring kernel (these systems fit its shared memory);
+    # 1 + ring 0: the barrier-per-level single-CTA kernel of round 1 (still used between 18 k and 25 k rows)
+    for syncfree, ring in ((0, 1), (1, 1), (1, 0)):
         s, _ = make_solver(cm, torch, ia, ja, a, mode=2)
         s.set_option("sptrsv_syncfree", syncfree)
+        s.set_option("sptrsv_ring", ring)
         drhs = dev(torch, rhs)
         out = torch.zeros(n, dtype=torch.float64, device="cuda")
         for rep in range(3):      # repeated sweeps reuse flags / tickets
             s.sptrsv(False, drhs.data_ptr(), out.data_ptr())
-            assert np.array_equal(out.cpu().numpy(), yl), "L sweep syncfree=%d rep=%d" % (syncfree, rep)
+            assert np.array_equal(out.cpu().numpy(), yl), "L sweep syncfree=%d ring=%d rep=%d" % (syncfree, ring, rep)
             s.sptrsv(True, drhs.data_ptr(), out.data_ptr())
-            assert np.array_equal(out.cpu().numpy(), yu), "U sweep syncfree=%d rep=%d" % (syncfree, rep)
+            assert np.array_equal(out.cpu().numpy(), yu), "U sweep syncfree=%d ring=%d rep=%d" % (syncfree, ring, rep)
+        # in place (rhs == out), as the preconditioned loop chains L into U
+        io = drhs.clone()
+        s.sptrsv(False, io.data_ptr(), io.data_ptr())
+        assert np.array_equal(io.cpu().numpy(), yl), "in-place L sweep syncfree=%d ring=%d" % (syncfree, ring)
         s.close()
 
 
