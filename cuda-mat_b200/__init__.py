@@ -55,7 +55,7 @@ EXPORTS = [
     "cudamat_ilu0_host", "cudamat_create", "cudamat_destroy", "cudamat_set_option",
     "cudamat_set_csr_host", "cudamat_set_csr_device", "cudamat_analyze", "cudamat_solve_device",
     "cudamat_get_history", "cudamat_spmv_device", "cudamat_dot_device", "cudamat_get_ilu0_host",
-    "cudamat_sptrsv_device", "cudamat_comm_p2p_enabled", "cudamat_write_mm", "cudamat_write_mm_vector", "cudamat_comm_unique_id", "cudamat_comm_init", "cudamat_partition_rows",
+    "cudamat_sptrsv_device", "cudamat_sweep_blocks", "cudamat_comm_p2p_enabled", "cudamat_write_mm", "cudamat_write_mm_vector", "cudamat_comm_unique_id", "cudamat_comm_init", "cudamat_partition_rows",
     "cudamat_halo_plan_host", "cudamat_tiled_plan_host", "cudamat_march_plan_host",
     "cudamat_gen_poisson3d_device", "cudamat_poisson3d_nnz", "cudamat_gen_xtrue_device",
     "cudamat_gen_random_dd_device", "cudamat_load_mm", "cudamat_free",
@@ -85,6 +85,7 @@ lib.cudamat_spmv_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void
 lib.cudamat_dot_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, c_dp]
 lib.cudamat_get_ilu0_host.argtypes = [C.c_void_p, c_dp]
 lib.cudamat_sptrsv_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+lib.cudamat_sweep_blocks.argtypes = [C.c_void_p]
 lib.cudamat_partition_rows.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
 lib.cudamat_halo_plan_host.argtypes = [C.c_int64, C.c_int64, C.c_int64, c_ip, C.c_int, C.POINTER(C.c_int64), c_ip,
                                        C.POINTER(c_ip), c_ip]
@@ -274,6 +275,9 @@ class Solver:
 
     def sptrsv(self, upper, d_rhs, d_out):
         _check(lib.cudamat_sptrsv_device(self.h, int(upper), d_rhs, d_out))
+
+    def sweep_blocks(self):
+        return int(lib.cudamat_sweep_blocks(self.h))
 
 
 def partition_rows(n_global, world, rank):

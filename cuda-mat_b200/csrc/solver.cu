@@ -832,6 +832,7 @@ int cudamat_get_ilu0_host(cudamat_solver *s, double *M_out) {
     return CUDAMAT_OK;
 }
 
+int cudamat_sweep_blocks(cudamat_solver *s) { return s ? cudamat::sweepblk_blocks(s) : 0; }
 int cudamat_sptrsv_device(cudamat_solver *s, int upper, const double *d_rhs, double *d_out) {
     if (!s || !d_rhs || !d_out) return CUDAMAT_E_INVALID;
     DeviceGuard dg(s->device);

@@ -289,6 +289,7 @@ void ilu0_release(cudamat_solver *s);
 // comm.cu
 int comm_halo_exchange(cudamat_solver *s, double *vec);
 int march_choose_zc(int S, int P, int G);
+int sweepblk_blocks(const cudamat_solver *s);
 bool comm_halo_planes(const cudamat_solver *s, int D, int *lo_base, int *hi_base);   // halo = whole planes of the two slab neighbours?
 int finish_reduction(cudamat_solver *s, const RedCtx &rc, int phase, int nq);   // groups + cross-rank exchange + final + scalar recurrence
 int launch_reduce_finish(cudamat_solver *s, const RedCtx &rc, int nq, int phase, int stage, const double *glob,

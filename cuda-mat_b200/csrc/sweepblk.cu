@@ -10,8 +10,9 @@
 // to-block dependencies (3 faces) go through global memory: blocks are handed out in block-wavefront order by a ticket, a
 // block waits for the done-flags of its three predecessor blocks, pulls their faces of the output vector into its halo layer,
 // and publishes its three outgoing faces + flag before the rest of its values.
-// Measured (tools/sptrsv_bench.py, B200): 256^3 L 0.47 ms / U 0.66 ms against 1.26 / 1.31 ms of the generic sweeps; 64^3 0.11 /
-// 0.14 ms against 0.21 / 0.22 ms.  CUDAMAT_SWEEP_DEBUG=1 prints the SM cycles per phase of a block.
+// Measured (tools/sptrsv_bench.py, B200): 256^3 L 0.43 ms / U 0.63 ms against 1.26 / 1.31 ms of the generic sweeps; 64^3 0.10 /
+// 0.14 ms against 0.21 / 0.22 ms; grids whose edges are not multiples of 16 (partial blocks): 100^3 0.17 / 0.26 against 0.33 /
+// 0.36 ms, 250^3 0.53 / 0.75 against 1.21 / 1.26 ms.  CUDAMAT_SWEEP_DEBUG=1 prints the SM cycles per phase of a block.
 //
 // Arithmetic is the spec's (oracle orc_sptrsv_*): per row acc = rhs; acc = fma(-M_ik, y_k, acc) over the
 // row's entries in ascending column order (L: -D, -a, -1; U: +1, +a, +D), U ends with one IEEE division — bit-identical to
@@ -44,7 +45,7 @@ struct SweepTable {                                                // cells of a
 
 struct BlockSweep {
     int nbx, nby, nbz, nblk;
-    int nx, ny;                                                    // line length a, lines per plane D / a
+    int nx, ny, nz;                                                // line length a, lines per plane D / a, planes
     int *d_order[2] = {nullptr, nullptr};                          // block ids in block-wavefront order (L ascending, U descending)
     double *d_coef[2] = {nullptr, nullptr};                        // [blk][2][pos][2]: L: M(-D), M(-a) | M(-1), -; U: M(+1), M(+a) | M(+D), diag
     unsigned char *d_pres[2] = {nullptr, nullptr};                 // [blk][pos] presence bits of the three entries
@@ -56,8 +57,9 @@ struct BlockSweep {
     SweepTable *h_table = nullptr;
 };
 
-// block-ordered factor records: thread per (block, position)
-__global__ void k_sblk_records(int nblk, int nbx, int nby, int nx, int ny, const __grid_constant__ SweepTable T, const int *ia,
+// block-ordered factor records: thread per (block, position).  Blocks at the far faces of a grid whose edges are not multiples
+// of 16 are partial: positions outside the grid get an all-zero record without the `valid` bit (8) and are never stored.
+__global__ void k_sblk_records(int nblk, int nbx, int nby, int nx, int ny, int nz, const __grid_constant__ SweepTable T, const int *ia,
                                const unsigned char *tmask, const double *M, double *coef_l, unsigned char *pres_l, double *coef_u,
                                unsigned char *pres_u) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,20 +70,35 @@ __global__ void k_sblk_records(int nblk, int nbx, int nby, int nx, int ny, const
         const unsigned c = T.cell[pos];
         int lx = c & 15, ly = (c >> 4) & 15, lz = c >> 8;
         if (u) { lx = kSB - 1 - lx; ly = kSB - 1 - ly; lz = kSB - 1 - lz; }           // U walks the block from the far corner
-        const long long g = ((long long)(bz * kSB + lz) * ny + (by * kSB + ly)) * nx + (bx * kSB + lx);
-        const unsigned m = tmask[g];                              // pattern (-D, -a, -1, 0, +1, +a, +D)
-        const int s = ia[g];
-        double c4[4] = {0.0, 0.0, 0.0, 0.0};
+        const int gx = bx * kSB + lx, gy = by * kSB + ly, gz = bz * kSB + lz;
+        double c4[4] = {0.0, 0.0, 0.0, u ? 1.0 : 0.0};
         unsigned pres = 0;
-        for (int e = 0; e < 3; ++e) {
-            const int q = u ? 4 + e : e;                           // ascending column order on either side of the diagonal
-            if (m & (1u << q)) { c4[e] = M[s + __popc(m & ((1u << q) - 1u))]; pres |= 1u << e; }
+        if (gx < nx && gy < ny && gz < nz) {
+            const long long g = ((long long)gz * ny + gy) * nx + gx;
+            const unsigned m = tmask[g];                          // pattern (-D, -a, -1, 0, +1, +a, +D)
+            const int s = ia[g];
+            pres = 8u;
+            for (int e = 0; e < 3; ++e) {
+                const int q = u ? 4 + e : e;                       // ascending column order on either side of the diagonal
+                if (m & (1u << q)) { c4[e] = M[s + __popc(m & ((1u << q) - 1u))]; pres |= 1u << e; }
+            }
+            if (u) c4[3] = M[s + __popc(m & 7u)];                 // the diagonal
         }
-        if (u) c4[3] = M[s + __popc(m & 7u)];                     // the diagonal
         double *dst = (u ? coef_u : coef_l) + (size_t)blk * kSBRows * 4 + (size_t)pos * 2;     // two planes of double2 per block
         dst[0] = c4[0]; dst[1] = c4[1]; dst[2 * kSBRows] = c4[2]; dst[2 * kSBRows + 1] = c4[3];
         (u ? pres_u : pres_l)[t] = (unsigned char)pres;
     }
+}
+// the kernel resolves a row's three predecessors by grid position: an entry that crosses a grid face (periodic stencils, a -1
+// entry at the start of a line, ...) would be read from the wrong place — such matrices keep the generic sweeps
+__global__ void k_sblk_check(int n, int nx, int ny, int nz, const unsigned char *tmask, int *bad) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int gx = row % nx, gy = (row / nx) % ny, gz = row / (nx * ny);
+    const unsigned m = tmask[row];
+    const bool ok = !((m & 1u) && gz == 0) && !((m & 2u) && gy == 0) && !((m & 4u) && gx == 0) && (m & 8u) &&
+                    !((m & 16u) && gx == nx - 1) && !((m & 32u) && gy == ny - 1) && !((m & 64u) && gz == nz - 1);
+    if (!ok) *bad = 1;
 }
 
 __device__ __forceinline__ uint32_t sb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,7 +125,7 @@ struct SweepSmem {
 constexpr size_t kSBSmem = sizeof(SweepSmem);                     // 211 KB: one CTA per SM
 
 template <bool UPPER>
-__global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int nbx, int nby, int nbz, int nx, int ny, const int *order,
+__global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int nbx, int nby, int nbz, int nx, int ny, int nz, const int *order,
                                                                    const double *coef, const unsigned char *pres, const double *rhs,
                                                                    double *out, int *flag, unsigned *ticket, int epoch, const int *status,
                                                                    const __grid_constant__ SweepTable T, const unsigned short *inv,
@@ -161,13 +178,15 @@ __global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int 
         long long ts[6]; if (dbg && tid == 0) ts[0] = clock64();
         const int bx = blk % nbx, by = (blk / nbx) % nby, bz = blk / (nbx * nby);
         const long long g0 = ((long long)(bz * kSB) * ny + by * kSB) * nx + bx * kSB;       // first cell of the block
+        const int ex = min(kSB, nx - bx * kSB), ey = min(kSB, ny - by * kSB), ez = min(kSB, nz - bz * kSB);     // < 16: a partial block at a far face
         // ---- independent of the predecessors: the right-hand side, coalesced from the vector, scattered to wavefront order ----
         {
             double rv[kPer];
 #pragma unroll
             for (int k = 0; k < kPer; ++k) {
                 const int i = tid + k * kSBThreads;
-                rv[k] = __ldg(rhs + g0 + (i >> 8) * plane + (long long)((i >> 4) & 15) * nx + (i & 15));
+                const bool in = (i & 15) < ex && ((i >> 4) & 15) < ey && (i >> 8) < ez;
+                rv[k] = in ? __ldg(rhs + g0 + (i >> 8) * plane + (long long)((i >> 4) & 15) * nx + (i & 15)) : 0.0;
             }
 #pragma unroll
             for (int k = 0; k < kPer; ++k) S.R[inv_r[k]] = rv[k];
@@ -192,9 +211,9 @@ __global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int 
             const int hx = UPPER ? kSB : -1;                      // coordinate of the halo layer relative to the block
             const bool has_x = UPPER ? bx + 1 < nbx : bx > 0, has_y = UPPER ? by + 1 < nby : by > 0, has_z = UPPER ? bz + 1 < nbz : bz > 0;
             double hv[3] = {0.0, 0.0, 0.0};
-            if (has_x) hv[0] = __ldcg(out + g0 + w * plane + (long long)u * nx + hx);
-            if (has_y) hv[1] = __ldcg(out + g0 + w * plane + (long long)hx * nx + u);
-            if (has_z) hv[2] = __ldcg(out + g0 + hx * plane + (long long)w * nx + u);
+            if (has_x && u < ey && w < ez) hv[0] = __ldcg(out + g0 + w * plane + (long long)u * nx + hx);
+            if (has_y && u < ex && w < ez) hv[1] = __ldcg(out + g0 + w * plane + (long long)hx * nx + u);
+            if (has_z && u < ex && w < ey) hv[2] = __ldcg(out + g0 + hx * plane + (long long)w * nx + u);
             if (has_x) S.Y[(w + OFF) * kSBPZ + (u + OFF) * kSBPY + (hx + OFF)] = hv[0];
             if (has_y) S.Y[(w + OFF) * kSBPZ + (hx + OFF) * kSBPY + (u + OFF)] = hv[1];
             if (has_z) S.Y[(hx + OFF) * kSBPZ + (w + OFF) * kSBPY + (u + OFF)] = hv[2];
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int 
             if (cur.p & 2u) y1 = *reinterpret_cast<const double *>(Yb + (int)cur.li + 8 * SY);
             if (cur.p & 4u) y2 = *reinterpret_cast<const double *>(Yb + (int)cur.li + 8 * (UPPER ? SZ : SX));
             load_ops(min(p1 + tid, kSBRows - 1), nxt);
-            const bool mine = tid < p1 - p0;
+            const bool mine = tid < p1 - p0 && (cur.p & 8u);      // bit 3: the cell exists (partial blocks)
             double acc = cur.r;                                    // ascending columns — U: +1, +a, +D, then the division; L: -D, -a, -1
             acc = __fma_rn(-cur.a.x, y0, acc);
             acc = __fma_rn(-cur.a.y, y1, acc);
@@ -254,9 +273,9 @@ __global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int 
         {
             const int u = tid & 15, w = tid >> 4;
             const int fx = UPPER ? 0 : kSB - 1;                   // the face the successors read
-            __stcg(out + g0 + w * plane + (long long)u * nx + fx, S.Y[(w + OFF) * kSBPZ + (u + OFF) * kSBPY + (fx + OFF)]);
-            __stcg(out + g0 + w * plane + (long long)fx * nx + u, S.Y[(w + OFF) * kSBPZ + (fx + OFF) * kSBPY + (u + OFF)]);
-            __stcg(out + g0 + fx * plane + (long long)w * nx + u, S.Y[(fx + OFF) * kSBPZ + (w + OFF) * kSBPY + (u + OFF)]);
+            if (fx < ex && u < ey && w < ez) __stcg(out + g0 + w * plane + (long long)u * nx + fx, S.Y[(w + OFF) * kSBPZ + (u + OFF) * kSBPY + (fx + OFF)]);
+            if (u < ex && fx < ey && w < ez) __stcg(out + g0 + w * plane + (long long)fx * nx + u, S.Y[(w + OFF) * kSBPZ + (fx + OFF) * kSBPY + (u + OFF)]);
+            if (u < ex && w < ey && fx < ez) __stcg(out + g0 + fx * plane + (long long)w * nx + u, S.Y[(fx + OFF) * kSBPZ + (w + OFF) * kSBPY + (u + OFF)]);
         }
         __syncthreads();                                           // the release below is cumulative over the CTA's face stores
         if (tid == 0) {
@@ -272,7 +291,7 @@ __global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int 
         for (int k = 0; k < kPer; ++k) {
             const int i = tid + k * kSBThreads;
             const int lx = i & 15, ly = (i >> 4) & 15, lz = i >> 8;
-            __stcg(out + g0 + lz * plane + (long long)ly * nx + lx, S.Y[(lz + OFF) * kSBPZ + (ly + OFF) * kSBPY + (lx + OFF)]);
+            if (lx < ex && ly < ey && lz < ez) __stcg(out + g0 + lz * plane + (long long)ly * nx + lx, S.Y[(lz + OFF) * kSBPZ + (ly + OFF) * kSBPY + (lx + OFF)]);
         }
         __syncthreads();
         blk = S.next_blk;                                          // (rewritten only after the next block's wavefronts)
@@ -289,19 +308,34 @@ void sweepblk_release(cudamat_solver *s) {
     s->bsweep = nullptr;
 }
 
-// builds the block plan after the factorisation when the MARCH analysis found the 7-point grid structure and the grid
-// edges are multiples of the block edge; otherwise the generic sweeps stay
+// builds the block plan after the factorisation when the class analysis (rowclass.cu) found the 7-point grid structure —
+// superset pattern (-D, -a, -1, 0, +1, +a, +D) with n = nx ny nz, a = nx, D = nx ny — and no entry crosses a grid face;
+// otherwise the generic sweeps stay.  Grid edges need not be multiples of the block edge (partial blocks at the far faces).
+// Systems the single-CTA shared-memory sweeps hold (<= 25 600 rows) are left to them.
 int sweepblk_plan(cudamat_solver *s) {
     sweepblk_release(s);
-    if (!s->opt_sptrsv_blocked || !s->march || s->comm || s->d_perm || s->march->shape != 1 || !s->cls[1].d_tmask) return CUDAMAT_OK;
-    const MarchPlan &M = *s->march;
-    const int nx = M.loff[5], D = M.D;                             // pattern (-D, -a, -1, 0, +1, +a, +D)
-    if (nx <= 0 || M.loff[1] != -nx || D % nx != 0) return CUDAMAT_OK;
-    const int ny = D / nx, nz = s->n / D;
-    if (nx % kSB || ny % kSB || nz % kSB || (long long)nx * ny * nz != s->n) return CUDAMAT_OK;
+    const RowClasses &C = s->cls[1];
+    if (!s->opt_sptrsv_blocked || s->comm || s->d_perm || !C.d_tmask || !C.h_tdict || C.h_tdict->sup_len != 7 || s->n <= 25600) return CUDAMAT_OK;
+    const int *so = C.h_tdict->sup_off;
+    const long long nx = so[5], D = so[6];
+    if (nx < 2 || D < 2 * nx || so[0] != -D || so[1] != -nx || so[2] != -1 || so[3] != 0 || so[4] != 1 || D % nx != 0 || s->n % D != 0) return CUDAMAT_OK;
+    const long long ny = D / nx, nz = s->n / D;
+    if (ny < 2 || nz < 2 || nx * ny * nz != s->n) return CUDAMAT_OK;
+    {
+        int *d_bad = nullptr, bad = 1;
+        CM_CUDA(dev_alloc((void **)&d_bad, sizeof(int)));
+        CM_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s->stream));
+        k_sblk_check<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->n, (int)nx, (int)ny, (int)nz, C.d_tmask, d_bad);
+        s->launches++;
+        CM_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CM_CUDA(cudaStreamSynchronize(s->stream));
+        dev_free(d_bad);
+        if (bad) return CUDAMAT_OK;
+    }
     BlockSweep *B = new BlockSweep();
     s->bsweep = B;
-    B->nx = nx; B->ny = ny; B->nbx = nx / kSB; B->nby = ny / kSB; B->nbz = nz / kSB; B->nblk = B->nbx * B->nby * B->nbz;
+    B->nx = (int)nx; B->ny = (int)ny; B->nz = (int)nz;
+    B->nbx = (int)((nx + kSB - 1) / kSB); B->nby = (int)((ny + kSB - 1) / kSB); B->nbz = (int)((nz + kSB - 1) / kSB); B->nblk = B->nbx * B->nby * B->nbz;
     // cells of a block in wavefront order
     B->h_table = new SweepTable();
     std::vector<int> cnt(kSBLevels + 1, 0);
@@ -340,7 +374,7 @@ int sweepblk_plan(cudamat_solver *s) {
     CM_CUDA(cudaMemsetAsync(B->d_flag, 0, sizeof(int) * (size_t)B->nblk, s->stream));
     CM_CUDA(cudaMemsetAsync(B->d_ticket, 0, sizeof(unsigned), s->stream));
     const long long total = (long long)nrec;
-    k_sblk_records<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(B->nblk, B->nbx, B->nby, nx, ny, *B->h_table, s->pre_ia, s->cls[1].d_tmask,
+    k_sblk_records<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(B->nblk, B->nbx, B->nby, (int)nx, (int)ny, (int)nz, *B->h_table, s->pre_ia, s->cls[1].d_tmask,
                                                                             s->d_M, B->d_coef[0], B->d_pres[0], B->d_coef[1], B->d_pres[1]);
     CM_CUDA(cudaGetLastError());
     CM_CUDA(cudaStreamSynchronize(s->stream));
@@ -355,6 +389,7 @@ int sweepblk_plan(cudamat_solver *s) {
 }
 
 bool sweepblk_active(const cudamat_solver *s) { return s->bsweep != nullptr; }
+int sweepblk_blocks(const cudamat_solver *s) { return s->bsweep ? s->bsweep->nblk : 0; }
 
 int launch_sptrsv_blocked(cudamat_solver *s, bool upper, const double *rhs, double *out) {
     BlockSweep *B = s->bsweep;
@@ -372,11 +407,11 @@ int launch_sptrsv_blocked(cudamat_solver *s, bool upper, const double *rhs, doub
     long long *dbg = nullptr;
     if (want_dbg) CM_CUDA(cudaMalloc(&dbg, sizeof(long long) * 6 * (size_t)B->nblk));
     if (upper)
-        CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_blocked<true>, B->nblk, B->nbx, B->nby, B->nbz, B->nx, B->ny, (const int *)B->d_order[u],
+        CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_blocked<true>, B->nblk, B->nbx, B->nby, B->nbz, B->nx, B->ny, B->nz, (const int *)B->d_order[u],
                                    (const double *)B->d_coef[u], (const unsigned char *)B->d_pres[u], rhs, out, B->d_flag, B->d_ticket, epoch,
                                    status, *B->h_table, (const unsigned short *)B->d_inv[u], dbg));
     else
-        CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_blocked<false>, B->nblk, B->nbx, B->nby, B->nbz, B->nx, B->ny, (const int *)B->d_order[u],
+        CM_CUDA(cudaLaunchKernelEx(&cfg, k_sptrsv_blocked<false>, B->nblk, B->nbx, B->nby, B->nbz, B->nx, B->ny, B->nz, (const int *)B->d_order[u],
                                    (const double *)B->d_coef[u], (const unsigned char *)B->d_pres[u], rhs, out, B->d_flag, B->d_ticket, epoch,
                                    status, *B->h_table, (const unsigned short *)B->d_inv[u], dbg));
     s->launches++;

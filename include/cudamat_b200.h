@@ -164,6 +164,8 @@ int cudamat_dot_device(cudamat_solver *s, const double *d_a, const double *d_b, 
 int cudamat_get_ilu0_host(cudamat_solver *s, double *M_out);
 /* out = L^{-1} rhs (upper = 0, unit diagonal) or U^{-1} rhs (upper = 1) on the analysed factor */
 int cudamat_sptrsv_device(cudamat_solver *s, int upper, const double *d_rhs, double *d_out);
+/* number of 16^3 blocks of the block-wavefront sweep plan (7-point grid factors, csrc/sweepblk.cu); 0: the generic sweeps run */
+int cudamat_sweep_blocks(cudamat_solver *s);
 
 /* ---- multi-GPU (one process per GPU; NCCL is dlopen()ed on first use) ----------------------- */
 /* The reference is single-GPU; sharding follows BASELINE.json's north_star: contiguous row

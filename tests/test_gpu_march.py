@@ -196,3 +196,72 @@ def test_block_wavefront_sweeps_bit_identical(cm, O, torch_cuda, p64):
         assert np.array_equal(s.history(), so["hist"])
         print("ILU0 64^3 blocked=%d: %d iterations, loop %.2f ms" % (blocked, st["iterations"], st["t_loop"] * 1e3))
         s.close()
+
+
+def _grid7(nx, ny, nz, periodic_x=False):
+    """7-point Dirichlet stencil (6, -1) on an nx x ny x nz grid, natural ordering; periodic_x adds the wrap-around entries of
+    the x lines.  (The ILU0 factor's values still differ from cell to cell near the faces.)"""
+    import scipy.sparse as sp
+    n = nx * ny * nz
+    idx = np.arange(n).reshape(nz, ny, nx)
+    rows, cols = [], []
+    def link(a, b):
+        rows.append(a.ravel()); cols.append(b.ravel())
+        rows.append(b.ravel()); cols.append(a.ravel())
+    link(idx[:, :, :-1], idx[:, :, 1:]); link(idx[:, :-1, :], idx[:, 1:, :]); link(idx[:-1, :, :], idx[1:, :, :])
+    if periodic_x:
+        link(idx[:, :, 0], idx[:, :, -1])
+    r = np.concatenate(rows); c = np.concatenate(cols)
+    A = sp.csr_matrix((np.full(len(r), -1.0), (r, c)), shape=(n, n))
+    A = A + sp.diags(np.full(n, 6.0))
+    A = A.tocsr(); A.sort_indices()
+    return A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(40, 40, 40), (30, 50, 70), (72, 17, 33), (33, 64, 48)])
+def test_block_wavefront_sweeps_partial_blocks(cm, O, torch_cuda, dims):
+    """Grid edges that are not multiples of the 16-cell block edge: partial blocks at the far faces.  L / U sweeps bit-identical
+    to the oracle's; the blocked kernel must actually be the one that ran (the plan reports its blocks)."""
+    torch = torch_cuda
+    nx, ny, nz = dims
+    ia, ja, a = _grid7(nx, ny, nz)
+    n = len(ia) - 1
+    Mo, _ = O.ilu0(ia, ja, a)
+    rhs = np.random.default_rng(5).standard_normal(n)
+    want = {0: O.sptrsv_lower_unit(ia, ja, Mo, rhs), 1: O.sptrsv_upper(ia, ja, Mo, rhs)}
+    for blocked in (1, 0):
+        s = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
+        s.set_option("sptrsv_blocked", blocked)
+        s.set_csr_host(a, ia, ja)
+        s.analyze(cm.MODE_ILU0)
+        assert np.array_equal(s.ilu0_values(len(a)), Mo)
+        assert s.sweep_blocks() == (blocked * -(-nx // 16) * -(-ny // 16) * -(-nz // 16))
+        drhs = _dev(torch, rhs)
+        for rep in range(2):
+            for upper in (0, 1):
+                out = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+                s.sptrsv(upper, drhs.data_ptr(), out.data_ptr())
+                torch.cuda.synchronize()
+                assert np.array_equal(out.cpu().numpy(), want[upper]), (dims, blocked, upper, rep)
+        s.close()
+
+
+@pytest.mark.gpu
+def test_block_wavefront_sweeps_refuse_wrap_around_entries(cm, O, torch_cuda):
+    """A periodic x direction has the 7 offsets of the grid stencil plus wrap-around entries: entries that cross a grid face would
+    be read from the wrong place, the plan must leave such a matrix to the generic sweeps (and those stay exact)."""
+    torch = torch_cuda
+    ia, ja, a = _grid7(32, 32, 32, periodic_x=True)
+    n = len(ia) - 1
+    s = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
+    s.set_csr_host(a, ia, ja)
+    s.analyze(cm.MODE_ILU0)
+    assert s.sweep_blocks() == 0
+    Mo, _ = O.ilu0(ia, ja, a)
+    rhs = np.random.default_rng(6).standard_normal(n)
+    out = torch.zeros(n, dtype=torch.float64, device="cuda")
+    s.sptrsv(0, _dev(torch, rhs).data_ptr(), out.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), O.sptrsv_lower_unit(ia, ja, Mo, rhs))
+    s.close()
