@@ -308,13 +308,6 @@ __device__ __forceinline__ void ring_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-// explicit 32-bit shared-memory addressing for the walker: with generic pointers the compiler rebuilt the shared window base
-// (S2R SR_CgaCtaId + LEA) in front of every predicated access — 128 dependent instructions per level, 610 cycles (ncu source
-// view, round 2)
-__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
-__device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-
 template <bool UPPER>
 __global__ void __launch_bounds__(kRingThreads, 1) k_sptrsv_ring(const int *order, const int *chunk_beg, const int *chunk_info, int nchunks,
                                                                   int len, int n, const int *p_cnt, const int *p_ptr, const int *p_col,

@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
             if (k + 2 + DEPTH <= lim) issue(gofs(k + 2 + DEPTH), st);
         };
         double2 stA[NV][PPT], stB[DEPTH > 1 ? NV : 1][DEPTH > 1 ? PPT : 1];
+        (void)stB;
         if (k0 + 2 <= lim) issue(gofs(k0 + 2), stA);
         if constexpr (DEPTH > 1) { if (k0 + 3 <= lim) issue(gofs(k0 + 3), stB); }
 #pragma unroll 1

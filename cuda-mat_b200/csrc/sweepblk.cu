@@ -6,7 +6,7 @@
 // iteration (profiles/r1b).  Here the grid is cut into 16^3 blocks (4096 rows).  Inside a block the 46 wavefronts are walked by
 // ONE CTA (one per SM, 211 KB of shared memory) with everything a wavefront touches in shared memory — the block's factor
 // records (TMA bulk copy, issued a whole block ahead), its right-hand side, the solved values — and a CTA barrier per wavefront
-// instead of a global round trip (~210 cycles per wavefront for L, ~375 for U with its IEEE division, measured).  Only block-
+// instead of a global round trip (~170 cycles per wavefront for L, ~340 for U with its IEEE division, measured).  Only block-
 // to-block dependencies (3 faces) go through global memory: blocks are handed out in block-wavefront order by a ticket, a
 // block waits for the done-flags of its three predecessor blocks, pulls their faces of the output vector into its halo layer,
 // and publishes its three outgoing faces + flag before the rest of its values.
@@ -234,19 +234,31 @@ __global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int 
         // fma(-0.0, +0.0, acc) = acc + (-0.0) = acc for every acc, so the FMA needs no predicate.  Threads beyond the wavefront run
         // on a clamped position and only skip the store.
         struct Ops { double2 a, b; double r, rcp; unsigned li, p; };
-        const unsigned char *Yb = reinterpret_cast<const unsigned char *>(S.Y);
+        const unsigned y_a = opaque_smem_addr(S.Y);                // explicit shared addresses on the chain (no S2R + LEA per access)
         auto load_ops = [&](int q, Ops &o) {
             o.a = reinterpret_cast<const double2 *>(S.C)[q]; o.b = reinterpret_cast<const double2 *>(S.C)[kSBRows + q];
             o.r = S.R[q]; o.li = S.li[q]; o.p = S.P[q];
-            if (UPPER) o.rcp = div_prepare(o.b.y);
         };
+        // U: the diagonal of a wavefront is read TWO wavefronts ahead, so that the reciprocal half of its division (MUFU + 5
+        // DFMA) has its operand in a register a whole wavefront before it is needed and issues in the shadow of the solved-value
+        // loads instead of in front of the quotient (in-order issue: whatever waits in front of the chain's next instruction is
+        // on the chain).  Tried and slower: the idle warps 6-7 computing the reciprocals into a shared-memory ring (U wavefront
+        // 342 -> 400 cycles: the helpers' own chain plus the 8-warp barrier).
+        auto load_diag = [&](int q) { return S.C[2 * (kSBRows + q) + 1]; };
         int p0 = 0, p1 = S.lp[1], p2 = S.lp[2];
+        double dg_ahead = 1.0;
         auto step = [&](const Ops &cur, Ops &nxt, int l) {
             const int p3 = S.lp[l + 3];                            // read a wavefront before it is needed
+            const unsigned ya = y_a + cur.li;
             double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-            if (cur.p & 1u) y0 = *reinterpret_cast<const double *>(Yb + (int)cur.li + 8 * (UPPER ? SX : SZ));
-            if (cur.p & 2u) y1 = *reinterpret_cast<const double *>(Yb + (int)cur.li + 8 * SY);
-            if (cur.p & 4u) y2 = *reinterpret_cast<const double *>(Yb + (int)cur.li + 8 * (UPPER ? SZ : SX));
+            if (cur.p & 1u) y0 = lds_f64((unsigned)((int)ya + 8 * (UPPER ? SX : SZ)));
+            if (cur.p & 2u) y1 = lds_f64((unsigned)((int)ya + 8 * SY));
+            if (cur.p & 4u) y2 = lds_f64((unsigned)((int)ya + 8 * (UPPER ? SZ : SX)));
+            if (UPPER) {
+                nxt.rcp = div_prepare(dg_ahead);                   // diagonal of wavefront l + 1, in a register since wavefront l - 1
+                asm volatile("" : "+d"(nxt.rcp));                  // here, not sunk into the dependent chain
+                dg_ahead = load_diag(min(p2 + tid, kSBRows - 1));  // diagonal of wavefront l + 2
+            }
             load_ops(min(p1 + tid, kSBRows - 1), nxt);
             const bool mine = tid < p1 - p0 && (cur.p & 8u);      // bit 3: the cell exists (partial blocks)
             double acc = cur.r;                                    // ascending columns — U: +1, +a, +D, then the division; L: -D, -a, -1
@@ -254,13 +266,15 @@ __global__ void __launch_bounds__(kSBThreads, 1) k_sptrsv_blocked(int nblk, int 
             acc = __fma_rn(-cur.a.y, y1, acc);
             acc = __fma_rn(-cur.b.x, y2, acc);
             if (UPPER && mine) acc = div_finish(acc, cur.b.y, cur.rcp);
-            if (mine) *reinterpret_cast<double *>(const_cast<unsigned char *>(Yb) + cur.li) = acc;
+            if (mine) sts_f64(ya, acc);
             asm volatile("bar.sync 1, %0;" ::"n"(kSBWalkers) : "memory");
             p0 = p1; p1 = p2; p2 = p3;
         };
         if (tid < kSBWalkers) {                                    // the widest wavefront has 192 cells: warps 6-7 only copy
             Ops oa, ob;
             load_ops(min(tid, kSBRows - 1), oa);
+            oa.rcp = 1.0; ob.rcp = 1.0;
+            if (UPPER) { oa.rcp = div_prepare(oa.b.y); dg_ahead = load_diag(min(p1 + tid, kSBRows - 1)); }
 #pragma unroll 1
             for (int l = 0; l < kSBLevels; l += 2) {               // 46 wavefronts: an even number
                 step(oa, ob, l);
