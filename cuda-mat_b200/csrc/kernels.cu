@@ -817,6 +817,27 @@ __global__ void __launch_bounds__(kCtaThreads) k_update_s(const VecArgs a) {
     halo_signal(a.hp, row_base, min(kTile, a.n - row_base));
 }
 
+// the same update on the first and the last plane of a slab shard only (S tiles each): the rows the neighbours need, pushed and
+// flagged BEFORE the folded SpMV 2 (MARCH MAKE_S) forms s for all rows on the fly — the full-size pass over r, v, s goes away
+__global__ void __launch_bounds__(kCtaThreads) k_update_s_boundary(const VecArgs a, int plane_tiles, int ntile) {
+    pdl_prologue();
+    if (a.sc->status != ST_RUNNING) return;
+    const int tid = threadIdx.x;
+    const int tile = (int)blockIdx.x < plane_tiles ? (int)blockIdx.x : ntile - 2 * plane_tiles + (int)blockIdx.x;
+    const int row_base = tile * kTile;
+    const double malpha = -a.sc->alpha;
+#pragma unroll
+    for (int j = 0; j < kSlabsPerWarp; ++j) {
+        const int row = row_base + j * kCtaThreads + tid;
+        if (row < a.n) {
+            const double q = __dadd_rn(__ldg(a.in0 + row), __dmul_rn(malpha, __ldg(a.in1 + row)));
+            a.out0[row] = q;
+            halo_store(a.hp, row, q);
+        }
+    }
+    halo_signal(a.hp, row_base, min(kTile, a.n - row_base));
+}
+
 // ilu0: r = fma(-alpha,v,r) ; x = fma(alpha,pw,x) ; red0 = r.r   (pbicgstab.cu:109-111)
 __global__ void __launch_bounds__(kCtaThreads) k_update_rx_ilu(const VecArgs a) {
     VEC_PROLOGUE
@@ -1046,6 +1067,19 @@ int launch_update_s(cudamat_solver *s, const double *r, const double *v, double 
     a.in0 = r; a.in1 = v; a.out0 = sv;
     if (hp) a.hp = *hp;
     LAUNCH_VEC(k_update_s, a);
+    return CUDAMAT_OK;
+}
+int launch_update_s_boundary(cudamat_solver *s, const double *r, const double *v, double *sv, const HaloPush *hp, int plane_tiles) {
+    VecArgs a = vec_args(s, PH_NONE);
+    a.in0 = r; a.in1 = v; a.out0 = sv;
+    if (hp) a.hp = *hp;
+    const int ntile = tiles_of(a.n);
+    if (ntile < 2 * plane_tiles) return launch_update_s(s, r, v, sv, hp);
+    { const int e_ = ev_mark(s, true); if (e_) return e_; }
+    CM_CUDA(launch_pdl2(k_update_s_boundary, 2 * plane_tiles, kCtaThreads, s->stream, a, plane_tiles, ntile));
+    s->launches++;
+    CM_CUDA(cudaGetLastError());
+    { const int e_ = ev_mark(s, false); if (e_) return e_; }
     return CUDAMAT_OK;
 }
 int launch_update_rx_ilu(cudamat_solver *s, const double *v, const double *pw, double *r, double *x) {

@@ -84,8 +84,11 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
     extern __shared__ __align__(16) double ring[];                 // 4 slots
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = M.S, P = M.P, Zc = M.Zc, n = a.n;
-    const int nlim = MODE == MARCH_LOAD_X ? M.n_tot : n;          // LOAD_X reads the operand incl. its halo region (sharded handles)
-    const int lo_base = MODE == MARCH_LOAD_X ? M.lo_base : -1, hi_base = MODE == MARCH_LOAD_X ? M.hi_base : -1;
+    // sharded handles: LOAD_X reads the operand incl. its halo region; MAKE_S forms s = r - alpha v for the shard's own planes and takes
+    // the neighbours' planes of s (pushed by k_update_s_boundary right before) from the halo region of the s vector (a.xout)
+    constexpr bool HALO_OK = MODE != MARCH_MAKE_P;
+    const int nlim = MODE == MARCH_LOAD_X ? M.n_tot : n;
+    const int lo_base = HALO_OK ? M.lo_base : -1, hi_base = HALO_OK ? M.hi_base : -1;
     pdl_sync();
     if (a.check_status && a.sc->status != ST_RUNNING) return;
     double c1 = 0.0, c2 = 0.0;                                     // MAKE_P: beta, -omega; MAKE_S: -alpha
@@ -101,7 +104,25 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
     const uint32_t coff = (uint32_t)(H + warp * 64 + 2 * lane) * 8u;
 
     // global loads of the tile whose buffer starts at element g0 = tile base - H -> registers
-    auto issue = [&](int g0, double2 (&st)[NV][PPT]) {
+    auto issue = [&](int g0, double2 (&st)[NV][PPT], bool halo = false) {
+        if (MODE == MARCH_MAKE_S && halo) {                        // a neighbour's plane of s: one vector, taken as it is
+            const int lim = M.n_tot;
+            if (g0 >= 0 && g0 + BUF <= lim) {
+                const double2 *src = reinterpret_cast<const double2 *>(a.xout + g0) + tid;
+#pragma unroll
+                for (int j = 0; j < PPT; ++j)
+                    if ((j + 1) * kCtaThreads <= PAIRS || tid + j * kCtaThreads < PAIRS) st[0][j] = __ldcg(src + j * kCtaThreads);
+            } else {
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) {
+                    const int g = g0 + 2 * (tid + j * kCtaThreads);
+                    const bool inb = tid + j * kCtaThreads < PAIRS;
+                    st[0][j].x = (inb && g >= 0 && g < lim) ? __ldcg(a.xout + g) : 0.0;
+                    st[0][j].y = (inb && g + 1 >= 0 && g + 1 < lim) ? __ldcg(a.xout + g + 1) : 0.0;
+                }
+            }
+            return;
+        }
         if (g0 >= 0 && g0 + BUF <= nlim) {                         // CTA-uniform: everything but the two ends of the vector
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
@@ -133,7 +154,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
         return __dadd_rn(r, __dmul_rn(c2, p));                     // pbicgstab.cu:698-700 (p = v here)
     };
     // registers -> operand values -> ring slot; centre pairs of an owned tile also go to global memory (written once)
-    auto convert = [&](int g0, int slot, bool owned, const double2 (&st)[NV][PPT]) {
+    auto convert = [&](int g0, int slot, bool owned, const double2 (&st)[NV][PPT], bool halo = false) {
         const uint32_t dst = ring_s + (uint32_t)(slot * BUF + 2 * tid) * 8u;
         double2 *gout = reinterpret_cast<double2 *>(a.xout + g0) + tid;
 #pragma unroll
@@ -141,8 +162,11 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
             const int pi = tid + j * kCtaThreads;
             if ((j + 1) * kCtaThreads <= PAIRS || pi < PAIRS) {
                 double2 o;
-                o.x = make(st[0][j].x, st[NV > 1 ? 1 : 0][j].x, st[NV > 2 ? 2 : 0][j].x);
-                o.y = make(st[0][j].y, st[NV > 1 ? 1 : 0][j].y, st[NV > 2 ? 2 : 0][j].y);
+                if (MODE == MARCH_MAKE_S && halo) o = st[0][j];
+                else {
+                    o.x = make(st[0][j].x, st[NV > 1 ? 1 : 0][j].x, st[NV > 2 ? 2 : 0][j].x);
+                    o.y = make(st[0][j].y, st[NV > 1 ? 1 : 0][j].y, st[NV > 2 ? 2 : 0][j].y);
+                }
                 sts128(dst + j * kCtaThreads * 16, o);
                 if (MODE != MARCH_LOAD_X && owned && 2 * pi >= H && 2 * pi < H + kTile) gout[j * kCtaThreads] = o;
             }
@@ -160,7 +184,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
         auto gofs = [&](int pl) -> int {
             return (pl < 0 ? lo_base : pl >= P ? hi_base : pl * S * kTile) + col * kTile - H;
         };
-        if (MODE == MARCH_LOAD_X && a.hw.nsrc > 0) {               // the neighbours' rows of this exchange have arrived?
+        if (HALO_OK && a.hw.nsrc > 0) {                            // the neighbours' rows of this exchange have arrived?
             if (k0 == 0 && lo_base >= 0) halo_wait(a.hw, col, a.sc ? &a.sc->status : nullptr);
             if (k1 == P - 1 && hi_base >= 0) halo_wait(a.hw, (P - 1) * S + col, a.sc ? &a.sc->status : nullptr);
         }
@@ -170,8 +194,9 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
             for (int pl = k0 - 1; pl <= k0 + 1; ++pl) {
                 if ((pl < 0 && lo_base < 0) || (pl >= P && hi_base < 0) || pl > P) continue;
                 const int g0 = gofs(pl);
-                issue(g0, st);
-                convert(g0, pl & 3, pl >= k0 && pl <= k1, st);
+                const bool halo = pl < 0 || pl >= P;
+                issue(g0, st, halo);
+                convert(g0, pl & 3, pl >= k0 && pl <= k1, st, halo);
             }
         }
         // Per-row side inputs of a plane — presence masks, dot operand u, shift d — are fetched one step AHEAD, right after
@@ -276,13 +301,13 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
                 }
                 if (gi == 1 && k < k1) fetch_side(k + 1);
             }
-            if (k + 2 <= lim) convert(((k + 2) * S + col) * kTile - H, (k + 2) & 3, k + 2 <= k1, st);
-            if (k + 2 + DEPTH <= lim) issue(gofs(k + 2 + DEPTH), st);
+            if (k + 2 <= lim) convert(((k + 2) * S + col) * kTile - H, (k + 2) & 3, k + 2 <= k1, st, k + 2 >= P);
+            if (k + 2 + DEPTH <= lim) issue(gofs(k + 2 + DEPTH), st, k + 2 + DEPTH >= P);
         };
         double2 stA[NV][PPT], stB[DEPTH > 1 ? NV : 1][DEPTH > 1 ? PPT : 1];
         (void)stB;
-        if (k0 + 2 <= lim) issue(gofs(k0 + 2), stA);
-        if constexpr (DEPTH > 1) { if (k0 + 3 <= lim) issue(gofs(k0 + 3), stB); }
+        if (k0 + 2 <= lim) issue(gofs(k0 + 2), stA, k0 + 2 >= P);
+        if constexpr (DEPTH > 1) { if (k0 + 3 <= lim) issue(gofs(k0 + 3), stB, k0 + 3 >= P); }
 #pragma unroll 1
         for (int k = k0; k <= k1; k += DEPTH) {
             step(k, stA);
@@ -403,8 +428,10 @@ int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old,
     return ev_mark(s, false);
 }
 // s = r - alpha v; t = (A + diag d) s; red0 = t . s, red1 = t . t                            (pbicgstab.cu:698-709)
-int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc) {
+int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc,
+                        const HaloWait *hw) {
     MarchArgs a{};
+    if (hw) a.hw = *hw;
     a.n = s->n; a.in0 = r; a.in1 = v; a.xout = sv; a.y = t; a.u = nullptr; a.d = d;
     a.tmask = s->march_tmask; a.rc = rc; a.sc = s->d_sc; a.check_status = 1;
     int e = ev_mark(s, true);

@@ -402,15 +402,16 @@ int rowclass_analyze(cudamat_solver *s) {
             M.lo_base = M.hi_base = -1; M.n_tot = n;
             bool usable = true;
             if (s->comm) {
-                static const bool env_off = [] { const char *e = getenv("CUDAMAT_MARCH_SHARDS"); return e && *e == '0'; }();
-                usable = comm_halo_planes(s, M.D, &M.lo_base, &M.hi_base) && s->opt_march_shards != 0 && !env_off;
+                static const int env_ms = [] { const char *e = getenv("CUDAMAT_MARCH_SHARDS"); return e && *e ? atoi(e) : -1; }();   // 0 off, 2 force
+                const int ms = env_ms >= 0 ? env_ms : s->opt_march_shards;
+                usable = comm_halo_planes(s, M.D, &M.lo_base, &M.hi_base) && ms != 0;
                 M.n_tot = n + s->nhalo;
-                // LOAD_X only (the folded updates would need the neighbours' r and v): MARCH beats TILED on a shard when its
-                // work items fill the CTA slots — 256^3 on 2 GPUs: 288 items for 296 slots, 3415 vs 3300 it/s (same box, A/B)
+                // MARCH beats TILED on a shard when its work items fill the CTA slots — 256^3 on 2 GPUs: 288 items for 296 slots,
+                // 3415 vs 3300 it/s; 512^3 on 2 GPUs: 256 items, 511 vs 520 it/s (same box, A/B)
                 int dev = 0, sms = 148;
                 if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                const int G = 2 * sms;                             // 512^3 on 2 GPUs: 256 items for 296 slots, 511 vs 520 it/s with TILED
-                if ((long long)march_choose_zc(M.S, M.P, G) * M.S * 20 < (long long)G * 19 && s->opt_march_shards < 2) usable = false;
+                const int G = 2 * sms;
+                if ((long long)march_choose_zc(M.S, M.P, G) * M.S * 20 < (long long)G * 19 && ms < 2) usable = false;
             }
             if (usable) {
                 s->march = new MarchPlan(M);

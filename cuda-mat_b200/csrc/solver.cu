@@ -356,8 +356,13 @@ static int solve_unprec(cudamat_solver *s, int mode, const double *d_b, const do
     int rc;
     // option "fuse": bit 0 folds the p update into SpMV 1 (MAKE_P), bit 1 the s update into SpMV 2 (MAKE_S)
     const bool persist = persist_eligible(s);                      // one cooperative kernel per batch of iterations (persist.cu)
-    const int fuse = persist ? 4 : (s->spmv_variant == CUDAMAT_SPMV_MARCH && march_available(s) && !s->comm &&
-                      (reinterpret_cast<uintptr_t>(d_d) & 15u) == 0) ? (s->opt_fuse & 3) : 0;   // 16-byte pairs (work vectors are 256-byte aligned)
+    // sharded handles: only the s update can be folded (bit 1), and only with the peer-memory halo path (the neighbours' planes of s
+    // are pushed by k_update_s_boundary) on shards of at least two planes
+    static const int env_sf = [] { const char *e = getenv("CUDAMAT_SHARD_FUSE"); return e && *e ? atoi(e) : -1; }();
+    const bool shard_fold = env_sf >= 0 ? env_sf != 0 : s->opt_shard_fuse != 0;
+    const int fuse_ok = !s->comm ? 3 : (shard_fold && comm_p2p(s) && s->march && s->march->P >= 2 && (s->march->lo_base >= 0 || s->march->hi_base >= 0)) ? 2 : 0;
+    const int fuse = persist ? 4 : (s->spmv_variant == CUDAMAT_SPMV_MARCH && march_available(s) &&
+                      (reinterpret_cast<uintptr_t>(d_d) & 15u) == 0) ? (s->opt_fuse & fuse_ok) : 0;   // 16-byte pairs (work vectors are 256-byte aligned)
     const bool fold_p = (fuse & 1) != 0, fold_s = (fuse & 2) != 0;
     const bool resume = s->opt_resume != 0 && s->last_mode == mode && s->last_fused == fuse && s->work != nullptr;
     if ((rc = ensure_work(s, fold_p ? 9 : 7))) return rc;
@@ -440,7 +445,23 @@ static int solve_unprec(cudamat_solver *s, int mode, const double *d_b, const do
             if (r2) return r2;
             if ((r2 = spmv_step(s, p_new, d_d, v_new, r0, 1, PH_U_A, 1, slot, 0))) return r2;       // :675-689
         }
-        if (fold_s) {
+        if (fold_s && s->comm) {
+            // slab shard: only the two boundary planes of s are formed (and pushed to the neighbours) by a vector kernel; the folded
+            // SpMV 2 forms s for the shard's own planes on the fly and reads the neighbours' planes from the halo region of s
+            HaloWait hw{};
+            int slot = comm_halo_push(s, sv, 1, &hp) ? 1 : -1;
+            s->time_slot = tm ? 3 : -1;
+            r2 = launch_update_s_boundary(s, r, v_new, sv, &hp, s->march->S);
+            s->time_slot = -1;
+            if (r2) return r2;
+            if (slot >= 0) comm_halo_wait(s, slot, &hw);
+            s->time_slot = tm ? 1 : -1;
+            RedCtx rcs = s->rc;
+            comm_begin_reduction(s, rcs);                          // stamp the reduction epoch (peer-memory all-gather of the partials)
+            r2 = launch_march_make_s(s, r, v_new, sv, t, d_d, rcs, &hw);
+            s->time_slot = -1;
+            if (r2 || (r2 = finish_reduction(s, rcs, PH_U_B, 2))) return r2;
+        } else if (fold_s) {
             s->time_slot = tm ? 1 : -1;
             r2 = launch_march_make_s(s, r, v_new, sv, t, d_d, s->rc);                               // :698-710
             s->time_slot = -1;
@@ -624,6 +645,7 @@ int cudamat_set_option(cudamat_solver *s, const char *key, int64_t value) {
     else if (!strcmp(key, "sptrsv_no_smem")) s->opt_sptrsv_no_smem = (int)value;
     else if (!strcmp(key, "sptrsv_ring")) s->opt_sptrsv_ring = (int)value;
     else if (!strcmp(key, "march_shards")) s->opt_march_shards = (int)value;
+    else if (!strcmp(key, "shard_fuse")) s->opt_shard_fuse = (int)value;
     else if (!strcmp(key, "class_tiles_per_cta")) s->opt_class_tiles_per_cta = (int)value;
     else if (!strcmp(key, "staged_stages")) { s->opt_staged_stages = (int)value; s->analyzed = false; }
     else if (!strcmp(key, "l2_fetch")) {

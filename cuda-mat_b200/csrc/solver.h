@@ -162,6 +162,7 @@ struct cudamat_solver {
     bool graph_used = false;
     int opt_sptrsv_no_smem = 0;            // 1: never use the single-CTA shared-memory sweep
     int opt_march_shards = 1;              // sharded handles: MARCH with the neighbours' planes read from the halo region (0: TILED, 2: even when the grid underfills)
+    int opt_shard_fuse = 0;                // sharded handles with MARCH: fold the s update into SpMV 2 (boundary planes pushed by a small kernel)
     int opt_sptrsv_ring = 1;               // small systems: role-split ring sweep (0: the barrier-per-level kernel of round 1)
     bool sptrsv_smem_ready = false;
     int sptrsv_grid = 0;
@@ -236,6 +237,7 @@ int launch_spmv(cudamat_solver *s, const SpmvArgs &a, int variant);
 int launch_init_resid(cudamat_solver *s, const double *b, const double *y, double *r, double *c1, double *c2, int phase);
 int launch_update_p(cudamat_solver *s, bool fma_form, const double *r, const double *v, double *p, const HaloPush *hp = nullptr);
 int launch_update_s(cudamat_solver *s, const double *r, const double *v, double *sv, const HaloPush *hp = nullptr);
+int launch_update_s_boundary(cudamat_solver *s, const double *r, const double *v, double *sv, const HaloPush *hp, int plane_tiles);
 int launch_update_rx_ilu(cudamat_solver *s, const double *v, const double *pw, double *r, double *x);
 int launch_update_xr(cudamat_solver *s, bool fma_form, const double *p, const double *sv, const double *t,
                      const double *rhat, double *x, double *r);
@@ -254,7 +256,8 @@ bool march_spmv_usable(const cudamat_solver *s, const SpmvArgs &a);     // incl.
 int launch_march_spmv(cudamat_solver *s, const SpmvArgs &a);
 int launch_march_make_p(cudamat_solver *s, const double *r, const double *p_old, const double *v_old, double *p_new, double *v_new,
                         const double *rhat, const double *d, const RedCtx &rc);
-int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc);
+int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, double *sv, double *t, const double *d, const RedCtx &rc,
+                        const HaloWait *hw = nullptr);
 
 // sweepblk.cu: block-wavefront triangular sweeps for ILU0 factors of 7-point grid stencils
 int sweepblk_plan(cudamat_solver *s);

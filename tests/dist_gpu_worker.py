@@ -44,6 +44,22 @@ def main():
         st = s.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=5000, tol=1e-10)
         dt = s.dot(x.data_ptr(), b.data_ptr())
         torch.cuda.synchronize()
+        # the same solve with the MARCH SpMV forced on the shard (neighbour planes read from the halo region) and the s update folded
+        # into SpMV 2 (boundary planes pushed by k_update_s_boundary): must reproduce the bits of the default path
+        march_ok = True
+        if N >= 64 and p2p:
+            s2 = cm.Solver(n, row0, row1)
+            s2.set_option("march_shards", 2); s2.set_option("shard_fuse", 1); s2.set_option("persist", 0)
+            s2.set_csr_device(nnz, a.data_ptr(), ia.data_ptr(), ja.data_ptr())
+            cm.Comm.init(s2, bytes(uid.cpu().tolist()), rank, world)
+            s2.analyze(cm.MODE_PLAIN)
+            x2 = torch.zeros(nloc, **f64)
+            st2 = s2.solve(cm.MODE_PLAIN, b.data_ptr(), x2.data_ptr(), maxit=5000, tol=1e-10)
+            torch.cuda.synchronize()
+            flag = torch.tensor([int(torch.equal(x2, x) and st2["iterations"] == st["iterations"] and st2["spmv_variant"] == 6 and st2["fused"] == 2)], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            march_ok = bool(flag.item())
+            s2.close()
         # block-Jacobi ILU(0) on the same sharded handle (each rank factors its diagonal block): must converge to the
         # same solution; the iteration count differs from the global ILU(0) of a single GPU by construction
         s.analyze(cm.MODE_ILU0)
@@ -81,10 +97,10 @@ def main():
             d1 = s1.dot(x1.data_ptr(), b1.data_ptr())
             torch.cuda.synchronize()
             ok = (torch.equal(bg, b1) and torch.equal(xg, x1) and st["iterations"] == st1["iterations"]
-                  and bool(st["converged"]) and dt == d1 and ilu_ok)
-            print("DIST N=%d world=%d p2p=%d variant=%d iters=%d/%d b_equal=%s x_equal=%s dot_equal=%s loop_ms=%.2f/%.2f block_ilu0_iters=%d err=%.1e %s"
+                  and bool(st["converged"]) and dt == d1 and ilu_ok and march_ok)
+            print("DIST N=%d world=%d p2p=%d variant=%d iters=%d/%d b_equal=%s x_equal=%s dot_equal=%s loop_ms=%.2f/%.2f block_ilu0_iters=%d err=%.1e march_fold_shard=%s %s"
                   % (N, world, int(p2p), st["spmv_variant"], st["iterations"], st1["iterations"], torch.equal(bg, b1), torch.equal(xg, x1), dt == d1,
-                     st["t_loop"] * 1e3, st1["t_loop"] * 1e3, sti["iterations"], ilu_err, "OK" if ok else "MISMATCH"), flush=True)
+                     st["t_loop"] * 1e3, st1["t_loop"] * 1e3, sti["iterations"], ilu_err, march_ok, "OK" if ok else "MISMATCH"), flush=True)
             s1.close()
         dist.barrier()
     dist.destroy_process_group()
