@@ -308,6 +308,12 @@ __device__ __forceinline__ void ring_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// entries kPlanW .. cnt - 1 of a long row, straight from CSR (kept out of the walker's loop body)
+static __device__ __noinline__ double ring_long_row_tail(double acc, int p0, int cnt, const double *M, const int *ja, const double *y) {
+    for (int pp = p0 + kPlanW; pp < p0 + cnt; ++pp) acc = __fma_rn(-M[pp], y[ja[pp]], acc);
+    return acc;
+}
+
 template <bool UPPER>
 __global__ void __launch_bounds__(kRingThreads, 1) k_sptrsv_ring(const int *order, const int *chunk_beg, const int *chunk_info, int nchunks,
                                                                   int len, int n, const int *p_cnt, const int *p_ptr, const int *p_col,
@@ -391,7 +397,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_sptrsv_ring(const int *orde
         // ---- the walker: the row of the NEXT chunk is read from its slot before the barrier of the current level whenever the
         //      loaders are ahead (one non-blocking test of the slot's full barrier), so the level-to-level chain is only
         //      barrier -> y[c] -> kPlanW DFMAs (-> division) -> y[i] -> barrier ----
-        struct Row { int i, cnt, last, beg; unsigned ya[kPlanW]; double m[kPlanW], dg, rcp, rhs; };
+        struct Row { int i, cnt, last, beg; unsigned yo[kPlanW]; double m[kPlanW], dg, rcp, rhs; };
         // (laundered through asm: otherwise the compiler re-derives the window base, S2R + LEA, at every use)
         auto opaque_addr = [](const void *p) { unsigned a = (unsigned)__cvta_generic_to_shared(p), b; asm volatile("mov.u32 %0, %1;" : "=r"(b) : "r"(a)); return b; };
         const unsigned y_a = opaque_addr(y), ring_a = opaque_addr(ring), full_a = opaque_addr(full), empty_a = opaque_addr(empty);
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_sptrsv_ring(const int *orde
             r.last = lds_s32(sb + kOffLast); r.beg = lds_s32(sb + kOffBeg);
             r.i = lds_s32(l4 + kOffI); r.cnt = lds_s32(l4 + kOffCnt);
 #pragma unroll
-            for (int q = 0; q < kPlanW; ++q) r.ya[q] = y_a + (unsigned)lds_s32(l4 + kOffC + q * 4 * kRingRows);
+            for (int q = 0; q < kPlanW; ++q) r.yo[q] = (unsigned)lds_s32(l4 + kOffC + q * 4 * kRingRows);      // byte offset; the address is formed at use
 #pragma unroll
             for (int q = 0; q < kPlanW; ++q) r.m[q] = lds_f64(l8 + kOffM + q * 8 * kRingRows);
             r.rhs = lds_f64(l8 + kOffRhs);
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_sptrsv_ring(const int *orde
             // the chain: y loads first, the next row's slot reads in their shadow, then the FMAs
             double yv[kPlanW];
 #pragma unroll
-            for (int q = 0; q < kPlanW; ++q) yv[q] = lds_f64(cur.ya[q]);
+            for (int q = 0; q < kPlanW; ++q) yv[q] = lds_f64(y_a + cur.yo[q]);
             have = false;
             if (j + 1 < nchunks) {
                 if (((j + 1) & (kRingBatch - 1)) != 0 || batch_full(j + 1, false)) { read_slot(j + 1, nxt); have = true; }
@@ -436,10 +442,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_sptrsv_ring(const int *orde
 #pragma unroll
             for (int q = 0; q < kPlanW; ++q) acc = __fma_rn(-cur.m[q], yv[q], acc);
             if (cur.i >= 0) {
-                if (cur.cnt > kPlanW) {                            // rare: the rest of a long row straight from CSR
-                    const int p0 = p_ptr[cur.beg + lt];
-                    for (int pp = p0 + kPlanW; pp < p0 + cur.cnt; ++pp) acc = __fma_rn(-M[pp], y[ja[pp]], acc);
-                }
+                if (cur.cnt > kPlanW) acc = ring_long_row_tail(acc, p_ptr[cur.beg + lt], cur.cnt, M, ja, y);   // rare, out of line
                 if (UPPER) acc = div_finish(acc, cur.dg, cur.rcp);
                 sts_f64(y_a + 8u * (unsigned)cur.i, acc);          // (a global store here would sit on the chain)
             }
