@@ -675,12 +675,11 @@ int cudamat_set_csr_host(cudamat_solver *s, int nnz, const double *A, const int 
     CM_CUDA(dev_alloc((void **)&s->own_ia, sizeof(int) * (size_t)(n + 1)));
     CM_CUDA(dev_alloc((void **)&s->own_ja, sizeof(int) * (size_t)std::max(nnz, 1) + 16));
     CM_CUDA(dev_alloc((void **)&s->own_a, sizeof(double) * (size_t)std::max(nnz, 1) + 16));
-    CM_CUDA(cudaMemcpyAsync(s->own_ia, iA, sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, s->stream));
-    if (nnz > 0) {
-        CM_CUDA(cudaMemcpyAsync(s->own_ja, jA, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
-        CM_CUDA(cudaMemcpyAsync(s->own_a, A, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
-    }
-    int rc = launch_normalize_base(s->stream, s->own_ia, n + 1, s->own_ja, nnz, base);
+    int rc = copy_h2d(s->own_ia, iA, sizeof(int) * (size_t)(n + 1), s->stream);
+    if (!rc && nnz > 0) rc = copy_h2d(s->own_ja, jA, sizeof(int) * (size_t)nnz, s->stream);
+    if (!rc && nnz > 0) rc = copy_h2d(s->own_a, A, sizeof(double) * (size_t)nnz, s->stream);
+    if (rc) return rc;
+    rc = launch_normalize_base(s->stream, s->own_ia, n + 1, s->own_ja, nnz, base);
     if (rc) return rc;
     // structure checks run on the device over the uploaded arrays (a host pass over nnz entries would cost as much
     // as the upload itself): monotone row pointers, column indices inside [0, n_global)
@@ -849,7 +848,8 @@ int cudamat_get_ilu0_host(cudamat_solver *s, double *M_out) {
     DeviceGuard dg(s->device);
     if (s->d_perm) { set_error("get_ilu0_host: the factor belongs to the multicolour-permuted matrix (option ilu0_reorder)"); return CUDAMAT_E_STATE; }
     if (s->pre_nnz != s->nnz) { set_error("get_ilu0_host: sharded handles hold a block-Jacobi factor of the local block (%lld entries), not A's pattern", (long long)s->pre_nnz); return CUDAMAT_E_STATE; }
-    CM_CUDA(cudaMemcpyAsync(M_out, s->d_M, sizeof(double) * (size_t)s->nnz, cudaMemcpyDeviceToHost, s->stream));
+    int rc = copy_d2h(M_out, s->d_M, sizeof(double) * (size_t)s->nnz, s->stream);
+    if (rc) return rc;
     CM_CUDA(cudaStreamSynchronize(s->stream));
     return CUDAMAT_OK;
 }
@@ -907,14 +907,14 @@ int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *
     HOST_CUDA(dev_alloc((void **)&d_x, nb));
     // uploads are ordered on the call's own stream (a legacy-stream cudaMemcpy from pageable memory is not ordered against
     // a cudaStreamNonBlocking stream); the host arrays stay untouched until the stream is synchronised by analyze / solve
-    HOST_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    HOST_TRY(copy_h2d(d_b, b, sizeof(double) * (size_t)n, s->stream));
     if (mode == CUDAMAT_MODE_SHIFTED || (mode == CUDAMAT_MODE_PLAIN && x0)) {
         HOST_CUDA(dev_alloc((void **)&d_x0, nb));
-        HOST_CUDA(cudaMemcpyAsync(d_x0, x0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+        HOST_TRY(copy_h2d(d_x0, x0, sizeof(double) * (size_t)n, s->stream));
     }
     if (mode != CUDAMAT_MODE_ILU0 && d) {
         HOST_CUDA(dev_alloc((void **)&d_d, nb));
-        HOST_CUDA(cudaMemcpyAsync(d_d, d, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+        HOST_TRY(copy_h2d(d_d, d, sizeof(double) * (size_t)n, s->stream));
     }
     HOST_CUDA(cudaStreamSynchronize(s->stream));
     st.t_h2d = now_s() - t0;
@@ -927,7 +927,7 @@ int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *
     }
     HOST_TRY(cudamat_solve_device(s, mode, d_b, d_x0, d_d, d_x, maxit, tol, &st));
     t0 = now_s();
-    HOST_CUDA(cudaMemcpyAsync(x, d_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    HOST_TRY(copy_d2h(x, d_x, sizeof(double) * (size_t)n, s->stream));
     HOST_CUDA(cudaStreamSynchronize(s->stream));
     st.t_d2h = now_s() - t0;
     st.kernel_launches = s->launches;

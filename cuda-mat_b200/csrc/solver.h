@@ -10,6 +10,11 @@ namespace cudamat {
 void set_error(const char *fmt, ...);
 cudaError_t dev_alloc(void **p, size_t bytes);     // solver.cu: pooled allocation for large buffers
 void dev_free(void *p);
+// hostcopy.cpp: copies between HOST arrays and the device, enqueued on / ordered against `stream`; pageable arrays of
+// 8 MB or more go through a threaded pinned staging area.  copy_h2d: src may be reused at return, dst is ready in stream
+// order.  copy_d2h: dst is complete only after the caller synchronises `stream` (the staged form completes it at return).
+int copy_h2d(void *dst, const void *src, size_t bytes, cudaStream_t stream);
+int copy_d2h(void *dst, const void *src, size_t bytes, cudaStream_t stream);
 bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
 #define CM_CUDA(call)                                                       \
     do {                                                                    \
