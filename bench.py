@@ -580,19 +580,19 @@ def single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, conver
     #      D2H of x inside the timed region; full solve to 1e-10.  Measured with pinned host arrays (the contract's e2e) and
     #      with pageable ones (what the reference's callers hand over: malloc'ed arrays, example.cpp:96-104,252), each as
     #      first call of the process (grows the library's device memory pool) and steady state ----
+    import ctypes as C
+
+    def host_solve(h_a, h_ia, h_ja, h_b, h_x, mode=None):
+        st = cm.Stats(); dt = C.c_double(0.0)
+        t0 = time.time()
+        rc = cm.lib.cudamat_bicgstab_host(cm.MODE_PLAIN if mode is None else mode, n, nnz, C.cast(h_a.data_ptr(), cm.c_dp), C.cast(h_ia.data_ptr(), cm.c_ip),
+                                          C.cast(h_ja.data_ptr(), cm.c_ip), None, None, C.cast(h_b.data_ptr(), cm.c_dp),
+                                          5000, 1e-10, 0, C.cast(h_x.data_ptr(), cm.c_dp), C.byref(dt), C.byref(st))
+        wall = time.time() - t0
+        cm._check(rc)
+        return wall, st
+
     try:
-        import ctypes as C
-
-        def host_solve(h_a, h_ia, h_ja, h_b, h_x):
-            st = cm.Stats(); dt = C.c_double(0.0)
-            t0 = time.time()
-            rc = cm.lib.cudamat_bicgstab_host(cm.MODE_PLAIN, n, nnz, C.cast(h_a.data_ptr(), cm.c_dp), C.cast(h_ia.data_ptr(), cm.c_ip),
-                                              C.cast(h_ja.data_ptr(), cm.c_ip), None, None, C.cast(h_b.data_ptr(), cm.c_dp),
-                                              5000, 1e-10, 0, C.cast(h_x.data_ptr(), cm.c_dp), C.byref(dt), C.byref(st))
-            wall = time.time() - t0
-            cm._check(rc)
-            return wall, st
-
         res = {}
         for kind in ("pageable", "pinned"):
             pin = kind == "pinned"
@@ -683,6 +683,19 @@ def single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, conver
                            "iters_per_s": st["iterations"] / st["t_loop"], "t_analysis_s": sa["t_analysis"], "t_ilu0_s": sa["t_ilu0"],
                            "levels": [sa["levels_l"], sa["levels_u"]], "rel_err_vs_xtrue": relerr}
             s2.close()
+            # the reference's live entry point end to end (bicgstab_lu_precond on malloc'ed host arrays, example.cpp:352): upload,
+            # both analyses, ILU0, loop, download, release — next to reference_gpu_ilu0.wall_s of the reference's own GPU code
+            hh = [t.cpu() for t in (a, ia, ja, b)]
+            hx = torch.empty(n, dtype=torch.float64)
+            walls = []
+            for _ in range(2):
+                wall, hst = host_solve(hh[0], hh[1], hh[2], hh[3], hx, mode=cm.MODE_ILU0)
+                walls.append(wall)
+            out["ilu0"]["e2e_host"] = {"wall_s": walls[-1], "wall_s_first_call": walls[0], "iterations": hst.iterations,
+                                       "iters_per_s": hst.iterations / walls[-1], "t_h2d_s": hst.t_h2d, "t_analysis_s": hst.t_analysis,
+                                       "t_ilu0_s": hst.t_ilu0, "t_loop_s": hst.t_loop, "t_d2h_s": hst.t_d2h,
+                                       "call": "cudamat_bicgstab_host(MODE_ILU0, tol=1e-10), pageable host arrays, second call"}
+            del hh, hx
             # opt-in multicolour ordering of the preconditioner: few levels, bandwidth-bound sweeps, weaker ILU(0)
             s3 = cm.Solver(n, stream=torch.cuda.current_stream().cuda_stream)
             s3.set_option("ilu0_reorder", 1)

@@ -490,8 +490,8 @@ static int ring_prepare(cudamat_solver *s) {
             }
         while (cb.size() % kRingBatch) { cb.push_back(0); ci.push_back(0); }       // empty chunks: the ring is handed over in whole batches
         LS.nchunks = (int)cb.size();
-        CM_CUDA(cudaMalloc(&LS.d_chunk_beg, sizeof(int) * std::max<size_t>(cb.size(), 1)));
-        CM_CUDA(cudaMalloc(&LS.d_chunk_info, sizeof(int) * std::max<size_t>(ci.size(), 1)));
+        CM_CUDA(dev_alloc((void **)&LS.d_chunk_beg, sizeof(int) * std::max<size_t>(cb.size(), 1)));
+        CM_CUDA(dev_alloc((void **)&LS.d_chunk_info, sizeof(int) * std::max<size_t>(ci.size(), 1)));
         CM_CUDA(cudaMemcpyAsync(LS.d_chunk_beg, cb.data(), sizeof(int) * cb.size(), cudaMemcpyHostToDevice, s->stream));
         CM_CUDA(cudaMemcpyAsync(LS.d_chunk_info, ci.data(), sizeof(int) * ci.size(), cudaMemcpyHostToDevice, s->stream));
         CM_CUDA(cudaStreamSynchronize(s->stream));             // the host vectors die here
@@ -693,9 +693,9 @@ static int device_schedule(cudamat_solver *s, bool upper, LevelSchedule &out) {
     }
     for (int l = 0; l < nlevels; ++l) out.level_ptr[l + 1] = out.level_ptr[l] + ((start[l + 1] - start[l] + 31) / 32) * 32;
     out.order_len = nlevels > 0 ? out.level_ptr[nlevels] : 0;
-    CM_CUDA(cudaMalloc(&out.d_order, sizeof(int) * (size_t)std::max(out.order_len, 1)));
+    CM_CUDA(dev_alloc((void **)&out.d_order, sizeof(int) * (size_t)std::max(out.order_len, 1)));
     CM_CUDA(cudaMemsetAsync(out.d_order, 0xff, sizeof(int) * (size_t)std::max(out.order_len, 1), s->stream));
-    CM_CUDA(cudaMalloc(&out.d_level_ptr, sizeof(int) * (size_t)(nlevels + 2)));
+    CM_CUDA(dev_alloc((void **)&out.d_level_ptr, sizeof(int) * (size_t)(nlevels + 2)));
     {
         std::vector<int> lp(out.level_ptr);
         lp.push_back(out.order_len);                       // level_ptr[nlevels + 1]: lets the kernel look one level ahead
@@ -722,9 +722,9 @@ static int build_schedule(cudamat_solver *s, const std::vector<int> &level, int 
     std::vector<int> order(out.order_len, -1), fill(nlevels, 0);
     for (int i = 0; i < n; ++i) { const int l = level[i]; order[out.level_ptr[l] + fill[l]++] = i; }
     out.nlevels = nlevels;
-    CM_CUDA(cudaMalloc(&out.d_order, sizeof(int) * (size_t)std::max(out.order_len, 1)));
+    CM_CUDA(dev_alloc((void **)&out.d_order, sizeof(int) * (size_t)std::max(out.order_len, 1)));
     CM_CUDA(cudaMemcpyAsync(out.d_order, order.data(), sizeof(int) * (size_t)out.order_len, cudaMemcpyHostToDevice, s->stream));
-    CM_CUDA(cudaMalloc(&out.d_level_ptr, sizeof(int) * (size_t)(nlevels + 2)));
+    CM_CUDA(dev_alloc((void **)&out.d_level_ptr, sizeof(int) * (size_t)(nlevels + 2)));
     {
         std::vector<int> lp(out.level_ptr);
         lp.push_back(out.order_len);                       // level_ptr[nlevels + 1]: lets the kernel look one level ahead
@@ -735,32 +735,35 @@ static int build_schedule(cudamat_solver *s, const std::vector<int> &level, int 
 }
 
 void ilu0_release(cudamat_solver *s) {
+    // the buffers go back to the stream-ordered pool (cudaFree of the 2 GB a 256^3 factor + plans hold costs more than a
+    // sweep pair): nothing enqueued on the handle's stream may still use them
+    cudaStreamSynchronize(s->stream);
     sweepblk_release(s);
-    if (s->d_M) cudaFree(s->d_M);
-    if (s->d_diag) cudaFree(s->d_diag);
+    if (s->d_M) dev_free(s->d_M);
+    if (s->d_diag) dev_free(s->d_diag);
     for (LevelSchedule *P : {&s->lvl_l, &s->lvl_u}) {
-        if (P->d_order) cudaFree(P->d_order);
-        if (P->d_level_ptr) cudaFree(P->d_level_ptr);
-        if (P->d_chunk_beg) cudaFree(P->d_chunk_beg);
-        if (P->d_chunk_info) cudaFree(P->d_chunk_info);
+        if (P->d_order) dev_free(P->d_order);
+        if (P->d_level_ptr) dev_free(P->d_level_ptr);
+        if (P->d_chunk_beg) dev_free(P->d_chunk_beg);
+        if (P->d_chunk_info) dev_free(P->d_chunk_info);
         P->d_chunk_beg = P->d_chunk_info = nullptr; P->nchunks = 0;
-        if (P->d_cnt) cudaFree(P->d_cnt);
-        if (P->d_ptr) cudaFree(P->d_ptr);
-        if (P->d_col) cudaFree(P->d_col);
-        if (P->d_val) cudaFree(P->d_val);
-        if (P->d_dg) cudaFree(P->d_dg);
+        if (P->d_cnt) dev_free(P->d_cnt);
+        if (P->d_ptr) dev_free(P->d_ptr);
+        if (P->d_col) dev_free(P->d_col);
+        if (P->d_val) dev_free(P->d_val);
+        if (P->d_dg) dev_free(P->d_dg);
     }
-    if (s->d_perm) cudaFree(s->d_perm);
-    if (s->prm_ia) cudaFree(s->prm_ia);
-    if (s->prm_ja) cudaFree(s->prm_ja);
-    if (s->prm_a) cudaFree(s->prm_a);
+    if (s->d_perm) dev_free(s->d_perm);
+    if (s->prm_ia) dev_free(s->prm_ia);
+    if (s->prm_ja) dev_free(s->prm_ja);
+    if (s->prm_a) dev_free(s->prm_a);
     s->d_perm = nullptr; s->prm_ia = nullptr; s->prm_ja = nullptr; s->prm_a = nullptr;
-    if (s->blk_ia) cudaFree(s->blk_ia);
-    if (s->blk_ja) cudaFree(s->blk_ja);
-    if (s->blk_a) cudaFree(s->blk_a);
+    if (s->blk_ia) dev_free(s->blk_ia);
+    if (s->blk_ja) dev_free(s->blk_ja);
+    if (s->blk_a) dev_free(s->blk_a);
     s->blk_ia = nullptr; s->blk_ja = nullptr; s->blk_a = nullptr; s->blk_nnz = 0;
-    if (s->d_flag) cudaFree(s->d_flag);
-    if (s->d_ticket) cudaFree(s->d_ticket);
+    if (s->d_flag) dev_free(s->d_flag);
+    if (s->d_ticket) dev_free(s->d_ticket);
     s->d_M = nullptr; s->d_diag = nullptr; s->lvl_l = LevelSchedule(); s->lvl_u = LevelSchedule();
     s->d_flag = nullptr; s->d_ticket = nullptr;
     s->ticket_base_l = s->ticket_base_u = 0; s->epoch = 0;
@@ -794,7 +797,7 @@ int exclusive_scan_inplace(int *d, int64_t cnt, cudaStream_t st);      // kernel
 
 static int build_local_block(cudamat_solver *s) {
     const int n = s->n;
-    CM_CUDA(cudaMalloc(&s->blk_ia, sizeof(int) * (size_t)(n + 1)));
+    CM_CUDA(dev_alloc((void **)&s->blk_ia, sizeof(int) * (size_t)(n + 1)));
     k_block_count<<<(n + 1 + 255) / 256, 256, 0, s->stream>>>(n, s->d_ia, s->d_ja, s->blk_ia);
     CM_CUDA(cudaGetLastError());
     int rc = exclusive_scan_inplace(s->blk_ia, (int64_t)n + 1, s->stream);
@@ -803,8 +806,8 @@ static int build_local_block(cudamat_solver *s) {
     CM_CUDA(cudaMemcpyAsync(&last, s->blk_ia + n, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));
     s->blk_nnz = last;
-    CM_CUDA(cudaMalloc(&s->blk_ja, sizeof(int) * (size_t)std::max(last, 1)));
-    CM_CUDA(cudaMalloc(&s->blk_a, sizeof(double) * (size_t)std::max(last, 1)));
+    CM_CUDA(dev_alloc((void **)&s->blk_ja, sizeof(int) * (size_t)std::max(last, 1)));
+    CM_CUDA(dev_alloc((void **)&s->blk_a, sizeof(double) * (size_t)std::max(last, 1)));
     if (n > 0) k_block_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->d_ia, s->d_ja, s->d_a, s->blk_ia, s->blk_ja, s->blk_a);
     CM_CUDA(cudaGetLastError());
     s->launches += 2;
@@ -892,7 +895,7 @@ static int build_multicolor(cudamat_solver *s) {
     // perm[new] = old: stable sort of the rows by colour
     CM_CUDA(dev_alloc((void **)&d_color2, sizeof(int) * (size_t)n));
     CM_CUDA(dev_alloc((void **)&d_iota, sizeof(int) * (size_t)n));
-    CM_CUDA(cudaMalloc(&s->d_perm, sizeof(int) * (size_t)n));
+    CM_CUDA(dev_alloc((void **)&s->d_perm, sizeof(int) * (size_t)n));
     CM_CUDA(dev_alloc((void **)&d_inv, sizeof(int) * (size_t)n));
     k_iota<<<(n + 255) / 256, 256, 0, s->stream>>>(n, d_iota);
     size_t tmp_bytes = 0;
@@ -902,12 +905,12 @@ static int build_multicolor(cudamat_solver *s) {
     CM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_color, d_color2, d_iota, s->d_perm, n, 0, 6, s->stream));
     k_invert_perm<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->d_perm, d_inv);
     // permuted CSR with ascending columns
-    CM_CUDA(cudaMalloc(&s->prm_ia, sizeof(int) * (size_t)(n + 1)));
+    CM_CUDA(dev_alloc((void **)&s->prm_ia, sizeof(int) * (size_t)(n + 1)));
     k_perm_count<<<(n + 1 + 255) / 256, 256, 0, s->stream>>>(n, s->d_perm, s->pre_ia, s->prm_ia);
     int rc = exclusive_scan_inplace(s->prm_ia, (int64_t)n + 1, s->stream);
     if (rc) return rc;
-    CM_CUDA(cudaMalloc(&s->prm_ja, sizeof(int) * (size_t)std::max<int64_t>(s->pre_nnz, 1)));
-    CM_CUDA(cudaMalloc(&s->prm_a, sizeof(double) * (size_t)std::max<int64_t>(s->pre_nnz, 1)));
+    CM_CUDA(dev_alloc((void **)&s->prm_ja, sizeof(int) * (size_t)std::max<int64_t>(s->pre_nnz, 1)));
+    CM_CUDA(dev_alloc((void **)&s->prm_a, sizeof(double) * (size_t)std::max<int64_t>(s->pre_nnz, 1)));
     k_perm_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->d_perm, d_inv, s->pre_ia, s->pre_ja, s->pre_a, s->prm_ia, s->prm_ja, s->prm_a);
     CM_CUDA(cudaGetLastError());
     CM_CUDA(cudaStreamSynchronize(s->stream));
@@ -931,7 +934,7 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     if (s->opt_ilu0_reorder) { int rcm = build_multicolor(s); if (rcm) return rcm; }
     const int64_t nnz = s->pre_nnz;
     int nl = 0, nu = 0, rc;
-    CM_CUDA(cudaMalloc(&s->d_diag, sizeof(int) * (size_t)std::max(n, 1)));
+    CM_CUDA(dev_alloc((void **)&s->d_diag, sizeof(int) * (size_t)std::max(n, 1)));
     if (!s->opt_host_analysis) {
         int *d_bad = nullptr;
         CM_CUDA(dev_alloc((void **)&d_bad, sizeof(int)));
@@ -985,10 +988,10 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
 
     // factorisation on a copy of A (pbicgstab.cu:316,359)
     t0 = now_s();
-    CM_CUDA(cudaMalloc(&s->d_M, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
+    CM_CUDA(dev_alloc((void **)&s->d_M, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
     CM_CUDA(cudaMemcpyAsync(s->d_M, s->pre_a, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, s->stream));
     int *d_zp = nullptr;
-    CM_CUDA(cudaMalloc(&d_zp, sizeof(int)));
+    CM_CUDA(dev_alloc((void **)&d_zp, sizeof(int)));
     const int big = 0x7fffffff;
     CM_CUDA(cudaMemcpyAsync(d_zp, &big, sizeof(int), cudaMemcpyHostToDevice, s->stream));
     for (int l = 0; l < nl; ++l) {
@@ -1001,17 +1004,17 @@ int ilu0_analyze_and_factor(cudamat_solver *s, cudamat_stats *st) {
     int zp = big;
     CM_CUDA(cudaMemcpyAsync(&zp, d_zp, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CM_CUDA(cudaStreamSynchronize(s->stream));
-    CM_CUDA(cudaFree(d_zp));
+    dev_free(d_zp);
     s->zero_pivot = (zp == big) ? 0 : -(1 + zp);
     // level-ordered sweep plans (coalesced operands for the sync-free sweeps)
     for (int u = 0; u < 2; ++u) {
         LevelSchedule &P = u ? s->lvl_u : s->lvl_l;
         const size_t len = (size_t)std::max(P.order_len, 1);
-        CM_CUDA(cudaMalloc(&P.d_cnt, sizeof(int) * len));
-        CM_CUDA(cudaMalloc(&P.d_ptr, sizeof(int) * len));
-        CM_CUDA(cudaMalloc(&P.d_col, sizeof(int) * len * kPlanW));
-        CM_CUDA(cudaMalloc(&P.d_val, sizeof(double) * len * kPlanW));
-        CM_CUDA(cudaMalloc(&P.d_dg, sizeof(double) * len));
+        CM_CUDA(dev_alloc((void **)&P.d_cnt, sizeof(int) * len));
+        CM_CUDA(dev_alloc((void **)&P.d_ptr, sizeof(int) * len));
+        CM_CUDA(dev_alloc((void **)&P.d_col, sizeof(int) * len * kPlanW));
+        CM_CUDA(dev_alloc((void **)&P.d_val, sizeof(double) * len * kPlanW));
+        CM_CUDA(dev_alloc((void **)&P.d_dg, sizeof(double) * len));
         if (P.order_len > 0) {
             const int grid = (P.order_len + 255) / 256;
             if (u) k_build_plan<true><<<grid, 256, 0, s->stream>>>(P.d_order, P.order_len, s->pre_ia, s->pre_ja, s->d_diag, s->d_M, P.d_cnt, P.d_ptr, P.d_col, P.d_val, P.d_dg);

@@ -1221,10 +1221,10 @@ __global__ void k_poisson_fill(int N, int64_t row0, int64_t row1, const int *ia,
 int exclusive_scan_inplace(int *d, int64_t cnt, cudaStream_t st) {
     void *tmp = nullptr; size_t bytes = 0;
     CM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, d, d, cnt, st));
-    CM_CUDA(cudaMalloc(&tmp, bytes ? bytes : 16));
+    CM_CUDA(dev_alloc(&tmp, bytes ? bytes : 16));
     CM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, d, d, cnt, st));
     CM_CUDA(cudaStreamSynchronize(st));
-    CM_CUDA(cudaFree(tmp));
+    dev_free(tmp);
     return CUDAMAT_OK;
 }
 
