@@ -716,11 +716,16 @@ def single_gpu_extras(args, cm, torch, s, N, n, nnz, ia, ja, a, b, x, xt, conver
         rs = np.random.RandomState(0)
         bb = 1.0 + 4.0 * rs.rand(m)
         best = None
+        wall_best = None
         for _ in range(3):
+            t0 = time.perf_counter()
             xx, dt, st = cm.bicgstab_lu_precond(ma, mia, mja, bb, maxit=2000, tol=1e-6)
+            w = time.perf_counter() - t0
+            wall_best = w if wall_best is None else min(wall_best, w)
             if best is None or dt < best[0]:
                 best = (dt, st)
         out["mat10000_ilu0"] = {"iterations": best[1]["iterations"], "t_loop_ms": best[0] * 1e3,
+                                "wall_ms_host_call": wall_best * 1e3,     # upload, both analyses, ILU0, loop, download, release (pageable arrays)
                                 "us_per_iteration": best[0] * 1e6 / max(best[1]["iterations"], 1),
                                 "iters_per_s": best[1]["iterations"] / best[0], "roofline": "n/a (latency-bound)"}
     except Exception as e:      # noqa: BLE001
