@@ -72,7 +72,7 @@ __device__ __forceinline__ void sts128(uint32_t ad, double2 v) { asm volatile("s
 //          length: planes and the 16-byte alignment of every tap are compile-time facts (5 aligned pair loads, 2 x 2
 //          single loads per two rows).
 // SHAPE 0: any other pattern of <= 8 entries: planes / offsets are kernel parameters, every tap is two 8-byte loads.
-template <int MODE, int NDOT, bool HAS_D, bool U_RING, int SHAPE, int HB>
+template <int MODE, int NDOT, bool HAS_D, bool U_RING, int SHAPE, int HB, bool SHARD_S = false>
 __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a, const __grid_constant__ MarchPlan M) {
     constexpr int SL = SHAPE == 1 ? 7 : 8;
     constexpr int H = HB * 256;
@@ -85,8 +85,11 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = M.S, P = M.P, Zc = M.Zc, n = a.n;
     // sharded handles: LOAD_X reads the operand incl. its halo region; MAKE_S forms s = r - alpha v for the shard's own planes and takes
-    // the neighbours' planes of s (pushed by k_update_s_boundary right before) from the halo region of the s vector (a.xout)
-    constexpr bool HALO_OK = MODE != MARCH_MAKE_P;
+    // the neighbours' planes of s (pushed by k_update_s_boundary right before) from the halo region of the s vector (a.xout).
+    // That MAKE_S form is its own instantiation (SHARD_S): the run-time plane test costs the single-GPU kernel its registers
+    // (156 bytes of spills, 107 -> 142-154 us at 256^3).
+    constexpr bool HALO_S = MODE == MARCH_MAKE_S && SHARD_S;
+    constexpr bool HALO_OK = MODE == MARCH_LOAD_X || HALO_S;
     const int nlim = MODE == MARCH_LOAD_X ? M.n_tot : n;
     const int lo_base = HALO_OK ? M.lo_base : -1, hi_base = HALO_OK ? M.hi_base : -1;
     pdl_sync();
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
 
     // global loads of the tile whose buffer starts at element g0 = tile base - H -> registers
     auto issue = [&](int g0, double2 (&st)[NV][PPT], bool halo = false) {
-        if (MODE == MARCH_MAKE_S && halo) {                        // a neighbour's plane of s: one vector, taken as it is
+        if (HALO_S && halo) {                                      // a neighbour's plane of s: one vector, taken as it is
             const int lim = M.n_tot;
             if (g0 >= 0 && g0 + BUF <= lim) {
                 const double2 *src = reinterpret_cast<const double2 *>(a.xout + g0) + tid;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_spmv_march(const MarchArgs a
             const int pi = tid + j * kCtaThreads;
             if ((j + 1) * kCtaThreads <= PAIRS || pi < PAIRS) {
                 double2 o;
-                if (MODE == MARCH_MAKE_S && halo) o = st[0][j];
+                if (HALO_S && halo) o = st[0][j];
                 else {
                     o.x = make(st[0][j].x, st[NV > 1 ? 1 : 0][j].x, st[NV > 2 ? 2 : 0][j].x);
                     o.y = make(st[0][j].y, st[NV > 1 ? 1 : 0][j].y, st[NV > 2 ? 2 : 0][j].y);
@@ -359,10 +362,10 @@ bool march_plan_host(const TiledDict &T, long long n, MarchPlan &M) {
 // items, 86 % of the slots).  Several rounds per CTA were tried for 512^3 (Zc = 9: 1152 items = 3.9 rounds, on paper 94 %
 // instead of 86 %): 245 instead of 275 it/s — CTAs drift apart and the neighbouring columns' shared halo lines leave the L2.
 int march_choose_zc(int S, int P, int G) { return std::max(1, std::min(G / std::max(1, S), std::max(1, P / 8))); }
-template <int MODE, int NDOT, bool HAS_D, bool U_RING, int SHAPE, int HB>
+template <int MODE, int NDOT, bool HAS_D, bool U_RING, int SHAPE, int HB, bool SHARD_S = false>
 static int launch_march_t(cudamat_solver *s, const MarchArgs &a) {
     MarchPlan M = *s->march;
-    const void *kern = (const void *)k_spmv_march<MODE, NDOT, HAS_D, U_RING, SHAPE, HB>;
+    const void *kern = (const void *)k_spmv_march<MODE, NDOT, HAS_D, U_RING, SHAPE, HB, SHARD_S>;
     const size_t smem = sizeof(double) * 4 * (size_t)(kTile + 2 * HB * 256) +
                         ((NDOT >= 1 && !U_RING) || HAS_D ? (HAS_D ? 4 : 2) * kCtaThreads * 16 : 0);
     static bool attr_set[64] = {};
@@ -387,11 +390,11 @@ static int launch_march_t(cudamat_solver *s, const MarchArgs &a) {
     CM_CUDA(cudaGetLastError());
     return CUDAMAT_OK;
 }
-template <int MODE, int NDOT, bool HAS_D, bool U_RING>
+template <int MODE, int NDOT, bool HAS_D, bool U_RING, bool SHARD_S = false>
 static int launch_march_m(cudamat_solver *s, const MarchArgs &a) {
     const MarchPlan &M = *s->march;
-    if (M.H <= 256) return M.shape == 1 ? launch_march_t<MODE, NDOT, HAS_D, U_RING, 1, 1>(s, a) : launch_march_t<MODE, NDOT, HAS_D, U_RING, 0, 1>(s, a);
-    return M.shape == 1 ? launch_march_t<MODE, NDOT, HAS_D, U_RING, 1, 2>(s, a) : launch_march_t<MODE, NDOT, HAS_D, U_RING, 0, 2>(s, a);
+    if (M.H <= 256) return M.shape == 1 ? launch_march_t<MODE, NDOT, HAS_D, U_RING, 1, 1, SHARD_S>(s, a) : launch_march_t<MODE, NDOT, HAS_D, U_RING, 0, 1, SHARD_S>(s, a);
+    return M.shape == 1 ? launch_march_t<MODE, NDOT, HAS_D, U_RING, 1, 2, SHARD_S>(s, a) : launch_march_t<MODE, NDOT, HAS_D, U_RING, 0, 2, SHARD_S>(s, a);
 }
 static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -436,7 +439,11 @@ int launch_march_make_s(cudamat_solver *s, const double *r, const double *v, dou
     a.tmask = s->march_tmask; a.rc = rc; a.sc = s->d_sc; a.check_status = 1;
     int e = ev_mark(s, true);
     if (e) return e;
-    if ((e = d ? launch_march_m<MARCH_MAKE_S, 2, true, true>(s, a) : launch_march_m<MARCH_MAKE_S, 2, false, true>(s, a))) return e;
+    // slab shards (planes of s behind a shard face come from the neighbours): the SHARD_S instantiation
+    const bool shard = s->march->lo_base >= 0 || s->march->hi_base >= 0;
+    if (shard) e = d ? launch_march_m<MARCH_MAKE_S, 2, true, true, true>(s, a) : launch_march_m<MARCH_MAKE_S, 2, false, true, true>(s, a);
+    else       e = d ? launch_march_m<MARCH_MAKE_S, 2, true, true>(s, a) : launch_march_m<MARCH_MAKE_S, 2, false, true>(s, a);
+    if (e) return e;
     return ev_mark(s, false);
 }
 

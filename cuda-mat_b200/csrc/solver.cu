@@ -56,8 +56,13 @@ static DevPool *pool_for_current_device() {
             props.location.id = dev;
             if (cudaMemPoolCreate(&P.pool, &props) == cudaSuccess &&
                 cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking) == cudaSuccess) {
+                // freed memory stays mapped up to this much: half of the device by default.  An 8 GB limit (round 1) sat inside
+                // the footprint of one 256^3 ILU0 solve (~8.5 GB of matrix, factor, sweep plans, vectors): the pool trimmed at
+                // every synchronisation and re-grew, 1.1 s per analysis
                 const char *mb = getenv("CUDAMAT_POOL_KEEP_MB");
-                unsigned long long keep = (mb ? strtoull(mb, nullptr, 10) : 8192ull) << 20;
+                size_t free_b = 0, total_b = 0;
+                if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 16ull << 30; }
+                unsigned long long keep = mb ? (strtoull(mb, nullptr, 10) << 20) : (unsigned long long)(total_b / 2);
                 cudaMemPoolSetAttribute(P.pool, cudaMemPoolAttrReleaseThreshold, &keep);
                 P.ok = true;
             }
