@@ -554,13 +554,18 @@ def multi_gpu_e2e(cm, torch, dist, N, n, row0, row1, nnz_loc, ia, ja, a, b, rank
         t0 = time.time()
         s2 = cm.Solver(n, row0, row1, stream=stream)
         s2.set_csr_host(h_a.numpy(), h_ia.numpy(), h_ja.numpy())
+        t1 = time.time()
         cm.Comm.init(s2, idb, rank, world)
+        t2 = time.time()
         s2.analyze(cm.MODE_PLAIN)
+        t3 = time.time()
         d_b = torch.empty(nloc, dtype=torch.float64, device="cuda"); d_b.copy_(h_b, non_blocking=True)
         d_x = torch.empty(nloc, dtype=torch.float64, device="cuda")
         st = s2.solve(cm.MODE_PLAIN, d_b.data_ptr(), d_x.data_ptr(), maxit=5000, tol=1e-10)
+        t4 = time.time()
         h_x.copy_(d_x)
         barrier()
+        phases = {"create_upload": t1 - t0, "comm_init": t2 - t1, "analyze": t3 - t2, "solve": t4 - t3, "d2h_barrier": time.time() - t4}
         wall = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(wall, op=dist.ReduceOp.MAX)
         wall = float(wall[0])
@@ -568,7 +573,7 @@ def multi_gpu_e2e(cm, torch, dist, N, n, row0, row1, nnz_loc, ia, ja, a, b, rank
         it = st["iterations"]
         return {"value": it / wall, "unit": UNIT, "h2d_bytes_per_step": (12 * nnz_loc + 4 * (nloc + 1) + 8 * nloc) * world / max(it, 1),
                 "d2h_bytes_per_step": 8 * n / max(it, 1), "iterations": it, "wall_s": wall, "t_loop_s": st["t_loop"],
-                "converged": bool(st["converged"]),
+                "converged": bool(st["converged"]), "phases_s_rank0": phases,
                 "call": "per rank: cudamat_set_csr_host + cudamat_comm_init + cudamat_analyze + cudamat_solve_device(tol=1e-10) on pinned host shards"}
     except Exception as e:      # noqa: BLE001
         return {"value": None, "error": str(e)}

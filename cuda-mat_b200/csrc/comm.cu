@@ -267,7 +267,8 @@ static int p2p_setup(cudamat_solver *s, const std::vector<int> &W) {
     struct Xchg { cudaIpcMemHandle_t work, arena; unsigned long long work_elems; long long n; int ok; int pad; };
     Xchg mine{}; memset(&mine, 0, sizeof mine);
     const size_t gbytes = sizeof(double) * (size_t)c->exch_count;
-    const size_t abytes = 4096 + 2 * ((gbytes + 255) / 256) * 256;
+    // rounded to whole 2 MB blocks: an IPC handle names the cudaMalloc BLOCK, which must not be shared with any other buffer (solver.cu)
+    const size_t abytes = ((4096 + 2 * ((gbytes + 255) / 256) * 256) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
     if (s->work && s->work_pooled) {                  // an arena from the memory pool cannot be shared over IPC
         cudaStreamSynchronize(s->stream); dev_free(s->work); s->work = nullptr; s->work_nvec = 0;
     }

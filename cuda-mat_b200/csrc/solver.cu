@@ -142,8 +142,13 @@ static int alloc_reduction(cudamat_solver *s) {
 // neighbour processes (cudaIpcOpenMemHandle / CloseMemHandle) and cudaFree of it cost ~0.4 s per handle; a recycled arena
 // keeps its IPC handle, so the neighbours' cached mappings (comm.cu) stay valid.
 static std::mutex g_arena_mu;
+constexpr size_t kIpcBlock = 2u << 20;
 static double *g_arena_ptr = nullptr; static size_t g_arena_bytes = 0;
 static cudaError_t shared_arena_get(double **p, size_t bytes, size_t *got) {
+    // whole 2 MB blocks: cudaMalloc packs smaller allocations into shared blocks, and an IPC handle names the BLOCK — a block that a
+    // neighbour process still maps (its cached mapping of an arena recycled or freed here) cannot be opened again for another
+    // buffer that happens to land in it (seen as: the second sharded handle of a process silently falling back to NCCL)
+    bytes = (bytes + kIpcBlock - 1) / kIpcBlock * kIpcBlock;
     {
         std::lock_guard<std::mutex> lk(g_arena_mu);
         if (g_arena_ptr && g_arena_bytes >= bytes) { *p = g_arena_ptr; *got = g_arena_bytes; g_arena_ptr = nullptr; g_arena_bytes = 0; return cudaSuccess; }

@@ -56,7 +56,14 @@ def main():
             x2 = torch.zeros(nloc, **f64)
             st2 = s2.solve(cm.MODE_PLAIN, b.data_ptr(), x2.data_ptr(), maxit=5000, tol=1e-10)
             torch.cuda.synchronize()
-            flag = torch.tensor([int(torch.equal(x2, x) and st2["iterations"] == st["iterations"] and st2["spmv_variant"] == 6 and st2["fused"] == 2)], device="cuda")
+            # the fold needs the peer-memory path on THIS handle (a handle whose IPC set-up failed solves over NCCL, unfolded)
+            p2p2 = cm.Comm.p2p_enabled(s2)
+            parts = (torch.equal(x2, x), st2["iterations"] == st["iterations"], st2["spmv_variant"] == 6, st2["fused"] == 2, p2p2)
+            if not all(parts):
+                print("DIST-MARCH-SHARD rank %d N=%d: x_equal=%s iterations %d/%d variant=%d fused=%d p2p=%d max|dx|=%.3e"
+                      % (rank, N, parts[0], st2["iterations"], st["iterations"], st2["spmv_variant"], st2["fused"], int(p2p2),
+                         float((x2 - x).abs().max())), flush=True)
+            flag = torch.tensor([int(all(parts))], device="cuda")
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             march_ok = bool(flag.item())
             s2.close()
