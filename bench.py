@@ -305,7 +305,10 @@ def run_ours(args):
         plan = [first] + [chunk] * ((K - first) // chunk) + ([(K - first) % chunk] if (K - first) % chunk else [])
         sol.set_option("resume", 0)
         sol.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=W, tol=0.0)
-        sol.set_option("time_spmv", 2 if K < 64 else 8)      # the main kernels of every 2nd (8th) iteration are event-timed
+        # the main kernels of every 2nd (8th) iteration are event-timed.  Sharded runs always use every 8th: an event-timed kernel
+        # leaves the PDL chain, its halo push comes late and the neighbour waits for it (2 GPUs, K = 20: 0.329 ms per step with
+        # every 2nd iteration instrumented against 0.293-0.301 with every 8th)
+        sol.set_option("time_spmv", 2 if (K < 64 and world == 1) else 8)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tk, nk, done, launches, prev = [0.0] * 4, [0] * 4, 0, 0, W
         barrier()
