@@ -65,7 +65,7 @@ bool is_pageable(const void *p) {
 // to_device: host -> pinned slot -> device; otherwise device -> pinned slot -> host
 int staged_copy(Stager &S, int dev, char *dst, const char *src, size_t bytes, bool to_device, cudaStream_t stream) {
     std::lock_guard<std::mutex> lk(S.mu);
-    if (!stager_init(S)) return -1;
+    if (!stager_init(S)) return 1;                       // not available: the caller takes the plain path
     // the copies start after everything already enqueued on the caller's stream (allocation reuse, the solve before a download)
     CM_CUDA(cudaEventRecord(S.fence, stream));
     const size_t nchunks = (bytes + kChunk - 1) / kChunk;
@@ -102,7 +102,10 @@ int staged_copy(Stager &S, int dev, char *dst, const char *src, size_t bytes, bo
     };
     std::vector<std::thread> th;
     th.reserve(nt);
-    for (int t = 1; t < nt; ++t) th.emplace_back(worker, t);
+    for (int t = 1; t < nt; ++t) {
+        try { th.emplace_back(worker, t); }
+        catch (...) { break; }                  // no more threads to be had: the chunk counter hands their work to the others
+    }
     worker(0);
     for (auto &x : th) x.join();
     if (failed.load()) {
@@ -126,7 +129,7 @@ int copy_h2d(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
     int dev = 0;
     if (bytes >= kStagedMin && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevStage && is_pageable(src)) {
         int rc = staged_copy(g_stagers[dev], dev, (char *)dst, (const char *)src, bytes, true, stream);
-        if (rc >= 0) return rc;
+        if (rc <= 0) return rc;
     }
     CM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     return CUDAMAT_OK;
@@ -137,7 +140,7 @@ int copy_d2h(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
     int dev = 0;
     if (bytes >= kStagedMin && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevStage && is_pageable(dst)) {
         int rc = staged_copy(g_stagers[dev], dev, (char *)dst, (const char *)src, bytes, false, stream);
-        if (rc >= 0) return rc;                // complete on the host at return
+        if (rc <= 0) return rc;                // done (complete on the host at return) or failed
     }
     CM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     return CUDAMAT_OK;
