@@ -591,3 +591,45 @@ def test_row_statistics_pick_the_stream_kernel_for_irregular_rows(cm, O, torch_c
     s, st = make_solver(cm, torch, R.indptr.astype(np.int32), R.indices.astype(np.int32), R.data)
     assert st["spmv_variant"] == cm.SPMV_ROWLANE, st
     s.close()
+
+
+def test_random_dd_one_million_rows_against_the_oracle(cm, O, torch_cuda):
+    """BASELINE config 4 at a size the oracle still walks in seconds (1 M rows, 9.5 M entries, 11 k rows of > 32 entries): the device
+    generator, the SpMV picked by the row statistics (STREAM, one pass and column-blocked) and 40 iterations of the loop give the
+    oracle's bits; the full solve converges to 1e-10 with the true residual to match."""
+    torch = torch_cuda
+    n = 1_000_000
+    ia, ja, a = O.random_dd(n, 20240)
+    nnz = len(ja)
+    dia = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    assert cm.gen_random_dd_device(n, 20240, dia.data_ptr()) == nnz
+    dja = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    da = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    cm.gen_random_dd_device(n, 20240, dia.data_ptr(), dja.data_ptr(), da.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(dia.cpu().numpy(), ia) and np.array_equal(dja.cpu().numpy(), ja) and np.array_equal(da.cpu().numpy(), a)
+    xt = O.xtrue(7, 0, n)
+    b = O.spmv(ia, ja, a, xt)
+    xo, so = O.bicgstab_unprec(ia, ja, a, b, maxit=40, tol=1e-10)
+    assert so["iterations"] == 40 and not so["converged"]
+    dxt, db = dev(torch, xt), dev(torch, b)
+    for K in (0, 3):                                     # 0: one pass (x fits the L2), 3: column-blocked form
+        s = cm.Solver(n)
+        s.set_option("stream_blocks", K)
+        s.set_csr_device(nnz, da.data_ptr(), dia.data_ptr(), dja.data_ptr(), keep=(dia, dja, da))
+        assert s.analyze(0)["spmv_variant"] == cm.SPMV_STREAM
+        dy = torch.zeros(n, dtype=torch.float64, device="cuda")
+        s.spmv(dxt.data_ptr(), dy.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(dy.cpu().numpy(), b), K
+        dx = torch.zeros(n, dtype=torch.float64, device="cuda")
+        r = s.solve(0, db.data_ptr(), dx.data_ptr(), maxit=40, tol=1e-10)
+        torch.cuda.synchronize()
+        assert r["iterations"] == 40 and r["nrm_r"] == so["nrm_r"] and np.array_equal(dx.cpu().numpy(), xo), K
+        assert np.array_equal(np.asarray(s.history())[:41], np.asarray(so["hist"])[:41]), K
+        r = s.solve(0, db.data_ptr(), dx.data_ptr(), maxit=2000, tol=1e-10)
+        s.spmv(dx.data_ptr(), dy.data_ptr())
+        torch.cuda.synchronize()
+        assert r["converged"] and float(torch.linalg.norm(db - dy)) <= 1.5e-10 * r["nrm_r0"]
+        assert float(torch.linalg.norm(dx - dxt) / torch.linalg.norm(dxt)) <= 1e-7
+        s.close()
