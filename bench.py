@@ -304,7 +304,7 @@ def run_ours(args):
         first = max(1, min(K, chunk - min(W, chunk - 1)))
         plan = [first] + [chunk] * ((K - first) // chunk) + ([(K - first) % chunk] if (K - first) % chunk else [])
         sol.set_option("resume", 0)
-        sol.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=W, tol=0.0)
+        launches0 = sol.solve(cm.MODE_PLAIN, b.data_ptr(), x.data_ptr(), maxit=W, tol=0.0)["kernel_launches"]
         # the main kernels of every 2nd (8th) iteration are event-timed.  Sharded runs always use every 8th: an event-timed kernel
         # leaves the PDL chain, its halo push comes late and the neighbour waits for it (2 GPUs, K = 20: 0.329 ms per step with
         # every 2nd iteration instrumented against 0.293-0.301 with every 8th)
@@ -319,7 +319,7 @@ def run_ours(args):
             done += st["iterations"] - (prev if i == 0 else 0)
             for q in range(4):
                 tk[q] += st["t_kernel"][q]; nk[q] += st["n_kernel"][q]
-            launches = st["kernel_launches"]
+            launches = st["kernel_launches"] - launches0     # the handle counts every launch since its creation
             fused = int(st["fused"])
         e1.record()
         barrier()
