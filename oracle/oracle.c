@@ -300,16 +300,18 @@ int orc_bicgstab_unprec(int n, const int *ia, const int *ja, const double *a,
  * ILU0 right-preconditioned BiCGSTAB — restates gpu_pbicgstab pbicgstab.cu:45-154,
  * cuBLAS semantics: axpy = one FMA per element, scal = one multiply.
  * ------------------------------------------------------------------------------- */
+/* The loop with the preconditioner built from its own CSR (pia, pja, pa): the matrix itself for the reference's algorithm,
+ * its block-diagonal part for the block-Jacobi ILU(0) of row-sharded handles (orc_bicgstab_ilu0_blocks). */
 ORC_CLONES
-int orc_bicgstab_ilu0(int n, const int *ia, const int *ja, const double *a,
-                      const double *b, int maxit, double tol, double *x,
-                      orc_stats *st, double *hist, int hist_cap) {
-    int base = ia[0];
+static int ilu0_loop(int n, const int *ia, const int *ja, const double *a,
+                     const int *pia, const int *pja, const double *pa,
+                     const double *b, int maxit, double tol, double *x,
+                     orc_stats *st, double *hist, int hist_cap) {
     size_t N = (size_t)(n > 0 ? n : 1);
-    int64_t nnz = ia[n] - base;
+    int64_t nnz = pia[n] - pia[0];
     double *M = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
     memset(st, 0, sizeof *st);
-    int fs = orc_ilu0(n, ia, ja, a, M);
+    int fs = orc_ilu0(n, pia, pja, pa, M);
     if (fs > 0) { free(M); st->breakdown = 4; return 0; }
     double *w = (double *)calloc(N * 7, sizeof(double));
     double *r = w, *rw = w + N, *p = w + 2 * N, *pw = w + 3 * N, *s = w + 4 * N,
@@ -342,8 +344,8 @@ int orc_bicgstab_ilu0(int n, const int *ia, const int *ja, const double *a,
                 p[k] = FMA(1.0, r[k], q);
             }
         }
-        orc_sptrsv_lower_unit(n, ia, ja, M, p, t);              /* :92-94 */
-        orc_sptrsv_upper(n, ia, ja, M, t, pw);                  /* :96-98 */
+        orc_sptrsv_lower_unit(n, pia, pja, M, p, t);            /* :92-94 */
+        orc_sptrsv_upper(n, pia, pja, M, t, pw);                /* :96-98 */
         orc_spmv(n, ia, ja, a, pw, NULL, v);                    /* :104 */
         double temp = orc_dot(n, rw, v);                        /* :106 */
         alpha = rho / temp;
@@ -355,8 +357,8 @@ int orc_bicgstab_ilu0(int n, const int *ia, const int *ja, const double *a,
         nrmr = sqrt(orc_dot(n, r, r));                          /* :111 */
         if (hist && nh < hist_cap) hist[nh++] = nrmr;
         if (nrmr < tol * nrmr0) { st->converged = 1; st->breakdown = 0; break; }   /* :116 */
-        orc_sptrsv_lower_unit(n, ia, ja, M, r, t);              /* :121-123 */
-        orc_sptrsv_upper(n, ia, ja, M, t, s);                   /* :125-127 */
+        orc_sptrsv_lower_unit(n, pia, pja, M, r, t);            /* :121-123 */
+        orc_sptrsv_upper(n, pia, pja, M, t, s);                 /* :125-127 */
         orc_spmv(n, ia, ja, a, s, NULL, t);                     /* :132 */
         temp = orc_dot(n, t, r);                                /* :135 */
         double temp2 = orc_dot(n, t, t);                        /* :136 */
@@ -377,6 +379,42 @@ int orc_bicgstab_ilu0(int n, const int *ia, const int *ja, const double *a,
     free(w);
     free(M);
     return st->converged;
+}
+
+int orc_bicgstab_ilu0(int n, const int *ia, const int *ja, const double *a,
+                      const double *b, int maxit, double tol, double *x,
+                      orc_stats *st, double *hist, int hist_cap) {
+    return ilu0_loop(n, ia, ja, a, ia, ja, a, b, maxit, tol, x, st, hist, hist_cap);
+}
+
+/* Block-Jacobi ILU(0): what a row-sharded handle runs (csrc/ilu0.cu build_local_block; the reference has no multi-GPU path).
+ * Rows [row_start[k], row_start[k+1]) form block k; the preconditioner is ILU(0) of the matrix with every entry outside the
+ * diagonal blocks dropped (= independent ILU(0) factors of the blocks); SpMV, dots and updates act on the whole system.
+ * The reduction tree is partition-independent, so the sharded GPU run must give these bits. */
+int orc_bicgstab_ilu0_blocks(int n, const int *ia, const int *ja, const double *a,
+                             int nblk, const int64_t *row_start,
+                             const double *b, int maxit, double tol, double *x,
+                             orc_stats *st, double *hist, int hist_cap) {
+    const int base = ia[0];
+    int64_t nnz = ia[n] - base;
+    int *pia = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    int *pja = (int *)malloc(sizeof(int) * (size_t)(nnz > 0 ? nnz : 1));
+    double *pa = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+    int q = 0;
+    pia[0] = base;
+    for (int k = 0; k < nblk; ++k) {
+        const int64_t r0 = row_start[k], r1 = row_start[k + 1];
+        for (int64_t i = r0; i < r1; ++i) {
+            for (int p = ia[i] - base; p < ia[i + 1] - base; ++p) {
+                const int64_t c = (int64_t)ja[p] - base;
+                if (c >= r0 && c < r1) { pja[q] = ja[p]; pa[q] = a[p]; ++q; }
+            }
+            pia[i + 1] = q + base;
+        }
+    }
+    int ret = ilu0_loop(n, ia, ja, a, pia, pja, pa, b, maxit, tol, x, st, hist, hist_cap);
+    free(pia); free(pja); free(pa);
+    return ret;
 }
 
 /* ---------------------------------------------------------------------------------

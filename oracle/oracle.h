@@ -81,6 +81,11 @@ int    orc_bicgstab_unprec(int n, const int *ia, const int *ja, const double *a,
 int    orc_bicgstab_ilu0(int n, const int *ia, const int *ja, const double *a,
                          const double *b, int maxit, double tol, double *x,
                          orc_stats *st, double *hist, int hist_cap);
+/* block-Jacobi ILU(0) of the diagonal blocks [row_start[k], row_start[k+1]) — the preconditioner of row-sharded handles */
+int    orc_bicgstab_ilu0_blocks(int n, const int *ia, const int *ja, const double *a,
+                                int nblk, const int64_t *row_start,
+                                const double *b, int maxit, double tol, double *x,
+                                orc_stats *st, double *hist, int hist_cap);
 
 /* ---- generators -------------------------------------- */
 /* rows [row0,row1) of the N^3 7-point Dirichlet Poisson matrix, base-0, global column

@@ -64,6 +64,9 @@ def lib():
         L.orc_bicgstab_ilu0.restype = C.c_int
         L.orc_bicgstab_ilu0.argtypes = [C.c_int, c_ip, c_ip, c_dp, c_dp, C.c_int, C.c_double,
                                         c_dp, C.POINTER(OrcStats), c_dp, C.c_int]
+        L.orc_bicgstab_ilu0_blocks.restype = C.c_int
+        L.orc_bicgstab_ilu0_blocks.argtypes = [C.c_int, c_ip, c_ip, c_dp, C.c_int, C.POINTER(C.c_int64), c_dp, C.c_int, C.c_double,
+                                               c_dp, C.POINTER(OrcStats), c_dp, C.c_int]
         L.orc_poisson3d.restype = C.c_int64
         L.orc_poisson3d.argtypes = [C.c_int, C.c_int64, C.c_int64, c_ip, c_ip, c_dp]
         L.orc_xtrue.argtypes = [C.c_uint64, C.c_int64, C.c_int64, c_dp]
@@ -168,6 +171,20 @@ def bicgstab_ilu0(ia, ja, a, b, maxit=2000, tol=1e-6):
     hist = np.zeros(2 * maxit + 2)
     lib().orc_bicgstab_ilu0(n, _ip(ia), _ip(ja), _dp(a), _dp(b), maxit, tol, _dp(x),
                             C.byref(st), _dp(hist), len(hist))
+    return x, _stats(st, hist)
+
+
+def bicgstab_ilu0_blocks(ia, ja, a, b, row_start, maxit=2000, tol=1e-6):
+    """ILU0-BiCGSTAB with the block-Jacobi ILU(0) of the diagonal blocks [row_start[k], row_start[k+1]) (sharded handles)."""
+    ia, ja, a, b = _i32(ia), _i32(ja), _f64(a), _f64(b)
+    rs = np.ascontiguousarray(row_start, dtype=np.int64)
+    n = len(ia) - 1
+    assert rs[0] == 0 and rs[-1] == n and np.all(np.diff(rs) >= 0)
+    x = np.zeros(n)
+    st = OrcStats()
+    hist = np.zeros(2 * maxit + 2)
+    lib().orc_bicgstab_ilu0_blocks(n, _ip(ia), _ip(ja), _dp(a), len(rs) - 1, rs.ctypes.data_as(C.POINTER(C.c_int64)), _dp(b),
+                                   maxit, tol, _dp(x), C.byref(st), _dp(hist), len(hist))
     return x, _stats(st, hist)
 
 

@@ -80,9 +80,11 @@ def main():
         per = max(cm.partition_rows(n, world, r)[1] - cm.partition_rows(n, world, r)[0] for r in range(world))
         pad = torch.zeros(per, **f64); pad[:nloc] = x
         padb = torch.zeros(per, **f64); padb[:nloc] = b
+        padi = torch.zeros(per, **f64); padi[:nloc] = xi
         xs = [torch.zeros(per, **f64) for _ in range(world)]
         bs = [torch.zeros(per, **f64) for _ in range(world)]
-        dist.all_gather(xs, pad); dist.all_gather(bs, padb)
+        xis = [torch.zeros(per, **f64) for _ in range(world)]
+        dist.all_gather(xs, pad); dist.all_gather(bs, padb); dist.all_gather(xis, padi)
         s.close()
         if rank == 0:
             sizes = [cm.partition_rows(n, world, r)[1] - cm.partition_rows(n, world, r)[0] for r in range(world)]
@@ -103,8 +105,19 @@ def main():
             st1 = s1.solve(cm.MODE_PLAIN, b1.data_ptr(), x1.data_ptr(), maxit=5000, tol=1e-10)
             d1 = s1.dot(x1.data_ptr(), b1.data_ptr())
             torch.cuda.synchronize()
+            # block-Jacobi ILU(0) against the CPU oracle's restatement of it (oracle.c orc_bicgstab_ilu0_blocks: ILU(0) of the
+            # diagonal blocks of the same row partition): same iteration count, same bits (sizes the oracle walks in seconds)
+            blk_ok = True
+            if n <= 64 ** 3:
+                O = ge.load_oracle()
+                oia, oja, oa = O.poisson3d(N)
+                rs = [0] + [cm.partition_rows(n, world, r)[1] for r in range(world)]
+                xo, so = O.bicgstab_ilu0_blocks(oia, oja, oa, bg.cpu().numpy(), rs, maxit=5000, tol=1e-10)
+                xig = torch.cat([xis[r][:sizes[r]] for r in range(world)]).cpu().numpy()
+                blk_ok = so["iterations"] == sti["iterations"] and bool(so["converged"]) and bool((xig == xo).all())
+                print("DIST-BLOCK-ILU0 N=%d world=%d: iterations %d (oracle %d) x_equal=%s" % (N, world, sti["iterations"], so["iterations"], bool((xig == xo).all())), flush=True)
             ok = (torch.equal(bg, b1) and torch.equal(xg, x1) and st["iterations"] == st1["iterations"]
-                  and bool(st["converged"]) and dt == d1 and ilu_ok and march_ok)
+                  and bool(st["converged"]) and dt == d1 and ilu_ok and march_ok and blk_ok)
             print("DIST N=%d world=%d p2p=%d variant=%d iters=%d/%d b_equal=%s x_equal=%s dot_equal=%s loop_ms=%.2f/%.2f block_ilu0_iters=%d err=%.1e march_fold_shard=%s %s"
                   % (N, world, int(p2p), st["spmv_variant"], st["iterations"], st1["iterations"], torch.equal(bg, b1), torch.equal(xg, x1), dt == d1,
                      st["t_loop"] * 1e3, st1["t_loop"] * 1e3, sti["iterations"], ilu_err, march_ok, "OK" if ok else "MISMATCH"), flush=True)
