@@ -290,4 +290,4 @@ def test_block_jacobi_counts_match_the_sharded_gpu_runs(O, N, world, iters):
     rs = [0] + [cm.partition_rows(n, world, r)[1] for r in range(world)]
     x, st = O.bicgstab_ilu0_blocks(ia, ja, a, b, rs, maxit=5000, tol=1e-10)
     assert st["converged"] and st["iterations"] == iters
-    assert np.linalg.norm(x - xt) <= 1e-7 * np.linalg.norm(xt)
+    assert np.linalg.norm(x - xt) <= 1e-6 * np.linalg.norm(xt)          # cond(A) ~ N^2 times the 1e-10 residual
