@@ -107,6 +107,8 @@ int         cudamat_device_count(void);
  *            bicgstab_lu_precond pbicgstab.cu:157-409   (mode ILU0:    d = x0 = NULL, x0 := ones)
  * x: caller-allocated n doubles; dtAlg (may be NULL) gets the loop seconds; st may be NULL.
  * debug != 0 prints the reference's trace lines (pbicgstab.cu:76,113,144,203,349-363,484,550).
+ * The host arrays may be pageable (malloc'ed, as example.cpp:96-104,252 passes them) or pinned: pageable arrays of 8 MB or
+ * more travel through a threaded pinned staging area (csrc/hostcopy.cpp), pinned ones are copied directly.
  * ------------------------------------------------------------------------------------------- */
 int cudamat_bicgstab_host(int mode, int n, int nnz, const double *A, const int *iA, const int *jA,
                           const double *d, const double *x0, const double *b,
